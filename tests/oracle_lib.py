@@ -1,0 +1,168 @@
+"""ctypes binding of the CPU oracle (oracle/_build/liborb_oracle.so).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def build():
+    """(Re)build the oracle shared object with the recipe committed under oracle/."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(ROOT, "oracle", "_build", "liborb_oracle.so")
+    odir = os.path.join(ROOT, "oracle")
+    srcs = [os.path.join(odir, f) for f in os.listdir(odir) if f.endswith((".cpp", ".h"))]
+    if (not os.path.exists(path)) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+        build()
+    L = C.CDLL(path)
+    L.orc_resize_linear_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int]
+    L.orc_gaussian7_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+    L.orc_fast9.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int]
+    L.orc_fast9.restype = C.c_int
+    L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+    L.orc_fast_atan2.restype = C.c_float
+    L.orc_cvround_f.argtypes = [C.c_float]
+    L.orc_cvround_f.restype = C.c_int
+    L.orc_hamming256.argtypes = [u8p, u8p]
+    L.orc_hamming256.restype = C.c_int
+    L.orc_cosf_sinf.argtypes = [f32p, C.c_int, f32p, f32p]
+    L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.orc_extractor_create.restype = C.c_void_p
+    L.orc_extractor_destroy.argtypes = [C.c_void_p]
+    L.orc_extractor_nlevels.argtypes = [C.c_void_p]
+    L.orc_extractor_tables.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p, i32p, i32p]
+    L.orc_extract.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, u8p, C.c_int]
+    L.orc_extract.restype = C.c_int
+    L.orc_level_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.orc_level_pixels.argtypes = [C.c_void_p, C.c_int]
+    L.orc_level_pixels.restype = C.c_void_p
+    L.orc_level_blurred.argtypes = [C.c_void_p, C.c_int]
+    L.orc_level_blurred.restype = C.c_void_p
+    L.orc_level_candidates.argtypes = [C.c_void_p, C.c_int, i32p, C.c_int]
+    L.orc_level_candidates.restype = C.c_int
+    L.orc_level_selected.argtypes = [C.c_void_p, C.c_int, i32p, C.c_int]
+    L.orc_level_selected.restype = C.c_int
+    L.orc_extractor_timers.argtypes = [C.c_void_p, f64p]
+    L.orc_match_bruteforce.argtypes = [u8p, C.c_int, u8p, C.c_int, i32p, i32p, i32p]
+    _LIB = L
+    return L
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_ptr(src, u8p), src.shape[1], src.shape[0], src.strides[0], _ptr(dst, u8p), dw, dh, dw)
+    return dst
+
+
+def gaussian7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().orc_gaussian7_u8(_ptr(src, u8p), src.shape[1], src.shape[0], src.strides[0], _ptr(dst, u8p), dst.strides[0])
+    return dst
+
+
+def fast9(img, threshold, nonmax=True, cap=1 << 16):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty((cap, 3), np.int32)
+    n = lib().orc_fast9(_ptr(img, u8p), img.shape[1], img.shape[0], img.strides[0], threshold, int(nonmax), _ptr(out, i32p), cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
+def cosf_sinf(x):
+    x = np.ascontiguousarray(x, np.float32)
+    c = np.empty_like(x)
+    s = np.empty_like(x)
+    lib().orc_cosf_sinf(_ptr(x, f32p), x.size, _ptr(c, f32p), _ptr(s, f32p))
+    return c, s
+
+
+class Extractor:
+    """Mirror of ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) on the oracle."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = lib()
+        self.h = self.L.orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        assert self.h
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_extractor_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sc, isc, s2, is2 = (np.empty(n, np.float32) for _ in range(4))
+        fpl = np.empty(n, np.int32)
+        umax = np.empty(16, np.int32)
+        self.L.orc_extractor_tables(self.h, _ptr(sc, f32p), _ptr(isc, f32p), _ptr(s2, f32p), _ptr(is2, f32p), _ptr(fpl, i32p), _ptr(umax, i32p))
+        return dict(scale=sc, inv_scale=isc, sigma2=s2, inv_sigma2=is2, features_per_level=fpl, umax=umax)
+
+    def __call__(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.nfeatures + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.orc_extract(self.h, _ptr(img, u8p), img.shape[1], img.shape[0], img.strides[0], kps.ctypes.data, _ptr(desc, u8p), cap)
+        assert 0 <= n <= cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level_size(self, l):
+        w, h = C.c_int(), C.c_int()
+        self.L.orc_level_size(self.h, l, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level_pixels(self, l, blurred=False):
+        w, h = self.level_size(l)
+        p = (self.L.orc_level_blurred if blurred else self.L.orc_level_pixels)(self.h, l)
+        if not p:
+            return None
+        return np.ctypeslib.as_array(C.cast(p, u8p), shape=(h, w)).copy()
+
+    def level_candidates(self, l, cap=1 << 17):
+        out = np.empty((cap, 3), np.int32)
+        n = self.L.orc_level_candidates(self.h, l, _ptr(out, i32p), cap)
+        return out[:min(n, cap)].copy()
+
+    def level_selected(self, l, cap=1 << 14):
+        out = np.empty((cap, 3), np.int32)
+        n = self.L.orc_level_selected(self.h, l, _ptr(out, i32p), cap)
+        return out[:min(n, cap)].copy()
+
+    def timers(self):
+        t = np.zeros(6, np.float64)
+        self.L.orc_extractor_timers(self.h, _ptr(t, f64p))
+        return dict(zip(["pyramid", "fast", "quadtree", "orient", "blur", "desc"], t.tolist()))
+
+
+def match_bruteforce(dq, dt):
+    dq = np.ascontiguousarray(dq, np.uint8)
+    dt = np.ascontiguousarray(dt, np.uint8)
+    nq, nt = dq.shape[0], dt.shape[0]
+    bi, bd, sd = (np.empty(nq, np.int32) for _ in range(3))
+    lib().orc_match_bruteforce(_ptr(dq, u8p), nq, _ptr(dt, u8p), nt, _ptr(bi, i32p), _ptr(bd, i32p), _ptr(sd, i32p))
+    return bi, bd, sd
