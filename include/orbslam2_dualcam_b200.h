@@ -89,6 +89,12 @@ int  orbx_synchronize(orbx_t*);
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 long long orbx_launch_count(const orbx_t*);
 
+/* Per-stage device timing for bench.py's roofline: when enabled, every orbx_extract_device call records CUDA events
+ * between its stages on the launching stream (up to 256 calls are kept).  orbx_stage_ms synchronises the stream, returns
+ * the summed milliseconds of {pyramid, fast cells, quadtree, describe} over the recorded calls, and resets. */
+int  orbx_profile(orbx_t*, int enable);
+int  orbx_stage_ms(orbx_t*, double* ms4, int* calls);
+
 /* Stage taps for parity tests (device -> host copies of intermediate results of the LAST extract call).
  *   orbx_debug_level:      level image of image index `img` (dense w*h into out)
  *   orbx_debug_candidates: FAST+NMS survivors of (img, level) as (x, y, score) int triplets relative to the
@@ -113,6 +119,10 @@ int  orbm_set_stream(orbm_t*, void* cuda_stream);
 int  orbm_synchronize(orbm_t*);
 long long orbm_launch_count(const orbm_t*);
 
+/* device time of the brute-force kernel over the recorded calls (same protocol as orbx_profile / orbx_stage_ms) */
+int  orbm_profile(orbm_t*, int enable);
+int  orbm_stage_ms(orbm_t*, double* ms1, int* calls);
+
 /* ORBmatcher::DescriptorDistance(a, b) (src/ORBmatcher.cc:2015-2031) for n descriptor pairs (HOST buffers). */
 int  orbm_descriptor_distance(orbm_t*, const uint8_t* a, const uint8_t* b, int n, int32_t* dist);
 
@@ -131,6 +141,14 @@ int  orbm_bruteforce(orbm_t*, const uint8_t* dq, const int32_t* nq, int q_capaci
 int  orbm_bruteforce_device(orbm_t*, const uint8_t* d_dq, const int32_t* d_nq, int q_capacity,
                             const uint8_t* d_dt, const int32_t* d_nt, int t_capacity, int pairs,
                             int32_t* d_best_idx, int32_t* d_best_d, int32_t* d_second_d);
+
+/* Same search over a POOL of descriptor sets (e.g. the [frames][cameras] output of orbx_extract_device): pair p matches
+ * set q_set[p] (queries) against set t_set[p] (train), e.g. camera c of frame k against camera c of frame k+1.
+ *   d_desc uint8 [n_sets][capacity][32], d_counts int32 [n_sets], d_q_set/d_t_set int32 [pairs]
+ *   outputs int32 [pairs][capacity] (entries >= counts[q_set[p]] untouched).  DEVICE buffers, asynchronous. */
+int  orbm_bruteforce_sets_device(orbm_t*, const uint8_t* d_desc, const int32_t* d_counts, int capacity, int n_sets,
+                                 const int32_t* d_q_set, const int32_t* d_t_set, int pairs,
+                                 int32_t* d_best_idx, int32_t* d_best_d, int32_t* d_second_d);
 
 #ifdef __cplusplus
 }

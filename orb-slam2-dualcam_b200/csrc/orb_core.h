@@ -12,14 +12,15 @@
 #pragma once
 #include <stdint.h>
 
+#include <cmath>
+#include <cstring>
+
 #if defined(__CUDACC__)
 #define ORB_HD __host__ __device__ __forceinline__
 #define ORB_HD_NOINLINE __host__ __device__
 #else
 #define ORB_HD inline
 #define ORB_HD_NOINLINE inline
-#include <cmath>
-#include <cstring>
 #endif
 
 namespace orbcore {

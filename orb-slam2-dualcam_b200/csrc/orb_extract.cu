@@ -1,0 +1,864 @@
+// orb_extract.cu -- sm_100a implementation of ORBextractor::operator() batched over frames x cameras.
+//
+// Reference path (file:line under /root/reference): src/ORBextractor.cc:1043-1105 operator(), :1107-1132 ComputePyramid,
+// :765-853 ComputeKeyPointsOctTree (+ cv::FAST per 30-px cell), :539-763 DistributeOctTree, :77-104 IC_Angle,
+// :108-147 computeOrbDescriptor (+ cv::GaussianBlur 7x7 s=2), bit_pattern_31_ :150-408.
+//
+// Kernel pipeline per orbx_extract_device() call (all images of the batch in every launch):
+//   resize_level_kernel   x (nlevels-1)   level l from level l-1, cv::resize INTER_LINEAR 8U fixed-point arithmetic
+//   fast_cells_kernel     x 1             one CTA per 30-px cell: FAST-9/16 score, cell-local NMS, ini/min threshold
+//                                         fallback, unordered packed candidate list per (image, level)
+//   quadtree_kernel       x 1             one CTA per (image, level): level-synchronous DistributeOctTree
+//   describe_kernel       x 1             one warp per keypoint: IC angle, 7x7 Gaussian of the 37x37 patch in shared
+//                                         memory, steered rBRIEF, cv::KeyPoint + 32-byte descriptor output
+// There is no CPU fallback: every entry point needs a CUDA device.
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "orb_common.h"
+#include "orb_core.h"
+#include "orb_geometry.h"
+#include "rbrief_pattern.h"
+
+using namespace orbcore;
+
+#define ORB_MAX_LEVELS 16
+#define ORB_MAX_ROOTS 16
+
+// ------------------------------------------------------------------------------------------------ device-side geometry
+struct LevelDev {
+    int w, h, pitch;                 // level image
+    unsigned long long img_stride;   // bytes between consecutive images of this level
+    int width, height;               // maxBorder - minBorder (detection frame, relative coordinates start at (16,16))
+    int wCell, hCell, nColsEff, nRowsEff;
+    int cand_off, cand_cap;          // slice of the per-image candidate array
+    int sel_off, sel_cap;            // slice of the per-image selected array
+    int quota, nIni;
+    float hX, scale;
+    int patch_size, valid;
+};
+
+struct ExtractParams {
+    int nlevels, n_images;
+    int iniTh, minTh;
+    int cells_per_image;
+    int cand_per_image, sel_per_image;
+    int cell_begin[ORB_MAX_LEVELS + 1];
+    LevelDev lv[ORB_MAX_LEVELS];
+    const uint8_t* base[ORB_MAX_LEVELS];   // level images (level 0 = the caller's batch)
+};
+
+// ------------------------------------------------------------------------------------------------ pyramid
+// cv::resize(INTER_LINEAR, 8UC1) as called at src/ORBextractor.cc:1120.  One thread = 4 destination pixels of one row.
+__global__ void __launch_bounds__(128) resize_level_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
+                                                           unsigned long long sstride, uint8_t* __restrict__ dst, int dw, int dh,
+                                                           int dpitch, unsigned long long dstride, const int* __restrict__ xofs,
+                                                           const int* __restrict__ ialpha /* 2 x int16 packed */,
+                                                           const int* __restrict__ yofs, const int* __restrict__ ibeta) {
+    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int dy = blockIdx.y;
+    if (dx0 >= dw) return;
+    const uint8_t* S = src + (unsigned long long)blockIdx.z * sstride;
+    uint8_t* D = dst + (unsigned long long)blockIdx.z * dstride + (size_t)dy * dpitch;
+    const int sy = yofs[dy];
+    const int r0 = min(max(sy, 0), sh - 1), r1 = min(max(sy + 1, 0), sh - 1);
+    const int bpk = ibeta[dy];
+    const int b0 = (short)(bpk & 0xffff), b1 = (short)(bpk >> 16);
+    const uint8_t* R0 = S + (size_t)r0 * spitch;
+    const uint8_t* R1 = S + (size_t)r1 * spitch;
+    uint32_t outw = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int dx = dx0 + k;
+        if (dx < dw) {
+            const int sx = xofs[dx];
+            const int sx1 = min(sx + 1, sw - 1);
+            const int apk = ialpha[dx];
+            const int a0 = (short)(apk & 0xffff), a1 = (short)(apk >> 16);
+            const int S0 = R0[sx] * a0 + R0[sx1] * a1;
+            const int S1 = R1[sx] * a0 + R1[sx1] * a1;
+            int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+            outw |= (uint32_t)v << (8 * k);
+        }
+    }
+    // rows are padded to a multiple of 16 bytes, so the full word store never leaves the row
+    *reinterpret_cast<uint32_t*>(D + dx0) = outw;
+}
+
+// ------------------------------------------------------------------------------------------------ FAST per cell
+// One CTA = one cell of ComputeKeyPointsOctTree's grid (src/ORBextractor.cc:789-829).  The cell's detection region is
+// [cj*wCell+3, (cj+1)*wCell+3) x [ci*hCell+3, (ci+1)*hCell+3) in border-relative coordinates (the last effective cell
+// runs to width-3 / height-3); regions of different cells tile the level exactly, NMS only looks at neighbours inside
+// the same region, and the iniTh -> minTh fallback is decided per cell -- exactly what 815 separate cv::FAST calls do.
+#define FAST_THREADS 128
+
+__global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_constant__ ExtractParams P,
+                                                                  uint32_t* __restrict__ cand, int* __restrict__ cand_count,
+                                                                  int tile_cap, int pix_cap) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* tile = smem;                                  // (dh+6) x tp raw pixels
+    uint8_t* score = tile + tile_cap;                      // dh x dw
+    uint16_t* list = reinterpret_cast<uint16_t*>(score + pix_cap);   // pixels that pass the compass pre-test
+    uint16_t* list2 = list + pix_cap;                      // pixels that are corners at min(iniTh, minTh)
+    __shared__ int s_n1, s_n2, s_cnt_ini, s_cnt_min, s_base, s_emit;
+
+    const int img = blockIdx.y;
+    int cell = blockIdx.x;
+    int l = 0;
+    while (l + 1 < P.nlevels && cell >= P.cell_begin[l + 1]) l++;
+    cell -= P.cell_begin[l];
+    const LevelDev& L = P.lv[l];
+    const int ci = cell / L.nColsEff, cj = cell - ci * L.nColsEff;
+    const int x0 = cj * L.wCell + 3, y0 = ci * L.hCell + 3;
+    const int x1 = (cj == L.nColsEff - 1) ? L.width - 3 : x0 + L.wCell;
+    const int y1 = (ci == L.nRowsEff - 1) ? L.height - 3 : y0 + L.hCell;
+    const int dw = x1 - x0, dh = y1 - y0;
+    if (dw <= 0 || dh <= 0) return;
+    const int tw = dw + 6, th = dh + 6;
+    const int tp = (tw + 3) & ~3;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_n1 = 0; s_n2 = 0; s_cnt_ini = 0; s_cnt_min = 0; s_emit = 0; }
+
+    // ---- stage the tile: absolute pixel (16 + x0 - 3 + tx, 16 + y0 - 3 + ty)
+    const uint8_t* src = P.base[l] + (unsigned long long)img * L.img_stride + (size_t)(16 + y0 - 3) * L.pitch + (16 + x0 - 3);
+    for (int i = tid; i < tw * th; i += FAST_THREADS) {
+        const int ty = i / tw, tx = i - ty * tw;
+        tile[ty * tp + tx] = __ldg(src + (size_t)ty * L.pitch + tx);
+    }
+    __syncthreads();
+
+    const int iniTh = min(max(P.iniTh, 0), 255), minTh = min(max(P.minTh, 0), 255);
+    const int tlow = min(iniTh, minTh);
+    const int npix = dw * dh;
+    const unsigned lane = tid & 31;
+
+    // ---- pass 1: compass pre-test, warp-compacted list of survivors
+    for (int i0 = 0; i0 < npix; i0 += FAST_THREADS) {
+        const int i = i0 + tid;
+        bool pass = false;
+        if (i < npix) {
+            const int y = i / dw, x = i - y * dw;
+            const uint8_t* p = tile + (y + 3) * tp + (x + 3);
+            pass = fast16_pretest(p[0], p[3 * tp], p[3], p[-3 * tp], p[-3], tlow);
+            score[i] = 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_n1, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) list[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
+    }
+    __syncthreads();
+
+    // ---- pass 2: exact corner score of the survivors
+    const int n1 = s_n1;
+    const int rdx[16] = ORB_RING_DX, rdy[16] = ORB_RING_DY;
+    for (int e = tid; e < n1; e += FAST_THREADS) {
+        const int i = list[e];
+        const int y = i / dw, x = i - y * dw;
+        const uint8_t* p = tile + (y + 3) * tp + (x + 3);
+        int ring[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) ring[k] = p[rdy[k] * tp + rdx[k]];
+        const int s = fast16_score(p[0], ring);
+        if (s >= tlow && s > 0) {
+            score[i] = (uint8_t)s;
+            list2[atomicAdd(&s_n2, 1)] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 3: strict 3x3 maximum inside the cell (threshold independent)
+    const int n2 = s_n2;
+    for (int e = tid; e < n2; e += FAST_THREADS) {
+        const int i = list2[e];
+        const int y = i / dw, x = i - y * dw;
+        const int s = score[i];
+        bool ismax = true;
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+                if (dx == 0 && dy == 0) continue;
+                const int xx = x + dx, yy = y + dy;
+                if (xx < 0 || xx >= dw || yy < 0 || yy >= dh) continue;
+                if (score[yy * dw + xx] >= s) ismax = false;
+            }
+        if (ismax) {
+            if (s >= iniTh) atomicAdd(&s_cnt_ini, 1);
+            if (s >= minTh) atomicAdd(&s_cnt_min, 1);
+            list2[e] = (uint16_t)(i | 0x8000);
+        }
+    }
+    __syncthreads();
+
+    // ---- emit: FAST(iniTh) result, or FAST(minTh) result when the former is empty (src/ORBextractor.cc:809-816)
+    const int t = s_cnt_ini > 0 ? iniTh : minTh;
+    const int nkeep = s_cnt_ini > 0 ? s_cnt_ini : s_cnt_min;
+    if (nkeep == 0) return;
+    if (tid == 0) s_base = atomicAdd(&cand_count[img * P.nlevels + l], nkeep);
+    __syncthreads();
+    uint32_t* out = cand + (size_t)img * P.cand_per_image + L.cand_off;
+    for (int e = tid; e < n2; e += FAST_THREADS) {
+        const int v = list2[e];
+        if (!(v & 0x8000)) continue;
+        const int i = v & 0x7fff;
+        const int s = score[i];
+        if (s < t) continue;
+        const int y = i / dw, x = i - y * dw;
+        const int pos = s_base + atomicAdd(&s_emit, 1);
+        if (pos < L.cand_cap) out[pos] = cand_pack(x0 + x, y0 + y, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ quadtree
+// DistributeOctTree (src/ORBextractor.cc:539-763) in its level-synchronous form (orb_core.h): every sweep is
+// (parallel) child histograms -> (parallel) split order -> (one thread) list rebuild -> (parallel) relabel.
+#define QT_THREADS 256
+
+__global__ void __launch_bounds__(QT_THREADS) quadtree_kernel(const __grid_constant__ ExtractParams P,
+                                                              const uint32_t* __restrict__ cand, const int* __restrict__ cand_count,
+                                                              uint16_t* __restrict__ node_of_all, uint32_t* __restrict__ sel,
+                                                              int* __restrict__ sel_count, int maxl, int* __restrict__ overflow) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    QtNode* bufA = reinterpret_cast<QtNode*>(smem);
+    QtNode* bufB = bufA + maxl;
+    int* cc = reinterpret_cast<int*>(bufB + maxl);
+    int* childpos = cc + 4 * maxl;
+    int* newpos = childpos + 4 * maxl;
+    int* order = newpos + maxl;
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(order + maxl);   // 72*maxl bytes in: 8-byte aligned
+    __shared__ int s_root_cnt[ORB_MAX_ROOTS], s_root_pos[ORB_MAX_ROOTS];
+    __shared__ int s_m, s_nx, s_m2, s_nexp;
+
+    const int l = blockIdx.x, img = blockIdx.y;
+    const LevelDev& L = P.lv[l];
+    const int tid = threadIdx.x;
+    int n = L.valid ? cand_count[img * P.nlevels + l] : 0;
+    if (n > L.cand_cap) { n = L.cand_cap; if (tid == 0) atomicExch(overflow, 1); }
+    if (n == 0) { if (tid == 0) sel_count[img * P.nlevels + l] = 0; return; }
+    const uint32_t* C = cand + (size_t)img * P.cand_per_image + L.cand_off;
+    uint16_t* node_of = node_of_all + (size_t)img * P.cand_per_image + L.cand_off;
+    const int N = L.quota;
+
+    // ---- roots (src/ORBextractor.cc:543-583)
+    if (tid < ORB_MAX_ROOTS) s_root_cnt[tid] = 0;
+    __syncthreads();
+    for (int p = tid; p < n; p += QT_THREADS) {
+        const int r = (int)fdiv_rn((float)cand_x(C[p]), L.hX);
+        node_of[p] = (uint16_t)r;
+        atomicAdd(&s_root_cnt[r], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        for (int i = 0; i < L.nIni; i++) {
+            s_root_pos[i] = -1;
+            if (s_root_cnt[i] == 0) continue;
+            QtNode r;
+            r.x0 = (int16_t)(int)fmul_rn(L.hX, (float)i);
+            r.x1 = (int16_t)(int)fmul_rn(L.hX, (float)(i + 1));
+            r.y0 = 0;
+            r.y1 = (int16_t)L.height;
+            r.cnt = s_root_cnt[i];
+            r.seq = i;
+            s_root_pos[i] = m;
+            bufA[m++] = r;
+        }
+        s_m = m;
+    }
+    __syncthreads();
+    for (int p = tid; p < n; p += QT_THREADS) node_of[p] = (uint16_t)s_root_pos[node_of[p]];
+    QtNode* cur = bufA;
+    QtNode* nxt = bufB;
+    int m = s_m;
+    bool finish = false, phase2 = false;
+    __syncthreads();
+
+    while (!finish) {
+        for (int i = tid; i < 4 * m; i += QT_THREADS) cc[i] = 0;
+        if (tid == 0) s_nx = 0;
+        __syncthreads();
+        // child histograms of the nodes that will (may) be split
+        for (int p = tid; p < n; p += QT_THREADS) {
+            const int i = node_of[p];
+            const QtNode nd = cur[i];
+            if (nd.cnt > 1) {
+                const uint32_t c = C[p];
+                atomicAdd(&cc[i * 4 + qt_quadrant(nd, cand_x(c), cand_y(c))], 1);
+            }
+        }
+        // split order: list order in the first phase (:598-664); descending (size, creation index) afterwards (:673-738)
+        for (int i = tid; i < m; i += QT_THREADS) {
+            const QtNode a = cur[i];
+            if (a.cnt <= 1) continue;
+            int rank = 0;
+            if (!phase2) {
+                for (int j = 0; j < i; j++) rank += cur[j].cnt > 1;
+            } else {
+                for (int j = 0; j < m; j++) {
+                    const QtNode b = cur[j];
+                    rank += (b.cnt > 1) && (b.cnt > a.cnt || (b.cnt == a.cnt && b.seq > a.seq));
+                }
+            }
+            order[rank] = i;
+            atomicAdd(&s_nx, 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int nexp = 0;
+            s_m2 = qt_rebuild(cur, m, cc, order, s_nx, phase2, N, nxt, childpos, newpos, &nexp);
+            s_nexp = nexp;
+        }
+        __syncthreads();
+        for (int p = tid; p < n; p += QT_THREADS) {
+            const int i = node_of[p];
+            int np = newpos[i];
+            if (np < 0) {
+                const uint32_t c = C[p];
+                np = childpos[i * 4 + qt_quadrant(cur[i], cand_x(c), cand_y(c))];
+            }
+            node_of[p] = (uint16_t)np;
+        }
+        const int m2 = s_m2;
+        if (m2 >= N || m2 == m) finish = true;
+        else if (!phase2 && m2 + 3 * s_nexp > N) phase2 = true;
+        m = m2;
+        QtNode* t = cur; cur = nxt; nxt = t;
+        __syncthreads();
+        if (m > maxl - 4) { if (tid == 0) atomicExch(overflow, 2); break; }
+    }
+
+    // ---- per node: highest response, first in vToDistributeKeys order on ties (src/ORBextractor.cc:744-760)
+    for (int i = tid; i < m; i += QT_THREADS) best[i] = 0ull;
+    __syncthreads();
+    for (int p = tid; p < n; p += QT_THREADS) {
+        const uint32_t c = C[p];
+        const uint32_t key = cand_order_key(cand_x(c), cand_y(c), L.wCell, L.hCell, L.nColsEff, L.nRowsEff);
+        const unsigned long long k = (((unsigned long long)cand_score(c) << 32) | (unsigned long long)(0xffffffffu - key)) + 1ull;
+        atomicMax(&best[node_of[p]], k);
+    }
+    __syncthreads();
+    uint32_t* S = sel + (size_t)img * P.sel_per_image + L.sel_off;
+    const int mout = min(m, L.sel_cap);
+    for (int i = tid; i < mout; i += QT_THREADS) {
+        const unsigned long long k = best[i] - 1ull;
+        const uint32_t key = 0xffffffffu - (uint32_t)(k & 0xffffffffull);
+        const int ci = key >> 24, cj = (key >> 16) & 255, ly = (key >> 8) & 255, lx = key & 255;
+        S[i] = cand_pack(cj * L.wCell + lx, ci * L.hCell + ly, (int)(k >> 32));
+    }
+    if (tid == 0) {
+        sel_count[img * P.nlevels + l] = mout;
+        if (m > L.sel_cap) atomicExch(overflow, 3);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ orientation + descriptor
+// One warp per keypoint.  The 43x43 raw patch (REFLECT_101 at the level border, like cv::GaussianBlur on the cloned
+// level, src/ORBextractor.cc:1085-1086) is staged in shared memory; IC_Angle (:77-104) reads its inner radius-15 disc;
+// the 7x7 sigma-2 Gaussian (integer kernel {18,34,48,56,48,34,18}, one rounding (acc + 2^15) >> 16) is evaluated for
+// the inner 37x37 pixels -- the only blurred pixels the steered pattern (:108-147) can touch.
+#define DESC_WARPS 4
+#define RAW_R 21
+#define RAW_W 43
+#define RAW_P 44
+#define BLR_R 18
+#define BLR_W 37
+#define BLR_P 40
+#define ROWP_P 38
+
+__device__ const int8_t g_pattern[1024] = {ORB_RBRIEF_PATTERN_VALUES};
+
+struct DescSmem {
+    uint8_t raw[RAW_W * RAW_P];
+    uint16_t rowp[RAW_W * ROWP_P];
+    uint8_t blur[BLR_W * BLR_P];
+};
+
+__device__ __forceinline__ int reflect101_dev(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(const __grid_constant__ ExtractParams P,
+                                                                   const uint32_t* __restrict__ sel, const int* __restrict__ sel_count,
+                                                                   orb_keypoint_t* __restrict__ kps, uint8_t* __restrict__ desc,
+                                                                   int* __restrict__ counts, int kp_capacity,
+                                                                   const int* __restrict__ umax) {
+    __shared__ DescSmem sm[DESC_WARPS];
+    __shared__ __align__(4) int8_t spat[1024];
+    __shared__ int s_umax[16];
+    const int img = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint32_t*>(spat)[i] = reinterpret_cast<const uint32_t*>(g_pattern)[i];
+    if (threadIdx.x < 16) s_umax[threadIdx.x] = umax[threadIdx.x];
+    __syncthreads();
+
+    // which keypoint: global slot -> (level, index) through the per-level counts of this image
+    const int slot = blockIdx.x * DESC_WARPS + warp;
+    int l = 0, idx = slot, total = 0;
+    bool found = false;
+    for (int k = 0; k < P.nlevels; k++) {
+        const int c = sel_count[img * P.nlevels + k];
+        if (!found && idx < c) { l = k; found = true; }
+        if (!found) idx -= c;
+        total += c;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[img] = min(total, kp_capacity);
+    if (!found || slot >= kp_capacity) return;
+
+    const LevelDev& L = P.lv[l];
+    const uint32_t c = sel[(size_t)img * P.sel_per_image + L.sel_off + idx];
+    const int cx = cand_x(c) + 16, cy = cand_y(c) + 16, response = cand_score(c);
+    const uint8_t* I = P.base[l] + (unsigned long long)img * L.img_stride;
+    DescSmem& S = sm[warp];
+
+    for (int i = lane; i < RAW_W * RAW_W; i += 32) {
+        const int ry = i / RAW_W, rx = i - ry * RAW_W;
+        const int yy = reflect101_dev(cy + ry - RAW_R, L.h), xx = reflect101_dev(cx + rx - RAW_R, L.w);
+        S.raw[ry * RAW_P + rx] = __ldg(I + (size_t)yy * L.pitch + xx);
+    }
+    __syncwarp();
+
+    // ---- IC_Angle
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - 15, au = u < 0 ? -u : u;
+        for (int v = -15; v <= 15; v++) {
+            if (au <= s_umax[v < 0 ? -v : v]) {
+                const int val = S.raw[(RAW_R + v) * RAW_P + RAW_R + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- Gaussian 7x7: rows, then columns
+    const int g0 = 18, g1 = 34, g2 = 48, g3 = 56;
+    for (int i = lane; i < RAW_W * BLR_W; i += 32) {
+        const int ry = i / BLR_W, x = i - ry * BLR_W;
+        const uint8_t* r = S.raw + ry * RAW_P + x;
+        S.rowp[ry * ROWP_P + x] = (uint16_t)(g0 * (r[0] + r[6]) + g1 * (r[1] + r[5]) + g2 * (r[2] + r[4]) + g3 * r[3]);
+    }
+    __syncwarp();
+    for (int i = lane; i < BLR_W * BLR_W; i += 32) {
+        const int y = i / BLR_W, x = i - y * BLR_W;
+        const uint16_t* r = S.rowp + y * ROWP_P + x;
+        const uint32_t acc = g0 * ((uint32_t)r[0] + r[6 * ROWP_P]) + g1 * ((uint32_t)r[ROWP_P] + r[5 * ROWP_P]) +
+                             g2 * ((uint32_t)r[2 * ROWP_P] + r[4 * ROWP_P]) + g3 * (uint32_t)r[3 * ROWP_P];
+        S.blur[y * BLR_P + x] = (uint8_t)((acc + 32768u) >> 16);
+    }
+    __syncwarp();
+
+    // ---- steered rBRIEF: pair k of word w is handled by lane k%32, the ballot is the little-endian descriptor word
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
+    const float arad = fmul_rn(angle, factorPI);
+    const float a = glibc_sincosf(arad, true), b = glibc_sincosf(arad, false);
+    uint32_t myword = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const uint32_t pk = reinterpret_cast<const uint32_t*>(spat)[w * 32 + lane];
+        const float px0 = (float)(int8_t)(pk & 0xff), py0 = (float)(int8_t)((pk >> 8) & 0xff);
+        const float px1 = (float)(int8_t)((pk >> 16) & 0xff), py1 = (float)(int8_t)(pk >> 24);
+        const int r0 = cv_round_f(fadd_rn(fmul_rn(px0, b), fmul_rn(py0, a)));
+        const int c0 = cv_round_f(fsub_rn(fmul_rn(px0, a), fmul_rn(py0, b)));
+        const int r1 = cv_round_f(fadd_rn(fmul_rn(px1, b), fmul_rn(py1, a)));
+        const int c1 = cv_round_f(fsub_rn(fmul_rn(px1, a), fmul_rn(py1, b)));
+        const int t0 = S.blur[(BLR_R + r0) * BLR_P + BLR_R + c0];
+        const int t1 = S.blur[(BLR_R + r1) * BLR_P + BLR_R + c1];
+        const uint32_t word = __ballot_sync(0xffffffffu, t0 < t1);
+        if (lane == w) myword = word;
+    }
+    const size_t o = (size_t)img * kp_capacity + slot;
+    if (lane < 8) reinterpret_cast<uint32_t*>(desc + o * 32)[lane] = myword;
+    if (lane == 0) {
+        orb_keypoint_t kp;
+        kp.x = (float)cx;
+        kp.y = (float)cy;
+        if (l != 0) { kp.x = fmul_rn(kp.x, L.scale); kp.y = fmul_rn(kp.y, L.scale); }
+        kp.size = (float)L.patch_size;
+        kp.angle = angle;
+        kp.response = (float)response;
+        kp.octave = l;
+        kp.class_id = -1;
+        kps[o] = kp;
+    }
+}
+
+// ================================================================================================ host side
+struct orbx {
+    int device = 0;
+    int W = 0, H = 0, cameras = 0, max_frames = 0, max_images = 0;
+    orbgeo::Geometry geo;
+    ExtractParams P;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // device buffers
+    uint8_t* d_levels = nullptr;       // levels 1.. of all images, level-major
+    uint8_t* d_input = nullptr;        // staging for the host API (level 0)
+    size_t input_pitch = 0;
+    int* d_tables = nullptr;           // resize tables of all levels
+    std::vector<size_t> tab_off;       // per level: offset (ints) of xofs, ialpha, yofs, ibeta
+    uint32_t* d_cand = nullptr;
+    uint16_t* d_node_of = nullptr;
+    int* d_cand_count = nullptr;       // [max_images][nlevels] followed by the overflow flag
+    uint32_t* d_sel = nullptr;
+    int* d_sel_count = nullptr;
+    int* d_umax = nullptr;
+    orb_keypoint_t* d_kps = nullptr;   // output staging for the host API
+    uint8_t* d_desc = nullptr;
+    int* d_counts = nullptr;
+    int out_capacity = 0;
+    // launch configuration
+    int fast_tile_cap = 0, fast_pix_cap = 0;
+    size_t fast_smem = 0, qt_smem = 0;
+    int qt_maxl = 0;
+    long long launches = 0;
+    // per-stage device timing (bench.py's roofline): ring of event sets, read back by orbx_stage_ms()
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;  // ORBX_PROF_SETS x 5
+    int prof_used = 0;
+    // last call (debug taps)
+    const uint8_t* last_imgs = nullptr;
+    size_t last_stride = 0;
+    int last_n_images = 0;
+};
+
+#define ORBX_PROF_SETS 256
+
+static void orbx_free(orbx* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
+    cudaFree(e->d_levels); cudaFree(e->d_input); cudaFree(e->d_tables); cudaFree(e->d_cand); cudaFree(e->d_node_of);
+    cudaFree(e->d_cand_count); cudaFree(e->d_sel); cudaFree(e->d_sel_count); cudaFree(e->d_umax);
+    cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_counts);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+extern "C" {
+
+int orbx_create(orbx_t** out, int device, int width, int height, int cameras, int max_frames, int nfeatures, float scaleFactor,
+                int nlevels, int iniThFAST, int minThFAST) {
+    if (!out) ORB_FAIL(ORB_E_INVALID, "orbx_create: out is NULL");
+    *out = nullptr;
+    if (width < 64 || height < 64 || width > 4000 || height > 4000) ORB_FAIL(ORB_E_INVALID, "orbx_create: image size %dx%d out of range [64,4000]", width, height);
+    if (cameras < 1 || max_frames < 1 || (long long)cameras * max_frames > 65535) ORB_FAIL(ORB_E_INVALID, "orbx_create: cameras*max_frames must be in [1,65535]");
+    if (nlevels < 1 || nlevels > ORB_MAX_LEVELS || nfeatures < 1 || !(scaleFactor > 1.0f)) ORB_FAIL(ORB_E_INVALID, "orbx_create: bad extractor parameters");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) ORB_FAIL(ORB_E_NO_DEVICE, "orbx_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) ORB_FAIL(ORB_E_NO_DEVICE, "orbx_create: device %d not present (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    ORB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) ORB_FAIL(ORB_E_NO_DEVICE, "orbx_create: device %d is sm_%d%d, the kernels are built for sm_100a only", device, prop.major, prop.minor);
+    ORB_CUDA(cudaSetDevice(device));
+
+    orbx* e = new (std::nothrow) orbx();
+    if (!e) ORB_FAIL(ORB_E_INVALID, "orbx_create: out of host memory");
+    e->device = device; e->W = width; e->H = height; e->cameras = cameras; e->max_frames = max_frames;
+    e->max_images = cameras * max_frames;
+    e->geo = orbgeo::make_geometry(width, height, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST);
+    const orbgeo::Geometry& g = e->geo;
+    ExtractParams& P = e->P;
+    memset(&P, 0, sizeof(P));
+    P.nlevels = nlevels; P.iniTh = iniThFAST; P.minTh = minThFAST;
+
+    size_t level_bytes = 0;           // per image, levels >= 1
+    std::vector<size_t> level_off(nlevels, 0);
+    int cells = 0, cand_total = 0, sel_total = 0, max_dw = 0, max_dh = 0, max_quota_l = 0;
+    for (int l = 0; l < nlevels; l++) {
+        const orbgeo::Level& G = g.lv[l];
+        LevelDev& L = P.lv[l];
+        if (G.w < 1 || G.h < 1) { orbx_free(e); ORB_FAIL(ORB_E_INVALID, "orbx_create: pyramid level %d is empty", l); }
+        L.w = G.w; L.h = G.h; L.pitch = G.pitch;
+        L.width = G.width; L.height = G.height; L.wCell = G.wCell; L.hCell = G.hCell;
+        L.nColsEff = G.nColsEff; L.nRowsEff = G.nRowsEff;
+        L.quota = G.quota; L.nIni = G.nIni; L.hX = G.hX; L.scale = G.scale; L.patch_size = G.patch_size;
+        // a level takes part only if it has at least one cell, a usable quadtree root and room for the 43x43 patch logic
+        L.valid = G.valid && G.nColsEff > 0 && G.nRowsEff > 0 && G.width > 6 && G.height > 6 && G.quota > 0;
+        if (L.valid && G.nIni > ORB_MAX_ROOTS) { orbx_free(e); ORB_FAIL(ORB_E_INVALID, "orbx_create: aspect ratio needs %d quadtree roots (max %d)", G.nIni, ORB_MAX_ROOTS); }
+        P.cell_begin[l] = cells;
+        L.cand_off = cand_total; L.sel_off = sel_total;
+        if (L.valid) {
+            cells += G.nColsEff * G.nRowsEff;
+            // strict 3x3 maxima inside a cell: at most ceil(w/2)*ceil(h/2) per cell
+            int cap = 0;
+            for (int ci = 0; ci < G.nRowsEff; ci++)
+                for (int cj = 0; cj < G.nColsEff; cj++) {
+                    const int x0 = cj * G.wCell + 3, y0 = ci * G.hCell + 3;
+                    const int x1 = cj == G.nColsEff - 1 ? G.width - 3 : x0 + G.wCell;
+                    const int y1 = ci == G.nRowsEff - 1 ? G.height - 3 : y0 + G.hCell;
+                    const int dw = std::max(x1 - x0, 0), dh = std::max(y1 - y0, 0);
+                    cap += ((dw + 1) / 2) * ((dh + 1) / 2);
+                    max_dw = std::max(max_dw, dw); max_dh = std::max(max_dh, dh);
+                }
+            L.cand_cap = cap;
+            L.sel_cap = std::max(G.quota + 2, 4 * G.nIni);
+            max_quota_l = std::max(max_quota_l, L.sel_cap);
+        }
+        cand_total += (L.cand_cap + 3) & ~3;
+        sel_total += (L.sel_cap + 3) & ~3;
+        if (l > 0) { level_off[l] = level_bytes; level_bytes += (size_t)G.pitch * G.h; }
+    }
+    P.cell_begin[nlevels] = cells;
+    for (int l = nlevels + 1; l <= ORB_MAX_LEVELS; l++) P.cell_begin[l] = cells;
+    P.cells_per_image = cells; P.cand_per_image = cand_total; P.sel_per_image = sel_total;
+    if (max_dw * max_dh > 0x7fff) { orbx_free(e); ORB_FAIL(ORB_E_INVALID, "orbx_create: cell of %dx%d pixels is too large", max_dw, max_dh); }
+
+    const size_t NI = (size_t)e->max_images;
+    cudaError_t ce = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) { if (ce == cudaSuccess) ce = cudaMalloc(p, bytes ? bytes : 16); };
+    alloc((void**)&e->d_levels, level_bytes * NI);
+    alloc((void**)&e->d_cand, (size_t)cand_total * NI * sizeof(uint32_t));
+    alloc((void**)&e->d_node_of, (size_t)cand_total * NI * sizeof(uint16_t));
+    alloc((void**)&e->d_cand_count, (NI * nlevels + 4) * sizeof(int));
+    alloc((void**)&e->d_sel, (size_t)sel_total * NI * sizeof(uint32_t));
+    alloc((void**)&e->d_sel_count, NI * nlevels * sizeof(int));
+    alloc((void**)&e->d_umax, 16 * sizeof(int));
+    // resize tables
+    std::vector<int> tabs;
+    e->tab_off.assign((size_t)nlevels * 4, 0);
+    for (int l = 1; l < nlevels; l++) {
+        const orbgeo::Level& G = g.lv[l];
+        e->tab_off[l * 4 + 0] = tabs.size();
+        for (int x = 0; x < G.w; x++) tabs.push_back(G.xofs[x]);
+        e->tab_off[l * 4 + 1] = tabs.size();
+        for (int x = 0; x < G.w; x++) tabs.push_back((int)((uint32_t)(uint16_t)G.ialpha[2 * x] | ((uint32_t)(uint16_t)G.ialpha[2 * x + 1] << 16)));
+        e->tab_off[l * 4 + 2] = tabs.size();
+        for (int y = 0; y < G.h; y++) tabs.push_back(G.yofs[y]);
+        e->tab_off[l * 4 + 3] = tabs.size();
+        for (int y = 0; y < G.h; y++) tabs.push_back((int)((uint32_t)(uint16_t)G.ibeta[2 * y] | ((uint32_t)(uint16_t)G.ibeta[2 * y + 1] << 16)));
+    }
+    alloc((void**)&e->d_tables, tabs.size() * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess && !tabs.empty()) ce = cudaMemcpy(e->d_tables, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->d_umax, g.umax.data(), 16 * sizeof(int), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        int rc = orbhost::check_cuda(ce, "orbx_create allocations", __FILE__, __LINE__);
+        orbx_free(e);
+        return rc;
+    }
+    e->stream = e->own_stream;
+    for (int l = 1; l < nlevels; l++) {
+        P.lv[l].img_stride = (unsigned long long)g.lv[l].pitch * g.lv[l].h;
+        P.base[l] = e->d_levels + level_off[l] * NI;
+    }
+    // FAST shared memory: tile + score + 2 lists
+    e->fast_pix_cap = (max_dw * max_dh + 15) & ~15;
+    e->fast_tile_cap = (((max_dw + 6 + 3) & ~3) * (max_dh + 6) + 15) & ~15;
+    e->fast_smem = (size_t)e->fast_tile_cap + e->fast_pix_cap + 2 * sizeof(uint16_t) * e->fast_pix_cap;
+    e->qt_maxl = (max_quota_l + 8 + 1) & ~1;
+    e->qt_smem = (size_t)e->qt_maxl * (2 * sizeof(QtNode) + 10 * sizeof(int) + sizeof(unsigned long long)) + 16;
+    if (e->fast_smem > 200 * 1024 || e->qt_smem > 200 * 1024) { orbx_free(e); ORB_FAIL(ORB_E_INVALID, "orbx_create: shared memory need too large (fast %zu, quadtree %zu)", e->fast_smem, e->qt_smem); }
+    ce = cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->fast_smem);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qt_smem);
+    if (ce != cudaSuccess) {
+        int rc = orbhost::check_cuda(ce, "cudaFuncSetAttribute", __FILE__, __LINE__);
+        orbx_free(e);
+        return rc;
+    }
+    *out = e;
+    return ORB_OK;
+}
+
+void orbx_destroy(orbx_t* e) { orbx_free(e); }
+
+int orbx_get_levels(const orbx_t* e) { return e ? e->geo.nlevels : ORB_E_INVALID; }
+
+int orbx_get_tables(const orbx_t* e, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* features_per_level, int32_t* umax16) {
+    if (!e) ORB_FAIL(ORB_E_INVALID, "orbx_get_tables: NULL handle");
+    for (int i = 0; i < e->geo.nlevels; i++) {
+        if (scale) scale[i] = e->geo.scale[i];
+        if (inv_scale) inv_scale[i] = e->geo.inv_scale[i];
+        if (sigma2) sigma2[i] = e->geo.sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = e->geo.inv_sigma2[i];
+        if (features_per_level) features_per_level[i] = e->geo.lv[i].quota;
+    }
+    if (umax16) for (int i = 0; i < 16; i++) umax16[i] = e->geo.umax[i];
+    return ORB_OK;
+}
+
+int orbx_max_keypoints(const orbx_t* e) {
+    if (!e) return ORB_E_INVALID;
+    int n = 0;
+    for (int l = 0; l < e->P.nlevels; l++) if (e->P.lv[l].valid) n += e->P.lv[l].sel_cap;
+    return n;
+}
+
+int orbx_level_size(const orbx_t* e, int level, int* w, int* h) {
+    if (!e || level < 0 || level >= e->P.nlevels) ORB_FAIL(ORB_E_INVALID, "orbx_level_size: bad argument");
+    if (w) *w = e->P.lv[level].w;
+    if (h) *h = e->P.lv[level].h;
+    return ORB_OK;
+}
+
+int orbx_set_stream(orbx_t* e, void* s) {
+    if (!e) ORB_FAIL(ORB_E_INVALID, "orbx_set_stream: NULL handle");
+    e->stream = s ? (cudaStream_t)s : e->own_stream;
+    return ORB_OK;
+}
+
+int orbx_synchronize(orbx_t* e) {
+    if (!e) ORB_FAIL(ORB_E_INVALID, "orbx_synchronize: NULL handle");
+    ORB_CUDA(cudaSetDevice(e->device));
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    return ORB_OK;
+}
+
+long long orbx_launch_count(const orbx_t* e) { return e ? e->launches : 0; }
+
+int orbx_extract_device(orbx_t* e, const uint8_t* d_imgs, int frames, size_t row_stride, orb_keypoint_t* d_kps, uint8_t* d_desc,
+                        int32_t* d_counts, int kp_capacity) {
+    if (!e) ORB_FAIL(ORB_E_INVALID, "orbx_extract: NULL handle");
+    if (frames == 0) return ORB_OK;
+    if (!d_imgs || !d_kps || !d_desc || !d_counts) ORB_FAIL(ORB_E_INVALID, "orbx_extract: NULL buffer");
+    if (frames < 0 || frames > e->max_frames) ORB_FAIL(ORB_E_INVALID, "orbx_extract: frames=%d exceeds max_frames=%d", frames, e->max_frames);
+    if (row_stride < (size_t)e->W) ORB_FAIL(ORB_E_INVALID, "orbx_extract: row_stride %zu < width %d", row_stride, e->W);
+    if (kp_capacity < orbx_max_keypoints(e)) ORB_FAIL(ORB_E_INVALID, "orbx_extract: kp_capacity %d < orbx_max_keypoints() = %d", kp_capacity, orbx_max_keypoints(e));
+    ORB_CUDA(cudaSetDevice(e->device));
+    const int NI = frames * e->cameras;
+    ExtractParams& P = e->P;
+    P.n_images = NI;
+    P.base[0] = d_imgs;
+    P.lv[0].pitch = (int)row_stride;
+    P.lv[0].img_stride = (unsigned long long)row_stride * e->H;
+    e->last_imgs = d_imgs; e->last_stride = row_stride; e->last_n_images = NI;
+    cudaStream_t st = e->stream;
+    const int L = P.nlevels;
+
+    ORB_CUDA(cudaMemsetAsync(e->d_cand_count, 0, ((size_t)e->max_images * L + 4) * sizeof(int), st));
+    cudaEvent_t* pev = (e->profile && e->prof_used < ORBX_PROF_SETS) ? &e->prof_ev[(size_t)e->prof_used * 5] : nullptr;
+    if (pev) ORB_CUDA(cudaEventRecord(pev[0], st));
+    for (int l = 1; l < L; l++) {
+        const LevelDev& S = P.lv[l - 1];
+        const LevelDev& D = P.lv[l];
+        dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), D.h, NI);
+        const int* T = e->d_tables;
+        resize_level_kernel<<<grid, 128, 0, st>>>(P.base[l - 1], S.w, S.h, S.pitch, S.img_stride, const_cast<uint8_t*>(P.base[l]), D.w, D.h,
+                                                  D.pitch, D.img_stride, T + e->tab_off[l * 4 + 0], T + e->tab_off[l * 4 + 1],
+                                                  T + e->tab_off[l * 4 + 2], T + e->tab_off[l * 4 + 3]);
+        e->launches++;
+    }
+    if (pev) ORB_CUDA(cudaEventRecord(pev[1], st));
+    int* d_overflow = e->d_cand_count + (size_t)e->max_images * L;
+    if (P.cells_per_image > 0) {
+        fast_cells_kernel<<<dim3(P.cells_per_image, NI), FAST_THREADS, e->fast_smem, st>>>(P, e->d_cand, e->d_cand_count, e->fast_tile_cap, e->fast_pix_cap);
+        e->launches++;
+    }
+    if (pev) ORB_CUDA(cudaEventRecord(pev[2], st));
+    quadtree_kernel<<<dim3(L, NI), QT_THREADS, e->qt_smem, st>>>(P, e->d_cand, e->d_cand_count, e->d_node_of, e->d_sel, e->d_sel_count, e->qt_maxl, d_overflow);
+    e->launches++;
+    if (pev) ORB_CUDA(cudaEventRecord(pev[3], st));
+    const int maxkp = orbx_max_keypoints(e);
+    describe_kernel<<<dim3((std::max(maxkp, 1) + DESC_WARPS - 1) / DESC_WARPS, NI), DESC_WARPS * 32, 0, st>>>(P, e->d_sel, e->d_sel_count, d_kps, d_desc, d_counts, kp_capacity, e->d_umax);
+    e->launches++;
+    if (pev) { ORB_CUDA(cudaEventRecord(pev[4], st)); e->prof_used++; }
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+int orbx_profile(orbx_t* e, int enable) {
+    if (!e) ORB_FAIL(ORB_E_INVALID, "orbx_profile: NULL handle");
+    ORB_CUDA(cudaSetDevice(e->device));
+    if (enable && e->prof_ev.empty()) {
+        e->prof_ev.resize((size_t)ORBX_PROF_SETS * 5);
+        for (cudaEvent_t& ev : e->prof_ev) ORB_CUDA(cudaEventCreate(&ev));
+    }
+    e->profile = enable != 0;
+    e->prof_used = 0;
+    return ORB_OK;
+}
+
+int orbx_stage_ms(orbx_t* e, double* ms4, int* calls) {
+    if (!e || !ms4) ORB_FAIL(ORB_E_INVALID, "orbx_stage_ms: bad argument");
+    ORB_CUDA(cudaSetDevice(e->device));
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < 4; k++) ms4[k] = 0.0;
+    for (int i = 0; i < e->prof_used; i++)
+        for (int k = 0; k < 4; k++) {
+            float ms = 0.f;
+            ORB_CUDA(cudaEventElapsedTime(&ms, e->prof_ev[(size_t)i * 5 + k], e->prof_ev[(size_t)i * 5 + k + 1]));
+            ms4[k] += ms;
+        }
+    if (calls) *calls = e->prof_used;
+    e->prof_used = 0;
+    return ORB_OK;
+}
+
+int orbx_extract(orbx_t* e, const uint8_t* imgs, int frames, size_t row_stride, orb_keypoint_t* kps, uint8_t* desc, int32_t* counts, int kp_capacity) {
+    if (!e) ORB_FAIL(ORB_E_INVALID, "orbx_extract: NULL handle");
+    if (frames == 0) return ORB_OK;   // empty input: silent return like src/ORBextractor.cc:1046-1047
+    if (!imgs || !kps || !desc || !counts) ORB_FAIL(ORB_E_INVALID, "orbx_extract: NULL buffer");
+    if (frames < 0 || frames > e->max_frames) ORB_FAIL(ORB_E_INVALID, "orbx_extract: frames=%d exceeds max_frames=%d", frames, e->max_frames);
+    if (row_stride < (size_t)e->W) ORB_FAIL(ORB_E_INVALID, "orbx_extract: row_stride %zu < width %d", row_stride, e->W);
+    if (kp_capacity < orbx_max_keypoints(e)) ORB_FAIL(ORB_E_INVALID, "orbx_extract: kp_capacity %d < orbx_max_keypoints() = %d", kp_capacity, orbx_max_keypoints(e));
+    ORB_CUDA(cudaSetDevice(e->device));
+    const size_t NI = (size_t)frames * e->cameras, NImax = (size_t)e->max_images;
+    if (!e->d_input) {
+        e->input_pitch = ((size_t)e->W + 15) & ~(size_t)15;
+        ORB_CUDA(cudaMalloc((void**)&e->d_input, e->input_pitch * e->H * NImax));
+    }
+    if (e->out_capacity < kp_capacity) {
+        cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_counts);
+        e->d_kps = nullptr; e->d_desc = nullptr; e->d_counts = nullptr; e->out_capacity = 0;
+        ORB_CUDA(cudaMalloc((void**)&e->d_kps, NImax * kp_capacity * sizeof(orb_keypoint_t)));
+        ORB_CUDA(cudaMalloc((void**)&e->d_desc, NImax * kp_capacity * 32));
+        ORB_CUDA(cudaMalloc((void**)&e->d_counts, NImax * sizeof(int)));
+        e->out_capacity = kp_capacity;
+    }
+    cudaStream_t st = e->stream;
+    ORB_CUDA(cudaMemcpy2DAsync(e->d_input, e->input_pitch, imgs, row_stride, e->W, (size_t)e->H * NI, cudaMemcpyHostToDevice, st));
+    int rc = orbx_extract_device(e, e->d_input, frames, e->input_pitch, e->d_kps, e->d_desc, e->d_counts, kp_capacity);
+    if (rc != ORB_OK) return rc;
+    ORB_CUDA(cudaMemcpyAsync(counts, e->d_counts, NI * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(kps, e->d_kps, NI * kp_capacity * sizeof(orb_keypoint_t), cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(desc, e->d_desc, NI * kp_capacity * 32, cudaMemcpyDeviceToHost, st));
+    int overflow = 0;
+    ORB_CUDA(cudaMemcpyAsync(&overflow, e->d_cand_count + NImax * e->P.nlevels, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    if (overflow) ORB_FAIL(ORB_E_OVERFLOW, "orbx_extract: internal capacity exceeded (code %d)", overflow);
+    return ORB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stage taps
+int orbx_debug_level(orbx_t* e, int img, int level, uint8_t* out, size_t out_bytes) {
+    if (!e || !out || level < 0 || level >= e->P.nlevels || img < 0 || img >= e->last_n_images) ORB_FAIL(ORB_E_INVALID, "orbx_debug_level: bad argument");
+    const LevelDev& L = e->P.lv[level];
+    if (out_bytes < (size_t)L.w * L.h) ORB_FAIL(ORB_E_INVALID, "orbx_debug_level: buffer too small");
+    ORB_CUDA(cudaSetDevice(e->device));
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    ORB_CUDA(cudaMemcpy2D(out, L.w, e->P.base[level] + (size_t)img * L.img_stride, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return ORB_OK;
+}
+
+static int debug_packed(orbx_t* e, int img, int level, int32_t* xys, int cap, bool selected, int add) {
+    if (!e || !xys || level < 0 || level >= e->P.nlevels || img < 0 || img >= e->last_n_images) ORB_FAIL(ORB_E_INVALID, "orbx_debug: bad argument");
+    const LevelDev& L = e->P.lv[level];
+    ORB_CUDA(cudaSetDevice(e->device));
+    ORB_CUDA(cudaStreamSynchronize(e->stream));
+    int n = 0;
+    ORB_CUDA(cudaMemcpy(&n, (selected ? e->d_sel_count : e->d_cand_count) + (size_t)img * e->P.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> tmp((size_t)std::max(n, 1));
+    const uint32_t* src = selected ? e->d_sel + (size_t)img * e->P.sel_per_image + L.sel_off : e->d_cand + (size_t)img * e->P.cand_per_image + L.cand_off;
+    if (n > 0) ORB_CUDA(cudaMemcpy(tmp.data(), src, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < cap; i++) {
+        xys[3 * i] = cand_x(tmp[i]) + add; xys[3 * i + 1] = cand_y(tmp[i]) + add; xys[3 * i + 2] = cand_score(tmp[i]);
+    }
+    return n;
+}
+
+int orbx_debug_candidates(orbx_t* e, int img, int level, int32_t* xys, int cap) { return debug_packed(e, img, level, xys, cap, false, 0); }
+int orbx_debug_selected(orbx_t* e, int img, int level, int32_t* xys, int cap) { return debug_packed(e, img, level, xys, cap, true, 16); }
+
+}  // extern "C"

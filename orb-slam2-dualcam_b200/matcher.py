@@ -1,0 +1,96 @@
+"""Host-side mirror of the reference's ORBmatcher Hamming searches (include/ORBmatcher.h) above the C-ABI."""
+import ctypes as C
+
+import numpy as np
+
+from .capi import check, lib, ptr
+
+
+class ORBmatcher:
+    TH_LOW = 50         # src/ORBmatcher.cc:58
+    TH_HIGH = 100       # src/ORBmatcher.cc:57
+    HISTO_LENGTH = 30   # src/ORBmatcher.cc:59
+
+    def __init__(self, nnratio=0.6, checkOri=True, max_pairs=1, max_query=4096, max_train=4096, device=0):
+        self._h = None
+        self.mfNNratio, self.mbCheckOrientation = nnratio, checkOri
+        h = C.c_void_p()
+        check(lib().orbm_create(C.byref(h), device, max_pairs, max_query, max_train))
+        self._h = h
+        self.max_pairs, self.max_query, self.max_train = max_pairs, max_query, max_train
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orbm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def DescriptorDistance(self, a, b):
+        """ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2015-2031); a, b: [..., 32] uint8 -> int32 [...]"""
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        assert a.shape == b.shape
+        out = np.empty(a.shape[0], np.int32)
+        check(lib().orbm_descriptor_distance(self._h, ptr(a), ptr(b), a.shape[0], ptr(out)))
+        return out if out.size != 1 else int(out[0])
+
+    def bruteforce(self, dq, nq, dt, nt):
+        """dq uint8 [P][Q][32], nq int32 [P], dt uint8 [P][T][32], nt int32 [P] -> best_idx, best_d, second_d int32 [P][Q]
+        (entries >= nq[p] hold -1 / 256 / 256)."""
+        dq = np.ascontiguousarray(dq, np.uint8)
+        dt = np.ascontiguousarray(dt, np.uint8)
+        nq = np.ascontiguousarray(nq, np.int32)
+        nt = np.ascontiguousarray(nt, np.int32)
+        P, Q, T = dq.shape[0], dq.shape[1], dt.shape[1]
+        assert dt.shape[0] == P and nq.shape == (P,) and nt.shape == (P,)
+        bi = np.full((P, Q), -1, np.int32)
+        bd = np.full((P, Q), 256, np.int32)
+        sd = np.full((P, Q), 256, np.int32)
+        check(lib().orbm_bruteforce(self._h, ptr(dq), ptr(nq), Q, ptr(dt), ptr(nt), T, P, ptr(bi), ptr(bd), ptr(sd)))
+        return bi, bd, sd
+
+    def bruteforce_device(self, d_dq, d_nq, d_dt, d_nt, out=None, stream=None):
+        """torch CUDA tensors; asynchronous on the current torch stream."""
+        import torch
+        P, Q, T = d_dq.shape[0], d_dq.shape[1], d_dt.shape[1]
+        dev = d_dq.device
+        if out is None:
+            out = tuple(torch.empty((P, Q), dtype=torch.int32, device=dev) for _ in range(3))
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        L = lib()
+        check(L.orbm_set_stream(self._h, st.cuda_stream))
+        check(L.orbm_bruteforce_device(self._h, d_dq.data_ptr(), d_nq.data_ptr(), Q, d_dt.data_ptr(), d_nt.data_ptr(), T, P,
+                                       out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr()))
+        return out
+
+    def bruteforce_sets_device(self, d_desc, d_counts, d_q_set, d_t_set, out=None, stream=None):
+        """d_desc uint8 [S][cap][32] (any leading shape flattening to S sets), d_counts int32 [S], q/t set ids int32 [P]."""
+        import torch
+        cap = d_desc.shape[-2]
+        S = d_desc.numel() // (cap * 32)
+        P = d_q_set.numel()
+        dev = d_desc.device
+        if out is None:
+            out = tuple(torch.empty((P, cap), dtype=torch.int32, device=dev) for _ in range(3))
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        L = lib()
+        check(L.orbm_set_stream(self._h, st.cuda_stream))
+        check(L.orbm_bruteforce_sets_device(self._h, d_desc.data_ptr(), d_counts.data_ptr(), cap, S, d_q_set.data_ptr(), d_t_set.data_ptr(), P,
+                                            out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr()))
+        return out
+
+    def profile(self, enable=True):
+        check(lib().orbm_profile(self._h, int(enable)))
+
+    def stage_ms(self):
+        ms = C.c_double()
+        n = C.c_int()
+        check(lib().orbm_stage_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def synchronize(self):
+        check(lib().orbm_synchronize(self._h))
+
+    def launch_count(self):
+        return int(lib().orbm_launch_count(self._h))

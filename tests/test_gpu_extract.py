@@ -1,0 +1,152 @@
+"""GPU parity of the extractor (through the C-ABI) against the CPU oracle and the committed golden vectors.
+Bit-exact bar: level pixels, FAST candidates, quadtree selection and order, keypoint records, descriptors."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from orbslam2_dualcam_b200 import ORBextractor, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "extract_*.npz")))
+KP_FIELDS = ("x", "y", "size", "angle", "response", "octave", "class_id")
+
+
+def _assert_same(kps, desc, rk, rd, tag=""):
+    assert len(kps) == len(rk), f"{tag}: {len(kps)} keypoints, oracle {len(rk)}"
+    for f in KP_FIELDS:
+        a, b = kps[f], rk[f]
+        if a.dtype.kind == "f":
+            a, b = a.view(np.uint32), b.view(np.uint32)
+        bad = np.nonzero(a != b)[0]
+        assert bad.size == 0, f"{tag}: field {f} differs at {bad[:5]} ({kps[f][bad[:5]]} vs {rk[f][bad[:5]]})"
+    bad = np.nonzero((desc != rd).any(1))[0]
+    assert bad.size == 0, f"{tag}: {bad.size} descriptors differ, first {bad[:5]}"
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[8:-4] for p in GOLDEN])
+def test_golden(path):
+    g = np.load(path)
+    img = g["img"]
+    ext = ORBextractor(nfeatures=int(g["args"][0]), width=img.shape[1], height=img.shape[0])
+    kps, desc = ext(img)
+    _assert_same(kps, desc, g["kps"], g["desc"], os.path.basename(path))
+
+
+def _cases():
+    rng = np.random.default_rng(11)
+    yield "textured", synth.dual_sequence(0, 1, 640, 480, cams=1)[0, 0], 1000
+    yield "textured720p", synth.dual_sequence(1, 1, 1280, 720, cams=1)[0, 0], 2000
+    yield "noise", rng.integers(0, 256, (240, 320), dtype=np.uint8), 500
+    yield "lowcontrast", (synth.dual_sequence(3, 1, 320, 240, cams=1)[0, 0] // 8 + 100).astype(np.uint8), 500
+    yield "flat", np.full((200, 300), 77, np.uint8), 300
+    yield "plateaus", np.kron(rng.integers(0, 2, (30, 40), dtype=np.uint8) * 200, np.ones((8, 8), np.uint8)), 400
+    yield "odd_size", synth.dual_sequence(4, 1, 333, 251, cams=1)[0, 0], 700
+
+
+@pytest.mark.parametrize("name,img,nf", list(_cases()), ids=[c[0] for c in _cases()])
+def test_stages_and_output_vs_oracle(name, img, nf):
+    H, W = img.shape
+    ora = O.Extractor(nfeatures=nf)
+    rk, rd = ora(img)
+    ext = ORBextractor(nfeatures=nf, width=W, height=H)
+    kps, desc = ext(img)
+    for l in range(8):
+        assert ext.level_size(l) == ora.level_size(l)
+        assert np.array_equal(ext.debug_level(0, l), ora.level_pixels(l)), f"{name}: level {l} pixels differ"
+        got = ext.debug_candidates(0, l)
+        ref = ora.level_candidates(l)
+        got = got[np.lexsort((got[:, 0], got[:, 1]))] if len(got) else got
+        ref_s = ref[np.lexsort((ref[:, 0], ref[:, 1]))] if len(ref) else ref
+        assert np.array_equal(got, ref_s), f"{name}: level {l} FAST candidates differ ({len(got)} vs {len(ref)})"
+        assert np.array_equal(ext.debug_selected(0, l), ora.level_selected(l)), f"{name}: level {l} quadtree differs"
+    _assert_same(kps, desc, rk, rd, name)
+
+
+def test_getters_match_oracle_tables():
+    ext = ORBextractor()
+    t = O.Extractor().tables()
+    assert np.array_equal(ext.GetScaleFactors(), t["scale"])
+    assert np.array_equal(ext.GetInverseScaleFactors(), t["inv_scale"])
+    assert np.array_equal(ext.GetScaleSigmaSquares(), t["sigma2"])
+    assert np.array_equal(ext.GetInverseScaleSigmaSquares(), t["inv_sigma2"])
+    assert ext.mnFeaturesPerLevel.tolist() == [217, 181, 151, 126, 105, 87, 73, 60]
+    assert ext.umax.tolist() == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    assert ext.GetLevels() == 8
+
+
+def test_dual_batch_matches_per_image_oracle():
+    """Both cameras of several dual-frames in ONE call (incl. a flat camera image: minTh fallback + empty levels)."""
+    imgs = synth.dual_sequence(7, 3, 640, 480, cams=2, flat_first=True)
+    ext = ORBextractor(width=640, height=480, cameras=2, max_frames=4)
+    kps, desc, counts = ext.extract_batch(imgs)
+    ora = O.Extractor()
+    for f in range(3):
+        for c in range(2):
+            rk, rd = ora(imgs[f, c])
+            n = counts[f, c]
+            _assert_same(kps[f, c, :n], desc[f, c, :n], rk, rd, f"frame {f} cam {c}")
+    assert counts[0, 1] == 0   # flat image: no corners at minTh either
+
+
+def test_row_stride_and_reuse():
+    """Padded host rows, and a second call on the same handle (stale candidate state must not leak)."""
+    a = synth.dual_sequence(9, 1, 640, 480, cams=1)[0, 0]
+    b = synth.dual_sequence(10, 1, 640, 480, cams=1)[0, 0]
+    ext = ORBextractor(width=640, height=480)
+    ora = O.Extractor()
+    padded = np.zeros((480, 704), np.uint8)
+    padded[:, :640] = a
+    k1, d1 = ext(padded[:, :640])
+    _assert_same(k1, d1, *ora(a), "padded")
+    k2, d2 = ext(b)
+    _assert_same(k2, d2, *ora(b), "second call")
+    k3, d3 = ext(a)
+    _assert_same(k3, d3, *ora(a), "third call")
+
+
+def test_device_api_full_batch_properties():
+    """BASELINE configs[1] size (256 dual-frames) through the device API: size-independent properties + sampled oracle parity."""
+    import torch
+    F = 256
+    imgs = synth.tiled_batch(3, F, 640, 480, 2, unique=8)
+    ext = ORBextractor(width=640, height=480, cameras=2, max_frames=F)
+    d = torch.from_numpy(imgs).cuda()
+    k, de, cnt = ext.extract_device(d)
+    torch.cuda.synchronize()
+    cnt = cnt.cpu().numpy()
+    kps = k.cpu().numpy().view(O.KP_DTYPE)[..., 0]
+    desc = de.cpu().numpy()
+    assert cnt.min() > 900 and cnt.max() <= ext.kp_capacity
+    # idempotence: same batch again gives the same bytes
+    k2, de2, cnt2 = ext.extract_device(d, k.clone(), de.clone(), None)
+    torch.cuda.synchronize()
+    assert torch.equal(de, de2) and np.array_equal(cnt, cnt2.cpu().numpy())
+    assert np.array_equal(kps, k2.cpu().numpy().view(O.KP_DTYPE)[..., 0])
+    # frames 0..7 are rendered frames; frame 8+j is a cyclic shift: every frame distinct, all valid
+    ora = O.Extractor()
+    for f, c in [(0, 0), (5, 1), (9, 0), (255, 1)]:
+        rk, rd = ora(imgs[f, c])
+        n = cnt[f, c]
+        _assert_same(kps[f, c, :n], desc[f, c, :n], rk, rd, f"frame {f} cam {c}")
+    # octaves are non-decreasing (level-major order) and keypoints stay inside the image
+    for f in range(0, F, 37):
+        for c in range(2):
+            n = cnt[f, c]
+            o = kps[f, c, :n]["octave"]
+            assert (np.diff(o) >= 0).all()
+            assert (kps[f, c, :n]["x"] >= 19).all() and (kps[f, c, :n]["x"] < 640).all()
+
+
+def test_errors():
+    from orbslam2_dualcam_b200 import OrbError
+    with pytest.raises(OrbError):
+        ORBextractor(width=10, height=10)
+    ext = ORBextractor(width=640, height=480)
+    with pytest.raises(AssertionError):
+        ext(np.zeros((480, 640), np.float32))
+    k, d = ext(np.zeros((0, 0), np.uint8))
+    assert len(k) == 0 and d.shape == (0, 32)
