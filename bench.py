@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- dual-frames/s of the hot path (ORB extract + brute-force match [+ LocalBA when built]) on N B200 GPUs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames 256]
+
+One "step" = one pass of the path over one batch of `--frames` synthetic dual-frames (2 x 640x480, 1000 features per
+camera, 8 levels, scale 1.2, iniTh 20 / minTh 7: BASELINE.json configs[1]): extract both cameras of every frame, then
+brute-force 256-bit Hamming match of camera c of frame k against camera c of frame k+1.  N > 1 (torchrun): every rank
+runs its own batch on its own GPU (independent sequences, no data-path collective: weak scaling); time = max over ranks.
+
+The JSON line follows the driver contract; see DESIGN.md "Measurement" for how every field is obtained.
+`--impl reference` times the CPU oracle (the reference's algorithm restated; the reference itself cannot be compiled in
+this image) on all host cores; this and the `cpu_baseline` leg are the only places bench.py executes oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+W, H, CAMS, NFEAT = 640, 480, 2, 1000
+METRIC = "frames/sec (dual 640x480, 1000 kpts/cam) extract+match+localBA"
+# algorithmic bytes, SURVEY.md §8(d)
+PYR_PIXELS = 950532                       # sum of the 8 level sizes of a 640x480 image
+BYTES_EXTRACT_IMAGE = 2911596             # read input + write levels 1..7 + 2 x read all levels + 60 B per keypoint
+BYTES_FAST_IMAGE = PYR_PIXELS             # the per-cell FAST kernel reads every level pixel once
+BYTES_MATCH_PAIR = 76000                  # (nq + nt) x 32 + nq x 12
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(seed, frames):
+    from orbslam2_dualcam_b200 import synth
+    a = synth.tiled_batch(seed, frames, W, H, CAMS, unique=16)
+    b = np.ascontiguousarray(np.roll(a, shift=(11, 7), axis=(2, 3)))   # a second, distinct batch (defeats L2 reuse across steps)
+    return a, b
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs (oracle)
+def cpu_path(frames_u8, threads):
+    """The reference algorithm on the host: extract both cameras of every dual-frame, match frame k -> k+1 per camera.
+    Returns seconds.  `threads` workers, each owning whole dual-frames (the oracle releases the GIL inside ctypes)."""
+    import oracle_lib as O
+    F = frames_u8.shape[0]
+    descs = [[None] * CAMS for _ in range(F)]
+
+    def extract_range(lo, hi):
+        ex = O.Extractor(NFEAT, 1.2, 8, 20, 7)
+        for f in range(lo, hi):
+            for c in range(CAMS):
+                descs[f][c] = ex(frames_u8[f, c])[1]
+
+    def match_range(lo, hi):
+        for f in range(lo, hi):
+            for c in range(CAMS):
+                O.match_bruteforce(descs[f][c], descs[(f + 1) % F][c])
+
+    def run(fn):
+        if threads == 1:
+            fn(0, F)
+            return
+        cuts = np.linspace(0, F, threads + 1).astype(int)
+        ts = [threading.Thread(target=fn, args=(cuts[i], cuts[i + 1])) for i in range(threads) if cuts[i + 1] > cuts[i]]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    t0 = time.perf_counter()
+    run(extract_range)
+    run(match_range)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle_lib as O
+    O.lib()
+    cores = os.cpu_count() or 1
+    sample = max(cores * 2, 16)
+    from orbslam2_dualcam_b200 import synth
+    frames = synth.tiled_batch(0, sample, W, H, CAMS, unique=16)
+    for _ in range(args.warmup):
+        cpu_path(frames[:cores], cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_path(frames, cores)
+    fps = sample * args.steps / t
+    desc = f"{sample} dual-frames per step, {cores} threads (one oracle instance per thread), extract+match"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "dual-frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"ORB extract+match, dual 2x{W}x{H}, {NFEAT} feats/cam, 8 levels, brute-force 256-bit Hamming (CPU oracle = reference algorithm restated)",
+                   "frames_per_step": sample, "stages": STAGES},
+        "cpu_baseline": {"value": fps, "unit": "dual-frames/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": fps, "unit": "dual-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+STAGES = "extract+match"
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from orbslam2_dualcam_b200 import ORBextractor, ORBmatcher
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F = args.frames
+    a, b = make_inputs(1000 * rank, F)
+    host = [torch.from_numpy(x).pin_memory() for x in (a, b)]
+    d_in = [h.to(dev) for h in host]
+    ext = ORBextractor(NFEAT, 1.2, 8, 20, 7, width=W, height=H, cameras=CAMS, max_frames=F, device=local_rank)
+    cap = ext.kp_capacity
+    P = F * CAMS
+    mat = ORBmatcher(max_pairs=P, max_query=cap, max_train=cap, device=local_rank)
+    q_set = torch.arange(P, dtype=torch.int32, device=dev)
+    t_set = ((q_set + CAMS) % P).to(torch.int32)          # same camera, next frame (cyclic)
+    d_kps = torch.zeros((F, CAMS, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros((F, CAMS, cap, 32), dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros((F, CAMS), dtype=torch.int32, device=dev)
+    d_match = tuple(torch.zeros((P, cap), dtype=torch.int32, device=dev) for _ in range(3))
+    h_kps, h_desc, h_cnt = (torch.empty_like(t, device="cpu").pin_memory() for t in (d_kps, d_desc, d_cnt))
+    h_match = tuple(torch.empty_like(t, device="cpu").pin_memory() for t in d_match)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(imgs):
+        ext.extract_device(imgs, d_kps, d_desc, d_cnt, stream=stream)
+        mat.bruteforce_sets_device(d_desc, d_cnt, q_set, t_set, out=d_match, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput (`value`)
+    for i in range(args.warmup):
+        step(d_in[i % 2])
+    barrier()
+    l0 = ext.launch_count() + mat.launch_count()
+    ext.profile(True)
+    mat.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record(stream)
+        for i in range(args.steps):
+            step(d_in[i % 2])
+        e1.record(stream)
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ext.launch_count() + mat.launch_count() - l0
+    stage_ms, calls = ext.stage_ms()
+    match_ms, mcalls = mat.stage_ms()
+    ext.profile(False)
+    mat.profile(False)
+    n_kp = int(d_cnt.sum().item())
+
+    # ---- end to end: pinned host images in, keypoints / descriptors / matches out to pinned host memory, every step
+    def e2e_step(i):
+        d_in[i % 2].copy_(host[i % 2], non_blocking=True)
+        step(d_in[i % 2])
+        h_cnt.copy_(d_cnt, non_blocking=True)
+        h_kps.copy_(d_kps, non_blocking=True)
+        h_desc.copy_(d_desc, non_blocking=True)
+        for hm, dm in zip(h_match, d_match):
+            hm.copy_(dm, non_blocking=True)
+        stream.synchronize()
+        return int(h_cnt.sum())      # the step's result is read on the host
+
+    for i in range(max(1, args.warmup // 2)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = host[0].numel()
+    d2h = sum(t.numel() * t.element_size() for t in (h_cnt, h_kps, h_desc) + h_match)
+
+    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = times.tolist()
+    if rank == 0:
+        peak, peak_kind = peaks()
+        total_frames = F * world
+        fps = total_frames * args.steps / (ms / 1e3)
+        e2e_fps = total_frames * args.steps / (e2e_ms / 1e3)
+        imgs_per_launch = F * CAMS
+        fast_ms = stage_ms["fast"] / max(calls, 1)
+        dom_name, dom_ms, dom_bytes = "fast_cells_kernel", fast_ms, BYTES_FAST_IMAGE * imgs_per_launch
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        step_bytes = (BYTES_EXTRACT_IMAGE * CAMS + BYTES_MATCH_PAIR * CAMS) * F
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(dom_name)
+        except Exception:
+            pass
+        out = {
+            "metric": METRIC, "value": fps, "unit": "dual-frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"ORB extract+match, batch of {F} dual-frames 2x{W}x{H} per GPU, {NFEAT} feats/cam, 8 levels x1.2, "
+                                   "brute-force 256-bit Hamming frame k -> k+1 per camera (BASELINE configs[1])",
+                       "frames_per_step_per_gpu": F, "stages": STAGES, "keypoints_per_step": n_kp,
+                       "l2": "two alternating input batches of 157 MB each (> 126 MB L2)", "parallelism": f"{world} independent replicas, no collective"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_fps, "unit": "dual-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                         "step_frac_of_hbm_roofline": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
+                         "stage_ms_per_step": {**{k: v / max(calls, 1) for k, v in stage_ms.items()}, "match": match_ms / max(mcalls, 1)}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sample = args.cpu_sample
+            t = cpu_path(a[:sample], 1)
+            out["cpu_baseline"] = {"value": sample / t, "unit": "dual-frames/s", "cores": 1, "kind": "port",
+                                   "sample": f"first {sample} dual-frames of the same batch, single thread, extract+match ({t:.1f} s)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("--cpu-sample", type=int, default=96)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
