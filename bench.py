@@ -192,7 +192,9 @@ def run_ours(args, rank, world, local_rank):
     d_match = tuple(torch.zeros((P, cap), dtype=torch.int32, device=dev) for _ in range(3))
     h_kps, h_desc, h_cnt = (torch.empty_like(t, device="cpu").pin_memory() for t in (d_kps, d_desc, d_cnt))
     h_match = tuple(torch.empty_like(t, device="cpu").pin_memory() for t in d_match)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)          # every kernel, copy and event of the timed regions goes through this stream
+    torch.cuda.set_stream(stream)
+    torch.cuda.synchronize(dev)
 
     def step(imgs):
         ext.extract_device(imgs, d_kps, d_desc, d_cnt, stream=stream)

@@ -84,7 +84,7 @@ int  orbx_extract(orbx_t*, const uint8_t* imgs, int frames, size_t row_stride,
 int  orbx_extract_device(orbx_t*, const uint8_t* d_imgs, int frames, size_t row_stride,
                          orb_keypoint_t* d_kps, uint8_t* d_desc, int32_t* d_counts, int kp_capacity);
 /* stream control for the device API */
-int  orbx_set_stream(orbx_t*, void* cuda_stream);   /* cudaStream_t; NULL = the handle's own stream */
+int  orbx_set_stream(orbx_t*, void* cuda_stream);   /* cudaStream_t; NULL = the handle's own stream; cudaStreamLegacy (0x1) = the default stream */
 int  orbx_synchronize(orbx_t*);
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 long long orbx_launch_count(const orbx_t*);

@@ -93,3 +93,9 @@ def ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data
     return a.data_ptr()
+
+
+def stream_handle(torch_stream):
+    """cudaStream_t value for the C-ABI.  torch's default stream is the legacy NULL stream, whose handle 0 means "the
+    handle's own stream" in orbx_set_stream / orbm_set_stream; cudaStreamLegacy (0x1) names it explicitly."""
+    return torch_stream.cuda_stream or 1

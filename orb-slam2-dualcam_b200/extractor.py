@@ -13,6 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
+from .capi import stream_handle as _stream_handle
 from .capi import KP_DTYPE, check, lib, ptr
 
 
@@ -111,7 +112,7 @@ class ORBextractor:
             d_counts = torch.empty((F, self.cameras), dtype=torch.int32, device=dev)
         st = stream if stream is not None else torch.cuda.current_stream(dev)
         L = lib()
-        check(L.orbx_set_stream(self._h, st.cuda_stream))
+        check(L.orbx_set_stream(self._h, _stream_handle(st)))
         check(L.orbx_extract_device(self._h, d_imgs.data_ptr(), F, self.width, d_kps.data_ptr(), d_desc.data_ptr(), d_counts.data_ptr(), cap))
         return d_kps, d_desc, d_counts
 

@@ -3,6 +3,7 @@ import ctypes as C
 
 import numpy as np
 
+from .capi import stream_handle as _stream_handle
 from .capi import check, lib, ptr
 
 
@@ -59,7 +60,7 @@ class ORBmatcher:
             out = tuple(torch.empty((P, Q), dtype=torch.int32, device=dev) for _ in range(3))
         st = stream if stream is not None else torch.cuda.current_stream(dev)
         L = lib()
-        check(L.orbm_set_stream(self._h, st.cuda_stream))
+        check(L.orbm_set_stream(self._h, _stream_handle(st)))
         check(L.orbm_bruteforce_device(self._h, d_dq.data_ptr(), d_nq.data_ptr(), Q, d_dt.data_ptr(), d_nt.data_ptr(), T, P,
                                        out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr()))
         return out
@@ -75,7 +76,7 @@ class ORBmatcher:
             out = tuple(torch.empty((P, cap), dtype=torch.int32, device=dev) for _ in range(3))
         st = stream if stream is not None else torch.cuda.current_stream(dev)
         L = lib()
-        check(L.orbm_set_stream(self._h, st.cuda_stream))
+        check(L.orbm_set_stream(self._h, _stream_handle(st)))
         check(L.orbm_bruteforce_sets_device(self._h, d_desc.data_ptr(), d_counts.data_ptr(), cap, S, d_q_set.data_ptr(), d_t_set.data_ptr(), P,
                                             out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr()))
         return out
