@@ -79,3 +79,132 @@ def random_descriptors(seed, n, p_flip=None, base=None):
         return rng.integers(0, 256, (n, 32), dtype=np.uint8)
     flips = np.packbits(rng.random((base.shape[0], 256)) < p_flip, axis=1)
     return base ^ flips
+
+
+# ------------------------------------------------------------------------------------------------ bundle adjustment
+# Dual rig of the reference's example settings (Dual-LenaCV.yaml:12-44): intrinsics of both cameras, extrinsic of camera 1.
+RIG_K = np.array([[558.4684, 560.0944, 326.7993, 262.9017],
+                  [546.597961663159, 546.254254416417, 332.758939924785, 247.385425357685]], np.float64)
+RIG_Q1 = (0.82351, -0.00262741, 0.567257, 0.00665084)     # qw qx qy qz
+RIG_T1 = (0.069481, -0.000909887, -0.0713882)
+
+
+def _quat_to_R(qw, qx, qy, qz):
+    n = np.sqrt(qw * qw + qx * qx + qy * qy + qz * qz)
+    qw, qx, qy, qz = qw / n, qx / n, qy / n, qz / n
+    return np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)],
+                     [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
+                     [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)]])
+
+
+def _rodrigues(w):
+    th = np.linalg.norm(w)
+    if th < 1e-12:
+        return np.eye(3)
+    k = w / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+
+def rig_extrinsics():
+    """(ext [2][3][4], adj [2][6][6]) as the reference holds them: float32 matrices; the 6x6 'adjoint' of
+    src/Cameras.cc:26-40 (upper-left R, lower-right R, upper-right R*[t]x; the lower-left block, which the reference never
+    writes, is pinned to 0)."""
+    ext = np.zeros((2, 3, 4), np.float32)
+    ext[0, :, :3] = np.eye(3)
+    ext[1, :, :3] = _quat_to_R(*RIG_Q1)
+    ext[1, :, 3] = RIG_T1
+    adj = np.zeros((2, 6, 6), np.float32)
+    for c in range(2):
+        R, t = ext[c, :, :3], ext[c, :, 3]
+        t_hat = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]], np.float32)
+        adj[c, :3, :3] = R
+        adj[c, 3:, 3:] = R
+        adj[c, :3, 3:] = (R @ t_hat).astype(np.float32)
+    return ext.astype(np.float64), adj.astype(np.float64)
+
+
+def ba_problem(seed=0, n_kf=20, n_points=4000, n_fixed_extra=0, obs_range=(5, 10), outlier_frac=0.05, W=640, H=480,
+               pose_noise=(0.02, 0.5), point_noise=0.05):
+    """Synthetic LocalBundleAdjustment input.  Returns a dict of numpy arrays in the layout of
+    orbba_problem_t plus the ground truth.  Pose 0 is the fixed one (fixId); `n_fixed_extra` more poses at the end are
+    fixed too (the reference's lFixedCameras)."""
+    rng = np.random.default_rng(seed)
+    ext, adj = rig_extrinsics()
+    nP = n_kf + n_fixed_extra
+    # rig trajectory (world <- rig), smooth: forward motion with gentle yaw/pitch
+    Twc = []
+    for i in range(nP):
+        s = i / max(nP - 1, 1)
+        R = _rodrigues(np.array([0.03 * np.sin(2 * s), 0.25 * s - 0.1, 0.02 * s]))
+        t = np.array([1.5 * s, 0.1 * np.sin(3 * s), 2.0 * s])
+        Twc.append((R, t))
+    gt_poses = np.zeros((nP, 3, 4))
+    for i, (R, t) in enumerate(Twc):
+        gt_poses[i, :, :3] = R.T
+        gt_poses[i, :, 3] = -R.T @ t
+
+    def project(Tcw, c, X):
+        pr = Tcw[:, :3] @ X + Tcw[:, 3]
+        pc = ext[c, :, :3] @ pr + ext[c, :, 3]
+        if pc[2] <= 0.1:
+            return None
+        u = RIG_K[c, 0] * pc[0] / pc[2] + RIG_K[c, 2]
+        v = RIG_K[c, 1] * pc[1] / pc[2] + RIG_K[c, 3]
+        if 0 <= u < W and 0 <= v < H:
+            return np.array([u, v])
+        return None
+
+    inv_sigma2 = np.ones(8, np.float32)
+    sc = np.float32(1.0)
+    for l in range(1, 8):
+        sc = np.float32(sc * np.float32(1.2))
+        inv_sigma2[l] = np.float32(1.0) / np.float32(sc * sc)
+    pts, e_pose, e_pt, e_cam, e_obs, e_info, e_out = [], [], [], [], [], [], []
+    while len(pts) < n_points:
+        k, c = int(rng.integers(0, nP)), int(rng.integers(0, 2))
+        u, v, d = rng.uniform(0, W), rng.uniform(0, H), rng.uniform(2, 20)
+        pc = np.array([(u - RIG_K[c, 2]) / RIG_K[c, 0] * d, (v - RIG_K[c, 3]) / RIG_K[c, 1] * d, d])
+        pr = ext[c, :, :3].T @ (pc - ext[c, :, 3])
+        X = gt_poses[k, :, :3].T @ (pr - gt_poses[k, :, 3])
+        vis = []
+        for kk in rng.permutation(nP):
+            for cc in rng.permutation(2):
+                p = project(gt_poses[kk], cc, X)
+                if p is not None:
+                    vis.append((int(kk), int(cc), p))
+                    break      # one observation per keyframe (MapPoint::mObservations is a map<KeyFrame, idx>)
+        want = int(rng.integers(obs_range[0], obs_range[1] + 1))
+        if len(vis) < 2:
+            continue
+        vis = vis[:want]
+        pid = len(pts)
+        pts.append(X)
+        for kk, cc, p in vis:
+            octave = int(rng.integers(0, 8))
+            noise = rng.normal(0, 1.2 ** octave, 2)
+            out = rng.random() < outlier_frac
+            if out:
+                noise = noise + rng.choice([-20.0, 20.0], 2)
+            e_pose.append(kk); e_pt.append(pid); e_cam.append(cc)
+            e_obs.append((p + noise).astype(np.float32))   # cv::KeyPoint::pt is float
+            e_info.append(inv_sigma2[octave]); e_out.append(out)
+    gt_points = np.array(pts)
+    # initial estimates: perturbed, then rounded to float32 (the reference keeps poses / points in CV_32F)
+    poses = gt_poses.copy()
+    for i in range(1, n_kf):
+        dR = _rodrigues(rng.normal(0, np.deg2rad(pose_noise[1]) / np.sqrt(3), 3))
+        poses[i, :, :3] = dR @ poses[i, :, :3]
+        poses[i, :, 3] = dR @ poses[i, :, 3] + rng.normal(0, pose_noise[0] / np.sqrt(3), 3)
+    points = gt_points + rng.normal(0, point_noise / np.sqrt(3), gt_points.shape)
+    fixed = np.zeros(nP, np.uint8)
+    fixed[0] = 1
+    fixed[n_kf:] = 1
+    order = np.lexsort((np.array(e_pose), np.array(e_pt)))   # edges listed per point, as the reference adds them
+    return dict(
+        poses=np.ascontiguousarray(poses.astype(np.float32).astype(np.float64).reshape(nP, 12)), pose_fixed=fixed,
+        points=np.ascontiguousarray(points.astype(np.float32).astype(np.float64)),
+        edge_pose=np.array(e_pose, np.int32)[order], edge_point=np.array(e_pt, np.int32)[order], edge_cam=np.array(e_cam, np.int32)[order],
+        edge_obs=np.ascontiguousarray(np.array(e_obs, np.float64)[order]), edge_inv_sigma2=np.array(e_info, np.float64)[order],
+        cam_K=RIG_K.astype(np.float32).astype(np.float64), cam_ext=np.ascontiguousarray(ext.reshape(2, 12)), cam_adj=np.ascontiguousarray(adj.reshape(2, 36)),
+        gt_poses=gt_poses.reshape(nP, 12), gt_points=gt_points, planted_outlier=np.array(e_out, bool)[order])

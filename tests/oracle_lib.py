@@ -166,3 +166,68 @@ def match_bruteforce(dq, dt):
     bi, bd, sd = (np.empty(nq, np.int32) for _ in range(3))
     lib().orc_match_bruteforce(_ptr(dq, u8p), nq, _ptr(dt, u8p), nt, _ptr(bi, i32p), _ptr(bd, i32p), _ptr(sd, i32p))
     return bi, bd, sd
+
+
+# ------------------------------------------------------------------------------------------------ bundle adjustment
+class BAProblemC(C.Structure):
+    _fields_ = [("n_poses", C.c_int32), ("n_points", C.c_int32), ("n_edges", C.c_int32), ("n_cams", C.c_int32),
+                ("poses", C.c_void_p), ("pose_fixed", C.c_void_p), ("points", C.c_void_p),
+                ("edge_pose", C.c_void_p), ("edge_point", C.c_void_p), ("edge_cam", C.c_void_p),
+                ("edge_obs", C.c_void_p), ("edge_inv_sigma2", C.c_void_p),
+                ("cam_K", C.c_void_p), ("cam_ext", C.c_void_p), ("cam_adj", C.c_void_p)]
+
+
+class BAStatsC(C.Structure):
+    _fields_ = [("initial_chi2", C.c_double), ("final_chi2", C.c_double), ("final_lambda", C.c_double),
+                ("iterations", C.c_int32), ("trials", C.c_int32), ("outliers", C.c_int32)]
+
+
+BA_KEYS = [("poses", np.float64), ("pose_fixed", np.uint8), ("points", np.float64), ("edge_pose", np.int32), ("edge_point", np.int32),
+           ("edge_cam", np.int32), ("edge_obs", np.float64), ("edge_inv_sigma2", np.float64), ("cam_K", np.float64),
+           ("cam_ext", np.float64), ("cam_adj", np.float64)]
+
+
+def ba_struct(p, cls=BAProblemC):
+    """dict of numpy arrays (synth.ba_problem layout) -> (C struct, keep-alive list)"""
+    keep = {k: np.ascontiguousarray(p[k], dt) for k, dt in BA_KEYS}
+    s = cls(n_poses=keep["pose_fixed"].shape[0], n_points=keep["points"].shape[0], n_edges=keep["edge_pose"].shape[0],
+            n_cams=keep["cam_K"].shape[0], **{k: keep[k].ctypes.data for k, _ in BA_KEYS})
+    return s, keep
+
+
+HUBER_MONO = float(np.float32(np.sqrt(5.991)))   # `const float thHuberMono = sqrt(5.991)`  src/Optimizer.cc:514
+
+
+def local_ba(p, its1=5, its2=10, huber_delta=HUBER_MONO, chi2_th=5.991, stop=None):
+    L = lib()
+    L.orc_local_ba.argtypes = [C.POINTER(BAProblemC), C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BAStatsC)]
+    s, keep = ba_struct(p)
+    poses = np.zeros((s.n_poses, 12)); points = np.zeros((s.n_points, 3)); out = np.zeros(s.n_edges, np.uint8)
+    st = BAStatsC()
+    rc = L.orc_local_ba(C.byref(s), its1, its2, huber_delta, chi2_th, stop.ctypes.data if stop is not None else None,
+                        poses.ctypes.data, points.ctypes.data, out.ctypes.data, C.byref(st))
+    return rc, poses, points, out.astype(bool), {f: getattr(st, f) for f, _ in BAStatsC._fields_}
+
+
+def global_ba(p, iterations=10, huber_delta=HUBER_MONO, stop=None):
+    L = lib()
+    L.orc_global_ba.argtypes = [C.POINTER(BAProblemC), C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BAStatsC)]
+    s, keep = ba_struct(p)
+    poses = np.zeros((s.n_poses, 12)); points = np.zeros((s.n_points, 3))
+    st = BAStatsC()
+    rc = L.orc_global_ba(C.byref(s), iterations, huber_delta, stop.ctypes.data if stop is not None else None,
+                         poses.ctypes.data, points.ctypes.data, C.byref(st))
+    return rc, poses, points, {f: getattr(st, f) for f, _ in BAStatsC._fields_}
+
+
+def ba_normal_equations(p, huber_delta=HUBER_MONO):
+    L = lib()
+    L.orc_ba_normal_equations.argtypes = [C.POINTER(BAProblemC), C.c_double] + [C.c_void_p] * 6
+    s, keep = ba_struct(p)
+    K = int((keep["pose_fixed"] == 0).sum())
+    Hpp = np.zeros((K, 6, 6)); bp = np.zeros((K, 6)); Hll = np.zeros((s.n_points, 3, 3)); bl = np.zeros((s.n_points, 3))
+    Hpl = np.zeros((s.n_edges, 6, 3)); chi2 = C.c_double()
+    k = L.orc_ba_normal_equations(C.byref(s), huber_delta, Hpp.ctypes.data, bp.ctypes.data, Hll.ctypes.data, bl.ctypes.data,
+                                  Hpl.ctypes.data, C.addressof(chi2))
+    assert k == K
+    return Hpp, bp, Hll, bl, Hpl, chi2.value
