@@ -150,6 +150,71 @@ int  orbm_bruteforce_sets_device(orbm_t*, const uint8_t* d_desc, const int32_t* 
                                  const int32_t* d_q_set, const int32_t* d_t_set, int pairs,
                                  int32_t* d_best_idx, int32_t* d_best_d, int32_t* d_second_d);
 
+/* ================================================================================================
+ * BUNDLE ADJUSTMENT -- replaces Optimizer::LocalBundleAdjustment / BundleAdjustment / GlobalBundleAdjustemnt
+ * (include/Optimizer.h:50-56, src/Optimizer.cc:62-248,407-696) together with the g2o machinery under them
+ * (dual-camera EdgeSE3ProjectXYZ, Huber kernel, BlockSolver_6_3 Schur complement, Levenberg-Marquardt).
+ *
+ * The adaptor flattens the graph it used to build with `new g2o::Vertex/Edge` (src/Optimizer.cc:460-580):
+ *   poses   rig poses Tcw = KeyFrame::GetPose(), row-major 3x4 [R|t] (CV_32F values widened to double), ascending mnId
+ *   fixed   1 for lFixedCameras and for mnId == fixId (src/Optimizer.cc:480,495)
+ *   points  MapPoint::GetWorldPos(), ascending mnId
+ *   edges   one per observation: pose index, point index, camera of the rig (KeyFrame::keypointToCam), undistorted
+ *           keypoint (mvTotalKeysUn[idx].pt), mvInvLevelSigma2[octave]
+ *   cams    per camera fx fy cx cy, extrinsic Cameras::getExtrinsici (3x4) and the 6x6 Cameras::getExtrinsicAdji
+ *           (src/Cameras.cc:17-40; passed through as opaque data, lower-left block as the caller holds it)
+ * ============================================================================================== */
+typedef struct {
+    int32_t n_poses, n_points, n_edges, n_cams;
+    const double*  poses;            /* [n_poses][12] */
+    const uint8_t* pose_fixed;       /* [n_poses] */
+    const double*  points;           /* [n_points][3] */
+    const int32_t* edge_pose;        /* [n_edges] */
+    const int32_t* edge_point;       /* [n_edges] */
+    const int32_t* edge_cam;         /* [n_edges] */
+    const double*  edge_obs;         /* [n_edges][2] */
+    const double*  edge_inv_sigma2;  /* [n_edges] */
+    const double*  cam_K;            /* [n_cams][4] */
+    const double*  cam_ext;          /* [n_cams][12] */
+    const double*  cam_adj;          /* [n_cams][36] */
+} orbba_problem_t;
+
+typedef struct {
+    double  initial_chi2, final_chi2, final_lambda;   /* robust chi2 before, chi2 after the last accepted step, last lambda */
+    int32_t iterations, trials, outliers;             /* LM outer iterations, linear solves, edges flagged at the end */
+    int32_t status;                                    /* ORB_OK or ORB_E_ABORTED */
+} orbba_stats_t;
+
+typedef struct orbba orbba_t;
+
+int  orbba_create(orbba_t** out, int device, int max_problems);
+void orbba_destroy(orbba_t*);
+int  orbba_set_stream(orbba_t*, void* cuda_stream);
+int  orbba_synchronize(orbba_t*);
+long long orbba_launch_count(const orbba_t*);
+
+/* Optimizer::LocalBundleAdjustment(pKF, pbStopFlag, pMap, fixId) on one flattened problem: optimize(its1 = 5) with
+ * Huber(delta = sqrt(5.991)), edges with chi2 > chi2_th (5.991) or non-positive depth leave the graph and the kernel is
+ * dropped, optimize(its2 = 10), final outlier classification (the observations the caller erases, src/Optimizer.cc:641-660).
+ * HOST buffers, synchronous.  `stop` = pbStopFlag (may be NULL): polled while the GPU works; returns ORB_E_ABORTED
+ * with the inputs unchanged if it was already set on entry (src/Optimizer.cc:582-584).
+ *   poses_out [n_poses][12], points_out [n_points][3], edge_outlier [n_edges], stats: any may be NULL. */
+int  orbba_local(orbba_t*, const orbba_problem_t* problem, int its1, int its2, double huber_delta, double chi2_th,
+                 const volatile uint8_t* stop, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats);
+/* Optimizer::BundleAdjustment(vpKFs, vpMP, nIterations, pbStopFlag, nLoopKF, bRobust): one optimize(iterations),
+ * Huber(huber_delta) when > 0, no outlier pass. */
+int  orbba_global(orbba_t*, const orbba_problem_t* problem, int iterations, double huber_delta, const volatile uint8_t* stop,
+                  double* poses_out, double* points_out, orbba_stats_t* stats);
+
+/* Batched form: n independent problems (one per keyframe / per sequence) solved concurrently, one persistent CTA each.
+ * upload = flatten + index + host->device; run = asynchronous on the handle's stream, always restarts from the uploaded
+ * estimates (its2 < 0: single round); download = results of problem p (synchronises). */
+int  orbba_upload(orbba_t*, const orbba_problem_t* problems, int n);
+int  orbba_run(orbba_t*, int its1, int its2, double huber_delta, double chi2_th);
+int  orbba_download(orbba_t*, int p, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats);
+int  orbba_profile(orbba_t*, int enable);
+int  orbba_stage_ms(orbba_t*, double* ms1, int* calls);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,8 +14,11 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "liborbslam2_dualcam_b200.so")
 SOURCES = ["orb_common.cu", "orb_extract.cu", "orb_match.cu", "orb_search.cu", "orb_ba.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
+# integer / bit-exact float paths: no FMA contraction; the FP64 bundle adjustment (1e-5 parity budget) keeps FMA
+FILE_FLAGS = {"orb_ba.cu": []}
+DEFAULT_FILE_FLAGS = ["-fmad=false"]
 
 
 def _nvcc():
@@ -45,7 +48,8 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
         if force or not os.path.exists(obj) or needs_build():
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = ([_nvcc()] + NVCC_FLAGS + FILE_FLAGS.get(os.path.basename(src), DEFAULT_FILE_FLAGS) +
+                   (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
             subprocess.run(cmd, check=True)
         objs.append(obj)
     subprocess.run([_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB] + objs, check=True)

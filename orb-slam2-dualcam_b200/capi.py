@@ -47,6 +47,18 @@ SIGNATURES = {
     "orbm_descriptor_distance": (C.c_int, [vp, vp, vp, C.c_int, vp]),
     "orbm_bruteforce": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp]),
     "orbm_bruteforce_device": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp]),
+    "orbba_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
+    "orbba_destroy": (None, [vp]),
+    "orbba_set_stream": (C.c_int, [vp, vp]),
+    "orbba_synchronize": (C.c_int, [vp]),
+    "orbba_launch_count": (C.c_longlong, [vp]),
+    "orbba_local": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
+    "orbba_global": (C.c_int, [vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]),
+    "orbba_upload": (C.c_int, [vp, vp, C.c_int]),
+    "orbba_run": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_double]),
+    "orbba_download": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
+    "orbba_profile": (C.c_int, [vp, C.c_int]),
+    "orbba_stage_ms": (C.c_int, [vp, f64p, C.POINTER(C.c_int)]),
     "orbm_bruteforce_sets_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp]),
 }
 

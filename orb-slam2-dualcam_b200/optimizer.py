@@ -1,0 +1,121 @@
+"""Host-side mirror of the reference's Optimizer bundle-adjustment entry points (include/Optimizer.h:50-56) above the C-ABI.
+
+    opt = Optimizer()
+    poses, points, outlier, stats = opt.LocalBundleAdjustment(problem)            # src/Optimizer.cc:407-696
+    poses, points, stats          = opt.GlobalBundleAdjustemnt(problem, nIterations=10, bRobust=True)   # :62-248
+
+`problem` is the flattened graph (dict of numpy arrays, see orbba_problem_t in include/orbslam2_dualcam_b200.h).
+"""
+import ctypes as C
+
+import numpy as np
+
+from .capi import check, lib, ptr
+from .capi import stream_handle as _stream_handle
+
+TH_HUBER_MONO = float(np.float32(np.sqrt(5.991)))    # `const float thHuberMono = sqrt(5.991)`  src/Optimizer.cc:514
+CHI2_MONO = 5.991                                     # src/Optimizer.cc:603
+
+
+class ProblemC(C.Structure):
+    _fields_ = [("n_poses", C.c_int32), ("n_points", C.c_int32), ("n_edges", C.c_int32), ("n_cams", C.c_int32),
+                ("poses", C.c_void_p), ("pose_fixed", C.c_void_p), ("points", C.c_void_p),
+                ("edge_pose", C.c_void_p), ("edge_point", C.c_void_p), ("edge_cam", C.c_void_p),
+                ("edge_obs", C.c_void_p), ("edge_inv_sigma2", C.c_void_p),
+                ("cam_K", C.c_void_p), ("cam_ext", C.c_void_p), ("cam_adj", C.c_void_p)]
+
+
+class StatsC(C.Structure):
+    _fields_ = [("initial_chi2", C.c_double), ("final_chi2", C.c_double), ("final_lambda", C.c_double),
+                ("iterations", C.c_int32), ("trials", C.c_int32), ("outliers", C.c_int32), ("status", C.c_int32)]
+
+    def asdict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_KEYS = [("poses", np.float64), ("pose_fixed", np.uint8), ("points", np.float64), ("edge_pose", np.int32), ("edge_point", np.int32),
+         ("edge_cam", np.int32), ("edge_obs", np.float64), ("edge_inv_sigma2", np.float64), ("cam_K", np.float64),
+         ("cam_ext", np.float64), ("cam_adj", np.float64)]
+
+
+def problem_struct(p):
+    keep = {k: np.ascontiguousarray(p[k], dt) for k, dt in _KEYS}
+    s = ProblemC(n_poses=keep["pose_fixed"].shape[0], n_points=keep["points"].shape[0], n_edges=keep["edge_pose"].shape[0],
+                 n_cams=keep["cam_K"].shape[0], **{k: keep[k].ctypes.data for k, _ in _KEYS})
+    return s, keep
+
+
+class Optimizer:
+    def __init__(self, max_problems=1, device=0):
+        self._h = None
+        h = C.c_void_p()
+        check(lib().orbba_create(C.byref(h), device, max_problems))
+        self._h = h
+        self._sizes = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orbba_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def LocalBundleAdjustment(self, problem, pbStopFlag=None, its1=5, its2=10, huber_delta=TH_HUBER_MONO, chi2_th=CHI2_MONO):
+        """-> (poses [nP][12], points [nL][3], outlier [nE] bool, stats dict); raises OrbError(-5) if the stop flag was set."""
+        s, keep = problem_struct(problem)
+        poses = np.zeros((s.n_poses, 12)); points = np.zeros((s.n_points, 3)); out = np.zeros(s.n_edges, np.uint8)
+        st = StatsC()
+        stop = None if pbStopFlag is None else pbStopFlag.ctypes.data
+        rc = lib().orbba_local(self._h, C.addressof(s), its1, its2, huber_delta, chi2_th, stop, ptr(poses), ptr(points), ptr(out), C.addressof(st))
+        if rc != -5:
+            check(rc)
+        return poses, points, out.astype(bool), st.asdict()
+
+    def GlobalBundleAdjustemnt(self, problem, nIterations=5, pbStopFlag=None, bRobust=True):
+        s, keep = problem_struct(problem)
+        poses = np.zeros((s.n_poses, 12)); points = np.zeros((s.n_points, 3))
+        st = StatsC()
+        stop = None if pbStopFlag is None else pbStopFlag.ctypes.data
+        rc = lib().orbba_global(self._h, C.addressof(s), nIterations, TH_HUBER_MONO if bRobust else 0.0, stop, ptr(poses), ptr(points), C.addressof(st))
+        if rc != -5:
+            check(rc)
+        return poses, points, st.asdict()
+
+    BundleAdjustment = GlobalBundleAdjustemnt
+
+    # ---- batched form
+    def upload(self, problems):
+        arr = (ProblemC * len(problems))()
+        keeps = []
+        for i, p in enumerate(problems):
+            s, keep = problem_struct(p)
+            arr[i] = s
+            keeps.append(keep)
+        check(lib().orbba_upload(self._h, C.addressof(arr), len(problems)))
+        self._sizes = [(a.n_poses, a.n_points, a.n_edges) for a in arr]
+
+    def run(self, its1=5, its2=10, huber_delta=TH_HUBER_MONO, chi2_th=CHI2_MONO, stream=None):
+        if stream is not None:
+            check(lib().orbba_set_stream(self._h, _stream_handle(stream)))
+        check(lib().orbba_run(self._h, its1, its2, huber_delta, chi2_th))
+
+    def download(self, p):
+        nP, nL, nE = self._sizes[p]
+        poses = np.zeros((nP, 12)); points = np.zeros((nL, 3)); out = np.zeros(nE, np.uint8)
+        st = StatsC()
+        check(lib().orbba_download(self._h, p, ptr(poses), ptr(points), ptr(out), C.addressof(st)))
+        return poses, points, out.astype(bool), st.asdict()
+
+    def synchronize(self):
+        check(lib().orbba_synchronize(self._h))
+
+    def launch_count(self):
+        return int(lib().orbba_launch_count(self._h))
+
+    def profile(self, enable=True):
+        check(lib().orbba_profile(self._h, int(enable)))
+
+    def stage_ms(self):
+        ms, n = C.c_double(), C.c_int()
+        check(lib().orbba_stage_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
