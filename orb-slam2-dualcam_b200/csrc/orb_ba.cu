@@ -7,15 +7,21 @@
 //   BlockSolver<6,3>::{buildSystem,setLambda,solve} .../core/block_solver.hpp:354-604 (Schur complement)
 //   OptimizationAlgorithmLevenberg::solve .../core/optimization_algorithm_levenberg.cpp:61-189, SE3Quat .../types/se3quat.h
 //
-// B200 formulation: ONE persistent CTA runs the whole optimisation of one problem -- both LM rounds, every trial, the
-// lambda policy and the outlier re-classification -- without returning to the host; a batch of independent problems
-// (one per keyframe / per sequence) fills the 148 SMs.  Everything is FP64.  No atomics: every sum has one owner
-//   per edge      residual, 2x6 / 2x3 Jacobians, Huber weight                       (thread per edge)
-//   per landmark  Hll, bl, (Hll + lambda I)^-1, back-substitution                   (thread per landmark, CSR by landmark)
-//   per pose      Hpp, bp, Schur right-hand side                                    (warp per pose, CSR by pose)
-//   per pose pair 6x6 block of the reduced camera matrix: Hpp - sum_l B_il Dinv_l B_jl^T  (warp per pair, list of (edge,edge) tuples)
-// so results are bit-reproducible run to run.  The reduced camera system (6K x 6K, K free poses) lives in shared
-// memory (K <= 26) and is factorised in place by LDL^T.
+// B200 formulation ("flat" batched LM).  A batch of independent problems (one per keyframe / per sequence) is concatenated
+// into one edge / landmark / pose index space and advanced in lock-step: one STEP = one LM trial of every unfinished
+// problem = six kernel launches over the whole batch; the LM policy (lambda, rho, trial / iteration counters, the
+// Huber -> outlier-removal -> plain round switch, the stop flag) lives in a per-problem state block on the device and is
+// advanced by the last CTA of the step, so the host never reads anything back between steps.  Everything is FP64 and
+// every sum has one owner and a fixed order (no floating-point atomics): results are bit-reproducible.
+//
+//   k_lin       thread / edge       residual, 2x6 and 2x3 Jacobians, Huber weight, B_e = Jp^T W Jl          (per LM iteration)
+//   k_build     thread / landmark   Hll, bl ;  CTA / free pose: Hpp, bp                                      (per LM iteration)
+//   k_trial_lm  thread / landmark   Dinv = (Hll + lambda I)^-1, Dinv bl, Y_e = B_e Dinv, Y_e bl            (per trial)
+//   k_pairs     warp / chunk of (edge, edge) tuples of one pose pair: partial 6x6 of  sum Y_a B_b^T ; warp / pose: Schur rhs
+//   k_solve     CTA / problem       reduced camera system in shared memory, LDL^T, pose increments, exp-map update
+//   k_back      thread / landmark   landmark increment, trial errors and chi2 of its edges; last CTA: LM decision
+// Blocks are laid out problem-major, so the CTAs resident at any time work on a handful of neighbouring problems and the
+// gathers of k_pairs (4x re-use of every Y_e / B_e block) are served by the 126 MB L2.
 #include <string.h>
 
 #include <algorithm>
@@ -24,22 +30,68 @@
 
 #include "orb_common.h"
 
-#define BA_T 512
-#define BA_WARPS (BA_T / 32)
-#define BA_JSTRIDE 21          // per-edge record: Jp[12] Jl[6] W r0 r1 (SoA: J[k * nE + e])
 #define BA_CAM_STRIDE 47       // fx fy cx cy | ext quat xyzw | ext t | adj[36]
+#define BA_REC 21              // per-edge linearisation record: Jl[6] W r0 r1 Jp[12]
+#define BA_TE 128              // threads per edge block
+#define BA_TL 128              // threads per landmark block
+#define BA_TP 128              // threads per pose block (k_build)
+#define BA_CH 256              // tuples per chunk (k_pairs)
+#define BA_TS 256              // threads of k_solve
+#define BA_HS_SMEM_N 156       // reduced camera system in shared memory up to 156 x 156 doubles (26 free poses)
 
-struct BAProb {
-    int nP, nL, nE, nC, K, n, nPairs, nTuples;
-    const int *e_pose, *e_pt, *e_cam, *pose_free;
+struct BAProb {                // static description of one problem inside the batch
+    int e0, nE, l0, nL, p0, nP, c0, nC, k0, K, n;
+    int pair0, nPairs;         // K (K + 1) / 2 pair slots
+    int chunk0, nChunksMax;    // chunk slots (upper bound)
+    int item0, nItems;         // k_pairs work items: nChunksMax chunk warps + K pose warps
+    int blkE0, nbE, blkL0, nbL;
+    long long tup0, eof0, hs_off;
+};
+
+struct BAState {
+    double lambda, ni, currentChi, iniChi, rho, initial_chi2, poseScale;
+    unsigned long long maxdiag_bits;
+    int cur, last;             // double-buffer index of the accepted estimate / of the errors computed last
+    int round, it, qmax, nBad, trials, iterations;
+    int need_build, round_start, mark, lambda_pending, solve_ok, skip, done, stopped, aborted;
+    unsigned ticket;
+    int nChunks, nTuples;
+};
+
+struct BABatch {               // kernel argument (by value)
+    int nProb;
+    const BAProb* prob;
+    BAState* state;
+    // static
+    const int *e_pose, *e_pt, *e_cam;          // global indices
     const double *e_obs, *e_info, *cam;
-    const int *pt_off, *pt_edges, *pose_off, *pose_edges, *pair_off, *pair_ij, *tuples;
+    const int* pt_off;                          // [Ltot + 1] global CSR (edges are grouped by landmark)
+    const int* pose_free;                       // [Ptot] global free index or -1
     const double *pose0, *pt0;
-    double *pose, *pose_bak, *pt, *pt_bak, *err, *J, *Hll, *bl, *Dinv, *db, *Hpp, *bp, *bs, *x, *Hs;
+    const int *blkE_prob, *blkL_prob, *item_prob;
+    // index built on the device
+    int* edge_of;                               // [landmark][free pose of the problem] -> edge or -1
+    int *pair_cnt, *pair_off, *pair_fchunk;      // per pair: tuples, first tuple, first chunk
+    int *chunk_pair, *chunk_start, *chunk_len;
+    int2* tuples;
+    // dynamic
+    double *pose[2], *pt[2], *err[2];
     unsigned char* level;
+    double *rec, *B, *Y, *v;                    // per edge: 21 / 18 / 18 / 6
+    double *Hll, *bl, *Dinv, *db;               // per landmark: 6 / 3 / 6 / 3
+    double *Hpp, *bp, *bs, *xp;                 // per free pose: 36 / 6 / 6 / 6
+    double *partial;                            // per chunk: 36
+    double *partE, *partL;                      // per edge block: chi, active ; per landmark block: chi, scale
+    double* Hs;                                 // reduced systems that do not fit in shared memory
+    // outputs
     double *poses_out, *points_out;
     unsigned char* outlier;
     orbba_stats_t* stats;
+    int* n_active;                              // mapped host memory
+    // run parameters
+    int its1, its2;
+    double delta, chi2_th;
+    const volatile int* stop;
 };
 
 // ------------------------------------------------------------------------------------------------ SE3 (unit quaternion xyzw + t)
@@ -94,8 +146,8 @@ __host__ __device__ inline void q_to_matrix(const double* q, double* R) {    // 
     R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
     R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
 }
-// pose <- exp(u) * pose  (VertexSE3Expmap::oplusImpl, SE3Quat::exp, SE3Quat::operator*)
-__device__ void se3_oplus(const double* u, double* s) {
+// out <- exp(u) * s  (VertexSE3Expmap::oplusImpl, SE3Quat::exp, SE3Quat::operator*)
+__device__ void se3_oplus(const double* u, const double* s, double* out) {
     const double ox = u[0], oy = u[1], oz = u[2];
     const double theta = sqrt(ox * ox + oy * oy + oz * oz);
     const double Om[9] = {0, -oz, oy, oz, 0, -ox, -oy, ox, 0};
@@ -121,9 +173,22 @@ __device__ void se3_oplus(const double* u, double* s) {
     q_rotate(e, s + 4, rt);
     q_mul(e, s, rq);
     q_normalize(rq);
-    s[0] = rq[0]; s[1] = rq[1]; s[2] = rq[2]; s[3] = rq[3];
-    s[4] = e[4] + rt[0]; s[5] = e[5] + rt[1]; s[6] = e[6] + rt[2];
+    out[0] = rq[0]; out[1] = rq[1]; out[2] = rq[2]; out[3] = rq[3];
+    out[4] = e[4] + rt[0]; out[5] = e[5] + rt[1]; out[6] = e[6] + rt[2];
 }
+
+// One definition of the reprojection (point -> rig -> camera) and of the residual, never inlined, so that every kernel
+// that evaluates an edge produces the same bits.
+__device__ __noinline__ void edge_project(const double* pose7, const double* pt3, const double* cam, double* pc) {
+    double pr[3];
+    se3_map(pose7, pt3, pr);
+    se3_map(cam + 4, pr, pc);
+}
+__device__ __noinline__ void edge_error(const double* pc, const double* cam, const double* obs, double* e2) {
+    e2[0] = obs[0] - (pc[0] / pc[2] * cam[0] + cam[2]);
+    e2[1] = obs[1] - (pc[1] / pc[2] * cam[1] + cam[3]);
+}
+__device__ __forceinline__ double huber_rho0(double e, double delta, double dsqr) { return e <= dsqr ? e : 2 * sqrt(e) * delta - dsqr; }
 
 // ------------------------------------------------------------------------------------------------ block reductions (fixed order)
 __device__ __forceinline__ double warp_sum(double v) {
@@ -131,266 +196,491 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ double block_sum(double v, double* red) {
+template <int NW>
+__device__ __forceinline__ double block_sum(double v, double* red) {   // red: NW doubles of shared memory
     v = warp_sum(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     double s = 0;
-    for (int w = 0; w < BA_WARPS; w++) s += red[w];
+#pragma unroll
+    for (int w = 0; w < NW; w++) s += red[w];
     return s;
 }
-__device__ double block_max(double v, double* red) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double s = 0;
-    for (int w = 0; w < BA_WARPS; w++) s = fmax(s, red[w]);
-    return s;
+__device__ __forceinline__ double lambda_eff(const BAState& S) {
+    return S.lambda_pending ? 1e-5 * __longlong_as_double((long long)S.maxdiag_bits) : S.lambda;
 }
 
-__device__ __forceinline__ void project_edge(const BAProb& P, int e, double* pc) {
-    double pr[3];
-    se3_map(P.pose + 7 * P.e_pose[e], P.pt + 3 * P.e_pt[e], pr);
-    se3_map(P.cam + BA_CAM_STRIDE * P.e_cam[e] + 4, pr, pc);
+// ------------------------------------------------------------------------------------------------ index construction
+__global__ void k_edge_of(BABatch A) {
+    const int b = blockIdx.x;
+    const int p = A.blkE_prob[b];
+    const BAProb P = A.prob[p];
+    const int e = P.e0 + (b - P.blkE0) * BA_TE + threadIdx.x;
+    if (e >= P.e0 + P.nE) return;
+    const int k = A.pose_free[A.e_pose[e]];
+    if (k >= 0) A.edge_of[P.eof0 + (long long)(A.e_pt[e] - P.l0) * P.K + (k - P.k0)] = e;
 }
-__device__ __forceinline__ double huber_rho0(double e, double delta, double dsqr) { return e <= dsqr ? e : 2 * sqrt(e) * delta - dsqr; }
-
-// computeActiveErrors + activeRobustChi2
-__device__ double compute_errors(const BAProb& P, bool robust, double delta, double dsqr, double* red) {
-    double local = 0;
-    for (int e = threadIdx.x; e < P.nE; e += BA_T) {
-        if (P.level[e]) continue;
-        double pc[3];
-        project_edge(P, e, pc);
-        const double* c = P.cam + BA_CAM_STRIDE * P.e_cam[e];
-        const double e0 = P.e_obs[2 * e] - (pc[0] / pc[2] * c[0] + c[2]);
-        const double e1 = P.e_obs[2 * e + 1] - (pc[1] / pc[2] * c[1] + c[3]);
-        P.err[2 * e] = e0; P.err[2 * e + 1] = e1;
-        const double c2 = (e0 * e0 + e1 * e1) * P.e_info[e];
-        local += robust ? huber_rho0(c2, delta, dsqr) : c2;
-    }
-    return block_sum(local, red);
+__device__ __forceinline__ void pair_decode(int pid, int K, int& i, int& j) {
+    i = 0;
+    int rem = pid;
+    while (rem >= K - i) { rem -= K - i; i++; }
+    j = i + rem;
 }
-
-// BlockSolver::buildSystem: linearizeOplus + constructQuadraticForm
-__device__ void build_system(const BAProb& P, bool robust, double delta, double dsqr) {
-    const int E = P.nE;
-    for (int e = threadIdx.x; e < E; e += BA_T) {
-        if (P.level[e]) continue;
-        const double* c = P.cam + BA_CAM_STRIDE * P.e_cam[e];
-        const double* ps = P.pose + 7 * P.e_pose[e];
-        double pc[3];
-        project_edge(P, e, pc);
-        const double X = pc[0], Y = pc[1], Z = pc[2], iz = -1. / Z;
-        const double t00 = iz * c[0], t02 = iz * (-X / Z * c[0]), t11 = iz * c[1], t12 = iz * (-Y / Z * c[1]);
-        double* J = P.J + e;
-        if (P.pose_free[P.e_pose[e]] >= 0) {
-            // (-1/z * tmp) * J3, J3 = [-skew(p) | I]
-            const double tJ[12] = {t02 * Y, t00 * Z - t02 * X, -t00 * Y, t00, 0, t02,
-                                   -t11 * Z + t12 * Y, -t12 * X, t11 * X, 0, t11, t12};
-            const double* A = c + 11;
-#pragma unroll
-            for (int i = 0; i < 2; i++)
-#pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    double s = 0;
-#pragma unroll
-                    for (int k = 0; k < 6; k++) s += tJ[i * 6 + k] * A[k * 6 + j];
-                    J[(size_t)(i * 6 + j) * E] = s;
-                }
-        }
-        double q[4], R[9];
-        q_mul(c + 4, ps, q);
-        q_normalize(q);
-        q_to_matrix(q, R);
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            J[(size_t)(12 + j) * E] = t00 * R[j] + t02 * R[6 + j];
-            J[(size_t)(15 + j) * E] = t11 * R[3 + j] + t12 * R[6 + j];
-        }
-        const double w = P.e_info[e], e0 = P.err[2 * e], e1 = P.err[2 * e + 1];
-        double wr = 1.0;
-        if (robust) {
-            const double c2 = (e0 * e0 + e1 * e1) * w;
-            if (c2 > dsqr) wr = delta / sqrt(c2);
-        }
-        J[(size_t)18 * E] = wr * w;
-        J[(size_t)19 * E] = -w * e0 * wr;
-        J[(size_t)20 * E] = -w * e1 * wr;
+// warp per pose pair (i <= j): number of landmarks observed by both
+__global__ void k_pair_count(BABatch A, const int* blkP_prob, const int* blkP_first) {
+    const int p = blkP_prob[blockIdx.x];
+    const BAProb P = A.prob[p];
+    const int pid = (blockIdx.x - blkP_first[blockIdx.x]) * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (pid >= P.nPairs) return;
+    int i, j;
+    pair_decode(pid, P.K, i, j);
+    const int* T = A.edge_of + P.eof0;
+    int cnt = 0;
+    for (int l0 = 0; l0 < P.nL; l0 += 32) {
+        const int l = l0 + lane;
+        const bool both = l < P.nL && T[(long long)l * P.K + i] >= 0 && T[(long long)l * P.K + j] >= 0;
+        cnt += __popc(__ballot_sync(0xffffffffu, both));
     }
-    __syncthreads();
-    // landmarks
-    for (int l = threadIdx.x; l < P.nL; l += BA_T) {
-        double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0, b0 = 0, b1 = 0, b2 = 0;
-        for (int k = P.pt_off[l]; k < P.pt_off[l + 1]; k++) {
-            const int e = P.pt_edges[k];
-            if (P.level[e]) continue;
-            const double* J = P.J + e;
-            const double a0 = J[(size_t)12 * E], a1 = J[(size_t)13 * E], a2 = J[(size_t)14 * E];
-            const double c0 = J[(size_t)15 * E], c1 = J[(size_t)16 * E], c2 = J[(size_t)17 * E];
-            const double W = J[(size_t)18 * E], r0 = J[(size_t)19 * E], r1 = J[(size_t)20 * E];
-            h00 += (a0 * a0 + c0 * c0) * W; h01 += (a0 * a1 + c0 * c1) * W; h02 += (a0 * a2 + c0 * c2) * W;
-            h11 += (a1 * a1 + c1 * c1) * W; h12 += (a1 * a2 + c1 * c2) * W; h22 += (a2 * a2 + c2 * c2) * W;
-            b0 += a0 * r0 + c0 * r1; b1 += a1 * r0 + c1 * r1; b2 += a2 * r0 + c2 * r1;
-        }
-        double* H = P.Hll + 9 * (size_t)l;
-        H[0] = h00; H[1] = h01; H[2] = h02; H[3] = h01; H[4] = h11; H[5] = h12; H[6] = h02; H[7] = h12; H[8] = h22;
-        P.bl[3 * l] = b0; P.bl[3 * l + 1] = b1; P.bl[3 * l + 2] = b2;
-    }
-    // poses: warp per free pose
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = warp; k < P.K; k += BA_WARPS) {
-        double h[21], b[6];
-#pragma unroll
-        for (int i = 0; i < 21; i++) h[i] = 0;
-#pragma unroll
-        for (int i = 0; i < 6; i++) b[i] = 0;
-        for (int t = P.pose_off[k] + lane; t < P.pose_off[k + 1]; t += 32) {
-            const int e = P.pose_edges[t];
-            if (P.level[e]) continue;
-            const double* J = P.J + e;
-            double a[6], c[6];
-#pragma unroll
-            for (int i = 0; i < 6; i++) { a[i] = J[(size_t)i * E]; c[i] = J[(size_t)(6 + i) * E]; }
-            const double W = J[(size_t)18 * E], r0 = J[(size_t)19 * E], r1 = J[(size_t)20 * E];
-            int u = 0;
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                b[i] += a[i] * r0 + c[i] * r1;
-#pragma unroll
-                for (int j = i; j < 6; j++) h[u++] += (a[i] * a[j] + c[i] * c[j]) * W;
+    if (lane == 0) A.pair_cnt[P.pair0 + pid] = cnt;
+}
+// one thread per problem: tuple offsets of the pairs and the chunk table
+__global__ void k_pair_scan(BABatch A) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.nProb) return;
+    const BAProb P = A.prob[p];
+    int off = 0, nc = 0;
+    for (int pid = 0; pid < P.nPairs; pid++) {
+        const int c = A.pair_cnt[P.pair0 + pid];
+        A.pair_off[P.pair0 + pid] = off;
+        A.pair_fchunk[P.pair0 + pid] = nc;
+        for (int s = 0; s < c; s += BA_CH) {
+            if (nc < P.nChunksMax) {
+                A.chunk_pair[P.chunk0 + nc] = pid;
+                A.chunk_start[P.chunk0 + nc] = off + s;
+                A.chunk_len[P.chunk0 + nc] = min(BA_CH, c - s);
             }
+            nc++;
         }
-#pragma unroll
-        for (int i = 0; i < 21; i++) h[i] = warp_sum(h[i]);
-#pragma unroll
-        for (int i = 0; i < 6; i++) b[i] = warp_sum(b[i]);
-        if (lane == 0) {
-            double* H = P.Hpp + 36 * (size_t)k;
-            int u = 0;
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                P.bp[6 * k + i] = b[i];
-#pragma unroll
-                for (int j = i; j < 6; j++) { H[i * 6 + j] = h[u]; H[j * 6 + i] = h[u]; u++; }
-            }
-        }
+        off += c;
     }
-    __syncthreads();
+    A.state[p].nChunks = min(nc, P.nChunksMax);
+    A.state[p].nTuples = off;
+}
+__global__ void k_pair_fill(BABatch A, const int* blkP_prob, const int* blkP_first) {
+    const int p = blkP_prob[blockIdx.x];
+    const BAProb P = A.prob[p];
+    const int pid = (blockIdx.x - blkP_first[blockIdx.x]) * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (pid >= P.nPairs) return;
+    int i, j;
+    pair_decode(pid, P.K, i, j);
+    const int* T = A.edge_of + P.eof0;
+    int2* out = A.tuples + P.tup0 + A.pair_off[P.pair0 + pid];
+    int pos = 0;
+    for (int l0 = 0; l0 < P.nL; l0 += 32) {
+        const int l = l0 + lane;
+        int a = -1, c = -1;
+        if (l < P.nL) { a = T[(long long)l * P.K + i]; c = T[(long long)l * P.K + j]; }
+        const bool both = a >= 0 && c >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, both);
+        if (both) out[pos + __popc(m & ((1u << lane) - 1))] = make_int2(a, c);
+        pos += __popc(m);
+    }
 }
 
-// BlockSolver::setLambda + solve: Schur complement, LDL^T of the reduced camera system, landmark back-substitution.
-// Returns false when the factorisation meets a zero pivot (g2o: linear solver failure -> the trial is rejected).
-__device__ bool solve_system(const BAProb& P, double lambda, double* Hs, int* s_flag) {
-    const int E = P.nE, n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int l = tid; l < P.nL; l += BA_T) {
-        const double* H = P.Hll + 9 * (size_t)l;
-        const double m0 = H[0] + lambda, m1 = H[1], m2 = H[2], m3 = H[3], m4 = H[4] + lambda, m5 = H[5], m6 = H[6], m7 = H[7], m8 = H[8] + lambda;
-        const double c00 = m4 * m8 - m5 * m7, c01 = m5 * m6 - m3 * m8, c02 = m3 * m7 - m4 * m6;
-        const double id = 1.0 / (m0 * c00 + m1 * c01 + m2 * c02);
-        double* D = P.Dinv + 9 * (size_t)l;
-        D[0] = c00 * id; D[1] = (m2 * m7 - m1 * m8) * id; D[2] = (m1 * m5 - m2 * m4) * id;
-        D[3] = c01 * id; D[4] = (m0 * m8 - m2 * m6) * id; D[5] = (m2 * m3 - m0 * m5) * id;
-        D[6] = c02 * id; D[7] = (m1 * m6 - m0 * m7) * id; D[8] = (m0 * m4 - m1 * m3) * id;
-        const double b0 = P.bl[3 * l], b1 = P.bl[3 * l + 1], b2 = P.bl[3 * l + 2];
-        P.db[3 * l] = D[0] * b0 + D[1] * b1 + D[2] * b2;
-        P.db[3 * l + 1] = D[3] * b0 + D[4] * b1 + D[5] * b2;
-        P.db[3 * l + 2] = D[6] * b0 + D[7] * b1 + D[8] * b2;
+// ------------------------------------------------------------------------------------------------ reset
+__global__ void k_reset(BABatch A, int stopped0) {
+    const int b = blockIdx.x;
+    const int p = A.blkE_prob[b];
+    const BAProb P = A.prob[p];
+    const int lb = b - P.blkE0, tid = threadIdx.x;
+    for (int e = P.e0 + lb * BA_TE + tid; e < min(P.e0 + (lb + 1) * BA_TE, P.e0 + P.nE); e += BA_TE) {
+        A.level[e] = 0;
+        A.err[0][2 * e] = 0; A.err[0][2 * e + 1] = 0; A.err[1][2 * e] = 0; A.err[1][2 * e + 1] = 0;
     }
-    for (int i = tid; i < n * n; i += BA_T) {
-        const int r = i / n, c = i - r * n;
-        const int kr = r / 6, kc = c / 6;
-        Hs[i] = kr == kc ? P.Hpp[36 * (size_t)kr + (r - 6 * kr) * 6 + (c - 6 * kc)] + (r == c ? lambda : 0.0) : 0.0;
+    // poses / points: strided over the problem's edge blocks (at least one block exists per problem)
+    for (int i = lb * BA_TE + tid; i < 7 * P.nP; i += P.nbE * BA_TE) { const double v = A.pose0[7 * (size_t)P.p0 + i]; A.pose[0][7 * (size_t)P.p0 + i] = v; A.pose[1][7 * (size_t)P.p0 + i] = v; }
+    for (int i = lb * BA_TE + tid; i < 3 * P.nL; i += P.nbE * BA_TE) { const double v = A.pt0[3 * (size_t)P.l0 + i]; A.pt[0][3 * (size_t)P.l0 + i] = v; A.pt[1][3 * (size_t)P.l0 + i] = v; }
+    if (lb == 0 && tid == 0) {
+        BAState& S = A.state[p];
+        const int nChunks = S.nChunks, nTuples = S.nTuples;
+        memset(&S, 0, sizeof(S));
+        S.nChunks = nChunks; S.nTuples = nTuples;
+        S.need_build = 1; S.round_start = 1; S.lambda_pending = 1; S.ni = 2;
+        if (stopped0) { S.done = 1; S.aborted = 1; }
+        if (P.nE == 0) S.done = 1;
     }
-    if (tid == 0) *s_flag = 1;
-    __syncthreads();
-    // reduced camera matrix: one warp per pose pair
-    for (int s = warp; s < P.nPairs; s += BA_WARPS) {
+}
+
+// ------------------------------------------------------------------------------------------------ k_lin
+__global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
+    __shared__ double red[BA_TE / 32];
+    const int b = blockIdx.x;
+    const int p = A.blkE_prob[b];
+    const BAState& S = A.state[p];
+    if (S.done || !S.need_build) return;
+    const BAProb& P = A.prob[p];
+    const int tid = threadIdx.x;
+    const int e = P.e0 + (b - P.blkE0) * BA_TE + tid;
+    const bool valid = e < P.e0 + P.nE;
+    const int cur = S.cur;
+    const bool robust = S.round == 0 && A.delta > 0;
+    const double delta = A.delta, dsqr = delta * delta;
+    double chi = 0, act = 0;
+    if (valid) {
+        const double* c = A.cam + BA_CAM_STRIDE * (size_t)A.e_cam[e];
+        const int pi = A.e_pose[e];
+        const double* ps = A.pose[cur] + 7 * (size_t)pi;
+        const double w = A.e_info[e];
+        double pc[3];
+        edge_project(ps, A.pt[cur] + 3 * (size_t)A.e_pt[e], c, pc);
+        int lvl = A.level[e];
+        if (S.mark) {   // e->chi2() > th || !e->isDepthPositive() -> level 1  (src/Optimizer.cc:598-613); chi2 from the errors computed last
+            const double l0 = A.err[S.last][2 * e], l1 = A.err[S.last][2 * e + 1];
+            lvl = ((l0 * l0 + l1 * l1) * w > A.chi2_th || !(pc[2] > 0.0)) ? 1 : 0;
+            A.level[e] = (unsigned char)lvl;
+            if (lvl) { A.err[0][2 * e] = l0; A.err[0][2 * e + 1] = l1; A.err[1][2 * e] = l0; A.err[1][2 * e + 1] = l1; }
+        }
+        double* R = A.rec + (size_t)BA_REC * e;
+        double* Bm = A.B + 18 * (size_t)e;
+        if (!lvl) {
+            double er[2];
+            if (S.round_start) {
+                edge_error(pc, c, A.e_obs + 2 * (size_t)e, er);
+                A.err[cur][2 * e] = er[0]; A.err[cur][2 * e + 1] = er[1];
+                const double c2 = (er[0] * er[0] + er[1] * er[1]) * w;
+                chi = robust ? huber_rho0(c2, delta, dsqr) : c2;
+            } else {
+                er[0] = A.err[cur][2 * e]; er[1] = A.err[cur][2 * e + 1];
+            }
+            act = 1;
+            const double X = pc[0], Y = pc[1], Z = pc[2], iz = -1. / Z;
+            const double t00 = iz * c[0], t02 = iz * (-X / Z * c[0]), t11 = iz * c[1], t12 = iz * (-Y / Z * c[1]);
+            double Jp[12];
+            const bool is_free = A.pose_free[pi] >= 0;
+            if (is_free) {
+                // (-1/z * tmp) * J3, J3 = [-skew(p) | I], then * Adj_ext   (types_six_dof_expmap.cpp:136-153)
+                const double tJ[12] = {t02 * Y, t00 * Z - t02 * X, -t00 * Y, t00, 0, t02,
+                                       -t11 * Z + t12 * Y, -t12 * X, t11 * X, 0, t11, t12};
+                const double* Ad = c + 11;
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        double s = 0;
+#pragma unroll
+                        for (int k = 0; k < 6; k++) s += tJ[i * 6 + k] * Ad[k * 6 + j];
+                        Jp[i * 6 + j] = s;
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 12; i++) Jp[i] = 0;
+            }
+            double q[4], Rm[9], Jl[6];
+            q_mul(c + 4, ps, q);
+            q_normalize(q);
+            q_to_matrix(q, Rm);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                Jl[j] = t00 * Rm[j] + t02 * Rm[6 + j];
+                Jl[3 + j] = t11 * Rm[3 + j] + t12 * Rm[6 + j];
+            }
+            double wr = 1.0;
+            if (robust) {
+                const double c2 = (er[0] * er[0] + er[1] * er[1]) * w;
+                if (c2 > dsqr) wr = delta / sqrt(c2);
+            }
+            const double W = wr * w;
+#pragma unroll
+            for (int j = 0; j < 6; j++) R[j] = Jl[j];
+            R[6] = W; R[7] = -w * er[0] * wr; R[8] = -w * er[1] * wr;
+#pragma unroll
+            for (int j = 0; j < 12; j++) R[9 + j] = Jp[j];
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int cc = 0; cc < 3; cc++) Bm[r * 3 + cc] = W * (Jp[r] * Jl[cc] + Jp[6 + r] * Jl[3 + cc]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < BA_REC; j++) R[j] = 0;
+#pragma unroll
+            for (int j = 0; j < 18; j++) Bm[j] = 0;
+        }
+    }
+    const double cs = block_sum<BA_TE / 32>(chi, red);
+    const double as = block_sum<BA_TE / 32>(act, red);
+    if (tid == 0) { A.partE[2 * (size_t)b] = cs; A.partE[2 * (size_t)b + 1] = as; }
+    if (b == P.blkE0 && tid == 0 && S.round_start) A.state[p].maxdiag_bits = 0ull;
+}
+
+// ------------------------------------------------------------------------------------------------ k_build
+// blocks [0, nLandmarkBlocks): thread per landmark -> Hll, bl ;  blocks beyond: CTA per free pose -> Hpp, bp
+__global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks, const int* pose_prob) {
+    __shared__ double red[BA_TL / 32];
+    const int tid = threadIdx.x;
+    if ((int)blockIdx.x < nLandmarkBlocks) {
+        const int b = blockIdx.x;
+        const int p = A.blkL_prob[b];
+        const BAState& S = A.state[p];
+        if (S.done || !S.need_build) return;
+        const BAProb& P = A.prob[p];
+        const int l = P.l0 + (b - P.blkL0) * BA_TL + tid;
+        double md = 0;
+        if (l < P.l0 + P.nL) {
+            double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0, b0 = 0, b1 = 0, b2 = 0;
+            for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
+                const double* R = A.rec + (size_t)BA_REC * e;
+                const double a0 = R[0], a1 = R[1], a2 = R[2], c0 = R[3], c1 = R[4], c2 = R[5], W = R[6], r0 = R[7], r1 = R[8];
+                h00 += (a0 * a0 + c0 * c0) * W; h01 += (a0 * a1 + c0 * c1) * W; h02 += (a0 * a2 + c0 * c2) * W;
+                h11 += (a1 * a1 + c1 * c1) * W; h12 += (a1 * a2 + c1 * c2) * W; h22 += (a2 * a2 + c2 * c2) * W;
+                b0 += a0 * r0 + c0 * r1; b1 += a1 * r0 + c1 * r1; b2 += a2 * r0 + c2 * r1;
+            }
+            double* H = A.Hll + 6 * (size_t)l;
+            H[0] = h00; H[1] = h01; H[2] = h02; H[3] = h11; H[4] = h12; H[5] = h22;
+            A.bl[3 * (size_t)l] = b0; A.bl[3 * (size_t)l + 1] = b1; A.bl[3 * (size_t)l + 2] = b2;
+            md = fmax(fabs(h00), fmax(fabs(h11), fabs(h22)));
+        }
+        if (S.it == 0) {   // computeLambdaInit: max |diag| over all free vertices
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+            if ((tid & 31) == 0 && md > 0) atomicMax(&A.state[p].maxdiag_bits, (unsigned long long)__double_as_longlong(md));
+        }
+        return;
+    }
+    // ---- pose part
+    const int kg = blockIdx.x - nLandmarkBlocks;       // global free-pose index
+    const int p = pose_prob[kg];
+    const BAState& S = A.state[p];
+    if (S.done || !S.need_build) return;
+    const BAProb& P = A.prob[p];
+    const int k = kg - P.k0;
+    const int pid = k * P.K - k * (k - 1) / 2;          // diagonal pair (k, k): its tuples (e, e) list the edges of pose k
+    const int2* T = A.tuples + P.tup0 + A.pair_off[P.pair0 + pid];
+    const int cnt = A.pair_cnt[P.pair0 + pid];
+    double h[21], bb[6];
+#pragma unroll
+    for (int i = 0; i < 21; i++) h[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) bb[i] = 0;
+    for (int t = tid; t < cnt; t += BA_TP) {
+        const double* R = A.rec + (size_t)BA_REC * T[t].x;
+        const double W = R[6], r0 = R[7], r1 = R[8];
+        double a[6], c[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) { a[i] = R[9 + i]; c[i] = R[15 + i]; }
+        int u = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            bb[i] += a[i] * r0 + c[i] * r1;
+#pragma unroll
+            for (int j = i; j < 6; j++) h[u++] += (a[i] * a[j] + c[i] * c[j]) * W;
+        }
+    }
+    double md = 0;
+    double* H = A.Hpp + 36 * (size_t)kg;
+    int u = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const double s = block_sum<BA_TP / 32>(bb[i], red);
+        if (tid == 0) A.bp[6 * (size_t)kg + i] = s;
+#pragma unroll
+        for (int j = i; j < 6; j++) {
+            const double hv = block_sum<BA_TP / 32>(h[u++], red);
+            if (tid == 0) { H[i * 6 + j] = hv; H[j * 6 + i] = hv; }
+            if (i == j) md = fmax(md, fabs(hv));
+        }
+    }
+    if (tid == 0 && S.it == 0 && md > 0) atomicMax(&A.state[p].maxdiag_bits, (unsigned long long)__double_as_longlong(md));
+}
+
+// ------------------------------------------------------------------------------------------------ k_trial_lm
+__global__ void __launch_bounds__(BA_TL) k_trial_lm(BABatch A) {
+    const int b = blockIdx.x;
+    const int p = A.blkL_prob[b];
+    const BAState& S = A.state[p];
+    if (S.done) return;
+    const BAProb& P = A.prob[p];
+    const int l = P.l0 + (b - P.blkL0) * BA_TL + threadIdx.x;
+    if (l >= P.l0 + P.nL) return;
+    const double lambda = lambda_eff(S);
+    const double* H = A.Hll + 6 * (size_t)l;
+    const double m0 = H[0] + lambda, m1 = H[1], m2 = H[2], m4 = H[3] + lambda, m5 = H[4], m8 = H[5] + lambda;
+    // cofactor inverse of the symmetric 3x3 (Eigen's fixed-size inverse in BlockSolver::solve, block_solver.hpp:381-395)
+    const double c00 = m4 * m8 - m5 * m5, c01 = m5 * m2 - m1 * m8, c02 = m1 * m5 - m4 * m2;
+    const double id = 1.0 / (m0 * c00 + m1 * c01 + m2 * c02);
+    const double d00 = c00 * id, d01 = c01 * id, d02 = c02 * id;
+    const double d11 = (m0 * m8 - m2 * m2) * id, d12 = (m2 * m1 - m0 * m5) * id, d22 = (m0 * m4 - m1 * m1) * id;
+    double* D = A.Dinv + 6 * (size_t)l;
+    D[0] = d00; D[1] = d01; D[2] = d02; D[3] = d11; D[4] = d12; D[5] = d22;
+    const double b0 = A.bl[3 * (size_t)l], b1 = A.bl[3 * (size_t)l + 1], b2 = A.bl[3 * (size_t)l + 2];
+    A.db[3 * (size_t)l] = d00 * b0 + d01 * b1 + d02 * b2;
+    A.db[3 * (size_t)l + 1] = d01 * b0 + d11 * b1 + d12 * b2;
+    A.db[3 * (size_t)l + 2] = d02 * b0 + d12 * b1 + d22 * b2;
+    for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
+        if (A.pose_free[A.e_pose[e]] < 0) continue;
+        const double* Bm = A.B + 18 * (size_t)e;
+        double* Ym = A.Y + 18 * (size_t)e;
+        double* ve = A.v + 6 * (size_t)e;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            const double x0 = Bm[r * 3], x1 = Bm[r * 3 + 1], x2 = Bm[r * 3 + 2];
+            const double y0 = x0 * d00 + x1 * d01 + x2 * d02, y1 = x0 * d01 + x1 * d11 + x2 * d12, y2 = x0 * d02 + x1 * d12 + x2 * d22;
+            Ym[r * 3] = y0; Ym[r * 3 + 1] = y1; Ym[r * 3 + 2] = y2;
+            ve[r] = y0 * b0 + y1 * b1 + y2 * b2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_pairs
+// warp per work item of a problem: items [0, nChunksMax) = chunk of <= BA_CH tuples of one pose pair -> partial 6x6 block of
+// sum Y_a B_b^T ; items [nChunksMax, nChunksMax + K) = free pose k -> Schur right-hand side bs_k = bp_k - sum_e Y_e bl.
+__global__ void __launch_bounds__(128) k_pairs(BABatch A, const int* blkI_first) {
+    const int p = A.item_prob[blockIdx.x];
+    const BAState& S = A.state[p];
+    if (S.done) return;
+    const BAProb& P = A.prob[p];
+    const int item = (blockIdx.x - blkI_first[blockIdx.x]) * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= P.nItems) return;
+    if (item < P.nChunksMax) {
+        if (item >= S.nChunks) return;
+        const int ch = P.chunk0 + item;
+        const int2* T = A.tuples + P.tup0 + A.chunk_start[ch];
+        const int len = A.chunk_len[ch];
         double acc[36];
 #pragma unroll
         for (int i = 0; i < 36; i++) acc[i] = 0;
-        for (int t = P.pair_off[s] + lane; t < P.pair_off[s + 1]; t += 32) {
-            const int a1 = P.tuples[2 * t], a2 = P.tuples[2 * t + 1];
-            if (P.level[a1] | P.level[a2]) continue;
-            const double* D = P.Dinv + 9 * (size_t)P.e_pt[a1];
-            const double* J1 = P.J + a1;
-            const double* J2 = P.J + a2;
-            const double u0 = J1[(size_t)12 * E], u1 = J1[(size_t)13 * E], u2 = J1[(size_t)14 * E];
-            const double v0 = J1[(size_t)15 * E], v1 = J1[(size_t)16 * E], v2 = J1[(size_t)17 * E];
-            const double ww = J1[(size_t)18 * E] * J2[(size_t)18 * E];
-            // G = Jl1 * Dinv (2x3), S = G * Jl2^T * (W1 W2) (2x2)
-            const double g00 = u0 * D[0] + u1 * D[3] + u2 * D[6], g01 = u0 * D[1] + u1 * D[4] + u2 * D[7], g02 = u0 * D[2] + u1 * D[5] + u2 * D[8];
-            const double g10 = v0 * D[0] + v1 * D[3] + v2 * D[6], g11 = v0 * D[1] + v1 * D[4] + v2 * D[7], g12 = v0 * D[2] + v1 * D[5] + v2 * D[8];
-            const double p0 = J2[(size_t)12 * E], p1 = J2[(size_t)13 * E], p2 = J2[(size_t)14 * E];
-            const double q0 = J2[(size_t)15 * E], q1 = J2[(size_t)16 * E], q2 = J2[(size_t)17 * E];
-            const double s00 = (g00 * p0 + g01 * p1 + g02 * p2) * ww, s01 = (g00 * q0 + g01 * q1 + g02 * q2) * ww;
-            const double s10 = (g10 * p0 + g11 * p1 + g12 * p2) * ww, s11 = (g10 * q0 + g11 * q1 + g12 * q2) * ww;
-            double m0[6], m1[6];   // rows of S * Jp2 (2x6)
+        for (int t = lane; t < len; t += 32) {
+            const int2 ab = T[t];
+            const double2* Yp = reinterpret_cast<const double2*>(A.Y + 18 * (size_t)ab.x);
+            const double2* Bp = reinterpret_cast<const double2*>(A.B + 18 * (size_t)ab.y);
+            double y[18], bq[18];
 #pragma unroll
-            for (int j = 0; j < 6; j++) {
-                const double x0 = J2[(size_t)j * E], x1 = J2[(size_t)(6 + j) * E];
-                m0[j] = s00 * x0 + s01 * x1;
-                m1[j] = s10 * x0 + s11 * x1;
-            }
+            for (int i = 0; i < 9; i++) { const double2 a = Yp[i], c = Bp[i]; y[2 * i] = a.x; y[2 * i + 1] = a.y; bq[2 * i] = c.x; bq[2 * i + 1] = c.y; }
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
-                const double y0 = J1[(size_t)i * E], y1 = J1[(size_t)(6 + i) * E];
+            for (int r = 0; r < 6; r++)
 #pragma unroll
-                for (int j = 0; j < 6; j++) acc[i * 6 + j] += y0 * m0[j] + y1 * m1[j];
-            }
+                for (int c = 0; c < 6; c++) acc[r * 6 + c] += y[r * 3] * bq[c * 3] + y[r * 3 + 1] * bq[c * 3 + 1] + y[r * 3 + 2] * bq[c * 3 + 2];
         }
-#pragma unroll
-        for (int i = 0; i < 36; i++) acc[i] = warp_sum(acc[i]);
-        const int i1 = P.pair_ij[2 * s], i2 = P.pair_ij[2 * s + 1];
-        // lanes write the entries they are responsible for: entry id = lane and lane + 32
+        double mine0 = 0, mine1 = 0;
 #pragma unroll
         for (int i = 0; i < 36; i++) {
-            if ((i & 31) == lane) {
-                const int r = i / 6, c = i - r * 6;
-                const size_t a = (size_t)(6 * i1 + r) * n + 6 * i2 + c;
-                const double v = Hs[a] - acc[i];
-                Hs[a] = v;
-                if (i1 != i2) Hs[(size_t)(6 * i2 + c) * n + 6 * i1 + r] = v;
-            }
+            const double s = warp_sum(acc[i]);
+            if ((i & 31) == lane) { if (i < 32) mine0 = s; else mine1 = s; }
         }
-    }
-    // Schur right-hand side: bs = bp - sum_e B_e db_l
-    for (int k = warp; k < P.K; k += BA_WARPS) {
+        double* out = A.partial + 36 * (size_t)ch;
+        out[lane] = mine0;
+        if (lane < 4) out[32 + lane] = mine1;
+    } else {
+        const int k = item - P.nChunksMax;
+        const int kg = P.k0 + k;
+        const int pid = k * P.K - k * (k - 1) / 2;
+        const int2* T = A.tuples + P.tup0 + A.pair_off[P.pair0 + pid];
+        const int cnt = A.pair_cnt[P.pair0 + pid];
         double cf[6];
 #pragma unroll
         for (int i = 0; i < 6; i++) cf[i] = 0;
-        for (int t = P.pose_off[k] + lane; t < P.pose_off[k + 1]; t += 32) {
-            const int e = P.pose_edges[t];
-            if (P.level[e]) continue;
-            const double* J = P.J + e;
-            const double* d = P.db + 3 * (size_t)P.e_pt[e];
-            const double W = J[(size_t)18 * E];
-            const double s0 = (J[(size_t)12 * E] * d[0] + J[(size_t)13 * E] * d[1] + J[(size_t)14 * E] * d[2]) * W;
-            const double s1 = (J[(size_t)15 * E] * d[0] + J[(size_t)16 * E] * d[1] + J[(size_t)17 * E] * d[2]) * W;
+        for (int t = lane; t < cnt; t += 32) {
+            const double* ve = A.v + 6 * (size_t)T[t].x;
 #pragma unroll
-            for (int i = 0; i < 6; i++) cf[i] += J[(size_t)i * E] * s0 + J[(size_t)(6 + i) * E] * s1;
+            for (int i = 0; i < 6; i++) cf[i] += ve[i];
         }
 #pragma unroll
         for (int i = 0; i < 6; i++) cf[i] = warp_sum(cf[i]);
         if (lane < 6) {
-            double v = cf[0];
+            double vsel = cf[0];
 #pragma unroll
-            for (int i = 1; i < 6; i++) if (lane == i) v = cf[i];
-            P.bs[6 * k + lane] = P.bp[6 * k + lane] - v;
+            for (int i = 1; i < 6; i++) if (lane == i) vsel = cf[i];
+            A.bs[6 * (size_t)kg + lane] = A.bp[6 * (size_t)kg + lane] - vsel;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------ k_solve
+// Ends a round for problem p (called by one thread).  Returns nothing; sets done or arms the next round.
+__device__ void round_over(const BABatch& A, BAState& S, bool stopped) {
+    if (S.round == 0 && A.its2 >= 0 && !stopped) {
+        S.round = 1; S.it = 0; S.mark = 1; S.round_start = 1; S.need_build = 1; S.lambda_pending = 1;
+    } else {
+        S.done = 1;
+    }
+}
+
+__global__ void __launch_bounds__(BA_TS) k_solve(BABatch A) {
+    extern __shared__ double sm_hs[];
+    __shared__ double red[BA_TS / 32];
+    __shared__ int s_go, s_ok;
+    const int p = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    BAState& S = A.state[p];
+    if (S.done) return;
+    const BAProb& P = A.prob[p];
+    const int n = P.n;
+    // ---- start of a round / of an iteration (thread 0)
+    if (tid == 0) {
+        int go = 1;
+        if (S.need_build) {
+            if (S.round_start) {
+                double chi0 = 0, act = 0;
+                for (int b = 0; b < P.nbE; b++) { chi0 += A.partE[2 * (size_t)(P.blkE0 + b)]; act += A.partE[2 * (size_t)(P.blkE0 + b) + 1]; }
+                if (S.round == 0) S.initial_chi2 = chi0;
+                const int its = S.round == 0 ? A.its1 : A.its2;
+                if (act == 0.0 || S.it >= its) {   // SparseOptimizer::optimize returns at once (sparse_optimizer.cpp:356-359) / optimize(0)
+                    if (act > 0.0) { S.currentChi = chi0; S.last = S.cur; }
+                    S.mark = 0; S.round_start = 0;
+                    round_over(A, S, false);
+                    S.skip = 1;
+                    go = 0;
+                } else {
+                    S.currentChi = chi0;
+                    S.last = S.cur;
+                    S.lambda = 1e-5 * __longlong_as_double((long long)S.maxdiag_bits);   // computeLambdaInit
+                    S.ni = 2; S.nBad = 0;
+                    S.lambda_pending = 0;
+                }
+            }
+            if (go) { S.iniChi = S.currentChi; S.qmax = 0; S.rho = 0; }
+        }
+        s_go = go;
+    }
     __syncthreads();
-    // LDL^T in place (lower triangle: L below the diagonal, D on it); right-looking
+    if (!s_go) return;
+    const double lambda = S.lambda;
+    double* Hs = n <= BA_HS_SMEM_N ? sm_hs : A.Hs + P.hs_off;
+    // ---- assemble the reduced camera system: diag blocks Hpp + lambda I, minus the pair partial sums (fixed chunk order)
+    for (int i = tid; i < n * n; i += BA_TS) {
+        const int r = i / n, c = i - r * n;
+        const int kr = r / 6, kc = c / 6;
+        Hs[i] = kr == kc ? A.Hpp[36 * (size_t)(P.k0 + kr) + (r - 6 * kr) * 6 + (c - 6 * kc)] + (r == c ? lambda : 0.0) : 0.0;
+    }
+    __syncthreads();
+    {
+        const int nCh = S.nChunks;
+        // chunks of one pair are consecutive: thread (pair, entry) walks them in order
+        for (int w = tid; w < P.nPairs * 36; w += BA_TS) {
+            const int pid = w / 36, en = w - pid * 36;
+            const int cnt = A.pair_cnt[P.pair0 + pid];
+            if (cnt == 0) continue;
+            const int first = A.pair_fchunk[P.pair0 + pid];
+            const int nc = (cnt + BA_CH - 1) / BA_CH;
+            double s = 0;
+            for (int c = 0; c < nc && first + c < nCh; c++) s += A.partial[36 * (size_t)(P.chunk0 + first + c) + en];
+            int i1, i2;
+            pair_decode(pid, P.K, i1, i2);
+            const int r = en / 6, c = en - r * 6;
+            const size_t a = (size_t)(6 * i1 + r) * n + 6 * i2 + c;
+            if (i1 != i2) { Hs[a] = -s; Hs[(size_t)(6 * i2 + c) * n + 6 * i1 + r] = -s; }
+            else Hs[a] -= s;
+        }
+    }
+    if (tid == 0) s_ok = 1;
+    __syncthreads();
+    // ---- LDL^T in place (lower triangle: L below the diagonal, D on it); right-looking
     for (int j = 0; j < n; j++) {
         const double dj = Hs[(size_t)j * n + j];
-        if (dj == 0.0 || !isfinite(dj)) { if (tid == 0) *s_flag = 0; break; }
-        for (int i = j + 1 + tid; i < n; i += BA_T) Hs[(size_t)i * n + j] /= dj;
+        if (dj == 0.0 || !isfinite(dj)) { if (tid == 0) s_ok = 0; break; }
+        for (int i = j + 1 + tid; i < n; i += BA_TS) Hs[(size_t)i * n + j] /= dj;
         __syncthreads();
         const int m = n - j - 1;
-        for (int idx = tid; idx < m * m; idx += BA_T) {
+        for (int idx = tid; idx < m * m; idx += BA_TS) {
             const int a = idx / m, b = idx - a * m;
             if (b > a) continue;
             const int i = j + 1 + a, k = j + 1 + b;
@@ -399,11 +689,11 @@ __device__ bool solve_system(const BAProb& P, double lambda, double* Hs, int* s_
         __syncthreads();
     }
     __syncthreads();
-    const bool ok = *s_flag != 0;
+    const bool ok = s_ok != 0;
+    double* x = A.xp + 6 * (size_t)P.k0;
     if (ok && warp == 0) {
-        // forward, diagonal, backward substitution by one warp (x kept in global memory, n <= a few hundred)
-        double* x = P.x;
-        for (int i = lane; i < n; i += 32) x[i] = P.bs[i];
+        const double* bs = A.bs + 6 * (size_t)P.k0;
+        for (int i = lane; i < n; i += 32) x[i] = bs[i];
         __syncwarp();
         for (int j = 0; j < n; j++) {
             const double xj = x[j];
@@ -418,221 +708,193 @@ __device__ bool solve_system(const BAProb& P, double lambda, double* Hs, int* s_
             __syncwarp();
         }
     }
+    if (!ok) for (int i = tid; i < n; i += BA_TS) x[i] = 0.0;   // g2o applies a stale x; the trial is rejected either way
     __syncthreads();
-    if (!ok) {
-        for (int i = tid; i < n + 3 * P.nL; i += BA_T) P.x[i] = 0.0;   // g2o applies the stale x; the trial is rejected either way
-        __syncthreads();
-        return false;
+    // ---- trial poses: exp(x) * pose for free poses, copy for fixed ones;  pose part of computeScale()
+    const int cur = S.cur;
+    for (int i = tid; i < P.nP; i += BA_TS) {
+        const int kg = A.pose_free[P.p0 + i];
+        const double* src = A.pose[cur] + 7 * (size_t)(P.p0 + i);
+        double* dst = A.pose[cur ^ 1] + 7 * (size_t)(P.p0 + i);
+        if (kg >= 0) se3_oplus(A.xp + 6 * (size_t)kg, src, dst);
+        else for (int q = 0; q < 7; q++) dst[q] = src[q];
     }
-    // landmarks: xl = Dinv (bl - B^T xp)
-    for (int l = tid; l < P.nL; l += BA_T) {
-        double c0 = P.bl[3 * l], c1 = P.bl[3 * l + 1], c2 = P.bl[3 * l + 2];
-        for (int k = P.pt_off[l]; k < P.pt_off[l + 1]; k++) {
-            const int e = P.pt_edges[k];
-            if (P.level[e]) continue;
-            const int pi = P.pose_free[P.e_pose[e]];
-            if (pi < 0) continue;
-            const double* J = P.J + e;
-            const double* xp = P.x + 6 * pi;
-            double s0 = 0, s1 = 0;
-#pragma unroll
-            for (int i = 0; i < 6; i++) { s0 += J[(size_t)i * E] * xp[i]; s1 += J[(size_t)(6 + i) * E] * xp[i]; }
-            const double W = J[(size_t)18 * E];
-            s0 *= W; s1 *= W;
-            c0 -= J[(size_t)12 * E] * s0 + J[(size_t)15 * E] * s1;
-            c1 -= J[(size_t)13 * E] * s0 + J[(size_t)16 * E] * s1;
-            c2 -= J[(size_t)14 * E] * s0 + J[(size_t)17 * E] * s1;
-        }
-        const double* D = P.Dinv + 9 * (size_t)l;
-        P.x[n + 3 * l] = D[0] * c0 + D[1] * c1 + D[2] * c2;
-        P.x[n + 3 * l + 1] = D[3] * c0 + D[4] * c1 + D[5] * c2;
-        P.x[n + 3 * l + 2] = D[6] * c0 + D[7] * c1 + D[8] * c2;
-    }
-    __syncthreads();
-    return true;
+    double sc = 0;
+    for (int j = tid; j < n; j += BA_TS) { const double xj = x[j]; sc += xj * (lambda * xj + A.bp[6 * (size_t)P.k0 + j]); }
+    sc = block_sum<BA_TS / 32>(sc, red);
+    if (tid == 0) { S.poseScale = sc; S.solve_ok = ok ? 1 : 0; }
 }
 
-// the stop flag lives in mapped host memory and may change at any time: one thread reads it, everybody uses that value
-__device__ bool read_stop(const volatile int* stop, int* s_tmp) {
-    __syncthreads();
-    if (threadIdx.x == 0) *s_tmp = stop ? *stop : 0;
-    __syncthreads();
-    return *s_tmp != 0;
-}
-
-struct LMState {
-    double lambda, ni, currentChi, tempChi, rho, iniChi;
-    int nBad, qmax, result, iterations, trials, stopped;
-};
-
-// SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg::solve inside
-__device__ void optimize(const BAProb& P, int iterations, bool robust, double delta, double* Hs, double* red, int* s_flag, int* s_stop,
-                         LMState* S, const volatile int* stop) {
-    const double dsqr = delta * delta;
-    const int tid = threadIdx.x, n = P.n, nx = P.n + 3 * P.nL;
-    {   // SparseOptimizer::optimize returns at once when nothing is active (sparse_optimizer.cpp:356-359)
-        double na = 0;
-        for (int e = tid; e < P.nE; e += BA_T) na += P.level[e] == 0;
-        if (block_sum(na, red) == 0.0) return;
-    }
-    bool ok = true;
-    for (int it = 0; it < iterations && ok; it++) {
-        if (read_stop(stop, s_stop)) { if (tid == 0) S->stopped = 1; break; }
-        const double chi0 = compute_errors(P, robust, delta, dsqr, red);
-        build_system(P, robust, delta, dsqr);
-        if (it == 0) {
-            double md = 0;
-            for (int i = tid; i < 6 * P.K; i += BA_T) md = fmax(md, fabs(P.Hpp[36 * (size_t)(i / 6) + (i % 6) * 7]));
-            for (int i = tid; i < 3 * P.nL; i += BA_T) md = fmax(md, fabs(P.Hll[9 * (size_t)(i / 3) + (i % 3) * 4]));
-            md = block_max(md, red);
-            if (tid == 0) { S->lambda = 1e-5 * md; S->ni = 2; S->nBad = 0; }
-        }
-        if (tid == 0) { S->currentChi = chi0; S->iniChi = chi0; S->qmax = 0; S->rho = 0; }
-        __syncthreads();
-        bool again = true;
-        while (again) {
-            for (int i = tid; i < 7 * P.nP; i += BA_T) P.pose_bak[i] = P.pose[i];     // push()
-            for (int i = tid; i < 3 * P.nL; i += BA_T) P.pt_bak[i] = P.pt[i];
-            const double lambda = S->lambda;
-            const bool ok2 = solve_system(P, lambda, Hs, s_flag);
-            for (int i = tid; i < P.nP; i += BA_T) {                                   // update()
-                const int k = P.pose_free[i];
-                if (k >= 0) se3_oplus(P.x + 6 * k, P.pose + 7 * i);
-            }
-            for (int i = tid; i < 3 * P.nL; i += BA_T) P.pt[i] += P.x[n + i];
-            __syncthreads();
-            double tempChi = compute_errors(P, robust, delta, dsqr, red);
-            if (!ok2) tempChi = 1.7976931348623157e308;
-            double sc = 0;                                                              // computeScale()
-            for (int j = tid; j < nx; j += BA_T) {
-                const double xj = P.x[j], bj = j < n ? P.bp[j] : P.bl[j - n];
-                sc += xj * (lambda * xj + bj);
-            }
-            sc = block_sum(sc, red) + 1e-3;
-            if (tid == 0) {
-                const double rho = (S->currentChi - tempChi) / sc;
-                S->rho = rho;
-                S->trials++;
-                if (rho > 0 && isfinite(tempChi)) {
-                    double alpha = 1. - pow(2 * rho - 1, 3.0);
-                    alpha = fmin(alpha, 2. / 3.);
-                    S->lambda *= fmax(1. / 3., alpha);
-                    S->ni = 2;
-                    S->currentChi = tempChi;
-                    S->result = 1;
-                } else {
-                    S->lambda *= S->ni;
-                    S->ni *= 2;
-                    S->result = 0;
-                }
-                S->qmax++;
-            }
-            __syncthreads();
-            if (S->result == 0) {                                                       // pop()
-                for (int i = tid; i < 7 * P.nP; i += BA_T) P.pose[i] = P.pose_bak[i];
-                for (int i = tid; i < 3 * P.nL; i += BA_T) P.pt[i] = P.pt_bak[i];
-            }
-            const bool stopped = read_stop(stop, s_stop);
-            again = S->rho < 0 && S->qmax < 10 && !stopped;
-            __syncthreads();
-        }
-        if (tid == 0) {
-            S->iterations++;
-            int res = 0;   // OK
-            if (S->qmax == 10 || S->rho == 0) res = 1;
-            else {
-                if ((S->iniChi - S->currentChi) * 1e3 < S->iniChi) S->nBad++; else S->nBad = 0;
-                if (S->nBad >= 3) res = 1;
-            }
-            S->result = res;
-        }
-        __syncthreads();
-        ok = S->result == 0;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(BA_T, 1) ba_kernel(const BAProb* __restrict__ probs, int its1, int its2, double delta, double chi2_th,
-                                                     const volatile int* stop, int hs_smem_n) {
-    extern __shared__ double sm_hs[];
-    __shared__ double red[BA_WARPS];
-    __shared__ int s_flag, s_stop;
-    __shared__ LMState S;
-    __shared__ BAProb sP;
+// ------------------------------------------------------------------------------------------------ k_back
+__global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
+    __shared__ double red[BA_TL / 32];
+    __shared__ int s_last;
+    const int b = blockIdx.x;
+    const int p = A.blkL_prob[b];
+    BAState& S = A.state[p];
+    if (S.done && !S.skip) return;
+    const BAProb& P = A.prob[p];
     const int tid = threadIdx.x;
-    if (tid == 0) sP = probs[blockIdx.x];
-    __syncthreads();
-    const BAProb& P = sP;
-    double* Hs = P.n <= hs_smem_n ? sm_hs : P.Hs;
-    for (int i = tid; i < 7 * P.nP; i += BA_T) P.pose[i] = P.pose0[i];
-    for (int i = tid; i < 3 * P.nL; i += BA_T) P.pt[i] = P.pt0[i];
-    for (int i = tid; i < P.nE; i += BA_T) { P.level[i] = 0; P.err[2 * i] = 0; P.err[2 * i + 1] = 0; }
-    if (tid == 0) { memset(&S, 0, sizeof(S)); }
-    __syncthreads();
-    const bool robust1 = delta > 0;
-    const double dsqr = delta * delta;
-    const bool stopped0 = read_stop(stop, &s_stop);
-    double initial = 0;
-    if (!stopped0 && P.nE > 0) {
-        initial = compute_errors(P, robust1, delta, dsqr, red);
-        optimize(P, its1, robust1, delta, Hs, red, &s_flag, &s_stop, &S, stop);
-        const bool more = its2 >= 0 && !read_stop(stop, &s_stop);
-        if (more) {
-            // chi2 > th or non-positive depth -> level 1; Huber off (src/Optimizer.cc:598-613)
-            for (int e = tid; e < P.nE; e += BA_T) {
-                const double c2 = (P.err[2 * e] * P.err[2 * e] + P.err[2 * e + 1] * P.err[2 * e + 1]) * P.e_info[e];
-                double pc[3];
-                project_edge(P, e, pc);
-                if (c2 > chi2_th || !(pc[2] > 0.0)) P.level[e] = 1;
+    const bool skip = S.skip != 0;
+    double chi = 0, sc = 0;
+    const int l = P.l0 + (b - P.blkL0) * BA_TL + tid;
+    if (!skip && l < P.l0 + P.nL) {
+        const int cur = S.cur;
+        const double lambda = S.lambda;
+        const bool robust = S.round == 0 && A.delta > 0;
+        const double delta = A.delta, dsqr = delta * delta;
+        double x0 = 0, x1 = 0, x2 = 0;
+        if (S.solve_ok) {
+            x0 = A.db[3 * (size_t)l]; x1 = A.db[3 * (size_t)l + 1]; x2 = A.db[3 * (size_t)l + 2];
+            for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
+                const int kg = A.pose_free[A.e_pose[e]];
+                if (kg < 0) continue;
+                const double* Ym = A.Y + 18 * (size_t)e;
+                const double* xp = A.xp + 6 * (size_t)kg;
+#pragma unroll
+                for (int r = 0; r < 6; r++) { x0 -= Ym[r * 3] * xp[r]; x1 -= Ym[r * 3 + 1] * xp[r]; x2 -= Ym[r * 3 + 2] * xp[r]; }
             }
-            __syncthreads();
-            optimize(P, its2, false, delta, Hs, red, &s_flag, &s_stop, &S, stop);
+        }
+        const double* po = A.pt[cur] + 3 * (size_t)l;
+        double pn[3] = {po[0] + x0, po[1] + x1, po[2] + x2};
+        double* pw = A.pt[cur ^ 1] + 3 * (size_t)l;
+        pw[0] = pn[0]; pw[1] = pn[1]; pw[2] = pn[2];
+        const double* bl = A.bl + 3 * (size_t)l;
+        sc = x0 * (lambda * x0 + bl[0]) + x1 * (lambda * x1 + bl[1]) + x2 * (lambda * x2 + bl[2]);
+        for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
+            if (A.level[e]) continue;
+            const double* c = A.cam + BA_CAM_STRIDE * (size_t)A.e_cam[e];
+            double pc[3], er[2];
+            edge_project(A.pose[cur ^ 1] + 7 * (size_t)A.e_pose[e], pn, c, pc);
+            edge_error(pc, c, A.e_obs + 2 * (size_t)e, er);
+            A.err[cur ^ 1][2 * e] = er[0]; A.err[cur ^ 1][2 * e + 1] = er[1];
+            const double c2 = (er[0] * er[0] + er[1] * er[1]) * A.e_info[e];
+            chi += robust ? huber_rho0(c2, delta, dsqr) : c2;
         }
     }
-    __syncthreads();
-    int nout = 0;
-    for (int e = tid; e < P.nE; e += BA_T) {
-        const double c2 = (P.err[2 * e] * P.err[2 * e] + P.err[2 * e + 1] * P.err[2 * e + 1]) * P.e_info[e];
-        double pc[3];
-        project_edge(P, e, pc);
-        const bool out = c2 > chi2_th || !(pc[2] > 0.0);
-        P.outlier[e] = out;
-        nout += out;
+    const double cs = block_sum<BA_TL / 32>(chi, red);
+    const double ss = block_sum<BA_TL / 32>(sc, red);
+    if (tid == 0) {
+        A.partL[2 * (size_t)b] = cs; A.partL[2 * (size_t)b + 1] = ss;
+        __threadfence();
+        const unsigned t = atomicAdd(&S.ticket, 1u);
+        s_last = (t == (unsigned)P.nbL - 1);
     }
-    const double tot = block_sum((double)nout, red);
-    for (int i = tid; i < P.nP; i += BA_T) {
+    __syncthreads();
+    if (!s_last || tid != 0) return;
+    // ---- the last CTA of the problem: LM decision (optimization_algorithm_levenberg.cpp:86-164)
+    __threadfence();
+    S.ticket = 0;
+    if (skip) { S.skip = 0; return; }
+    double tempChi = 0, scale = 0;
+    const volatile double* PL = A.partL;
+    for (int q = 0; q < P.nbL; q++) { tempChi += PL[2 * (size_t)(P.blkL0 + q)]; scale += PL[2 * (size_t)(P.blkL0 + q) + 1]; }
+    if (!S.solve_ok) tempChi = 1.7976931348623157e308;
+    scale = (S.poseScale + scale) + 1e-3;
+    const double rho = (S.currentChi - tempChi) / scale;
+    S.rho = rho;
+    S.trials++;
+    int accepted;
+    if (rho > 0 && isfinite(tempChi)) {
+        double alpha = 1. - pow(2 * rho - 1, 3.0);
+        alpha = fmin(alpha, 2. / 3.);
+        S.lambda *= fmax(1. / 3., alpha);
+        S.ni = 2;
+        S.currentChi = tempChi;
+        accepted = 1;
+    } else {
+        S.lambda *= S.ni;
+        S.ni *= 2;
+        accepted = 0;
+    }
+    S.qmax++;
+    S.last = S.cur ^ 1;
+    if (accepted) S.cur ^= 1;           // pop() is a no-op: the rejected estimate stays in the other buffer
+    const bool stopped = A.stop && *A.stop != 0;
+    const bool again = rho < 0 && S.qmax < 10 && !stopped;
+    S.mark = 0; S.round_start = 0;
+    if (again) { S.need_build = 0; return; }
+    S.iterations++;
+    int res = 0;
+    if (S.qmax == 10 || rho == 0) res = 1;
+    else {
+        if ((S.iniChi - S.currentChi) * 1e3 < S.iniChi) S.nBad++; else S.nBad = 0;
+        if (S.nBad >= 3) res = 1;
+    }
+    S.it++;
+    S.need_build = 1;
+    const int its = S.round == 0 ? A.its1 : A.its2;
+    if (stopped) S.stopped = 1;
+    if (res || S.it >= its || stopped) round_over(A, S, stopped);
+}
+
+// ------------------------------------------------------------------------------------------------ final
+__global__ void __launch_bounds__(BA_TE) k_final(BABatch A) {
+    __shared__ double red[BA_TE / 32];
+    const int b = blockIdx.x;
+    const int p = A.blkE_prob[b];
+    const BAState& S = A.state[p];
+    const BAProb& P = A.prob[p];
+    const int lb = b - P.blkE0, tid = threadIdx.x;
+    const int cur = S.cur;
+    const int e = P.e0 + lb * BA_TE + tid;
+    double nout = 0;
+    if (e < P.e0 + P.nE) {
+        const double l0 = A.err[S.last][2 * e], l1 = A.err[S.last][2 * e + 1];
+        double pc[3];
+        edge_project(A.pose[cur] + 7 * (size_t)A.e_pose[e], A.pt[cur] + 3 * (size_t)A.e_pt[e], A.cam + BA_CAM_STRIDE * (size_t)A.e_cam[e], pc);
+        const bool out = (l0 * l0 + l1 * l1) * A.e_info[e] > A.chi2_th || !(pc[2] > 0.0);
+        A.outlier[e] = out;
+        nout = out;
+    }
+    nout = block_sum<BA_TE / 32>(nout, red);
+    if (tid == 0) A.partE[2 * (size_t)b] = nout;
+    for (int i = lb * BA_TE + tid; i < P.nP; i += P.nbE * BA_TE) {
         double R[9];
-        const double* s = P.pose + 7 * i;
+        const double* s = A.pose[cur] + 7 * (size_t)(P.p0 + i);
         q_to_matrix(s, R);
-        double* o = P.poses_out + 12 * (size_t)i;
+        double* o = A.poses_out + 12 * (size_t)(P.p0 + i);
         for (int r = 0; r < 3; r++) { o[r * 4] = R[r * 3]; o[r * 4 + 1] = R[r * 3 + 1]; o[r * 4 + 2] = R[r * 3 + 2]; o[r * 4 + 3] = s[4 + r]; }
     }
-    for (int i = tid; i < 3 * P.nL; i += BA_T) P.points_out[i] = P.pt[i];
-    if (tid == 0) {
+    for (int i = lb * BA_TE + tid; i < 3 * P.nL; i += P.nbE * BA_TE) A.points_out[3 * (size_t)P.l0 + i] = A.pt[cur][3 * (size_t)P.l0 + i];
+}
+__global__ void k_stats(BABatch A) {   // one CTA
+    __shared__ int s_active;
+    if (threadIdx.x == 0) s_active = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < A.nProb; p += blockDim.x) {
+        const BAState& S = A.state[p];
+        const BAProb& P = A.prob[p];
+        double tot = 0;
+        if (P.nE > 0) for (int b = 0; b < P.nbE; b++) tot += A.partE[2 * (size_t)(P.blkE0 + b)];
         orbba_stats_t st;
-        st.initial_chi2 = initial; st.final_chi2 = S.currentChi; st.final_lambda = S.lambda;
+        st.initial_chi2 = S.initial_chi2; st.final_chi2 = S.currentChi; st.final_lambda = S.lambda;
         st.iterations = S.iterations; st.trials = S.trials; st.outliers = (int)tot;
-        st.status = stopped0 ? ORB_E_ABORTED : ORB_OK;
-        *P.stats = st;
+        st.status = S.aborted ? ORB_E_ABORTED : ORB_OK;
+        A.stats[p] = st;
+        if (!S.done) atomicAdd(&s_active, 1);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) *A.n_active = s_active;   // mapped host memory, read by finish()
 }
 
 // ================================================================================================ host side
 struct orbba {
     int device = 0, max_problems = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    // uploaded batch
     int n = 0;
+    BABatch A;                               // device pointers of the uploaded batch
     std::vector<BAProb> probs;
-    std::vector<int> nP, nL, nE;
-    uint8_t* d_static = nullptr; size_t static_cap = 0;
-    uint8_t* d_dynamic = nullptr; size_t dynamic_cap = 0;
-    BAProb* d_probs = nullptr; size_t probs_cap = 0;
-    std::vector<size_t> out_off;     // per problem: offsets of poses_out, points_out, outlier, stats inside d_dynamic
-    int* h_stop = nullptr;           // pinned + mapped: device-visible stop flag
-    int* d_stop = nullptr;
-    int max_n = 0, hs_smem_n = 0;
-    size_t smem_bytes = 0;
+    std::vector<std::vector<int>> perm;      // per problem: caller edge index of every stored edge (empty = identity)
+    uint8_t* d_arena = nullptr; size_t arena_cap = 0;
+    uint8_t* h_stage = nullptr; size_t stage_cap = 0;   // pinned staging of the static arrays
+    int *d_blkP_prob = nullptr, *d_blkP_first = nullptr, *d_blkI_first = nullptr, *d_pose_prob = nullptr;
+    int nbE = 0, nbL = 0, nbP = 0, nbI = 0, Ktot = 0, max_n = 0;
+    long long Etot = 0, Ltot = 0, Ptot = 0;
+    int* h_flags = nullptr;                  // pinned + mapped: [0] stop flag, [1] active problems after the last step
+    int* d_flags = nullptr;
+    bool pending = false;                    // steps were enqueued and not yet checked for completion
+    int its1 = 0, its2 = 0;
     long long launches = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     bool profile = false;
@@ -642,25 +904,56 @@ struct orbba {
 static void orbba_free(orbba* b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    cudaFree(b->d_static); cudaFree(b->d_dynamic); cudaFree(b->d_probs);
-    if (b->h_stop) cudaFreeHost(b->h_stop);
+    cudaFree(b->d_arena);
+    if (b->h_stage) cudaFreeHost(b->h_stage);
+    if (b->h_flags) cudaFreeHost(b->h_flags);
     if (b->ev[0]) { cudaEventDestroy(b->ev[0]); cudaEventDestroy(b->ev[1]); }
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
 }
 
 namespace {
-struct Blob {
-    std::vector<uint8_t> bytes;
-    size_t add(const void* p, size_t n) {
-        const size_t off = (bytes.size() + 15) & ~(size_t)15;
-        bytes.resize(off + n);
-        if (p && n) memcpy(bytes.data() + off, p, n);
-        return off;
-    }
+struct Layout {   // bump allocator over one buffer; offsets are 256-byte aligned
+    size_t cur = 0;
+    size_t add(size_t bytes) { const size_t off = (cur + 255) & ~(size_t)255; cur = off + bytes; return off; }
 };
-size_t bump(size_t& cur, size_t n) { const size_t off = (cur + 15) & ~(size_t)15; cur = off + n; return off; }
 }  // namespace
+
+static int launch_steps(orbba* b, int steps) {
+    const BABatch& A = b->A;
+    cudaStream_t st = b->stream;
+    const int hs_n = std::min(b->max_n, BA_HS_SMEM_N);
+    const size_t smem = (size_t)hs_n * hs_n * sizeof(double);
+    for (int s = 0; s < steps; s++) {
+        k_lin<<<b->nbE, BA_TE, 0, st>>>(A);
+        k_build<<<b->nbL + b->Ktot, BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
+        k_trial_lm<<<b->nbL, BA_TL, 0, st>>>(A);
+        if (b->nbI > 0) k_pairs<<<b->nbI, 128, 0, st>>>(A, b->d_blkI_first);
+        k_solve<<<b->n, BA_TS, smem, st>>>(A);
+        k_back<<<b->nbL, BA_TL, 0, st>>>(A);
+        b->launches += 5 + (b->nbI > 0);
+    }
+    b->h_flags[1] = 0;
+    k_final<<<b->nbE, BA_TE, 0, st>>>(A);
+    k_stats<<<1, 256, 0, st>>>(A);
+    b->launches += 2;
+    ORB_CUDA(cudaGetLastError());
+    return ORB_OK;
+}
+
+// waits for the enqueued steps; problems that needed more LM trials than were enqueued get further steps
+static int finish(orbba* b) {
+    if (!b->pending) return ORB_OK;
+    ORB_CUDA(cudaStreamSynchronize(b->stream));
+    int guard = 0;
+    while (b->h_flags[1] > 0 && guard++ < 64) {
+        int rc = launch_steps(b, 4);
+        if (rc != ORB_OK) return rc;
+        ORB_CUDA(cudaStreamSynchronize(b->stream));
+    }
+    b->pending = false;
+    return ORB_OK;
+}
 
 extern "C" {
 
@@ -678,14 +971,13 @@ int orbba_create(orbba_t** out, int device, int max_problems) {
     orbba* b = new (std::nothrow) orbba();
     if (!b) ORB_FAIL(ORB_E_INVALID, "orbba_create: out of host memory");
     b->device = device; b->max_problems = max_problems;
+    memset(&b->A, 0, sizeof(b->A));
     cudaError_t ce = cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking);
-    if (ce == cudaSuccess) ce = cudaHostAlloc((void**)&b->h_stop, sizeof(int), cudaHostAllocMapped);
-    if (ce == cudaSuccess) { *b->h_stop = 0; ce = cudaHostGetDevicePointer((void**)&b->d_stop, b->h_stop, 0); }
+    if (ce == cudaSuccess) ce = cudaHostAlloc((void**)&b->h_flags, 4 * sizeof(int), cudaHostAllocMapped);
+    if (ce == cudaSuccess) { memset(b->h_flags, 0, 4 * sizeof(int)); ce = cudaHostGetDevicePointer((void**)&b->d_flags, b->h_flags, 0); }
     if (ce == cudaSuccess) ce = cudaEventCreate(&b->ev[0]);
     if (ce == cudaSuccess) ce = cudaEventCreate(&b->ev[1]);
-    // reduced camera system in shared memory up to 200 KB
-    b->hs_smem_n = 156;   // 156^2 * 8 = 194,688 B  (26 free poses)
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(ba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->hs_smem_n * b->hs_smem_n * 8);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_HS_SMEM_N * BA_HS_SMEM_N * 8);
     if (ce != cudaSuccess) { int rc = orbhost::check_cuda(ce, "orbba_create", __FILE__, __LINE__); orbba_free(b); return rc; }
     b->stream = b->own_stream;
     *out = b;
@@ -696,30 +988,36 @@ void orbba_destroy(orbba_t* b) { orbba_free(b); }
 
 int orbba_set_stream(orbba_t* b, void* s) {
     if (!b) ORB_FAIL(ORB_E_INVALID, "orbba_set_stream: NULL handle");
+    int rc = finish(b);
+    if (rc != ORB_OK) return rc;
     b->stream = s ? (cudaStream_t)s : b->own_stream;
     return ORB_OK;
 }
 int orbba_synchronize(orbba_t* b) {
     if (!b) ORB_FAIL(ORB_E_INVALID, "orbba_synchronize: NULL handle");
     ORB_CUDA(cudaSetDevice(b->device));
+    int rc = finish(b);
+    if (rc != ORB_OK) return rc;
     ORB_CUDA(cudaStreamSynchronize(b->stream));
     return ORB_OK;
 }
 long long orbba_launch_count(const orbba_t* b) { return b ? b->launches : 0; }
 
-// Flattens, indexes and uploads a batch of problems (host -> device, asynchronous on the handle's stream).
+// Validates, concatenates and uploads a batch of problems, then builds the (pose pair -> edge tuples) index on the device.
 int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     if (!b || (!problems && n > 0)) ORB_FAIL(ORB_E_INVALID, "orbba_upload: bad argument");
     if (n < 0 || n > b->max_problems) ORB_FAIL(ORB_E_INVALID, "orbba_upload: n=%d exceeds max_problems=%d", n, b->max_problems);
     ORB_CUDA(cudaSetDevice(b->device));
-    Blob blob;
+    int rc = finish(b);
+    if (rc != ORB_OK) return rc;
+    b->n = 0;
     b->probs.assign(n, BAProb());
-    b->nP.assign(n, 0); b->nL.assign(n, 0); b->nE.assign(n, 0);
-    b->out_off.assign((size_t)n * 4, 0);
-    std::vector<std::vector<size_t>> soff(n);
-    size_t dyn = 0;
-    std::vector<std::vector<size_t>> doff(n);
-    b->max_n = 0;
+    b->perm.assign(n, std::vector<int>());
+    if (n == 0) return ORB_OK;
+    // ---- pass 1: sizes
+    long long Etot = 0, Ltot = 0, Ptot = 0, Ctot = 0, Ktot = 0, pairTot = 0, tupTot = 0, chunkTot = 0, eofTot = 0, hsTot = 0, itemTot = 0;
+    int nbE = 0, nbL = 0, nbP = 0, nbI = 0, max_n = 0;
+    std::vector<std::vector<int>> pose_free_local(n), f_count(n);
     for (int p = 0; p < n; p++) {
         const orbba_problem_t& Q = problems[p];
         const int nP = Q.n_poses, nL = Q.n_points, nE = Q.n_edges, nC = Q.n_cams;
@@ -727,140 +1025,187 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         if ((nP && (!Q.poses || !Q.pose_fixed)) || (nL && !Q.points) || (nE && (!Q.edge_pose || !Q.edge_point || !Q.edge_cam || !Q.edge_obs || !Q.edge_inv_sigma2)) ||
             !Q.cam_K || !Q.cam_ext || !Q.cam_adj)
             ORB_FAIL(ORB_E_INVALID, "orbba_upload: problem %d has a NULL array", p);
-        std::vector<int> pose_free(nP, -1);
+        std::vector<int>& pf = pose_free_local[p];
+        pf.assign(nP, -1);
         int K = 0;
-        for (int i = 0; i < nP; i++) if (!Q.pose_fixed[i]) pose_free[i] = K++;
-        for (int e = 0; e < nE; e++)
+        for (int i = 0; i < nP; i++) if (!Q.pose_fixed[i]) pf[i] = K++;
+        bool grouped = true;
+        for (int e = 0; e < nE; e++) {
             if (Q.edge_pose[e] < 0 || Q.edge_pose[e] >= nP || Q.edge_point[e] < 0 || Q.edge_point[e] >= nL || Q.edge_cam[e] < 0 || Q.edge_cam[e] >= nC)
                 ORB_FAIL(ORB_E_INVALID, "orbba_upload: problem %d edge %d indexes out of range", p, e);
-        // CSR by landmark / by free pose (edge ids ascending inside every list)
-        std::vector<int> pt_off(nL + 1, 0), pose_off(K + 1, 0);
-        for (int e = 0; e < nE; e++) { pt_off[Q.edge_point[e] + 1]++; const int k = pose_free[Q.edge_pose[e]]; if (k >= 0) pose_off[k + 1]++; }
-        for (int i = 0; i < nL; i++) pt_off[i + 1] += pt_off[i];
-        for (int i = 0; i < K; i++) pose_off[i + 1] += pose_off[i];
-        std::vector<int> pt_edges(nE), pose_edges(pose_off[K]);
-        {
-            std::vector<int> c1(pt_off.begin(), pt_off.end() - 1), c2(pose_off.begin(), pose_off.end() - 1);
-            for (int e = 0; e < nE; e++) { pt_edges[c1[Q.edge_point[e]]++] = e; const int k = pose_free[Q.edge_pose[e]]; if (k >= 0) pose_edges[c2[k]++] = e; }
+            if (e > 0 && Q.edge_point[e] < Q.edge_point[e - 1]) grouped = false;
         }
-        // (edge, edge) tuples per pose pair (upper block triangle incl. diagonal)
-        std::vector<std::vector<int>> per_pair((size_t)K * K);
-        for (int l = 0; l < nL; l++)
-            for (int a = pt_off[l]; a < pt_off[l + 1]; a++) {
-                const int ea = pt_edges[a], ka = pose_free[Q.edge_pose[ea]];
-                if (ka < 0) continue;
-                for (int c = a; c < pt_off[l + 1]; c++) {
-                    const int ec = pt_edges[c], kc = pose_free[Q.edge_pose[ec]];
-                    if (kc < 0) continue;
-                    if (ka <= kc) { per_pair[(size_t)ka * K + kc].push_back(ea); per_pair[(size_t)ka * K + kc].push_back(ec); }
-                    else { per_pair[(size_t)kc * K + ka].push_back(ec); per_pair[(size_t)kc * K + ka].push_back(ea); }
-                }
+        if (!grouped) {   // stable counting sort by landmark (the reference adds edges landmark by landmark, src/Optimizer.cc:530-575)
+            std::vector<int> cnt(nL + 1, 0);
+            for (int e = 0; e < nE; e++) cnt[Q.edge_point[e] + 1]++;
+            for (int l = 0; l < nL; l++) cnt[l + 1] += cnt[l];
+            b->perm[p].resize(nE);
+            for (int e = 0; e < nE; e++) b->perm[p][cnt[Q.edge_point[e]]++] = e;
+        }
+        // free-pose observations per landmark; one observation per (landmark, keyframe) as in MapPoint::mObservations
+        std::vector<int>& fc = f_count[p];
+        fc.assign(nL, 0);
+        std::vector<int> stamp(nP, -1);
+        long long tup = 0;
+        const std::vector<int>& pm = b->perm[p];
+        for (int s = 0; s < nE; s++) {
+            const int e = pm.empty() ? s : pm[s];
+            const int l = Q.edge_point[e], ps = Q.edge_pose[e];
+            if (stamp[ps] == l) ORB_FAIL(ORB_E_INVALID, "orbba_upload: problem %d observes landmark %d twice from pose %d (MapPoint::mObservations holds one per keyframe)", p, l, ps);
+            stamp[ps] = l;
+            if (pf[ps] >= 0) fc[l]++;
+        }
+        for (int l = 0; l < nL; l++) tup += (long long)fc[l] * (fc[l] + 1) / 2;
+        if (tup > 0x7fffffffLL || (long long)K * (K + 1) / 2 > 4000000LL) ORB_FAIL(ORB_E_INVALID, "orbba_upload: problem %d is too large for the pair index (%d free poses)", p, K);
+        BAProb& P = b->probs[p];
+        P.e0 = (int)Etot; P.nE = nE; P.l0 = (int)Ltot; P.nL = nL; P.p0 = (int)Ptot; P.nP = nP; P.c0 = (int)Ctot; P.nC = nC;
+        P.k0 = (int)Ktot; P.K = K; P.n = 6 * K;
+        P.pair0 = (int)pairTot; P.nPairs = K * (K + 1) / 2;
+        P.chunk0 = (int)chunkTot; P.nChunksMax = P.nPairs + (int)(tup / BA_CH);
+        P.item0 = (int)itemTot; P.nItems = P.nChunksMax + K;
+        P.blkE0 = nbE; P.nbE = std::max(1, (nE + BA_TE - 1) / BA_TE);
+        P.blkL0 = nbL; P.nbL = std::max(1, (nL + BA_TL - 1) / BA_TL);
+        P.tup0 = tupTot; P.eof0 = eofTot; P.hs_off = hsTot;
+        Etot += nE; Ltot += nL; Ptot += nP; Ctot += nC; Ktot += K; pairTot += P.nPairs; tupTot += tup; chunkTot += P.nChunksMax;
+        itemTot += P.nItems; eofTot += (long long)nL * K;
+        if (P.n > BA_HS_SMEM_N) hsTot += (long long)P.n * P.n;
+        nbE += P.nbE; nbL += P.nbL; nbP += (P.nPairs + 3) / 4; nbI += (P.nItems + 3) / 4;
+        max_n = std::max(max_n, P.n);
+        if (Etot > 0x7fffffffLL || eofTot > 0x7fffffffLL * 4) ORB_FAIL(ORB_E_INVALID, "orbba_upload: batch too large");
+    }
+    // ---- layout: static (staged from the host) then device-only
+    Layout L;
+    const size_t o_prob = L.add(sizeof(BAProb) * n);
+    const size_t o_epose = L.add(4 * Etot), o_ept = L.add(4 * Etot), o_ecam = L.add(4 * Etot);
+    const size_t o_eobs = L.add(16 * Etot), o_einfo = L.add(8 * Etot), o_cam = L.add(8 * BA_CAM_STRIDE * Ctot);
+    const size_t o_ptoff = L.add(4 * (Ltot + 1)), o_pfree = L.add(4 * Ptot), o_pose0 = L.add(56 * Ptot), o_pt0 = L.add(24 * Ltot);
+    const size_t o_blkE = L.add(4 * (size_t)nbE), o_blkL = L.add(4 * (size_t)nbL), o_item = L.add(4 * (size_t)std::max(nbI, 1));
+    const size_t o_blkPp = L.add(4 * (size_t)std::max(nbP, 1)), o_blkPf = L.add(4 * (size_t)std::max(nbP, 1)), o_blkIf = L.add(4 * (size_t)std::max(nbI, 1));
+    const size_t o_poseprob = L.add(4 * (size_t)std::max<long long>(Ktot, 1));
+    const size_t static_bytes = L.add(0);
+    const size_t o_state = L.add(sizeof(BAState) * n);
+    const size_t o_eof = L.add(4 * (size_t)eofTot), o_pcnt = L.add(4 * (size_t)pairTot), o_poff = L.add(4 * (size_t)pairTot), o_pfch = L.add(4 * (size_t)pairTot);
+    const size_t o_cpair = L.add(4 * (size_t)chunkTot), o_cstart = L.add(4 * (size_t)chunkTot), o_clen = L.add(4 * (size_t)chunkTot);
+    const size_t o_tup = L.add(8 * (size_t)tupTot);
+    const size_t o_pose_a = L.add(56 * Ptot), o_pose_b = L.add(56 * Ptot), o_pt_a = L.add(24 * Ltot), o_pt_b = L.add(24 * Ltot);
+    const size_t o_err_a = L.add(16 * Etot), o_err_b = L.add(16 * Etot), o_level = L.add(Etot);
+    const size_t o_rec = L.add(8 * BA_REC * (size_t)Etot), o_B = L.add(144 * (size_t)Etot), o_Y = L.add(144 * (size_t)Etot), o_v = L.add(48 * (size_t)Etot);
+    const size_t o_Hll = L.add(48 * Ltot), o_bl = L.add(24 * Ltot), o_Dinv = L.add(48 * Ltot), o_db = L.add(24 * Ltot);
+    const size_t o_Hpp = L.add(288 * Ktot), o_bp = L.add(48 * Ktot), o_bs = L.add(48 * Ktot), o_xp = L.add(48 * Ktot);
+    const size_t o_partial = L.add(288 * (size_t)chunkTot), o_partE = L.add(16 * (size_t)nbE), o_partL = L.add(16 * (size_t)nbL);
+    const size_t o_Hs = L.add(8 * (size_t)hsTot);
+    const size_t o_poses_out = L.add(96 * Ptot), o_points_out = L.add(24 * Ltot), o_outlier = L.add(Etot), o_stats = L.add(sizeof(orbba_stats_t) * n);
+    const size_t total = L.add(0) + 256;
+    if (total > b->arena_cap) {
+        cudaFree(b->d_arena); b->d_arena = nullptr; b->arena_cap = 0;
+        ORB_CUDA(cudaMalloc((void**)&b->d_arena, total));
+        b->arena_cap = total;
+    }
+    if (static_bytes > b->stage_cap) {
+        if (b->h_stage) cudaFreeHost(b->h_stage);
+        b->h_stage = nullptr; b->stage_cap = 0;
+        ORB_CUDA(cudaHostAlloc((void**)&b->h_stage, static_bytes + 256, cudaHostAllocDefault));
+        b->stage_cap = static_bytes;
+    }
+    uint8_t* H = b->h_stage;
+    uint8_t* D = b->d_arena;
+    // ---- pass 2: fill the staging buffer
+    memcpy(H + o_prob, b->probs.data(), sizeof(BAProb) * n);
+    int *h_epose = (int*)(H + o_epose), *h_ept = (int*)(H + o_ept), *h_ecam = (int*)(H + o_ecam), *h_ptoff = (int*)(H + o_ptoff), *h_pfree = (int*)(H + o_pfree);
+    double *h_eobs = (double*)(H + o_eobs), *h_einfo = (double*)(H + o_einfo), *h_cam = (double*)(H + o_cam), *h_pose0 = (double*)(H + o_pose0), *h_pt0 = (double*)(H + o_pt0);
+    int *h_blkE = (int*)(H + o_blkE), *h_blkL = (int*)(H + o_blkL), *h_item = (int*)(H + o_item), *h_blkPp = (int*)(H + o_blkPp), *h_blkPf = (int*)(H + o_blkPf),
+        *h_blkIf = (int*)(H + o_blkIf), *h_poseprob = (int*)(H + o_poseprob);
+    int bP = 0, bI = 0;
+    for (int p = 0; p < n; p++) {
+        const orbba_problem_t& Q = problems[p];
+        const BAProb& P = b->probs[p];
+        const std::vector<int>& pm = b->perm[p];
+        for (int s = 0; s < P.nE; s++) {
+            const int e = pm.empty() ? s : pm[s];
+            const size_t g = (size_t)P.e0 + s;
+            h_epose[g] = P.p0 + Q.edge_pose[e]; h_ept[g] = P.l0 + Q.edge_point[e]; h_ecam[g] = P.c0 + Q.edge_cam[e];
+            h_eobs[2 * g] = Q.edge_obs[2 * e]; h_eobs[2 * g + 1] = Q.edge_obs[2 * e + 1]; h_einfo[g] = Q.edge_inv_sigma2[e];
+        }
+        {   // CSR by landmark over the grouped edge order
+            int e = P.e0;
+            for (int l = 0; l < P.nL; l++) {
+                h_ptoff[P.l0 + l] = e;
+                while (e < P.e0 + P.nE && h_ept[e] == P.l0 + l) e++;
             }
-        std::vector<int> pair_off(1, 0), pair_ij, tuples;
-        for (int i = 0; i < K; i++)
-            for (int j = i; j < K; j++) {
-                const std::vector<int>& v = per_pair[(size_t)i * K + j];
-                if (v.empty()) continue;
-                pair_ij.push_back(i); pair_ij.push_back(j);
-                tuples.insert(tuples.end(), v.begin(), v.end());
-                pair_off.push_back((int)tuples.size() / 2);
-            }
-        const int nPairs = (int)pair_ij.size() / 2, nTuples = (int)tuples.size() / 2;
-        // cameras and initial estimates
-        std::vector<double> cam((size_t)nC * BA_CAM_STRIDE), pose0((size_t)7 * nP);
-        for (int c = 0; c < nC; c++) {
-            double* D = &cam[(size_t)c * BA_CAM_STRIDE];
-            for (int i = 0; i < 4; i++) D[i] = Q.cam_K[4 * c + i];
+        }
+        for (int i = 0; i < P.nP; i++) h_pfree[P.p0 + i] = pose_free_local[p][i] >= 0 ? P.k0 + pose_free_local[p][i] : -1;
+        for (int k = 0; k < P.K; k++) h_poseprob[P.k0 + k] = p;
+        for (int c = 0; c < P.nC; c++) {
+            double* Dc = h_cam + (size_t)BA_CAM_STRIDE * (P.c0 + c);
+            for (int i = 0; i < 4; i++) Dc[i] = Q.cam_K[4 * c + i];
             const double* T = Q.cam_ext + 12 * c;
             const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
-            q_from_matrix(R, D + 4);
-            if (D[7] < 0) for (int i = 4; i < 8; i++) D[i] = -D[i];
-            const double nn = sqrt(D[4] * D[4] + D[5] * D[5] + D[6] * D[6] + D[7] * D[7]);
-            for (int i = 4; i < 8; i++) D[i] /= nn;
-            D[8] = T[3]; D[9] = T[7]; D[10] = T[11];
-            for (int i = 0; i < 36; i++) D[11 + i] = Q.cam_adj[36 * c + i];
+            q_from_matrix(R, Dc + 4);
+            if (Dc[7] < 0) for (int i = 4; i < 8; i++) Dc[i] = -Dc[i];
+            const double nn = sqrt(Dc[4] * Dc[4] + Dc[5] * Dc[5] + Dc[6] * Dc[6] + Dc[7] * Dc[7]);
+            for (int i = 4; i < 8; i++) Dc[i] /= nn;
+            Dc[8] = T[3]; Dc[9] = T[7]; Dc[10] = T[11];
+            for (int i = 0; i < 36; i++) Dc[11 + i] = Q.cam_adj[36 * c + i];
         }
-        for (int i = 0; i < nP; i++) {   // Converter::toSE3Quat + SE3Quat(R, t)
+        for (int i = 0; i < P.nP; i++) {   // Converter::toSE3Quat + SE3Quat(R, t)
             const double* T = Q.poses + 12 * i;
-            double* D = &pose0[(size_t)7 * i];
+            double* Dp = h_pose0 + 7 * (size_t)(P.p0 + i);
             const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
-            q_from_matrix(R, D);
-            if (D[3] < 0) for (int k = 0; k < 4; k++) D[k] = -D[k];
-            const double nn = sqrt(D[0] * D[0] + D[1] * D[1] + D[2] * D[2] + D[3] * D[3]);
-            for (int k = 0; k < 4; k++) D[k] /= nn;
-            D[4] = T[3]; D[5] = T[7]; D[6] = T[11];
+            q_from_matrix(R, Dp);
+            if (Dp[3] < 0) for (int k = 0; k < 4; k++) Dp[k] = -Dp[k];
+            const double nn = sqrt(Dp[0] * Dp[0] + Dp[1] * Dp[1] + Dp[2] * Dp[2] + Dp[3] * Dp[3]);
+            for (int k = 0; k < 4; k++) Dp[k] /= nn;
+            Dp[4] = T[3]; Dp[5] = T[7]; Dp[6] = T[11];
         }
-        BAProb& P = b->probs[p];
-        P.nP = nP; P.nL = nL; P.nE = nE; P.nC = nC; P.K = K; P.n = 6 * K; P.nPairs = nPairs; P.nTuples = nTuples;
-        b->nP[p] = nP; b->nL[p] = nL; b->nE[p] = nE;
-        b->max_n = std::max(b->max_n, 6 * K);
-        std::vector<size_t>& so = soff[p];
-        so.push_back(blob.add(Q.edge_pose, sizeof(int) * nE));
-        so.push_back(blob.add(Q.edge_point, sizeof(int) * nE));
-        so.push_back(blob.add(Q.edge_cam, sizeof(int) * nE));
-        so.push_back(blob.add(pose_free.data(), sizeof(int) * nP));
-        so.push_back(blob.add(Q.edge_obs, sizeof(double) * 2 * nE));
-        so.push_back(blob.add(Q.edge_inv_sigma2, sizeof(double) * nE));
-        so.push_back(blob.add(cam.data(), sizeof(double) * cam.size()));
-        so.push_back(blob.add(pt_off.data(), sizeof(int) * pt_off.size()));
-        so.push_back(blob.add(pt_edges.data(), sizeof(int) * pt_edges.size()));
-        so.push_back(blob.add(pose_off.data(), sizeof(int) * pose_off.size()));
-        so.push_back(blob.add(pose_edges.data(), sizeof(int) * pose_edges.size()));
-        so.push_back(blob.add(pair_off.data(), sizeof(int) * pair_off.size()));
-        so.push_back(blob.add(pair_ij.data(), sizeof(int) * pair_ij.size()));
-        so.push_back(blob.add(tuples.data(), sizeof(int) * tuples.size()));
-        so.push_back(blob.add(pose0.data(), sizeof(double) * pose0.size()));
-        so.push_back(blob.add(Q.points, sizeof(double) * 3 * nL));
-        // dynamic arena
-        std::vector<size_t>& d = doff[p];
-        const size_t nn = (size_t)6 * K;
-        const size_t sizes[] = {sizeof(double) * 7 * nP, sizeof(double) * 7 * nP, sizeof(double) * 3 * nL, sizeof(double) * 3 * nL,
-                                sizeof(double) * 2 * nE, sizeof(double) * BA_JSTRIDE * nE, sizeof(double) * 9 * nL, sizeof(double) * 3 * nL,
-                                sizeof(double) * 9 * nL, sizeof(double) * 3 * nL, sizeof(double) * 36 * K, sizeof(double) * 6 * K,
-                                sizeof(double) * 6 * K, sizeof(double) * (nn + 3 * nL), nn > (size_t)b->hs_smem_n ? sizeof(double) * nn * nn : 0,
-                                (size_t)nE, sizeof(double) * 12 * nP, sizeof(double) * 3 * nL, (size_t)nE, sizeof(orbba_stats_t)};
-        for (size_t s : sizes) d.push_back(bump(dyn, s));
+        if (P.nL) memcpy(h_pt0 + 3 * (size_t)P.l0, Q.points, sizeof(double) * 3 * P.nL);
+        for (int q = 0; q < P.nbE; q++) h_blkE[P.blkE0 + q] = p;
+        for (int q = 0; q < P.nbL; q++) h_blkL[P.blkL0 + q] = p;
+        const int bp4 = (P.nPairs + 3) / 4, bi4 = (P.nItems + 3) / 4;
+        for (int q = 0; q < bp4; q++) { h_blkPp[bP + q] = p; h_blkPf[bP + q] = bP; }
+        for (int q = 0; q < bi4; q++) { h_item[bI + q] = p; h_blkIf[bI + q] = bI; }
+        bP += bp4; bI += bi4;
     }
-    if (blob.bytes.size() > b->static_cap) {
-        cudaFree(b->d_static); b->d_static = nullptr; b->static_cap = 0;
-        ORB_CUDA(cudaMalloc((void**)&b->d_static, blob.bytes.size() + 64));
-        b->static_cap = blob.bytes.size();
+    h_ptoff[Ltot] = (int)Etot;
+    // ---- device pointers
+    BABatch& A = b->A;
+    memset(&A, 0, sizeof(A));
+    A.nProb = n;
+    A.prob = (const BAProb*)(D + o_prob); A.state = (BAState*)(D + o_state);
+    A.e_pose = (const int*)(D + o_epose); A.e_pt = (const int*)(D + o_ept); A.e_cam = (const int*)(D + o_ecam);
+    A.e_obs = (const double*)(D + o_eobs); A.e_info = (const double*)(D + o_einfo); A.cam = (const double*)(D + o_cam);
+    A.pt_off = (const int*)(D + o_ptoff); A.pose_free = (const int*)(D + o_pfree);
+    A.pose0 = (const double*)(D + o_pose0); A.pt0 = (const double*)(D + o_pt0);
+    A.blkE_prob = (const int*)(D + o_blkE); A.blkL_prob = (const int*)(D + o_blkL); A.item_prob = (const int*)(D + o_item);
+    b->d_blkP_prob = (int*)(D + o_blkPp); b->d_blkP_first = (int*)(D + o_blkPf); b->d_blkI_first = (int*)(D + o_blkIf); b->d_pose_prob = (int*)(D + o_poseprob);
+    A.edge_of = (int*)(D + o_eof); A.pair_cnt = (int*)(D + o_pcnt); A.pair_off = (int*)(D + o_poff); A.pair_fchunk = (int*)(D + o_pfch);
+    A.chunk_pair = (int*)(D + o_cpair); A.chunk_start = (int*)(D + o_cstart); A.chunk_len = (int*)(D + o_clen);
+    A.tuples = (int2*)(D + o_tup);
+    A.pose[0] = (double*)(D + o_pose_a); A.pose[1] = (double*)(D + o_pose_b); A.pt[0] = (double*)(D + o_pt_a); A.pt[1] = (double*)(D + o_pt_b);
+    A.err[0] = (double*)(D + o_err_a); A.err[1] = (double*)(D + o_err_b); A.level = D + o_level;
+    A.rec = (double*)(D + o_rec); A.B = (double*)(D + o_B); A.Y = (double*)(D + o_Y); A.v = (double*)(D + o_v);
+    A.Hll = (double*)(D + o_Hll); A.bl = (double*)(D + o_bl); A.Dinv = (double*)(D + o_Dinv); A.db = (double*)(D + o_db);
+    A.Hpp = (double*)(D + o_Hpp); A.bp = (double*)(D + o_bp); A.bs = (double*)(D + o_bs); A.xp = (double*)(D + o_xp);
+    A.partial = (double*)(D + o_partial); A.partE = (double*)(D + o_partE); A.partL = (double*)(D + o_partL); A.Hs = (double*)(D + o_Hs);
+    A.poses_out = (double*)(D + o_poses_out); A.points_out = (double*)(D + o_points_out); A.outlier = D + o_outlier;
+    A.stats = (orbba_stats_t*)(D + o_stats);
+    A.stop = b->d_flags; A.n_active = b->d_flags + 1;
+    b->nbE = nbE; b->nbL = nbL; b->nbP = nbP; b->nbI = nbI; b->Ktot = (int)Ktot; b->max_n = max_n;
+    b->Etot = Etot; b->Ltot = Ltot; b->Ptot = Ptot;
+    // ---- upload + index construction on the device
+    cudaStream_t st = b->stream;
+    ORB_CUDA(cudaMemcpyAsync(D, H, static_bytes, cudaMemcpyHostToDevice, st));
+    ORB_CUDA(cudaMemsetAsync(D + o_state, 0, sizeof(BAState) * n, st));
+    if (eofTot) ORB_CUDA(cudaMemsetAsync(D + o_eof, 0xff, 4 * (size_t)eofTot, st));
+    k_edge_of<<<nbE, BA_TE, 0, st>>>(A);
+    if (nbP > 0) {
+        k_pair_count<<<nbP, 128, 0, st>>>(A, b->d_blkP_prob, b->d_blkP_first);
+        k_pair_scan<<<(n + 63) / 64, 64, 0, st>>>(A);
+        k_pair_fill<<<nbP, 128, 0, st>>>(A, b->d_blkP_prob, b->d_blkP_first);
+        b->launches += 3;
     }
-    if (dyn > b->dynamic_cap) {
-        cudaFree(b->d_dynamic); b->d_dynamic = nullptr; b->dynamic_cap = 0;
-        ORB_CUDA(cudaMalloc((void**)&b->d_dynamic, dyn + 64));
-        b->dynamic_cap = dyn;
-    }
-    if ((size_t)n > b->probs_cap) {
-        cudaFree(b->d_probs); b->d_probs = nullptr; b->probs_cap = 0;
-        ORB_CUDA(cudaMalloc((void**)&b->d_probs, sizeof(BAProb) * (size_t)n));
-        b->probs_cap = n;
-    }
-    for (int p = 0; p < n; p++) {
-        BAProb& P = b->probs[p];
-        const std::vector<size_t>& so = soff[p];
-        const uint8_t* S = b->d_static;
-        P.e_pose = (const int*)(S + so[0]); P.e_pt = (const int*)(S + so[1]); P.e_cam = (const int*)(S + so[2]); P.pose_free = (const int*)(S + so[3]);
-        P.e_obs = (const double*)(S + so[4]); P.e_info = (const double*)(S + so[5]); P.cam = (const double*)(S + so[6]);
-        P.pt_off = (const int*)(S + so[7]); P.pt_edges = (const int*)(S + so[8]); P.pose_off = (const int*)(S + so[9]); P.pose_edges = (const int*)(S + so[10]);
-        P.pair_off = (const int*)(S + so[11]); P.pair_ij = (const int*)(S + so[12]); P.tuples = (const int*)(S + so[13]);
-        P.pose0 = (const double*)(S + so[14]); P.pt0 = (const double*)(S + so[15]);
-        const std::vector<size_t>& d = doff[p];
-        uint8_t* D = b->d_dynamic;
-        P.pose = (double*)(D + d[0]); P.pose_bak = (double*)(D + d[1]); P.pt = (double*)(D + d[2]); P.pt_bak = (double*)(D + d[3]);
-        P.err = (double*)(D + d[4]); P.J = (double*)(D + d[5]); P.Hll = (double*)(D + d[6]); P.bl = (double*)(D + d[7]);
-        P.Dinv = (double*)(D + d[8]); P.db = (double*)(D + d[9]); P.Hpp = (double*)(D + d[10]); P.bp = (double*)(D + d[11]);
-        P.bs = (double*)(D + d[12]); P.x = (double*)(D + d[13]); P.Hs = (double*)(D + d[14]);
-        P.level = D + d[15]; P.poses_out = (double*)(D + d[16]); P.points_out = (double*)(D + d[17]); P.outlier = D + d[18];
-        P.stats = (orbba_stats_t*)(D + d[19]);
-        b->out_off[(size_t)p * 4 + 0] = d[16]; b->out_off[(size_t)p * 4 + 1] = d[17]; b->out_off[(size_t)p * 4 + 2] = d[18]; b->out_off[(size_t)p * 4 + 3] = d[19];
-    }
+    b->launches += 1;
+    ORB_CUDA(cudaGetLastError());
     b->n = n;
-    if (n == 0) return ORB_OK;
-    // the blob / descriptor vectors are pageable: these copies complete before returning
-    ORB_CUDA(cudaMemcpyAsync(b->d_static, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice, b->stream));
-    ORB_CUDA(cudaMemcpyAsync(b->d_probs, b->probs.data(), sizeof(BAProb) * (size_t)n, cudaMemcpyHostToDevice, b->stream));
-    ORB_CUDA(cudaStreamSynchronize(b->stream));
     return ORB_OK;
 }
 
@@ -871,13 +1216,17 @@ int orbba_run(orbba_t* b, int its1, int its2, double huber_delta, double chi2_th
     if (b->n == 0) return ORB_OK;
     if (its1 < 0) ORB_FAIL(ORB_E_INVALID, "orbba_run: its1 < 0");
     ORB_CUDA(cudaSetDevice(b->device));
-    const int hs_n = std::min(b->max_n, b->hs_smem_n);
-    const size_t smem = (size_t)hs_n * hs_n * sizeof(double);
+    int rc = finish(b);
+    if (rc != ORB_OK) return rc;
+    b->A.its1 = its1; b->A.its2 = its2; b->A.delta = huber_delta; b->A.chi2_th = chi2_th;
     if (b->profile) ORB_CUDA(cudaEventRecord(b->ev[0], b->stream));
-    ba_kernel<<<b->n, BA_T, smem, b->stream>>>(b->d_probs, its1, its2, huber_delta, chi2_th, b->d_stop, b->hs_smem_n);
+    k_reset<<<b->nbE, BA_TE, 0, b->stream>>>(b->A, b->h_flags[0] != 0);
     b->launches++;
+    // one step per LM trial; accepted-first-try iterations need its1 + its2 steps, plus one step per round switch
+    rc = launch_steps(b, its1 + std::max(its2, 0) + 3);
+    if (rc != ORB_OK) return rc;
     if (b->profile) { ORB_CUDA(cudaEventRecord(b->ev[1], b->stream)); b->prof_pending = true; }
-    ORB_CUDA(cudaGetLastError());
+    b->pending = true;
     return ORB_OK;
 }
 
@@ -889,6 +1238,8 @@ int orbba_profile(orbba_t* b, int enable) {
 int orbba_stage_ms(orbba_t* b, double* ms1, int* calls) {   // only the LAST run is kept per synchronisation: call after each run
     if (!b || !ms1) ORB_FAIL(ORB_E_INVALID, "orbba_stage_ms: bad argument");
     ORB_CUDA(cudaSetDevice(b->device));
+    int rc = finish(b);
+    if (rc != ORB_OK) return rc;
     ORB_CUDA(cudaStreamSynchronize(b->stream));
     if (b->prof_pending) {
         float ms = 0;
@@ -905,39 +1256,48 @@ int orbba_stage_ms(orbba_t* b, double* ms1, int* calls) {   // only the LAST run
 int orbba_download(orbba_t* b, int p, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats) {
     if (!b || p < 0 || p >= b->n) ORB_FAIL(ORB_E_INVALID, "orbba_download: bad argument");
     ORB_CUDA(cudaSetDevice(b->device));
-    const size_t* o = &b->out_off[(size_t)p * 4];
+    int rc = finish(b);
+    if (rc != ORB_OK) return rc;
+    const BAProb& P = b->probs[p];
     cudaStream_t st = b->stream;
-    if (poses_out && b->nP[p]) ORB_CUDA(cudaMemcpyAsync(poses_out, b->d_dynamic + o[0], sizeof(double) * 12 * b->nP[p], cudaMemcpyDeviceToHost, st));
-    if (points_out && b->nL[p]) ORB_CUDA(cudaMemcpyAsync(points_out, b->d_dynamic + o[1], sizeof(double) * 3 * b->nL[p], cudaMemcpyDeviceToHost, st));
-    if (edge_outlier && b->nE[p]) ORB_CUDA(cudaMemcpyAsync(edge_outlier, b->d_dynamic + o[2], b->nE[p], cudaMemcpyDeviceToHost, st));
-    if (stats) ORB_CUDA(cudaMemcpyAsync(stats, b->d_dynamic + o[3], sizeof(orbba_stats_t), cudaMemcpyDeviceToHost, st));
+    std::vector<uint8_t> tmp;
+    if (poses_out && P.nP) ORB_CUDA(cudaMemcpyAsync(poses_out, b->A.poses_out + 12 * (size_t)P.p0, sizeof(double) * 12 * P.nP, cudaMemcpyDeviceToHost, st));
+    if (points_out && P.nL) ORB_CUDA(cudaMemcpyAsync(points_out, b->A.points_out + 3 * (size_t)P.l0, sizeof(double) * 3 * P.nL, cudaMemcpyDeviceToHost, st));
+    if (edge_outlier && P.nE) {
+        if (b->perm[p].empty()) ORB_CUDA(cudaMemcpyAsync(edge_outlier, b->A.outlier + P.e0, P.nE, cudaMemcpyDeviceToHost, st));
+        else { tmp.resize(P.nE); ORB_CUDA(cudaMemcpyAsync(tmp.data(), b->A.outlier + P.e0, P.nE, cudaMemcpyDeviceToHost, st)); }
+    }
+    if (stats) ORB_CUDA(cudaMemcpyAsync(stats, b->A.stats + p, sizeof(orbba_stats_t), cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
+    if (!tmp.empty()) for (int s = 0; s < P.nE; s++) edge_outlier[b->perm[p][s]] = tmp[s];
     return ORB_OK;
 }
 
 // Optimizer::LocalBundleAdjustment for ONE problem, host buffers in and out, synchronous.  `stop` (may be NULL) is
-// polled while the kernel runs and forwarded to the device, which checks it before every LM iteration and trial
+// polled while the kernels run and forwarded to the device, which reads it after every LM trial
 // (g2o: SparseOptimizer::terminate(), sparse_optimizer.cpp:376, optimization_algorithm_levenberg.cpp:149).
 int orbba_local(orbba_t* b, const orbba_problem_t* problem, int its1, int its2, double huber_delta, double chi2_th,
                 const volatile uint8_t* stop, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats) {
     if (!b || !problem) ORB_FAIL(ORB_E_INVALID, "orbba_local: bad argument");
     ORB_CUDA(cudaSetDevice(b->device));
-    *b->h_stop = (stop && *stop) ? 1 : 0;
+    b->h_flags[0] = (stop && *stop) ? 1 : 0;
     int rc = orbba_upload(b, problem, 1);
     if (rc != ORB_OK) return rc;
     rc = orbba_run(b, its1, its2, huber_delta, chi2_th);
     if (rc != ORB_OK) return rc;
-    cudaEvent_t done = b->ev[1];
-    if (!b->profile) ORB_CUDA(cudaEventRecord(done, b->stream));
-    for (;;) {
-        const cudaError_t q = cudaEventQuery(done);
-        if (q == cudaSuccess) break;
-        if (q != cudaErrorNotReady) return orbhost::check_cuda(q, "cudaEventQuery", __FILE__, __LINE__);
-        if (stop && *stop) *b->h_stop = 1;
+    if (stop) {
+        cudaEvent_t done = b->ev[1];
+        if (!b->profile) ORB_CUDA(cudaEventRecord(done, b->stream));
+        for (;;) {
+            const cudaError_t q = cudaEventQuery(done);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) return orbhost::check_cuda(q, "cudaEventQuery", __FILE__, __LINE__);
+            if (*stop) b->h_flags[0] = 1;
+        }
     }
     orbba_stats_t st;
     rc = orbba_download(b, 0, poses_out, points_out, edge_outlier, &st);
-    *b->h_stop = 0;
+    b->h_flags[0] = 0;
     if (rc != ORB_OK) return rc;
     if (stats) *stats = st;
     return st.status;
