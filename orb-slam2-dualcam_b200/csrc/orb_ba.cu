@@ -315,6 +315,7 @@ __global__ void k_reset(BABatch A, int stopped0) {
 // ------------------------------------------------------------------------------------------------ k_lin
 __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
     __shared__ double red[BA_TE / 32];
+    __shared__ double s_rec[BA_TE * BA_REC], s_B[BA_TE * 18];
     const int b = blockIdx.x;
     const int p = A.blkE_prob[b];
     const BAState& S = A.state[p];
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
             A.level[e] = (unsigned char)lvl;
             if (lvl) { A.err[0][2 * e] = l0; A.err[0][2 * e + 1] = l1; A.err[1][2 * e] = l0; A.err[1][2 * e + 1] = l1; }
         }
-        double* R = A.rec + (size_t)BA_REC * e;
-        double* Bm = A.B + 18 * (size_t)e;
+        double* R = s_rec + BA_REC * tid;       // staged in shared memory, written out coalesced below
+        double* Bm = s_B + 18 * tid;
         if (!lvl) {
             double er[2];
             if (S.round_start) {
@@ -408,8 +409,16 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
         }
     }
     const double cs = block_sum<BA_TE / 32>(chi, red);
-    const double as = block_sum<BA_TE / 32>(act, red);
+    const double as = block_sum<BA_TE / 32>(act, red);   // (the barriers inside also publish s_rec / s_B)
     if (tid == 0) { A.partE[2 * (size_t)b] = cs; A.partE[2 * (size_t)b + 1] = as; }
+    {
+        const int ebase = P.e0 + (b - P.blkE0) * BA_TE;
+        const int nv = min(BA_TE, P.e0 + P.nE - ebase);
+        double* gr = A.rec + (size_t)BA_REC * ebase;
+        double* gb = A.B + 18 * (size_t)ebase;
+        for (int i = tid; i < BA_REC * nv; i += BA_TE) gr[i] = s_rec[i];
+        for (int i = tid; i < 18 * nv; i += BA_TE) gb[i] = s_B[i];
+    }
     if (b == P.blkE0 && tid == 0 && S.round_start) A.state[p].maxdiag_bits = 0ull;
 }
 
@@ -494,40 +503,41 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
 }
 
 // ------------------------------------------------------------------------------------------------ k_trial_lm
-__global__ void __launch_bounds__(BA_TL) k_trial_lm(BABatch A) {
+// (Hll + lambda I)^-1 of a landmark: cofactor inverse of the symmetric 3x3 (Eigen's fixed-size inverse in
+// BlockSolver::solve, block_solver.hpp:381-395).  d = {d00, d01, d02, d11, d12, d22}
+__device__ __forceinline__ void landmark_dinv(const double* H, double lambda, double* d) {
+    const double m0 = H[0] + lambda, m1 = H[1], m2 = H[2], m4 = H[3] + lambda, m5 = H[4], m8 = H[5] + lambda;
+    const double c00 = m4 * m8 - m5 * m5, c01 = m5 * m2 - m1 * m8, c02 = m1 * m5 - m4 * m2;
+    const double id = 1.0 / (m0 * c00 + m1 * c01 + m2 * c02);
+    d[0] = c00 * id; d[1] = c01 * id; d[2] = c02 * id;
+    d[3] = (m0 * m8 - m2 * m2) * id; d[4] = (m2 * m1 - m0 * m5) * id; d[5] = (m0 * m4 - m1 * m1) * id;
+}
+// thread per (edge, row r of the 6x3 block): Y_e[r] = B_e[r] Dinv, v_e[r] = Y_e[r] . bl   -- consecutive threads touch
+// consecutive 24-byte rows, so the B reads and Y writes are fully coalesced
+#define BA_TT 256
+__global__ void __launch_bounds__(BA_TT) k_trial_lm(BABatch A) {
     const int b = blockIdx.x;
-    const int p = A.blkL_prob[b];
+    const int p = A.blkE_prob[b];
     const BAState& S = A.state[p];
     if (S.done) return;
     const BAProb& P = A.prob[p];
-    const int l = P.l0 + (b - P.blkL0) * BA_TL + threadIdx.x;
-    if (l >= P.l0 + P.nL) return;
     const double lambda = lambda_eff(S);
-    const double* H = A.Hll + 6 * (size_t)l;
-    const double m0 = H[0] + lambda, m1 = H[1], m2 = H[2], m4 = H[3] + lambda, m5 = H[4], m8 = H[5] + lambda;
-    // cofactor inverse of the symmetric 3x3 (Eigen's fixed-size inverse in BlockSolver::solve, block_solver.hpp:381-395)
-    const double c00 = m4 * m8 - m5 * m5, c01 = m5 * m2 - m1 * m8, c02 = m1 * m5 - m4 * m2;
-    const double id = 1.0 / (m0 * c00 + m1 * c01 + m2 * c02);
-    const double d00 = c00 * id, d01 = c01 * id, d02 = c02 * id;
-    const double d11 = (m0 * m8 - m2 * m2) * id, d12 = (m2 * m1 - m0 * m5) * id, d22 = (m0 * m4 - m1 * m1) * id;
-    double* D = A.Dinv + 6 * (size_t)l;
-    D[0] = d00; D[1] = d01; D[2] = d02; D[3] = d11; D[4] = d12; D[5] = d22;
-    const double b0 = A.bl[3 * (size_t)l], b1 = A.bl[3 * (size_t)l + 1], b2 = A.bl[3 * (size_t)l + 2];
-    A.db[3 * (size_t)l] = d00 * b0 + d01 * b1 + d02 * b2;
-    A.db[3 * (size_t)l + 1] = d01 * b0 + d11 * b1 + d12 * b2;
-    A.db[3 * (size_t)l + 2] = d02 * b0 + d12 * b1 + d22 * b2;
-    for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
+    const int ebase = P.e0 + (b - P.blkE0) * BA_TE;
+    const int nrows = 6 * min(BA_TE, P.e0 + P.nE - ebase);
+    for (int q = threadIdx.x; q < nrows; q += BA_TT) {
+        const int el = q / 6, r = q - el * 6;
+        const int e = ebase + el;
         if (A.pose_free[A.e_pose[e]] < 0) continue;
-        const double* Bm = A.B + 18 * (size_t)e;
-        double* Ym = A.Y + 18 * (size_t)e;
-        double* ve = A.v + 6 * (size_t)e;
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-            const double x0 = Bm[r * 3], x1 = Bm[r * 3 + 1], x2 = Bm[r * 3 + 2];
-            const double y0 = x0 * d00 + x1 * d01 + x2 * d02, y1 = x0 * d01 + x1 * d11 + x2 * d12, y2 = x0 * d02 + x1 * d12 + x2 * d22;
-            Ym[r * 3] = y0; Ym[r * 3 + 1] = y1; Ym[r * 3 + 2] = y2;
-            ve[r] = y0 * b0 + y1 * b1 + y2 * b2;
-        }
+        const int l = A.e_pt[e];
+        double d[6];
+        landmark_dinv(A.Hll + 6 * (size_t)l, lambda, d);
+        const double* Br = A.B + 18 * (size_t)e + 3 * r;
+        const double x0 = Br[0], x1 = Br[1], x2 = Br[2];
+        const double y0 = x0 * d[0] + x1 * d[1] + x2 * d[2], y1 = x0 * d[1] + x1 * d[3] + x2 * d[4], y2 = x0 * d[2] + x1 * d[4] + x2 * d[5];
+        double* Yr = A.Y + 18 * (size_t)e + 3 * r;
+        Yr[0] = y0; Yr[1] = y1; Yr[2] = y2;
+        const double* bl = A.bl + 3 * (size_t)l;
+        A.v[6 * (size_t)e + r] = y0 * bl[0] + y1 * bl[1] + y2 * bl[2];
     }
 }
 
@@ -605,10 +615,11 @@ __device__ void round_over(const BABatch& A, BAState& S, bool stopped) {
     }
 }
 
-__global__ void __launch_bounds__(BA_TS) k_solve(BABatch A) {
+__global__ void __launch_bounds__(BA_TS) k_solve(BABatch A, int hs_smem_doubles) {
     extern __shared__ double sm_hs[];
     __shared__ double red[BA_TS / 32];
     __shared__ int s_go, s_ok;
+    double* s_lcol = sm_hs + hs_smem_doubles;   // n doubles after the matrix
     const int p = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     BAState& S = A.state[p];
     if (S.done) return;
@@ -644,12 +655,15 @@ __global__ void __launch_bounds__(BA_TS) k_solve(BABatch A) {
     __syncthreads();
     if (!s_go) return;
     const double lambda = S.lambda;
+    const int ld = n | 1;                      // odd row stride: column accesses are bank-conflict free
     double* Hs = n <= BA_HS_SMEM_N ? sm_hs : A.Hs + P.hs_off;
     // ---- assemble the reduced camera system: diag blocks Hpp + lambda I, minus the pair partial sums (fixed chunk order)
-    for (int i = tid; i < n * n; i += BA_TS) {
-        const int r = i / n, c = i - r * n;
-        const int kr = r / 6, kc = c / 6;
-        Hs[i] = kr == kc ? A.Hpp[36 * (size_t)(P.k0 + kr) + (r - 6 * kr) * 6 + (c - 6 * kc)] + (r == c ? lambda : 0.0) : 0.0;
+    for (int r = warp; r < n; r += BA_TS / 32) {
+        const int kr = r / 6;
+        for (int c = lane; c < n; c += 32) {
+            const int kc = c / 6;
+            Hs[(size_t)r * ld + c] = kr == kc ? A.Hpp[36 * (size_t)(P.k0 + kr) + (r - 6 * kr) * 6 + (c - 6 * kc)] + (r == c ? lambda : 0.0) : 0.0;
+        }
     }
     __syncthreads();
     {
@@ -666,25 +680,24 @@ __global__ void __launch_bounds__(BA_TS) k_solve(BABatch A) {
             int i1, i2;
             pair_decode(pid, P.K, i1, i2);
             const int r = en / 6, c = en - r * 6;
-            const size_t a = (size_t)(6 * i1 + r) * n + 6 * i2 + c;
-            if (i1 != i2) { Hs[a] = -s; Hs[(size_t)(6 * i2 + c) * n + 6 * i1 + r] = -s; }
+            const size_t a = (size_t)(6 * i1 + r) * ld + 6 * i2 + c;
+            if (i1 != i2) { Hs[a] = -s; Hs[(size_t)(6 * i2 + c) * ld + 6 * i1 + r] = -s; }
             else Hs[a] -= s;
         }
     }
     if (tid == 0) s_ok = 1;
     __syncthreads();
-    // ---- LDL^T in place (lower triangle: L below the diagonal, D on it); right-looking
+    // ---- LDL^T in place (lower triangle: L below the diagonal, D on it); right-looking, one column per step:
+    //      lcol[i] = L_ij, then row i of the trailing lower triangle -= L_ij * d_j * L_kj  (warp per row, lanes along the row)
     for (int j = 0; j < n; j++) {
-        const double dj = Hs[(size_t)j * n + j];
+        const double dj = Hs[(size_t)j * ld + j];
         if (dj == 0.0 || !isfinite(dj)) { if (tid == 0) s_ok = 0; break; }
-        for (int i = j + 1 + tid; i < n; i += BA_TS) Hs[(size_t)i * n + j] /= dj;
+        for (int i = j + 1 + tid; i < n; i += BA_TS) { const double l = Hs[(size_t)i * ld + j] / dj; Hs[(size_t)i * ld + j] = l; s_lcol[i] = l; }
         __syncthreads();
-        const int m = n - j - 1;
-        for (int idx = tid; idx < m * m; idx += BA_TS) {
-            const int a = idx / m, b = idx - a * m;
-            if (b > a) continue;
-            const int i = j + 1 + a, k = j + 1 + b;
-            Hs[(size_t)i * n + k] -= Hs[(size_t)i * n + j] * dj * Hs[(size_t)k * n + j];
+        for (int i = j + 1 + warp; i < n; i += BA_TS / 32) {
+            const double li = s_lcol[i] * dj;
+            double* row = Hs + (size_t)i * ld;
+            for (int k = j + 1 + lane; k <= i; k += 32) row[k] -= li * s_lcol[k];
         }
         __syncthreads();
     }
@@ -693,20 +706,22 @@ __global__ void __launch_bounds__(BA_TS) k_solve(BABatch A) {
     double* x = A.xp + 6 * (size_t)P.k0;
     if (ok && warp == 0) {
         const double* bs = A.bs + 6 * (size_t)P.k0;
-        for (int i = lane; i < n; i += 32) x[i] = bs[i];
+        double* xs = s_lcol;                   // the solve runs on the shared copy
+        for (int i = lane; i < n; i += 32) xs[i] = bs[i];
         __syncwarp();
         for (int j = 0; j < n; j++) {
-            const double xj = x[j];
-            for (int i = j + 1 + lane; i < n; i += 32) x[i] -= Hs[(size_t)i * n + j] * xj;
+            const double xj = xs[j];
+            for (int i = j + 1 + lane; i < n; i += 32) xs[i] -= Hs[(size_t)i * ld + j] * xj;
             __syncwarp();
         }
-        for (int i = lane; i < n; i += 32) x[i] /= Hs[(size_t)i * n + i];
+        for (int i = lane; i < n; i += 32) xs[i] /= Hs[(size_t)i * ld + i];
         __syncwarp();
         for (int j = n - 1; j >= 0; j--) {
-            const double xj = x[j];
-            for (int i = lane; i < j; i += 32) x[i] -= Hs[(size_t)j * n + i] * xj;
+            const double xj = xs[j];
+            for (int i = lane; i < j; i += 32) xs[i] -= Hs[(size_t)j * ld + i] * xj;
             __syncwarp();
         }
+        for (int i = lane; i < n; i += 32) x[i] = xs[i];
     }
     if (!ok) for (int i = tid; i < n; i += BA_TS) x[i] = 0.0;   // g2o applies a stale x; the trial is rejected either way
     __syncthreads();
@@ -744,8 +759,11 @@ __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
         const bool robust = S.round == 0 && A.delta > 0;
         const double delta = A.delta, dsqr = delta * delta;
         double x0 = 0, x1 = 0, x2 = 0;
-        if (S.solve_ok) {
-            x0 = A.db[3 * (size_t)l]; x1 = A.db[3 * (size_t)l + 1]; x2 = A.db[3 * (size_t)l + 2];
+        const double* bl = A.bl + 3 * (size_t)l;
+        if (S.solve_ok) {   // xl = Dinv (bl - sum B_e^T xp) = Dinv bl - sum Y_e^T xp   (block_solver.hpp:461-481)
+            double d[6];
+            landmark_dinv(A.Hll + 6 * (size_t)l, lambda, d);
+            x0 = d[0] * bl[0] + d[1] * bl[1] + d[2] * bl[2]; x1 = d[1] * bl[0] + d[3] * bl[1] + d[4] * bl[2]; x2 = d[2] * bl[0] + d[4] * bl[1] + d[5] * bl[2];
             for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
                 const int kg = A.pose_free[A.e_pose[e]];
                 if (kg < 0) continue;
@@ -759,7 +777,6 @@ __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
         double pn[3] = {po[0] + x0, po[1] + x1, po[2] + x2};
         double* pw = A.pt[cur ^ 1] + 3 * (size_t)l;
         pw[0] = pn[0]; pw[1] = pn[1]; pw[2] = pn[2];
-        const double* bl = A.bl + 3 * (size_t)l;
         sc = x0 * (lambda * x0 + bl[0]) + x1 * (lambda * x1 + bl[1]) + x2 * (lambda * x2 + bl[2]);
         for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
             if (A.level[e]) continue;
@@ -922,14 +939,15 @@ struct Layout {   // bump allocator over one buffer; offsets are 256-byte aligne
 static int launch_steps(orbba* b, int steps) {
     const BABatch& A = b->A;
     cudaStream_t st = b->stream;
-    const int hs_n = std::min(b->max_n, BA_HS_SMEM_N);
-    const size_t smem = (size_t)hs_n * hs_n * sizeof(double);
+    const int hs_n = b->max_n <= BA_HS_SMEM_N ? b->max_n : BA_HS_SMEM_N;   // problems above the limit keep their matrix in global memory
+    const int hs_doubles = hs_n * (hs_n | 1);
+    const size_t smem = ((size_t)hs_doubles + std::max(b->max_n, 1)) * sizeof(double);
     for (int s = 0; s < steps; s++) {
         k_lin<<<b->nbE, BA_TE, 0, st>>>(A);
         k_build<<<b->nbL + b->Ktot, BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
-        k_trial_lm<<<b->nbL, BA_TL, 0, st>>>(A);
+        k_trial_lm<<<b->nbE, BA_TT, 0, st>>>(A);
         if (b->nbI > 0) k_pairs<<<b->nbI, 128, 0, st>>>(A, b->d_blkI_first);
-        k_solve<<<b->n, BA_TS, smem, st>>>(A);
+        k_solve<<<b->n, BA_TS, smem, st>>>(A, hs_doubles);
         k_back<<<b->nbL, BA_TL, 0, st>>>(A);
         b->launches += 5 + (b->nbI > 0);
     }
@@ -977,7 +995,7 @@ int orbba_create(orbba_t** out, int device, int max_problems) {
     if (ce == cudaSuccess) { memset(b->h_flags, 0, 4 * sizeof(int)); ce = cudaHostGetDevicePointer((void**)&b->d_flags, b->h_flags, 0); }
     if (ce == cudaSuccess) ce = cudaEventCreate(&b->ev[0]);
     if (ce == cudaSuccess) ce = cudaEventCreate(&b->ev[1]);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_HS_SMEM_N * BA_HS_SMEM_N * 8);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     if (ce != cudaSuccess) { int rc = orbhost::check_cuda(ce, "orbba_create", __FILE__, __LINE__); orbba_free(b); return rc; }
     b->stream = b->own_stream;
     *out = b;
@@ -1068,10 +1086,11 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         P.tup0 = tupTot; P.eof0 = eofTot; P.hs_off = hsTot;
         Etot += nE; Ltot += nL; Ptot += nP; Ctot += nC; Ktot += K; pairTot += P.nPairs; tupTot += tup; chunkTot += P.nChunksMax;
         itemTot += P.nItems; eofTot += (long long)nL * K;
-        if (P.n > BA_HS_SMEM_N) hsTot += (long long)P.n * P.n;
+        if (P.n > BA_HS_SMEM_N) hsTot += (long long)P.n * (P.n | 1);
         nbE += P.nbE; nbL += P.nbL; nbP += (P.nPairs + 3) / 4; nbI += (P.nItems + 3) / 4;
         max_n = std::max(max_n, P.n);
         if (Etot > 0x7fffffffLL || eofTot > 0x7fffffffLL * 4) ORB_FAIL(ORB_E_INVALID, "orbba_upload: batch too large");
+        if (P.n > 3000) ORB_FAIL(ORB_E_INVALID, "orbba_upload: problem %d has %d free poses; above 500 use the distributed global BA entry points", p, K);
     }
     // ---- layout: static (staged from the host) then device-only
     Layout L;
