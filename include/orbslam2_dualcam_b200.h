@@ -212,8 +212,14 @@ int  orbba_global(orbba_t*, const orbba_problem_t* problem, int iterations, doub
 int  orbba_upload(orbba_t*, const orbba_problem_t* problems, int n);
 int  orbba_run(orbba_t*, int its1, int its2, double huber_delta, double chi2_th);
 int  orbba_download(orbba_t*, int p, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats);
+/* results of every problem of the last run, concatenated in upload order: poses_out [sum n_poses][12], points_out
+ * [sum n_points][3], edge_outlier [sum n_edges], stats [n].  Any pointer may be NULL.  Synchronises. */
+int  orbba_download_batch(orbba_t*, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats);
 int  orbba_profile(orbba_t*, int enable);
 int  orbba_stage_ms(orbba_t*, double* ms1, int* calls);
+/* device time of the six kernels of the LM step {linearise, build, Schur blocks, Schur pairs, reduced solve, back-substitution +
+ * errors + LM decision}, summed over the steps recorded since the last call; *steps = LM steps summed. */
+int  orbba_kernel_ms(orbba_t*, double* ms6, int* steps);
 
 #ifdef __cplusplus
 }

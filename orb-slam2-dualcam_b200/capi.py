@@ -57,6 +57,8 @@ SIGNATURES = {
     "orbba_upload": (C.c_int, [vp, vp, C.c_int]),
     "orbba_run": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_double]),
     "orbba_download": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
+    "orbba_download_batch": (C.c_int, [vp, vp, vp, vp, vp]),
+    "orbba_kernel_ms": (C.c_int, [vp, f64p, C.POINTER(C.c_int)]),
     "orbba_profile": (C.c_int, [vp, C.c_int]),
     "orbba_stage_ms": (C.c_int, [vp, f64p, C.POINTER(C.c_int)]),
     "orbm_bruteforce_sets_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp]),

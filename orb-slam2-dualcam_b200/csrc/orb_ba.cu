@@ -916,7 +916,10 @@ struct orbba {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     bool profile = false;
     double prof_ms = 0; int prof_calls = 0; bool prof_pending = false;
+    std::vector<cudaEvent_t> kev;            // per-kernel timing: BA_KEV_STEPS x 7 events
+    int kev_steps = 0;
 };
+#define BA_KEV_STEPS 96
 
 static void orbba_free(orbba* b) {
     if (!b) return;
@@ -925,6 +928,7 @@ static void orbba_free(orbba* b) {
     if (b->h_stage) cudaFreeHost(b->h_stage);
     if (b->h_flags) cudaFreeHost(b->h_flags);
     if (b->ev[0]) { cudaEventDestroy(b->ev[0]); cudaEventDestroy(b->ev[1]); }
+    for (cudaEvent_t e : b->kev) cudaEventDestroy(e);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
 }
@@ -943,12 +947,20 @@ static int launch_steps(orbba* b, int steps) {
     const int hs_doubles = hs_n * (hs_n | 1);
     const size_t smem = ((size_t)hs_doubles + std::max(b->max_n, 1)) * sizeof(double);
     for (int s = 0; s < steps; s++) {
+        cudaEvent_t* kv = (b->profile && b->kev_steps < BA_KEV_STEPS && !b->kev.empty()) ? &b->kev[(size_t)7 * b->kev_steps] : nullptr;
+        if (kv) cudaEventRecord(kv[0], st);
         k_lin<<<b->nbE, BA_TE, 0, st>>>(A);
+        if (kv) cudaEventRecord(kv[1], st);
         k_build<<<b->nbL + b->Ktot, BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
+        if (kv) cudaEventRecord(kv[2], st);
         k_trial_lm<<<b->nbE, BA_TT, 0, st>>>(A);
+        if (kv) cudaEventRecord(kv[3], st);
         if (b->nbI > 0) k_pairs<<<b->nbI, 128, 0, st>>>(A, b->d_blkI_first);
+        if (kv) cudaEventRecord(kv[4], st);
         k_solve<<<b->n, BA_TS, smem, st>>>(A, hs_doubles);
+        if (kv) cudaEventRecord(kv[5], st);
         k_back<<<b->nbL, BA_TL, 0, st>>>(A);
+        if (kv) { cudaEventRecord(kv[6], st); b->kev_steps++; }
         b->launches += 5 + (b->nbI > 0);
     }
     b->h_flags[1] = 0;
@@ -1251,6 +1263,12 @@ int orbba_run(orbba_t* b, int its1, int its2, double huber_delta, double chi2_th
 
 int orbba_profile(orbba_t* b, int enable) {
     if (!b) ORB_FAIL(ORB_E_INVALID, "orbba_profile: NULL handle");
+    ORB_CUDA(cudaSetDevice(b->device));
+    if (enable && b->kev.empty()) {
+        b->kev.resize((size_t)BA_KEV_STEPS * 7);
+        for (cudaEvent_t& e : b->kev) ORB_CUDA(cudaEventCreate(&e));
+    }
+    b->kev_steps = 0;
     b->profile = enable != 0; b->prof_ms = 0; b->prof_calls = 0; b->prof_pending = false;
     return ORB_OK;
 }
@@ -1268,6 +1286,51 @@ int orbba_stage_ms(orbba_t* b, double* ms1, int* calls) {   // only the LAST run
     *ms1 = b->prof_ms;
     if (calls) *calls = b->prof_calls;
     b->prof_ms = 0; b->prof_calls = 0;
+    return ORB_OK;
+}
+
+// Device time per kernel of the LM step {k_lin, k_build, k_trial_lm, k_pairs, k_solve, k_back}, summed over the steps recorded
+// since the last call (profiling must be enabled); *steps = number of steps summed.
+int orbba_kernel_ms(orbba_t* b, double* ms6, int* steps) {
+    if (!b || !ms6) ORB_FAIL(ORB_E_INVALID, "orbba_kernel_ms: bad argument");
+    ORB_CUDA(cudaSetDevice(b->device));
+    int rc = finish(b);
+    if (rc != ORB_OK) return rc;
+    ORB_CUDA(cudaStreamSynchronize(b->stream));
+    for (int k = 0; k < 6; k++) ms6[k] = 0;
+    for (int s = 0; s < b->kev_steps; s++)
+        for (int k = 0; k < 6; k++) {
+            float ms = 0;
+            ORB_CUDA(cudaEventElapsedTime(&ms, b->kev[(size_t)7 * s + k], b->kev[(size_t)7 * s + k + 1]));
+            ms6[k] += ms;
+        }
+    if (steps) *steps = b->kev_steps;
+    b->kev_steps = 0;
+    return ORB_OK;
+}
+
+// Results of every problem of the last run, concatenated in upload order: poses_out [sum n_poses][12], points_out
+// [sum n_points][3], edge_outlier [sum n_edges] (caller's edge order), stats [n].  Any pointer may be NULL.  Synchronises.
+int orbba_download_batch(orbba_t* b, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats) {
+    if (!b) ORB_FAIL(ORB_E_INVALID, "orbba_download_batch: NULL handle");
+    if (b->n == 0) return ORB_OK;
+    ORB_CUDA(cudaSetDevice(b->device));
+    int rc = finish(b);
+    if (rc != ORB_OK) return rc;
+    cudaStream_t st = b->stream;
+    if (poses_out && b->Ptot) ORB_CUDA(cudaMemcpyAsync(poses_out, b->A.poses_out, sizeof(double) * 12 * b->Ptot, cudaMemcpyDeviceToHost, st));
+    if (points_out && b->Ltot) ORB_CUDA(cudaMemcpyAsync(points_out, b->A.points_out, sizeof(double) * 3 * b->Ltot, cudaMemcpyDeviceToHost, st));
+    if (edge_outlier && b->Etot) ORB_CUDA(cudaMemcpyAsync(edge_outlier, b->A.outlier, (size_t)b->Etot, cudaMemcpyDeviceToHost, st));
+    if (stats) ORB_CUDA(cudaMemcpyAsync(stats, b->A.stats, sizeof(orbba_stats_t) * b->n, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    if (edge_outlier)
+        for (int p = 0; p < b->n; p++) {
+            const std::vector<int>& pm = b->perm[p];
+            if (pm.empty()) continue;
+            const BAProb& P = b->probs[p];
+            std::vector<uint8_t> tmp(edge_outlier + P.e0, edge_outlier + P.e0 + P.nE);
+            for (int s2 = 0; s2 < P.nE; s2++) edge_outlier[P.e0 + pm[s2]] = tmp[s2];
+        }
     return ORB_OK;
 }
 

@@ -84,19 +84,31 @@ class Optimizer:
     BundleAdjustment = GlobalBundleAdjustemnt
 
     # ---- batched form
-    def upload(self, problems):
+    @staticmethod
+    def prepare(problems):
+        """list of problem dicts -> (ctypes array of orbba_problem_t, keep-alive list); reusable across upload() calls"""
         arr = (ProblemC * len(problems))()
         keeps = []
         for i, p in enumerate(problems):
             s, keep = problem_struct(p)
             arr[i] = s
             keeps.append(keep)
-        check(lib().orbba_upload(self._h, C.addressof(arr), len(problems)))
+        return arr, keeps
+
+    def upload(self, problems):
+        arr, keeps = problems if isinstance(problems, tuple) else self.prepare(problems)
+        check(lib().orbba_upload(self._h, C.addressof(arr), len(arr)))
         self._sizes = [(a.n_poses, a.n_points, a.n_edges) for a in arr]
+
+    def set_stream(self, stream):
+        h = _stream_handle(stream)
+        if getattr(self, "_stream_h", None) != h:
+            check(lib().orbba_set_stream(self._h, h))
+            self._stream_h = h
 
     def run(self, its1=5, its2=10, huber_delta=TH_HUBER_MONO, chi2_th=CHI2_MONO, stream=None):
         if stream is not None:
-            check(lib().orbba_set_stream(self._h, _stream_handle(stream)))
+            self.set_stream(stream)
         check(lib().orbba_run(self._h, its1, its2, huber_delta, chi2_th))
 
     def download(self, p):
@@ -105,6 +117,23 @@ class Optimizer:
         st = StatsC()
         check(lib().orbba_download(self._h, p, ptr(poses), ptr(points), ptr(out), C.addressof(st)))
         return poses, points, out.astype(bool), st.asdict()
+
+    def download_batch(self, out=None):
+        """Results of all problems of the last run, concatenated in upload order -> (poses [sumP][12], points [sumL][3],
+        outlier uint8 [sumE], stats list).  `out` = preallocated (poses, points, outlier) numpy arrays / pinned torch tensors."""
+        nP = sum(a for a, _, _ in self._sizes); nL = sum(b for _, b, _ in self._sizes); nE = sum(c for _, _, c in self._sizes)
+        if out is None:
+            out = (np.zeros((nP, 12)), np.zeros((nL, 3)), np.zeros(nE, np.uint8))
+        st = (StatsC * len(self._sizes))()
+        check(lib().orbba_download_batch(self._h, ptr(out[0]), ptr(out[1]), ptr(out[2]), C.addressof(st)))
+        return out[0], out[1], out[2], [s.asdict() for s in st]
+
+    def kernel_ms(self):
+        """device ms of {k_lin, k_build, k_trial_lm, k_pairs, k_solve, k_back} summed over the recorded LM steps -> (dict, steps)"""
+        ms = (C.c_double * 6)()
+        n = C.c_int()
+        check(lib().orbba_kernel_ms(self._h, ms, C.byref(n)))
+        return dict(zip(["k_lin", "k_build", "k_trial_lm", "k_pairs", "k_solve", "k_back"], list(ms))), n.value
 
     def synchronize(self):
         check(lib().orbba_synchronize(self._h))
