@@ -150,6 +150,105 @@ int  orbm_bruteforce_sets_device(orbm_t*, const uint8_t* d_desc, const int32_t* 
                                  const int32_t* d_q_set, const int32_t* d_t_set, int pairs,
                                  int32_t* d_best_idx, int32_t* d_best_d, int32_t* d_second_d);
 
+/* ------------------------------------------------------------------------------------------------
+ * Guided searches.  The adaptor flattens what the reference loops read from Frame / KeyFrame / MapPoint into the PODs
+ * below; the sequential "claim" semantics of the reference (a keypoint that received a map point is skipped by the map
+ * points that follow, src/ORBmatcher.cc:589-591, :216) are reproduced exactly: distances are computed in parallel, the
+ * claims are resolved in input order.  HOST buffers, synchronous.
+ * ---------------------------------------------------------------------------------------------- */
+#define ORBM_GRID_COLS 64       /* FRAME_GRID_COLS  include/Frame.h:40 */
+#define ORBM_GRID_ROWS 48       /* FRAME_GRID_ROWS  include/Frame.h:39 */
+
+/* a Frame as the searches see it (src/Frame.cc:141-199): undistorted keypoints of all cameras concatenated camera-major
+ * (= the global index order of mvTotalKeysUn), their descriptors, per-camera image bounds and the pyramid scale factors.
+ * The 64x48 grid (Frame::PosInGrid / mvGrids, src/Frame.cc:179-196,380-390) is built on the device. */
+typedef struct {
+    int32_t n_cams;
+    const int32_t* n_kp;            /* [n_cams]      Frame::mvN */
+    const orb_keypoint_t* kps_un;   /* [totalN]      Frame::mvTotalKeysUn (pt, angle, octave are read) */
+    const uint8_t* desc;            /* [totalN][32]  rows of mvDescriptors[c] */
+    const float* bounds;            /* [n_cams][4]   mvMinX, mvMaxX, mvMinY, mvMaxY */
+    int32_t n_levels;
+    const float* scale_factors;     /* [n_levels]    mvScaleFactors */
+} orbm_frame_t;
+
+/* what ORBmatcher::SearchByProjection(pF, vpMapPoints, th) reads from a MapPoint (src/ORBmatcher.cc:547-573) */
+typedef struct {
+    int32_t valid;          /* pMP && pMP->mbTrackInView && !pMP->isBad() */
+    int32_t cam;            /* mTrackProjCamera */
+    float   u, v;           /* mTrackProjX, mTrackProjY */
+    int32_t level;          /* mnTrackScaleLevel */
+    float   view_cos;       /* mTrackViewCos */
+    int32_t obs_positive;   /* Observations() > 0: once assigned, the keypoint is skipped by later map points (:589-591) */
+    uint8_t desc[32];       /* GetDescriptor() */
+} orbm_mp_t;
+
+/* ORBmatcher::SearchByProjection(FramePtr pF, const vector<MapPointPtr>& vpMapPoints, float th)  (TrackLocalMap; src/ORBmatcher.cc:539-624).
+ *   blocked   uint8 [totalN]  1 iff pF->mvpMapPoints[g] && pF->mvpMapPoints[g]->Observations() > 0 on entry
+ *   kp_to_mp  int32 [totalN]  in/out: entry g is set to i when vpMapPoints[i] is written into pF->mvpMapPoints[g] (:618)
+ *   nmatches  the function's return value */
+int  orbm_search_by_projection(orbm_t*, const orbm_frame_t* frame, const orbm_mp_t* mps, int n, float th, float nnratio,
+                               const uint8_t* blocked, int32_t* kp_to_mp, int32_t* nmatches);
+
+/* the last frame as ORBmatcher::SearchByProjectionOnCam(pFcurt, query, pFlast, th) reads it (src/ORBmatcher.cc:975-1036), one entry per
+ * last-frame keypoint (global index) */
+typedef struct {
+    int32_t n;                    /* pFlast->totalN */
+    const int32_t* cam;           /* [n]     keypointToCam */
+    const uint8_t* valid;         /* [n]     mvpMapPoints[i] && !isBad() */
+    const float*   pos;           /* [n][3]  GetWorldPos() */
+    const uint8_t* desc;          /* [n][32] GetDescriptor() */
+    const int32_t* octave;        /* [n]     mvTotalKeysUn[i].octave */
+    const float*   angle;         /* [n]     mvTotalKeysUn[i].angle */
+    const uint8_t* obs_positive;  /* [n]     Observations() > 0 */
+} orbm_lastframe_t;
+
+/* ORBmatcher::SearchByProjection(pCurrentFrame, pLastFrame, th, bMapScaled)  (TrackWithMotionModel; src/ORBmatcher.cc:634-690, 954-1113).
+ *   Rsw, tsw   float [n_cams][9] / [n_cams][3]: rotation / translation of Tsw = mvExtrinsics[c] * mTcw (:962-967)
+ *   K          float [n_cams][4]: mvfx, mvfy, mvcx, mvcy
+ *   kp_to_last int32 [totalN] in/out: entry g is set to i when pFlast->mvpMapPoints[i] is written into pFcurt->mvpMapPoints[g],
+ *              and back to -1 when the rotation-histogram check removes it (:1082-1101)
+ *   per_cam    int32 [n_cams] (may be NULL): matches per camera; cameras after one with <= 20 matches are not searched and the
+ *              total is REPLACED by that camera's count (:664-667, upstream behaviour) */
+int  orbm_search_by_projection_last(orbm_t*, const orbm_frame_t* cur, const float* Rsw, const float* tsw, const float* K,
+                                    const orbm_lastframe_t* last, float th, int check_orientation, int map_scaled,
+                                    const uint8_t* blocked, int32_t* kp_to_last, int32_t* per_cam, int32_t* nmatches);
+
+/* one side of SearchByBoW: descriptors, keypoint angles and the DBoW2::FeatureVector of every camera flattened to CSR
+ * (std::map<NodeId, vector<unsigned>> -> node ids ascending, camera-local feature indices) */
+typedef struct {
+    int32_t n_cams;
+    const int32_t* n_kp;          /* [n_cams] */
+    const uint8_t* desc;          /* [totalN][32] */
+    const float*   angle;         /* [totalN]  mvvkeysUnTemp[c][i].angle */
+    const int32_t* node_first;    /* [n_cams + 1] range of camera c's nodes in node_id / node_off */
+    const int32_t* node_id;       /* [n_nodes] ascending inside a camera */
+    const int32_t* node_off;      /* [n_nodes + 1] into idx */
+    const int32_t* idx;           /* camera-local feature indices */
+} orbm_bowside_t;
+
+/* ORBmatcher::SearchByBoW(pF, pKF, vpMapPointMatches, bMapScaled) -> SearchByBoWCrossCam(pF, c, pKF, c, ...)  (src/ORBmatcher.cc:102-294).
+ *   kf_mp_valid uint8 [KF totalN]  pKF->GetMapPointMatches()[g] && !isBad()
+ *   f_to_kf     int32 [F totalN]   out: global KF keypoint index whose map point lands in vpMapPointMatches[g], else -1 */
+int  orbm_search_by_bow(orbm_t*, const orbm_bowside_t* F, const orbm_bowside_t* KF, const uint8_t* kf_mp_valid, float nnratio,
+                        int check_orientation, int map_scaled, int32_t* f_to_kf, int32_t* nmatches);
+
+/* Frame::isInFrustum(pMP, viewingCosLimit, bForAllCam) + MapPoint::PredictScale for n map points (src/Frame.cc:244-312,
+ * src/MapPoint.cc:440-455): the producer of orbm_mp_t {cam, u, v, level, view_cos}. */
+typedef struct {
+    int32_t n_cams, n_levels;
+    const float* Rsw;             /* [n_cams][9]  rotation of mvExtrinsics[c] * mTcw */
+    const float* tsw;             /* [n_cams][3] */
+    const float* Ow;              /* [n_cams][3]  Frame::GetCameraCenter(c) */
+    const float* K;               /* [n_cams][4]  fx fy cx cy */
+    const float* bounds;          /* [n_cams][4]  mvMinX, mvMaxX, mvMinY, mvMaxY */
+    float log_scale_factor;       /* mfLogScaleFactor */
+} orbm_frustum_t;
+/*   pos, normal float [n][3]; max_dist, min_dist float [n] = mfMaxDistance, mfMinDistance (the 1.2 / 0.8 invariance factors are applied inside)
+ *   out int32 [n][3] = {mbTrackInView, mTrackProjCamera, mnTrackScaleLevel};  uvc float [n][3] = {mTrackProjX, mTrackProjY, mTrackViewCos} */
+int  orbm_is_in_frustum(orbm_t*, const orbm_frustum_t* frame, const float* pos, const float* normal, const float* max_dist,
+                        const float* min_dist, int n, float viewing_cos_limit, int for_all_cams, int32_t* out, float* uvc);
+
 /* ================================================================================================
  * BUNDLE ADJUSTMENT -- replaces Optimizer::LocalBundleAdjustment / BundleAdjustment / GlobalBundleAdjustemnt
  * (include/Optimizer.h:50-56, src/Optimizer.cc:62-248,407-696) together with the g2o machinery under them

@@ -61,8 +61,69 @@ SIGNATURES = {
     "orbba_kernel_ms": (C.c_int, [vp, f64p, C.POINTER(C.c_int)]),
     "orbba_profile": (C.c_int, [vp, C.c_int]),
     "orbba_stage_ms": (C.c_int, [vp, f64p, C.POINTER(C.c_int)]),
+    "orbm_search_by_projection": (C.c_int, [vp, vp, vp, C.c_int, C.c_float, C.c_float, vp, vp, vp]),
+    "orbm_search_by_projection_last": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "orbm_search_by_bow": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp]),
+    "orbm_is_in_frustum": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp]),
     "orbm_bruteforce_sets_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp]),
 }
+
+# ---- PODs of the guided searches (include/orbslam2_dualcam_b200.h)
+MP_DTYPE = np.dtype([("valid", "<i4"), ("cam", "<i4"), ("u", "<f4"), ("v", "<f4"), ("level", "<i4"), ("view_cos", "<f4"),
+                     ("obs_positive", "<i4"), ("desc", "u1", (32,))])
+assert MP_DTYPE.itemsize == 60
+
+
+class FrameC(C.Structure):
+    _fields_ = [("n_cams", C.c_int32), ("n_kp", vp), ("kps_un", vp), ("desc", vp), ("bounds", vp), ("n_levels", C.c_int32), ("scale_factors", vp)]
+
+
+class LastFrameC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("cam", vp), ("valid", vp), ("pos", vp), ("desc", vp), ("octave", vp), ("angle", vp), ("obs_positive", vp)]
+
+
+class BowSideC(C.Structure):
+    _fields_ = [("n_cams", C.c_int32), ("n_kp", vp), ("desc", vp), ("angle", vp), ("node_first", vp), ("node_id", vp), ("node_off", vp), ("idx", vp)]
+
+
+class FrustumC(C.Structure):
+    _fields_ = [("n_cams", C.c_int32), ("n_levels", C.c_int32), ("Rsw", vp), ("tsw", vp), ("Ow", vp), ("K", vp), ("bounds", vp),
+                ("log_scale_factor", C.c_float)]
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+def frame_struct(f, cls=FrameC):
+    """dict(n_kp, kps_un (KP_DTYPE), desc, bounds, scale_factors) -> (struct, keep-alive)"""
+    keep = dict(n_kp=_c(f["n_kp"], np.int32), kps_un=_c(f["kps_un"], KP_DTYPE), desc=_c(f["desc"], np.uint8), bounds=_c(f["bounds"], np.float32),
+                scale_factors=_c(f["scale_factors"], np.float32))
+    s = cls(n_cams=len(keep["n_kp"]), n_kp=keep["n_kp"].ctypes.data, kps_un=keep["kps_un"].ctypes.data, desc=keep["desc"].ctypes.data,
+            bounds=keep["bounds"].ctypes.data, n_levels=len(keep["scale_factors"]), scale_factors=keep["scale_factors"].ctypes.data)
+    return s, keep
+
+
+def lastframe_struct(l, cls=LastFrameC):
+    keep = dict(cam=_c(l["cam"], np.int32), valid=_c(l["valid"], np.uint8), pos=_c(l["pos"], np.float32), desc=_c(l["desc"], np.uint8),
+                octave=_c(l["octave"], np.int32), angle=_c(l["angle"], np.float32), obs_positive=_c(l["obs_positive"], np.uint8))
+    s = cls(n=len(keep["cam"]), **{k: v.ctypes.data for k, v in keep.items()})
+    return s, keep
+
+
+def bowside_struct(b, cls=BowSideC):
+    keep = dict(n_kp=_c(b["n_kp"], np.int32), desc=_c(b["desc"], np.uint8), angle=_c(b["angle"], np.float32), node_first=_c(b["node_first"], np.int32),
+                node_id=_c(b["node_id"], np.int32), node_off=_c(b["node_off"], np.int32), idx=_c(b["idx"], np.int32))
+    s = cls(n_cams=len(keep["n_kp"]), **{k: v.ctypes.data for k, v in keep.items()})
+    return s, keep
+
+
+def frustum_struct(q, cls=FrustumC):
+    keep = dict(Rsw=_c(q["Rsw"], np.float32), tsw=_c(q["tsw"], np.float32), Ow=_c(q["Ow"], np.float32), K=_c(q["K"], np.float32),
+                bounds=_c(q["bounds"], np.float32))
+    s = cls(n_cams=keep["Rsw"].shape[0], n_levels=int(q["n_levels"]), log_scale_factor=float(q["log_scale_factor"]), **{k: v.ctypes.data for k, v in keep.items()})
+    return s, keep
+
 
 _LIB = None
 

@@ -25,7 +25,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "orb_common.h"
@@ -934,6 +937,16 @@ static void orbba_free(orbba* b) {
 }
 
 namespace {
+// runs fn(0..n-1) on up to 16 host threads (problems are independent); inline for a single item
+template <class F>
+void parallel_for(int n, F fn) {
+    const int nt = std::min({n, 16, (int)std::max(1u, std::thread::hardware_concurrency())});
+    if (nt <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+    std::atomic<int> next(0);
+    std::vector<std::thread> ts;
+    for (int t = 0; t < nt; t++) ts.emplace_back([&]() { for (int i; (i = next.fetch_add(1)) < n;) fn(i); });
+    for (std::thread& t : ts) t.join();
+}
 struct Layout {   // bump allocator over one buffer; offsets are 256-byte aligned
     size_t cur = 0;
     size_t add(size_t bytes) { const size_t off = (cur + 255) & ~(size_t)255; cur = off + bytes; return off; }
@@ -1044,25 +1057,28 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     b->probs.assign(n, BAProb());
     b->perm.assign(n, std::vector<int>());
     if (n == 0) return ORB_OK;
-    // ---- pass 1: sizes
-    long long Etot = 0, Ltot = 0, Ptot = 0, Ctot = 0, Ktot = 0, pairTot = 0, tupTot = 0, chunkTot = 0, eofTot = 0, hsTot = 0, itemTot = 0;
-    int nbE = 0, nbL = 0, nbP = 0, nbI = 0, max_n = 0;
-    std::vector<std::vector<int>> pose_free_local(n), f_count(n);
-    for (int p = 0; p < n; p++) {
+    // ---- pass 1a: per-problem analysis (validation, free-pose numbering, landmark grouping, tuple count) on all host cores
+    std::vector<std::vector<int>> pose_free_local(n);
+    std::vector<long long> tups(n, 0);
+    std::vector<int> Ks(n, 0);
+    std::vector<std::string> errs(n);
+    parallel_for(n, [&](int p) {
         const orbba_problem_t& Q = problems[p];
         const int nP = Q.n_poses, nL = Q.n_points, nE = Q.n_edges, nC = Q.n_cams;
-        if (nP < 0 || nL < 0 || nE < 0 || nC < 1) ORB_FAIL(ORB_E_INVALID, "orbba_upload: problem %d has negative sizes", p);
+        char msg[256];
+        if (nP < 0 || nL < 0 || nE < 0 || nC < 1) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d has negative sizes", p); errs[p] = msg; return; }
         if ((nP && (!Q.poses || !Q.pose_fixed)) || (nL && !Q.points) || (nE && (!Q.edge_pose || !Q.edge_point || !Q.edge_cam || !Q.edge_obs || !Q.edge_inv_sigma2)) ||
-            !Q.cam_K || !Q.cam_ext || !Q.cam_adj)
-            ORB_FAIL(ORB_E_INVALID, "orbba_upload: problem %d has a NULL array", p);
+            !Q.cam_K || !Q.cam_ext || !Q.cam_adj) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d has a NULL array", p); errs[p] = msg; return; }
         std::vector<int>& pf = pose_free_local[p];
         pf.assign(nP, -1);
         int K = 0;
         for (int i = 0; i < nP; i++) if (!Q.pose_fixed[i]) pf[i] = K++;
+        Ks[p] = K;
         bool grouped = true;
         for (int e = 0; e < nE; e++) {
-            if (Q.edge_pose[e] < 0 || Q.edge_pose[e] >= nP || Q.edge_point[e] < 0 || Q.edge_point[e] >= nL || Q.edge_cam[e] < 0 || Q.edge_cam[e] >= nC)
-                ORB_FAIL(ORB_E_INVALID, "orbba_upload: problem %d edge %d indexes out of range", p, e);
+            if (Q.edge_pose[e] < 0 || Q.edge_pose[e] >= nP || Q.edge_point[e] < 0 || Q.edge_point[e] >= nL || Q.edge_cam[e] < 0 || Q.edge_cam[e] >= nC) {
+                snprintf(msg, sizeof(msg), "orbba_upload: problem %d edge %d indexes out of range", p, e); errs[p] = msg; return;
+            }
             if (e > 0 && Q.edge_point[e] < Q.edge_point[e - 1]) grouped = false;
         }
         if (!grouped) {   // stable counting sort by landmark (the reference adds edges landmark by landmark, src/Optimizer.cc:530-575)
@@ -1073,20 +1089,35 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
             for (int e = 0; e < nE; e++) b->perm[p][cnt[Q.edge_point[e]]++] = e;
         }
         // free-pose observations per landmark; one observation per (landmark, keyframe) as in MapPoint::mObservations
-        std::vector<int>& fc = f_count[p];
-        fc.assign(nL, 0);
         std::vector<int> stamp(nP, -1);
         long long tup = 0;
+        int run = 0, prev = -1;
         const std::vector<int>& pm = b->perm[p];
         for (int s = 0; s < nE; s++) {
             const int e = pm.empty() ? s : pm[s];
             const int l = Q.edge_point[e], ps = Q.edge_pose[e];
-            if (stamp[ps] == l) ORB_FAIL(ORB_E_INVALID, "orbba_upload: problem %d observes landmark %d twice from pose %d (MapPoint::mObservations holds one per keyframe)", p, l, ps);
+            if (stamp[ps] == l) {
+                snprintf(msg, sizeof(msg), "orbba_upload: problem %d observes landmark %d twice from pose %d (MapPoint::mObservations holds one per keyframe)", p, l, ps);
+                errs[p] = msg; return;
+            }
             stamp[ps] = l;
-            if (pf[ps] >= 0) fc[l]++;
+            if (l != prev) { tup += (long long)run * (run + 1) / 2; run = 0; prev = l; }
+            if (pf[ps] >= 0) run++;
         }
-        for (int l = 0; l < nL; l++) tup += (long long)fc[l] * (fc[l] + 1) / 2;
-        if (tup > 0x7fffffffLL || (long long)K * (K + 1) / 2 > 4000000LL) ORB_FAIL(ORB_E_INVALID, "orbba_upload: problem %d is too large for the pair index (%d free poses)", p, K);
+        tup += (long long)run * (run + 1) / 2;
+        tups[p] = tup;
+        if (tup > 0x7fffffffLL || (long long)K * (K + 1) / 2 > 4000000LL) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d is too large for the pair index (%d free poses)", p, K); errs[p] = msg; return; }
+        if (6 * K > 3000) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d has %d free poses; above 500 use the distributed global BA entry points", p, K); errs[p] = msg; }
+    });
+    for (int p = 0; p < n; p++) if (!errs[p].empty()) ORB_FAIL(ORB_E_INVALID, "%s", errs[p].c_str());
+    // ---- pass 1b: offsets
+    long long Etot = 0, Ltot = 0, Ptot = 0, Ctot = 0, Ktot = 0, pairTot = 0, tupTot = 0, chunkTot = 0, eofTot = 0, hsTot = 0, itemTot = 0;
+    int nbE = 0, nbL = 0, nbP = 0, nbI = 0, max_n = 0;
+    std::vector<int> bP0(n), bI0(n);
+    for (int p = 0; p < n; p++) {
+        const orbba_problem_t& Q = problems[p];
+        const int nP = Q.n_poses, nL = Q.n_points, nE = Q.n_edges, nC = Q.n_cams, K = Ks[p];
+        const long long tup = tups[p];
         BAProb& P = b->probs[p];
         P.e0 = (int)Etot; P.nE = nE; P.l0 = (int)Ltot; P.nL = nL; P.p0 = (int)Ptot; P.nP = nP; P.c0 = (int)Ctot; P.nC = nC;
         P.k0 = (int)Ktot; P.K = K; P.n = 6 * K;
@@ -1096,13 +1127,13 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         P.blkE0 = nbE; P.nbE = std::max(1, (nE + BA_TE - 1) / BA_TE);
         P.blkL0 = nbL; P.nbL = std::max(1, (nL + BA_TL - 1) / BA_TL);
         P.tup0 = tupTot; P.eof0 = eofTot; P.hs_off = hsTot;
+        bP0[p] = nbP; bI0[p] = nbI;
         Etot += nE; Ltot += nL; Ptot += nP; Ctot += nC; Ktot += K; pairTot += P.nPairs; tupTot += tup; chunkTot += P.nChunksMax;
         itemTot += P.nItems; eofTot += (long long)nL * K;
         if (P.n > BA_HS_SMEM_N) hsTot += (long long)P.n * (P.n | 1);
         nbE += P.nbE; nbL += P.nbL; nbP += (P.nPairs + 3) / 4; nbI += (P.nItems + 3) / 4;
         max_n = std::max(max_n, P.n);
         if (Etot > 0x7fffffffLL || eofTot > 0x7fffffffLL * 4) ORB_FAIL(ORB_E_INVALID, "orbba_upload: batch too large");
-        if (P.n > 3000) ORB_FAIL(ORB_E_INVALID, "orbba_upload: problem %d has %d free poses; above 500 use the distributed global BA entry points", p, K);
     }
     // ---- layout: static (staged from the host) then device-only
     Layout L;
@@ -1146,8 +1177,8 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     double *h_eobs = (double*)(H + o_eobs), *h_einfo = (double*)(H + o_einfo), *h_cam = (double*)(H + o_cam), *h_pose0 = (double*)(H + o_pose0), *h_pt0 = (double*)(H + o_pt0);
     int *h_blkE = (int*)(H + o_blkE), *h_blkL = (int*)(H + o_blkL), *h_item = (int*)(H + o_item), *h_blkPp = (int*)(H + o_blkPp), *h_blkPf = (int*)(H + o_blkPf),
         *h_blkIf = (int*)(H + o_blkIf), *h_poseprob = (int*)(H + o_poseprob);
-    int bP = 0, bI = 0;
-    for (int p = 0; p < n; p++) {
+    parallel_for(n, [&](int p) {
+        const int bP = bP0[p], bI = bI0[p];
         const orbba_problem_t& Q = problems[p];
         const BAProb& P = b->probs[p];
         const std::vector<int>& pm = b->perm[p];
@@ -1194,8 +1225,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         const int bp4 = (P.nPairs + 3) / 4, bi4 = (P.nItems + 3) / 4;
         for (int q = 0; q < bp4; q++) { h_blkPp[bP + q] = p; h_blkPf[bP + q] = bP; }
         for (int q = 0; q < bi4; q++) { h_item[bI + q] = p; h_blkIf[bI + q] = bI; }
-        bP += bp4; bI += bi4;
-    }
+    });
     h_ptoff[Ltot] = (int)Etot;
     // ---- device pointers
     BABatch& A = b->A;

@@ -92,6 +92,11 @@ static void orbm_free(orbm* m) {
     delete m;
 }
 
+// accessors for orb_search.cu (the guided searches share the matcher handle)
+cudaStream_t orbm_stream_of(orbm* m) { return m->stream; }
+int orbm_device_of(orbm* m) { return m->device; }
+void orbm_count_launches(orbm* m, int n) { m->launches += n; }
+
 extern "C" {
 
 int orbm_create(orbm_t** out, int device, int max_pairs, int max_query, int max_train) {

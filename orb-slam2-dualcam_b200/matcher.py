@@ -3,6 +3,7 @@ import ctypes as C
 
 import numpy as np
 
+from . import capi
 from .capi import stream_handle as _stream_handle
 from .capi import check, lib, ptr
 
@@ -35,6 +36,59 @@ class ORBmatcher:
         out = np.empty(a.shape[0], np.int32)
         check(lib().orbm_descriptor_distance(self._h, ptr(a), ptr(b), a.shape[0], ptr(out)))
         return out if out.size != 1 else int(out[0])
+
+    # ---- guided searches (host arrays in, host arrays out; the frame / map points are given flattened, see capi.*_struct)
+    def SearchByProjection(self, frame, mps, th=3.0, blocked=None, kp_to_mp=None):
+        """ORBmatcher::SearchByProjection(pF, vpMapPoints, th) (src/ORBmatcher.cc:539-624).
+        frame: dict(n_kp, kps_un, desc, bounds, scale_factors); mps: structured array capi.MP_DTYPE.
+        -> (nmatches, kp_to_mp int32 [totalN]: index of the map point written into mvpMapPoints[g], -1 = untouched)"""
+        fs, keep = capi.frame_struct(frame)
+        mps = np.ascontiguousarray(mps, capi.MP_DTYPE)
+        total = int(np.sum(keep["n_kp"]))
+        blocked = np.zeros(total, np.uint8) if blocked is None else np.ascontiguousarray(blocked, np.uint8)
+        out = np.full(total, -1, np.int32) if kp_to_mp is None else kp_to_mp
+        n = C.c_int32()
+        check(lib().orbm_search_by_projection(self._h, C.addressof(fs), ptr(mps), len(mps), th, self.mfNNratio, ptr(blocked), ptr(out), C.addressof(n)))
+        return n.value, out
+
+    def SearchByProjectionLast(self, cur, Rsw, tsw, K, last, th, bMapScaled=True, blocked=None):
+        """ORBmatcher::SearchByProjection(pCurrentFrame, pLastFrame, th, bMapScaled) (src/ORBmatcher.cc:634-690, 954-1113).
+        -> (nmatches, kp_to_last int32 [totalN], per_cam int32 [n_cams])"""
+        fs, keep = capi.frame_struct(cur)
+        ls, lkeep = capi.lastframe_struct(last)
+        Rsw, tsw, K = (np.ascontiguousarray(a, np.float32) for a in (Rsw, tsw, K))
+        total = int(np.sum(keep["n_kp"]))
+        blocked = np.zeros(total, np.uint8) if blocked is None else np.ascontiguousarray(blocked, np.uint8)
+        out = np.full(total, -1, np.int32)
+        per_cam = np.zeros(len(keep["n_kp"]), np.int32)
+        n = C.c_int32()
+        check(lib().orbm_search_by_projection_last(self._h, C.addressof(fs), ptr(Rsw), ptr(tsw), ptr(K), C.addressof(ls), th, int(self.mbCheckOrientation),
+                                                   int(bMapScaled), ptr(blocked), ptr(out), ptr(per_cam), C.addressof(n)))
+        return n.value, out, per_cam
+
+    def SearchByBoW(self, F, KF, kf_mp_valid, bMapScaled=True):
+        """ORBmatcher::SearchByBoW(pF, pKF, vpMapPointMatches, bMapScaled) (src/ORBmatcher.cc:102-294).
+        F, KF: dict(n_kp, desc, angle, node_first, node_id, node_off, idx) -> (nmatches, f_to_kf int32 [F totalN])"""
+        fs, fk = capi.bowside_struct(F)
+        ks, kk = capi.bowside_struct(KF)
+        valid = np.ascontiguousarray(kf_mp_valid, np.uint8)
+        out = np.full(int(np.sum(fk["n_kp"])), -1, np.int32)
+        n = C.c_int32()
+        check(lib().orbm_search_by_bow(self._h, C.addressof(fs), C.addressof(ks), ptr(valid), self.mfNNratio, int(self.mbCheckOrientation), int(bMapScaled),
+                                       ptr(out), C.addressof(n)))
+        return n.value, out
+
+    def isInFrustum(self, frame, pos, normal, max_dist, min_dist, viewingCosLimit=0.5, bForAllCam=True):
+        """Frame::isInFrustum + MapPoint::PredictScale for n map points (src/Frame.cc:244-312, src/MapPoint.cc:440-455).
+        -> (out int32 [n][3] = in_view, cam, level ; uvc float32 [n][3] = u, v, viewCos)"""
+        qs, keep = capi.frustum_struct(frame)
+        pos, normal, max_dist, min_dist = (np.ascontiguousarray(a, np.float32) for a in (pos, normal, max_dist, min_dist))
+        n = len(max_dist)
+        out = np.zeros((n, 3), np.int32)
+        uvc = np.zeros((n, 3), np.float32)
+        check(lib().orbm_is_in_frustum(self._h, C.addressof(qs), ptr(pos), ptr(normal), ptr(max_dist), ptr(min_dist), n, viewingCosLimit, int(bForAllCam),
+                                       ptr(out), ptr(uvc)))
+        return out, uvc
 
     def bruteforce(self, dq, nq, dt, nt):
         """dq uint8 [P][Q][32], nq int32 [P], dt uint8 [P][T][32], nt int32 [P] -> best_idx, best_d, second_d int32 [P][Q]

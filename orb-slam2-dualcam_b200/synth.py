@@ -208,3 +208,163 @@ def ba_problem(seed=0, n_kf=20, n_points=4000, n_fixed_extra=0, obs_range=(5, 10
         edge_obs=np.ascontiguousarray(np.array(e_obs, np.float64)[order]), edge_inv_sigma2=np.array(e_info, np.float64)[order],
         cam_K=RIG_K.astype(np.float32).astype(np.float64), cam_ext=np.ascontiguousarray(ext.reshape(2, 12)), cam_adj=np.ascontiguousarray(adj.reshape(2, 36)),
         gt_poses=gt_poses.reshape(nP, 12), gt_points=gt_points, planted_outlier=np.array(e_out, bool)[order])
+
+
+# ------------------------------------------------------------------------------------------------ guided searches
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+MP_DTYPE = np.dtype([("valid", "<i4"), ("cam", "<i4"), ("u", "<f4"), ("v", "<f4"), ("level", "<i4"), ("view_cos", "<f4"),
+                     ("obs_positive", "<i4"), ("desc", "u1", (32,))])
+
+
+def scale_factors(n_levels=8, f=1.2):
+    s = np.ones(n_levels, np.float32)
+    for i in range(1, n_levels):
+        s[i] = np.float32(s[i - 1] * np.float32(f))
+    return s
+
+
+def search_frame(seed, n_kp=(1000, 1000), W=640, H=480, n_levels=8, clustered=True):
+    """A dual Frame as the searches see it: undistorted keypoints (a few fall outside the image bounds, as undistortion can
+    produce), descriptors, bounds, scale factors."""
+    rng = np.random.default_rng(seed)
+    total = int(sum(n_kp))
+    kps = np.zeros(total, KP_DTYPE)
+    off = 0
+    for n in n_kp:
+        if clustered and n > 0:
+            centres = rng.uniform([20, 20], [W - 20, H - 20], (max(n // 25, 1), 2))
+            pts = centres[rng.integers(0, len(centres), n)] + rng.normal(0, 12, (n, 2))
+        else:
+            pts = rng.uniform([-3, -3], [W + 3, H + 3], (n, 2))
+        kps["x"][off:off + n] = pts[:, 0]
+        kps["y"][off:off + n] = pts[:, 1]
+        off += n
+    kps["octave"] = rng.integers(0, n_levels, total)
+    kps["angle"] = rng.uniform(0, 360, total)
+    kps["size"] = 31
+    kps["class_id"] = -1
+    bounds = np.tile(np.array([0, W, 0, H], np.float32), (len(n_kp), 1))
+    return dict(n_kp=np.array(n_kp, np.int32), kps_un=kps, desc=random_descriptors(seed + 1, total), bounds=bounds, scale_factors=scale_factors(n_levels))
+
+
+def local_map_points(seed, frame, n_mp, p_flip=0.08, frac_invalid=0.1, frac_obs0=0.05):
+    """Map points of TrackLocalMap projected into `frame`: most sit near an existing keypoint with a noisy copy of its
+    descriptor (so that windows hold the true match plus distractors), some project to empty areas."""
+    rng = np.random.default_rng(seed)
+    kps, n_kp = frame["kps_un"], frame["n_kp"]
+    first = np.concatenate([[0], np.cumsum(n_kp)])
+    total = int(first[-1])
+    mps = np.zeros(n_mp, MP_DTYPE)
+    if total == 0:
+        mps["valid"] = 1
+        mps["u"] = rng.uniform(0, 640, n_mp); mps["v"] = rng.uniform(0, 480, n_mp)
+        mps["level"] = rng.integers(0, len(frame["scale_factors"]), n_mp)
+        mps["desc"] = random_descriptors(seed + 3, n_mp)
+        return mps
+    g = rng.integers(0, total, n_mp)
+    cam = np.searchsorted(first, g, side="right") - 1
+    mps["cam"] = cam
+    mps["u"] = kps["x"][g] + rng.normal(0, 2.5, n_mp)
+    mps["v"] = kps["y"][g] + rng.normal(0, 2.5, n_mp)
+    nl = len(frame["scale_factors"])
+    mps["level"] = np.clip(kps["octave"][g] + rng.integers(-1, 2, n_mp), 0, nl - 1)
+    mps["view_cos"] = rng.choice(np.array([0.9, 0.9985, 0.999, 0.7], np.float32), n_mp)
+    mps["desc"] = random_descriptors(seed + 2, n_mp, p_flip, frame["desc"][g])
+    far = rng.random(n_mp) < 0.1
+    mps["u"][far] = rng.uniform(-50, 700, far.sum()); mps["v"][far] = rng.uniform(-50, 530, far.sum())
+    mps["valid"] = rng.random(n_mp) >= frac_invalid
+    mps["obs_positive"] = rng.random(n_mp) >= frac_obs0
+    return mps
+
+
+def motion_model_scene(seed, n_pts=(900, 800), W=640, H=480, n_levels=8, rot_outliers=0.15, p_flip=0.06):
+    """TrackWithMotionModel inputs: 3-D points seen by each camera of the rig in the last frame, the current frame's keypoints
+    (their projections under the current pose + noise + distractors) and the per-camera Rsw / tsw / K of the current frame."""
+    rng = np.random.default_rng(seed)
+    ext, _ = rig_extrinsics()
+    Rcw = _rodrigues(np.array([0.01, -0.02, 0.005]))
+    tcw = np.array([0.03, -0.01, 0.05])
+    C = len(n_pts)
+    Rsw = np.zeros((C, 9), np.float32); tsw = np.zeros((C, 3), np.float32)
+    K = RIG_K[:C].astype(np.float32)
+    cur_kps, cur_desc, last = [], [], dict(cam=[], valid=[], pos=[], desc=[], octave=[], angle=[], obs_positive=[])
+    for c in range(C):
+        R = (ext[c, :, :3] @ Rcw).astype(np.float32); t = (ext[c, :, :3] @ tcw + ext[c, :, 3]).astype(np.float32)
+        Rsw[c] = R.reshape(9); tsw[c] = t
+        n = n_pts[c]
+        uv = rng.uniform([5, 5], [W - 5, H - 5], (n, 2)); d = rng.uniform(2, 15, n)
+        pc = np.stack([(uv[:, 0] - K[c, 2]) / K[c, 0] * d, (uv[:, 1] - K[c, 3]) / K[c, 1] * d, d], 1)
+        Xw = (pc - t) @ R.astype(np.float64)          # R^T (pc - t)
+        k = np.zeros(n + n // 3, KP_DTYPE)
+        k["x"][:n] = uv[:, 0] + rng.normal(0, 1.5, n); k["y"][:n] = uv[:, 1] + rng.normal(0, 1.5, n)
+        k["x"][n:] = rng.uniform(0, W, n // 3); k["y"][n:] = rng.uniform(0, H, n // 3)
+        k["octave"] = rng.integers(0, n_levels, len(k)); k["angle"] = rng.uniform(0, 360, len(k)); k["class_id"] = -1
+        dsc = random_descriptors(seed * 7 + c, len(k))
+        cur_kps.append(k); cur_desc.append(dsc)
+        ang = (k["angle"][:n] + 12.0 + rng.normal(0, 2, n)) % 360
+        bad = rng.random(n) < rot_outliers
+        ang[bad] = rng.uniform(0, 360, bad.sum())
+        last["cam"].append(np.full(n, c)); last["valid"].append(rng.random(n) > 0.1); last["pos"].append(Xw)
+        last["desc"].append(random_descriptors(seed * 11 + c, n, p_flip, dsc[:n]))
+        last["octave"].append(np.clip(k["octave"][:n] + rng.integers(-1, 2, n), 0, n_levels - 1)); last["angle"].append(ang)
+        last["obs_positive"].append(rng.random(n) > 0.03)
+    cur = dict(n_kp=np.array([len(k) for k in cur_kps], np.int32), kps_un=np.concatenate(cur_kps), desc=np.concatenate(cur_desc),
+               bounds=np.tile(np.array([0, W, 0, H], np.float32), (C, 1)), scale_factors=scale_factors(n_levels))
+    lastd = {k: np.concatenate(v) for k, v in last.items()}
+    perm = rng.permutation(len(lastd["cam"]))         # last-frame keypoints of the two cameras interleave in no particular order here
+    lastd = {k: v[np.sort(perm)] if k == "_" else v for k, v in lastd.items()}
+    return cur, Rsw, tsw, K, lastd
+
+
+def bow_scene(seed, n_kp=(1000, 900), n_nodes=90, p_flip=0.05, frac_valid=0.6):
+    """SearchByBoW inputs: a KeyFrame and a Frame whose features are noisy copies of key-frame features that mostly fall into the
+    same vocabulary node (DBoW2::FeatureVector flattened to CSR: node ids ascending, camera-local indices ascending)."""
+    rng = np.random.default_rng(seed)
+    C = len(n_kp)
+
+    def csr(nodes_per_cam):
+        node_first, node_id, node_off, idx = [0], [], [0], []
+        for nodes in nodes_per_cam:
+            for nid in np.unique(nodes):
+                node_id.append(int(nid)); idx.extend(np.flatnonzero(nodes == nid).tolist()); node_off.append(len(idx))
+            node_first.append(len(node_id))
+        return dict(node_first=np.array(node_first, np.int32), node_id=np.array(node_id, np.int32), node_off=np.array(node_off, np.int32),
+                    idx=np.array(idx, np.int32))
+
+    kdesc, knodes, fdesc, fnodes, kang, fang = [], [], [], [], [], []
+    for c, n in enumerate(n_kp):
+        d = random_descriptors(seed * 31 + c, n)
+        nodes = rng.integers(0, n_nodes, n) * 7 + 3           # sparse node ids
+        nf = int(n * 1.1)
+        pick = rng.integers(0, max(n, 1), nf)
+        fd = random_descriptors(seed * 37 + c, nf, p_flip, d[pick]) if n else random_descriptors(seed * 37 + c, nf)
+        fn = nodes[pick].copy() if n else rng.integers(0, n_nodes, nf) * 7 + 3
+        stray = rng.random(nf) < 0.1
+        fn[stray] = rng.integers(0, n_nodes + 5, stray.sum()) * 7 + 3
+        ka = rng.normal(75.0, 3, n) % 360
+        bad = rng.random(n) < 0.1
+        ka[bad] = rng.uniform(0, 360, bad.sum())
+        kdesc.append(d); knodes.append(nodes); fdesc.append(fd); fnodes.append(fn); kang.append(ka); fang.append(rng.normal(30.0, 3, nf) % 360)
+    KF = dict(n_kp=np.array(n_kp, np.int32), desc=np.concatenate(kdesc), angle=np.concatenate(kang).astype(np.float32), **csr(knodes))
+    F = dict(n_kp=np.array([len(x) for x in fdesc], np.int32), desc=np.concatenate(fdesc), angle=np.concatenate(fang).astype(np.float32), **csr(fnodes))
+    valid = (rng.random(int(sum(n_kp))) < frac_valid).astype(np.uint8)
+    return F, KF, valid
+
+
+def frustum_scene(seed, n=3000, W=640, H=480, n_levels=8):
+    rng = np.random.default_rng(seed)
+    ext, _ = rig_extrinsics()
+    Rcw = _rodrigues(np.array([0.02, 0.05, -0.01])); tcw = np.array([0.1, 0.0, -0.2])
+    Rsw = np.zeros((2, 9), np.float32); tsw = np.zeros((2, 3), np.float32); Ow = np.zeros((2, 3), np.float32)
+    for c in range(2):
+        R = ext[c, :, :3] @ Rcw; t = ext[c, :, :3] @ tcw + ext[c, :, 3]
+        Rsw[c] = R.reshape(9); tsw[c] = t; Ow[c] = -R.T @ t
+    pos = rng.uniform([-15, -8, -5], [15, 8, 25], (n, 3)).astype(np.float32)
+    normal = pos - Ow[0] + rng.normal(0, 3.0, (n, 3))
+    normal = (normal / np.linalg.norm(normal, axis=1, keepdims=True)).astype(np.float32)
+    d = np.linalg.norm(pos - Ow[0], axis=1)
+    max_dist = (d * rng.uniform(0.6, 3.0, n)).astype(np.float32)
+    min_dist = (max_dist / 1.2 ** (n_levels - 1)).astype(np.float32)
+    frame = dict(Rsw=Rsw, tsw=tsw, Ow=Ow, K=RIG_K.astype(np.float32), bounds=np.tile(np.array([0, W, 0, H], np.float32), (2, 1)), n_levels=n_levels,
+                 log_scale_factor=np.float32(np.log(np.float32(1.2))))
+    return frame, pos, normal, max_dist, min_dist

@@ -231,3 +231,68 @@ def ba_normal_equations(p, huber_delta=HUBER_MONO):
                                   Hpl.ctypes.data, C.addressof(chi2))
     assert k == K
     return Hpp, bp, Hll, bl, Hpl, chi2.value
+
+
+# ------------------------------------------------------------------------------------------------ guided searches
+def _capi():
+    from orbslam2_dualcam_b200 import capi
+    return capi
+
+
+def search_by_projection(frame, mps, th=3.0, nnratio=0.6, blocked=None):
+    cp = _capi()
+    fs, keep = cp.frame_struct(frame)
+    mps = np.ascontiguousarray(mps, cp.MP_DTYPE)
+    total = int(np.sum(keep["n_kp"]))
+    blocked = np.zeros(total, np.uint8) if blocked is None else np.ascontiguousarray(blocked, np.uint8)
+    out = np.full(total, -1, np.int32)
+    L = lib()
+    L.orc_search_by_projection.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.orc_search_by_projection.restype = C.c_int
+    n = L.orc_search_by_projection(C.addressof(fs), mps.ctypes.data, len(mps), th, nnratio, blocked.ctypes.data, out.ctypes.data)
+    return n, out
+
+
+def search_by_projection_last(cur, Rsw, tsw, K, last, th, check_ori=True, map_scaled=True, blocked=None):
+    cp = _capi()
+    fs, keep = cp.frame_struct(cur)
+    ls, lkeep = cp.lastframe_struct(last)
+    Rsw, tsw, K = (np.ascontiguousarray(a, np.float32) for a in (Rsw, tsw, K))
+    total = int(np.sum(keep["n_kp"]))
+    blocked = np.zeros(total, np.uint8) if blocked is None else np.ascontiguousarray(blocked, np.uint8)
+    out = np.full(total, -1, np.int32)
+    per_cam = np.zeros(len(keep["n_kp"]), np.int32)
+    L = lib()
+    L.orc_search_by_projection_last.argtypes = [C.c_void_p] * 5 + [C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_search_by_projection_last.restype = C.c_int
+    n = L.orc_search_by_projection_last(C.addressof(fs), Rsw.ctypes.data, tsw.ctypes.data, K.ctypes.data, C.addressof(ls), th, int(check_ori), int(map_scaled),
+                                        blocked.ctypes.data, out.ctypes.data, per_cam.ctypes.data)
+    return n, out, per_cam
+
+
+def search_by_bow(F, KF, kf_mp_valid, nnratio=0.7, check_ori=True, map_scaled=True):
+    cp = _capi()
+    fs, fk = cp.bowside_struct(F)
+    ks, kk = cp.bowside_struct(KF)
+    valid = np.ascontiguousarray(kf_mp_valid, np.uint8)
+    out = np.full(int(np.sum(fk["n_kp"])), -1, np.int32)
+    L = lib()
+    L.orc_search_by_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    L.orc_search_by_bow.restype = C.c_int
+    n = L.orc_search_by_bow(C.addressof(fs), C.addressof(ks), valid.ctypes.data, nnratio, int(check_ori), int(map_scaled), out.ctypes.data)
+    return n, out
+
+
+def is_in_frustum(frame, pos, normal, max_dist, min_dist, cos_limit=0.5, for_all=True):
+    cp = _capi()
+    qs, keep = cp.frustum_struct(frame)
+    pos, normal, max_dist, min_dist = (np.ascontiguousarray(a, np.float32) for a in (pos, normal, max_dist, min_dist))
+    n = len(max_dist)
+    out = np.zeros((n, 3), np.int32)
+    uvc = np.zeros((n, 3), np.float32)
+    L = lib()
+    L.orc_is_in_frustum.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_is_in_frustum.restype = None
+    L.orc_is_in_frustum(C.addressof(qs), pos.ctypes.data, normal.ctypes.data, max_dist.ctypes.data, min_dist.ctypes.data, n, cos_limit, int(for_all),
+                        out.ctypes.data, uvc.ctypes.data)
+    return out, uvc
