@@ -320,6 +320,29 @@ int  orbba_stage_ms(orbba_t*, double* ms1, int* calls);
  * errors + LM decision}, summed over the steps recorded since the last call; *steps = LM steps summed. */
 int  orbba_kernel_ms(orbba_t*, double* ms6, int* steps);
 
+/* ------------------------------------------------------------------------------------------------
+ * GlobalBundleAdjustemnt for large maps, on one GPU or landmark-partitioned over the GPUs of a node (BASELINE.json configs[4]:
+ * 2000 key frames x 2 cameras, 200k map points).  One process per GPU; key-frame poses are replicated, rank r owns the map
+ * points `index mod world == r` and their edges; per LM trial ONE NCCL all-reduce (sum, FP64) of the reduced camera system
+ * [Hschur | bschur] and one of two scalars; the dense Cholesky of the reduced system (cuSOLVER) and the LM policy are replicated.
+ *   rank 0:      orbba_dist_unique_id(id)  -> broadcast the 128 bytes to the other ranks by any means (torch.distributed, MPI, a file)
+ *   every rank:  orbba_dist_create(&h, device, rank, world, id)  (world == 1: id may be NULL, no NCCL needed)
+ *                orbba_dist_optimize(h, shard, ...)   collective
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct orbgba orbgba_t;
+int  orbba_dist_unique_id(uint8_t* id128);
+int  orbba_dist_create(orbgba_t** out, int device, int rank, int world, const uint8_t* id128);
+void orbba_dist_destroy(orbgba_t*);
+long long orbba_dist_launch_count(const orbgba_t*);
+/* Optimizer::BundleAdjustment(vpKFs, vpMP, nIterations, pbStopFlag, nLoopKF, bRobust) (src/Optimizer.cc:70-248) on this rank's shard:
+ * `shard` holds ALL poses (identical on every rank) and this rank's points / edges (edge_point indexes the local point array).
+ * poses_out [n_poses][12] (identical on every rank), points_out [n_points][3] (local points).  huber_delta <= 0: no kernel. */
+int  orbba_dist_optimize(orbgba_t*, const orbba_problem_t* shard, int iterations, double huber_delta, const volatile uint8_t* stop,
+                         double* poses_out, double* points_out, orbba_stats_t* stats);
+/* device milliseconds spent in the [Hschur | bschur] all-reduce and in the dense solve during the last optimize call, and the
+ * bytes this rank contributed to all-reduces */
+int  orbba_dist_timing(const orbgba_t*, double* allreduce_ms, double* solve_ms, double* allreduce_bytes);
+
 #ifdef __cplusplus
 }
 #endif

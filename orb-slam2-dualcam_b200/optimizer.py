@@ -148,3 +148,75 @@ class Optimizer:
         ms, n = C.c_double(), C.c_int()
         check(lib().orbba_stage_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+# ------------------------------------------------------------------------------------------------ distributed global BA
+def shard_problem(problem, rank, world):
+    """Landmark partition of SURVEY.md §8(e): rank r keeps the map points `index % world == r` and their edges; poses, fixed
+    flags and cameras are replicated.  Returns a problem dict whose edge_point indexes the local point array, plus the global
+    indices of the kept points / edges (`point_ids`, `edge_ids`) for scattering results back."""
+    pts = np.arange(rank, len(problem["points"]), world)
+    keep = (problem["edge_point"] % world) == rank
+    out = dict(problem)
+    out["points"] = np.ascontiguousarray(problem["points"][pts])
+    for k in ("edge_pose", "edge_cam", "edge_obs", "edge_inv_sigma2"):
+        out[k] = np.ascontiguousarray(problem[k][keep])
+    out["edge_point"] = np.ascontiguousarray(problem["edge_point"][keep] // world).astype(np.int32)
+    out["point_ids"] = pts
+    out["edge_ids"] = np.flatnonzero(keep)
+    return out
+
+
+class DistributedOptimizer:
+    """Optimizer::GlobalBundleAdjustemnt over the GPUs of a node (one process per GPU): include/orbslam2_dualcam_b200.h orbba_dist_*."""
+
+    def __init__(self, rank=0, world=1, device=0, unique_id=None):
+        self._h = None
+        h = C.c_void_p()
+        uid = None if unique_id is None else (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        check(lib().orbba_dist_create(C.byref(h), device, rank, world, uid))
+        self._h, self._uid = h, uid
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        check(lib().orbba_dist_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch_distributed(cls, device):
+        """Creates the library's own NCCL communicator next to an initialised torch.distributed group (the 128-byte id travels
+        through broadcast_object_list)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.unique_id() if rank == 0 else None] if world > 1 else [None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        return cls(rank, world, device, box[0])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orbba_dist_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def GlobalBundleAdjustemnt(self, shard, nIterations=5, pbStopFlag=None, bRobust=True):
+        """collective; -> (poses [nP][12] identical on every rank, local points [nL_local][3], stats)"""
+        s, keep = problem_struct(shard)
+        poses = np.zeros((s.n_poses, 12)); points = np.zeros((s.n_points, 3))
+        st = StatsC()
+        stop = None if pbStopFlag is None else pbStopFlag.ctypes.data
+        rc = lib().orbba_dist_optimize(self._h, C.addressof(s), nIterations, TH_HUBER_MONO if bRobust else 0.0, stop, ptr(poses), ptr(points), C.addressof(st))
+        if rc != -5:
+            check(rc)
+        return poses, points, st.asdict()
+
+    def timing(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        check(lib().orbba_dist_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(allreduce_ms=a.value, solve_ms=b.value, allreduce_bytes=c.value)
+
+    def launch_count(self):
+        return int(lib().orbba_dist_launch_count(self._h))

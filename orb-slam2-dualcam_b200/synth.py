@@ -368,3 +368,62 @@ def frustum_scene(seed, n=3000, W=640, H=480, n_levels=8):
     frame = dict(Rsw=Rsw, tsw=tsw, Ow=Ow, K=RIG_K.astype(np.float32), bounds=np.tile(np.array([0, W, 0, H], np.float32), (2, 1)), n_levels=n_levels,
                  log_scale_factor=np.float32(np.log(np.float32(1.2))))
     return frame, pos, normal, max_dist, min_dist
+
+
+def gba_problem(seed=0, n_kf=2000, n_points=200000, obs=8, outlier_frac=0.02, W=640, H=480, pose_noise=(0.01, 0.2), point_noise=0.03):
+    """Synthetic GlobalBundleAdjustemnt input, vectorised: a long smooth rig trajectory, every map point
+    placed in front of a random key frame and observed by up to `obs` neighbouring key frames (whichever camera of the rig sees it).
+    Same dict layout as ba_problem; pose 0 is fixed."""
+    rng = np.random.default_rng(seed)
+    ext, adj = rig_extrinsics()
+    s = np.arange(n_kf) / max(n_kf - 1, 1)
+    L = 0.15 * n_kf                                            # 15 cm between key frames
+    gt = np.zeros((n_kf, 3, 4))
+    for i in range(n_kf):
+        R = _rodrigues(np.array([0.02 * np.sin(6 * s[i]), 0.8 * np.sin(3 * s[i]), 0.01 * s[i]]))
+        t = np.array([L * s[i], 0.2 * np.sin(5 * s[i]), 0.3 * L * np.sin(2 * s[i])])
+        gt[i, :, :3] = R.T
+        gt[i, :, 3] = -R.T @ t
+    K = RIG_K
+    k0 = rng.integers(0, n_kf, n_points); c0 = rng.integers(0, 2, n_points)
+    u = rng.uniform(40, W - 40, n_points); v = rng.uniform(40, H - 40, n_points); d = rng.uniform(2, 12, n_points)
+    pc = np.stack([(u - K[c0, 2]) / K[c0, 0] * d, (v - K[c0, 3]) / K[c0, 1] * d, d], 1)
+    pr = np.einsum("nji,nj->ni", ext[c0][:, :, :3], pc - ext[c0][:, :, 3])
+    X = np.einsum("nji,nj->ni", gt[k0][:, :, :3], pr - gt[k0][:, :, 3])
+    inv_sigma2 = (1.0 / (scale_factors(8).astype(np.float64) ** 2)).astype(np.float32)
+    e_pose, e_pt, e_cam, e_obs = [], [], [], []
+    for dk in range(-(obs // 2), obs - obs // 2):
+        kk = k0 + dk
+        ok = (kk >= 0) & (kk < n_kf)
+        kk = np.clip(kk, 0, n_kf - 1)
+        prr = np.einsum("nij,nj->ni", gt[kk][:, :, :3], X) + gt[kk][:, :, 3]
+        seen = np.zeros(n_points, bool)
+        for c in (0, 1):
+            pcc = prr @ ext[c, :, :3].T + ext[c, :, 3]
+            z = np.where(pcc[:, 2] > 0.2, pcc[:, 2], 1.0)
+            uu = K[c, 0] * pcc[:, 0] / z + K[c, 2]; vv = K[c, 1] * pcc[:, 1] / z + K[c, 3]
+            vis = ok & ~seen & (pcc[:, 2] > 0.2) & (uu >= 0) & (uu < W) & (vv >= 0) & (vv < H)
+            idx = np.flatnonzero(vis)
+            e_pose.append(kk[idx]); e_pt.append(idx); e_cam.append(np.full(len(idx), c)); e_obs.append(np.stack([uu[idx], vv[idx]], 1))
+            seen |= vis
+    e_pose = np.concatenate(e_pose); e_pt = np.concatenate(e_pt); e_cam = np.concatenate(e_cam); e_obs = np.concatenate(e_obs)
+    octave = rng.integers(0, 8, len(e_pose))
+    noise = rng.normal(0, 1, (len(e_pose), 2)) * (1.2 ** octave)[:, None]
+    out = rng.random(len(e_pose)) < outlier_frac
+    noise[out] += rng.choice([-20.0, 20.0], (int(out.sum()), 2))
+    e_obs = (e_obs + noise).astype(np.float32).astype(np.float64)
+    order = np.lexsort((e_pose, e_pt))
+    poses = gt.copy()
+    for i in range(1, n_kf):
+        dR = _rodrigues(rng.normal(0, np.deg2rad(pose_noise[1]) / np.sqrt(3), 3))
+        poses[i, :, :3] = dR @ poses[i, :, :3]
+        poses[i, :, 3] = dR @ poses[i, :, 3] + rng.normal(0, pose_noise[0] / np.sqrt(3), 3)
+    points = X + rng.normal(0, point_noise / np.sqrt(3), X.shape)
+    fixed = np.zeros(n_kf, np.uint8)
+    fixed[0] = 1
+    return dict(poses=np.ascontiguousarray(poses.astype(np.float32).astype(np.float64).reshape(n_kf, 12)), pose_fixed=fixed,
+                points=np.ascontiguousarray(points.astype(np.float32).astype(np.float64)),
+                edge_pose=e_pose[order].astype(np.int32), edge_point=e_pt[order].astype(np.int32), edge_cam=e_cam[order].astype(np.int32),
+                edge_obs=np.ascontiguousarray(e_obs[order]), edge_inv_sigma2=inv_sigma2[octave][order].astype(np.float64),
+                cam_K=RIG_K.astype(np.float32).astype(np.float64), cam_ext=np.ascontiguousarray(ext.reshape(2, 12)), cam_adj=np.ascontiguousarray(adj.reshape(2, 36)),
+                gt_poses=gt.reshape(n_kf, 12), gt_points=X, planted_outlier=out[order])
