@@ -289,6 +289,9 @@ typedef struct orbba orbba_t;
 int  orbba_create(orbba_t** out, int device, int max_problems);
 void orbba_destroy(orbba_t*);
 int  orbba_set_stream(orbba_t*, void* cuda_stream);
+/* optional second stream for orbba_upload (host->device copies + index kernels); orbba_run waits for the upload through an event.
+ * Lets the upload of one handle overlap with the run of another handle that shares the compute stream.  NULL = use the compute stream. */
+int  orbba_set_copy_stream(orbba_t*, void* cuda_stream);
 int  orbba_synchronize(orbba_t*);
 long long orbba_launch_count(const orbba_t*);
 

@@ -50,6 +50,7 @@ SIGNATURES = {
     "orbba_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
     "orbba_destroy": (None, [vp]),
     "orbba_set_stream": (C.c_int, [vp, vp]),
+    "orbba_set_copy_stream": (C.c_int, [vp, vp]),
     "orbba_synchronize": (C.c_int, [vp]),
     "orbba_launch_count": (C.c_longlong, [vp]),
     "orbba_local": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp]),

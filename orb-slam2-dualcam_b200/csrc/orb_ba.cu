@@ -462,30 +462,43 @@ __global__ void __launch_bounds__(128) k_pairs(BABatch A, const int* blkI_first)
         const int ch = P.chunk0 + item;
         const int2* T = A.tuples + P.tup0 + A.chunk_start[ch];
         const int len = A.chunk_len[ch];
-        double acc[36];
+        // two lanes per tuple: lane parity h owns rows 3h..3h+2 of the 6x6 block (half the accumulators -> twice the occupancy);
+        // both lanes read the same B_b (one transaction), each reads its half of Y_a
+        const int h = lane & 1, slot = lane >> 1;
+        double acc[18];
 #pragma unroll
-        for (int i = 0; i < 36; i++) acc[i] = 0;
-        for (int t = lane; t < len; t += 32) {
+        for (int i = 0; i < 18; i++) acc[i] = 0;
+        for (int t = slot; t < len; t += 16) {
             const int2 ab = T[t];
-            const double2* Yp = reinterpret_cast<const double2*>(A.Y + 18 * (size_t)ab.x);
+            const double* Yp = A.Y + 18 * (size_t)ab.x + 9 * h;
             const double2* Bp = reinterpret_cast<const double2*>(A.B + 18 * (size_t)ab.y);
-            double y[18], bq[18];
+            double y[9], bq[18];
+            if (h == 0) {
 #pragma unroll
-            for (int i = 0; i < 9; i++) { const double2 a = Yp[i], c = Bp[i]; y[2 * i] = a.x; y[2 * i + 1] = a.y; bq[2 * i] = c.x; bq[2 * i + 1] = c.y; }
+                for (int i = 0; i < 4; i++) { const double2 a = reinterpret_cast<const double2*>(Yp)[i]; y[2 * i] = a.x; y[2 * i + 1] = a.y; }
+                y[8] = Yp[8];
+            } else {
+                y[0] = Yp[0];
 #pragma unroll
-            for (int r = 0; r < 6; r++)
+                for (int i = 0; i < 4; i++) { const double2 a = reinterpret_cast<const double2*>(Yp + 1)[i]; y[1 + 2 * i] = a.x; y[2 + 2 * i] = a.y; }
+            }
+#pragma unroll
+            for (int i = 0; i < 9; i++) { const double2 c = Bp[i]; bq[2 * i] = c.x; bq[2 * i + 1] = c.y; }
+#pragma unroll
+            for (int r = 0; r < 3; r++)
 #pragma unroll
                 for (int c = 0; c < 6; c++) acc[r * 6 + c] += y[r * 3] * bq[c * 3] + y[r * 3 + 1] * bq[c * 3 + 1] + y[r * 3 + 2] * bq[c * 3 + 2];
         }
-        double mine0 = 0, mine1 = 0;
 #pragma unroll
-        for (int i = 0; i < 36; i++) {
-            const double s = warp_sum(acc[i]);
-            if ((i & 31) == lane) { if (i < 32) mine0 = s; else mine1 = s; }
+        for (int i = 0; i < 18; i++) {
+#pragma unroll
+            for (int o = 16; o > 1; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
         }
-        double* out = A.partial + 36 * (size_t)ch;
-        out[lane] = mine0;
-        if (lane < 4) out[32 + lane] = mine1;
+        if (lane < 2) {
+            double* out = A.partial + 36 * (size_t)ch + 18 * h;
+#pragma unroll
+            for (int i = 0; i < 18; i++) out[i] = acc[i];
+        }
     } else {
         const int k = item - P.nChunksMax;
         const int kg = P.k0 + k;
@@ -805,6 +818,9 @@ __global__ void k_stats(BABatch A) {   // one CTA
 struct orbba {
     int device = 0, max_problems = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // optional: uploads (host->device + index kernels) go here, runs wait for them
+    cudaEvent_t up_ev = nullptr;
+    bool up_pending = false;
     int n = 0;
     BABatch A;                               // device pointers of the uploaded batch
     std::vector<BAProb> probs;
@@ -834,6 +850,7 @@ static void orbba_free(orbba* b) {
     if (b->h_stage) cudaFreeHost(b->h_stage);
     if (b->h_flags) cudaFreeHost(b->h_flags);
     if (b->ev[0]) { cudaEventDestroy(b->ev[0]); cudaEventDestroy(b->ev[1]); }
+    if (b->up_ev) cudaEventDestroy(b->up_ev);
     for (cudaEvent_t e : b->kev) cudaEventDestroy(e);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
@@ -923,6 +940,7 @@ int orbba_create(orbba_t** out, int device, int max_problems) {
     if (ce == cudaSuccess) { memset(b->h_flags, 0, 4 * sizeof(int)); ce = cudaHostGetDevicePointer((void**)&b->d_flags, b->h_flags, 0); }
     if (ce == cudaSuccess) ce = cudaEventCreate(&b->ev[0]);
     if (ce == cudaSuccess) ce = cudaEventCreate(&b->ev[1]);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->up_ev, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     if (ce != cudaSuccess) { int rc = orbhost::check_cuda(ce, "orbba_create", __FILE__, __LINE__); orbba_free(b); return rc; }
     b->stream = b->own_stream;
@@ -937,6 +955,13 @@ int orbba_set_stream(orbba_t* b, void* s) {
     int rc = finish(b);
     if (rc != ORB_OK) return rc;
     b->stream = s ? (cudaStream_t)s : b->own_stream;
+    return ORB_OK;
+}
+int orbba_set_copy_stream(orbba_t* b, void* s) {
+    if (!b) ORB_FAIL(ORB_E_INVALID, "orbba_set_copy_stream: NULL handle");
+    int rc = finish(b);
+    if (rc != ORB_OK) return rc;
+    b->copy_stream = (cudaStream_t)s;
     return ORB_OK;
 }
 int orbba_synchronize(orbba_t* b) {
@@ -1155,8 +1180,8 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     A.stop = b->d_flags; A.n_active = b->d_flags + 1;
     b->nbE = nbE; b->nbL = nbL; b->nbP = nbP; b->nbI = nbI; b->Ktot = (int)Ktot; b->max_n = max_n;
     b->Etot = Etot; b->Ltot = Ltot; b->Ptot = Ptot;
-    // ---- upload + index construction on the device
-    cudaStream_t st = b->stream;
+    // ---- upload + index construction on the device (on the copy stream when one is set: overlaps with a run of another handle)
+    cudaStream_t st = b->copy_stream ? b->copy_stream : b->stream;
     ORB_CUDA(cudaMemcpyAsync(D, H, static_bytes, cudaMemcpyHostToDevice, st));
     ORB_CUDA(cudaMemsetAsync(D + o_state, 0, sizeof(BAState) * n, st));
     if (eofTot) ORB_CUDA(cudaMemsetAsync(D + o_eof, 0xff, 4 * (size_t)eofTot, st));
@@ -1169,6 +1194,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     }
     b->launches += 1;
     ORB_CUDA(cudaGetLastError());
+    if (b->copy_stream) { ORB_CUDA(cudaEventRecord(b->up_ev, st)); b->up_pending = true; }
     b->n = n;
     return ORB_OK;
 }
@@ -1183,6 +1209,7 @@ int orbba_run(orbba_t* b, int its1, int its2, double huber_delta, double chi2_th
     int rc = finish(b);
     if (rc != ORB_OK) return rc;
     b->A.its1 = its1; b->A.its2 = its2; b->A.delta = huber_delta; b->A.chi2_th = chi2_th;
+    if (b->up_pending) { ORB_CUDA(cudaStreamWaitEvent(b->stream, b->up_ev, 0)); b->up_pending = false; }
     if (b->profile) ORB_CUDA(cudaEventRecord(b->ev[0], b->stream));
     k_reset<<<b->nbE, BA_TE, 0, b->stream>>>(b->A, b->h_flags[0] != 0);
     b->launches++;

@@ -96,15 +96,18 @@ __global__ void __launch_bounds__(128) resize_level_kernel(const uint8_t* __rest
 // the same region, and the iniTh -> minTh fallback is decided per cell -- exactly what 815 separate cv::FAST calls do.
 #define FAST_THREADS 128
 
+// floor(i / d) for the small operands of this kernel: m = ceil(2^20 / d), exact while i * d < 2^20
+__device__ __forceinline__ int fastdiv20(int i, unsigned m) { return (int)(((unsigned)i * m) >> 20); }
+
 __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_constant__ ExtractParams P,
                                                                   uint32_t* __restrict__ cand, int* __restrict__ cand_count,
                                                                   int tile_cap, int pix_cap) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* tile = smem;                                  // (dh+6) x tp raw pixels
+    uint8_t* tile = smem;                                  // (dh+6) rows of raw pixels, 4-byte aligned like the source rows
     uint8_t* score = tile + tile_cap;                      // dh x dw
     uint16_t* list = reinterpret_cast<uint16_t*>(score + pix_cap);   // pixels that pass the compass pre-test
-    uint16_t* list2 = list + pix_cap;                      // pixels that are corners at min(iniTh, minTh)
-    __shared__ int s_n1, s_n2, s_cnt_ini, s_cnt_min, s_base, s_emit;
+    uint16_t* list2 = list + pix_cap;                      // pixels that are corners at the current threshold
+    __shared__ int s_n1, s_n2, s_keep, s_base, s_emit;
 
     const int img = blockIdx.y;
     int cell = blockIdx.x;
@@ -119,99 +122,103 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
     const int dw = x1 - x0, dh = y1 - y0;
     if (dw <= 0 || dh <= 0) return;
     const int tw = dw + 6, th = dh + 6;
-    const int tp = (tw + 3) & ~3;
     const int tid = threadIdx.x;
-    if (tid == 0) { s_n1 = 0; s_n2 = 0; s_cnt_ini = 0; s_cnt_min = 0; s_emit = 0; }
-
-    // ---- stage the tile: absolute pixel (16 + x0 - 3 + tx, 16 + y0 - 3 + ty)
-    const uint8_t* src = P.base[l] + (unsigned long long)img * L.img_stride + (size_t)(16 + y0 - 3) * L.pitch + (16 + x0 - 3);
-    for (int i = tid; i < tw * th; i += FAST_THREADS) {
-        const int ty = i / tw, tx = i - ty * tw;
-        tile[ty * tp + tx] = __ldg(src + (size_t)ty * L.pitch + tx);
-    }
-    __syncthreads();
-
-    const int iniTh = min(max(P.iniTh, 0), 255), minTh = min(max(P.minTh, 0), 255);
-    const int tlow = min(iniTh, minTh);
-    const int npix = dw * dh;
     const unsigned lane = tid & 31;
 
-    // ---- pass 1: compass pre-test, warp-compacted list of survivors
-    for (int i0 = 0; i0 < npix; i0 += FAST_THREADS) {
-        const int i = i0 + tid;
-        bool pass = false;
-        if (i < npix) {
-            const int y = i / dw, x = i - y * dw;
-            const uint8_t* p = tile + (y + 3) * tp + (x + 3);
-            pass = fast16_pretest(p[0], p[3 * tp], p[3], p[-3 * tp], p[-3], tlow);
-            score[i] = 0;
+    // ---- stage the tile with aligned 32-bit loads: absolute pixel (16 + x0 - 3 + tx, 16 + y0 - 3 + ty) -> tile[ty * tp + dx + tx]
+    const int gx0 = 16 + x0 - 3, ax0 = gx0 & ~3, dx = gx0 - ax0;
+    const int nw = (dx + tw + 3) >> 2, tp = nw * 4;
+    {
+        const uint8_t* src = P.base[l] + (unsigned long long)img * L.img_stride + (size_t)(16 + y0 - 3) * L.pitch + ax0;
+        const unsigned m_nw = ((1u << 20) + nw - 1) / nw;
+        uint32_t* tw32 = reinterpret_cast<uint32_t*>(tile);
+        for (int i = tid; i < nw * th; i += FAST_THREADS) {
+            const int ty = fastdiv20(i, m_nw), wx = i - ty * nw;
+            tw32[i] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)ty * L.pitch) + wx);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(&s_n1, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (pass) list[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
     }
-    __syncthreads();
-
-    // ---- pass 2: exact corner score of the survivors
-    const int n1 = s_n1;
+    const int npix = dw * dh;
+    for (int i = tid; i < ((npix + 3) >> 2); i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0;
+    const unsigned m_dw = ((1u << 20) + dw - 1) / dw;
+    const uint8_t* T0 = tile + 3 * tp + dx + 3;            // pixel (0, 0) of the detection region
+    const int iniTh = min(max(P.iniTh, 0), 255), minTh = min(max(P.minTh, 0), 255);
     const int rdx[16] = ORB_RING_DX, rdy[16] = ORB_RING_DY;
-    for (int e = tid; e < n1; e += FAST_THREADS) {
-        const int i = list[e];
-        const int y = i / dw, x = i - y * dw;
-        const uint8_t* p = tile + (y + 3) * tp + (x + 3);
-        int ring[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) ring[k] = p[rdy[k] * tp + rdx[k]];
-        const int s = fast16_score(p[0], ring);
-        if (s >= tlow && s > 0) {
-            score[i] = (uint8_t)s;
-            list2[atomicAdd(&s_n2, 1)] = (uint16_t)i;
-        }
-    }
-    __syncthreads();
 
-    // ---- pass 3: strict 3x3 maximum inside the cell (threshold independent)
-    const int n2 = s_n2;
-    for (int e = tid; e < n2; e += FAST_THREADS) {
-        const int i = list2[e];
-        const int y = i / dw, x = i - y * dw;
-        const int s = score[i];
-        bool ismax = true;
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-                if (dx == 0 && dy == 0) continue;
-                const int xx = x + dx, yy = y + dy;
-                if (xx < 0 || xx >= dw || yy < 0 || yy >= dh) continue;
-                if (score[yy * dw + xx] >= s) ismax = false;
+    // cv::FAST(cell, iniTh) and, only when that finds nothing, cv::FAST(cell, minTh)   (src/ORBextractor.cc:809-816)
+    int t = iniTh, nkeep = 0;
+    for (int round = 0; round < 2; round++) {
+        if (tid == 0) { s_n1 = 0; s_n2 = 0; s_keep = 0; s_emit = 0; }
+        __syncthreads();
+        // ---- pass 1: compass pre-test at threshold t, warp-compacted list of survivors
+        for (int i0 = 0; i0 < npix; i0 += FAST_THREADS) {
+            const int i = i0 + tid;
+            bool pass = false;
+            if (i < npix) {
+                const int y = fastdiv20(i, m_dw), x = i - y * dw;
+                const uint8_t* p = T0 + y * tp + x;
+                pass = fast16_pretest(p[0], p[3 * tp], p[3], p[-3 * tp], p[-3], t);
             }
-        if (ismax) {
-            if (s >= iniTh) atomicAdd(&s_cnt_ini, 1);
-            if (s >= minTh) atomicAdd(&s_cnt_min, 1);
-            list2[e] = (uint16_t)(i | 0x8000);
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_n1, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) list[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
         }
+        __syncthreads();
+        // ---- pass 2: exact corner score of the survivors
+        const int n1 = s_n1;
+        for (int e = tid; e < n1; e += FAST_THREADS) {
+            const int i = list[e];
+            const int y = fastdiv20(i, m_dw), x = i - y * dw;
+            const uint8_t* p = T0 + y * tp + x;
+            int ring[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) ring[k] = p[rdy[k] * tp + rdx[k]];
+            const int s = fast16_score(p[0], ring);
+            if (s >= t && s > 0) {
+                score[i] = (uint8_t)s;
+                list2[atomicAdd(&s_n2, 1)] = (uint16_t)i;
+            }
+        }
+        __syncthreads();
+        // ---- pass 3: strict 3x3 maximum inside the cell (non-corners score 0)
+        const int n2 = s_n2;
+        for (int e = tid; e < n2; e += FAST_THREADS) {
+            const int i = list2[e];
+            const int y = fastdiv20(i, m_dw), x = i - y * dw;
+            const int s = score[i];
+            bool ismax = true;
+#pragma unroll
+            for (int ddy = -1; ddy <= 1; ddy++)
+#pragma unroll
+                for (int ddx = -1; ddx <= 1; ddx++) {
+                    if (ddx == 0 && ddy == 0) continue;
+                    const int xx = x + ddx, yy = y + ddy;
+                    if (xx < 0 || xx >= dw || yy < 0 || yy >= dh) continue;
+                    if (score[yy * dw + xx] >= s) ismax = false;
+                }
+            if (ismax) { atomicAdd(&s_keep, 1); list2[e] = (uint16_t)(i | 0x8000); }
+        }
+        __syncthreads();
+        nkeep = s_keep;
+        if (nkeep > 0 || minTh >= iniTh) break;            // found corners, or the fallback threshold cannot find more
+        t = minTh;
+        __syncthreads();
     }
-    __syncthreads();
-
-    // ---- emit: FAST(iniTh) result, or FAST(minTh) result when the former is empty (src/ORBextractor.cc:809-816)
-    const int t = s_cnt_ini > 0 ? iniTh : minTh;
-    const int nkeep = s_cnt_ini > 0 ? s_cnt_ini : s_cnt_min;
     if (nkeep == 0) return;
+
+    // ---- emit (unordered; the reference order is a function of (x, y), see cand_order_key)
     if (tid == 0) s_base = atomicAdd(&cand_count[img * P.nlevels + l], nkeep);
     __syncthreads();
     uint32_t* out = cand + (size_t)img * P.cand_per_image + L.cand_off;
+    const int n2 = s_n2;
     for (int e = tid; e < n2; e += FAST_THREADS) {
         const int v = list2[e];
         if (!(v & 0x8000)) continue;
         const int i = v & 0x7fff;
-        const int s = score[i];
-        if (s < t) continue;
-        const int y = i / dw, x = i - y * dw;
+        const int y = fastdiv20(i, m_dw), x = i - y * dw;
         const int pos = s_base + atomicAdd(&s_emit, 1);
-        if (pos < L.cand_cap) out[pos] = cand_pack(x0 + x, y0 + y, s);
+        if (pos < L.cand_cap) out[pos] = cand_pack(x0 + x, y0 + y, score[i]);
     }
 }
 
@@ -365,11 +372,13 @@ __global__ void __launch_bounds__(QT_THREADS) quadtree_kernel(const __grid_const
 #define DESC_WARPS 4
 #define RAW_R 21
 #define RAW_W 43
-#define RAW_P 44
+#define RAW_P 52               // row pitch in bytes: 13 words (odd) -> lanes on different rows hit different banks; holds 43 + 3 alignment bytes
+#define RAW_NW 12              // aligned words staged per row (covers 3 alignment bytes + 43 pixels)
 #define BLR_R 18
 #define BLR_W 37
 #define BLR_P 40
 #define ROWP_P 38
+#define SEG 19                 // the 37 outputs of a blur line are produced as two sliding runs of 19 / 18
 
 __device__ const int8_t g_pattern[1024] = {ORB_RBRIEF_PATTERN_VALUES};
 
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(const __grid_
                                                                    orb_keypoint_t* __restrict__ kps, uint8_t* __restrict__ desc,
                                                                    int* __restrict__ counts, int kp_capacity,
                                                                    const int* __restrict__ umax) {
-    __shared__ DescSmem sm[DESC_WARPS];
+    __shared__ __align__(16) DescSmem sm[DESC_WARPS];
     __shared__ __align__(4) int8_t spat[1024];
     __shared__ int s_umax[16];
     const int img = blockIdx.y;
@@ -418,12 +427,26 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(const __grid_
     const uint8_t* I = P.base[l] + (unsigned long long)img * L.img_stride;
     DescSmem& S = sm[warp];
 
-    for (int i = lane; i < RAW_W * RAW_W; i += 32) {
-        const int ry = i / RAW_W, rx = i - ry * RAW_W;
-        const int yy = reflect101_dev(cy + ry - RAW_R, L.h), xx = reflect101_dev(cx + rx - RAW_R, L.w);
-        S.raw[ry * RAW_P + rx] = __ldg(I + (size_t)yy * L.pitch + xx);
+    // ---- 43x43 raw patch.  Interior keypoints (the common case): 12 aligned words per row; raw[ry * RAW_P + dx + rx] holds
+    //      pixel (cx - 21 + rx, cy - 21 + ry).  Patches that leave the image: REFLECT_101 byte gather (dx = 0).
+    int dx = 0;
+    if (cx - RAW_R >= 0 && cx + RAW_R < L.w && cy - RAW_R >= 0 && cy + RAW_R < L.h) {
+        const int gx0 = cx - RAW_R, ax0 = gx0 & ~3;
+        dx = gx0 - ax0;
+        const uint8_t* src = I + (size_t)(cy - RAW_R) * L.pitch + ax0;
+        for (int i = lane; i < RAW_W * RAW_NW; i += 32) {
+            const int ry = i / RAW_NW, wx = i - ry * RAW_NW;
+            reinterpret_cast<uint32_t*>(S.raw + ry * RAW_P)[wx] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)ry * L.pitch) + wx);
+        }
+    } else {
+        for (int i = lane; i < RAW_W * RAW_W; i += 32) {
+            const int ry = i / RAW_W, rx = i - ry * RAW_W;
+            const int yy = reflect101_dev(cy + ry - RAW_R, L.h), xx = reflect101_dev(cx + rx - RAW_R, L.w);
+            S.raw[ry * RAW_P + rx] = __ldg(I + (size_t)yy * L.pitch + xx);
+        }
     }
     __syncwarp();
+    const uint8_t* RAW = S.raw + dx;
 
     // ---- IC_Angle
     int m10 = 0, m01 = 0;
@@ -431,7 +454,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(const __grid_
         const int u = lane - 15, au = u < 0 ? -u : u;
         for (int v = -15; v <= 15; v++) {
             if (au <= s_umax[v < 0 ? -v : v]) {
-                const int val = S.raw[(RAW_R + v) * RAW_P + RAW_R + u];
+                const int val = RAW[(RAW_R + v) * RAW_P + RAW_R + u];
                 m10 += u * val;
                 m01 += v * val;
             }
@@ -444,20 +467,33 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(const __grid_
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- Gaussian 7x7: rows, then columns
+    // ---- Gaussian 7x7: rows, then columns.  A lane produces a run of SEG consecutive outputs of one line with a 7-tap sliding
+    //      window in registers (one load per output).
     const int g0 = 18, g1 = 34, g2 = 48, g3 = 56;
-    for (int i = lane; i < RAW_W * BLR_W; i += 32) {
-        const int ry = i / BLR_W, x = i - ry * BLR_W;
-        const uint8_t* r = S.raw + ry * RAW_P + x;
-        S.rowp[ry * ROWP_P + x] = (uint16_t)(g0 * (r[0] + r[6]) + g1 * (r[1] + r[5]) + g2 * (r[2] + r[4]) + g3 * r[3]);
+    for (int it = lane; it < RAW_W * 2; it += 32) {
+        const int ry = it >> 1, xb = (it & 1) * SEG, n = (it & 1) ? BLR_W - SEG : SEG;
+        const uint8_t* r = RAW + ry * RAW_P + xb;
+        uint16_t* o = S.rowp + ry * ROWP_P + xb;
+        int p0 = r[0], p1 = r[1], p2 = r[2], p3 = r[3], p4 = r[4], p5 = r[5];
+#pragma unroll
+        for (int x = 0; x < SEG; x++) {
+            const int p6 = (x < n) ? r[x + 6] : 0;
+            if (x < n) o[x] = (uint16_t)(g0 * (p0 + p6) + g1 * (p1 + p5) + g2 * (p2 + p4) + g3 * p3);
+            p0 = p1; p1 = p2; p2 = p3; p3 = p4; p4 = p5; p5 = p6;
+        }
     }
     __syncwarp();
-    for (int i = lane; i < BLR_W * BLR_W; i += 32) {
-        const int y = i / BLR_W, x = i - y * BLR_W;
-        const uint16_t* r = S.rowp + y * ROWP_P + x;
-        const uint32_t acc = g0 * ((uint32_t)r[0] + r[6 * ROWP_P]) + g1 * ((uint32_t)r[ROWP_P] + r[5 * ROWP_P]) +
-                             g2 * ((uint32_t)r[2 * ROWP_P] + r[4 * ROWP_P]) + g3 * (uint32_t)r[3 * ROWP_P];
-        S.blur[y * BLR_P + x] = (uint8_t)((acc + 32768u) >> 16);
+    for (int it = lane; it < BLR_W * 2; it += 32) {
+        const int x = it >> 1, yb = (it & 1) * SEG, n = (it & 1) ? BLR_W - SEG : SEG;
+        const uint16_t* r = S.rowp + yb * ROWP_P + x;
+        uint8_t* o = S.blur + yb * BLR_P + x;
+        uint32_t p0 = r[0], p1 = r[ROWP_P], p2 = r[2 * ROWP_P], p3 = r[3 * ROWP_P], p4 = r[4 * ROWP_P], p5 = r[5 * ROWP_P];
+#pragma unroll
+        for (int y = 0; y < SEG; y++) {
+            const uint32_t p6 = (y < n) ? r[(y + 6) * ROWP_P] : 0u;
+            if (y < n) o[y * BLR_P] = (uint8_t)((g0 * (p0 + p6) + g1 * (p1 + p5) + g2 * (p2 + p4) + g3 * p3 + 32768u) >> 16);
+            p0 = p1; p1 = p2; p2 = p3; p3 = p4; p4 = p5; p5 = p6;
+        }
     }
     __syncwarp();
 
@@ -656,7 +692,7 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
     }
     // FAST shared memory: tile + score + 2 lists
     e->fast_pix_cap = (max_dw * max_dh + 15) & ~15;
-    e->fast_tile_cap = (((max_dw + 6 + 3) & ~3) * (max_dh + 6) + 15) & ~15;
+    e->fast_tile_cap = (((3 + max_dw + 6 + 3) & ~3) * (max_dh + 6) + 15) & ~15;   // rows start at a 4-byte aligned source address
     e->fast_smem = (size_t)e->fast_tile_cap + e->fast_pix_cap + 2 * sizeof(uint16_t) * e->fast_pix_cap;
     e->qt_maxl = (max_quota_l + 8 + 1) & ~1;
     e->qt_smem = (size_t)e->qt_maxl * (2 * sizeof(QtNode) + 10 * sizeof(int) + sizeof(unsigned long long)) + 16;
@@ -725,6 +761,7 @@ int orbx_extract_device(orbx_t* e, const uint8_t* d_imgs, int frames, size_t row
     if (!d_imgs || !d_kps || !d_desc || !d_counts) ORB_FAIL(ORB_E_INVALID, "orbx_extract: NULL buffer");
     if (frames < 0 || frames > e->max_frames) ORB_FAIL(ORB_E_INVALID, "orbx_extract: frames=%d exceeds max_frames=%d", frames, e->max_frames);
     if (row_stride < (size_t)e->W) ORB_FAIL(ORB_E_INVALID, "orbx_extract: row_stride %zu < width %d", row_stride, e->W);
+    if (((uintptr_t)d_imgs & 15) || (row_stride & 15)) ORB_FAIL(ORB_E_INVALID, "orbx_extract_device: images must be 16-byte aligned with row_stride %% 16 == 0");
     if (kp_capacity < orbx_max_keypoints(e)) ORB_FAIL(ORB_E_INVALID, "orbx_extract: kp_capacity %d < orbx_max_keypoints() = %d", kp_capacity, orbx_max_keypoints(e));
     ORB_CUDA(cudaSetDevice(e->device));
     const int NI = frames * e->cameras;

@@ -106,6 +106,9 @@ class Optimizer:
             check(lib().orbba_set_stream(self._h, h))
             self._stream_h = h
 
+    def set_copy_stream(self, stream):
+        check(lib().orbba_set_copy_stream(self._h, _stream_handle(stream) if stream is not None else None))
+
     def run(self, its1=5, its2=10, huber_delta=TH_HUBER_MONO, chi2_th=CHI2_MONO, stream=None):
         if stream is not None:
             self.set_stream(stream)
