@@ -41,7 +41,14 @@ struct LevelDev {
     int patch_size, valid;
 };
 
+struct CellDesc {                  // one cell of ComputeKeyPointsOctTree's grid, precomputed at create
+    short x0, y0, dw, dh;          // detection region (border-relative), see fast_cells_kernel
+    int level;
+    unsigned m_dw;                 // ceil(2^20 / dw)
+};
+
 struct ExtractParams {
+    const CellDesc* cells;         // [cells_per_image]
     int nlevels, n_images;
     int iniTh, minTh;
     int cells_per_image;
@@ -110,16 +117,10 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
     __shared__ int s_n1, s_n2, s_keep, s_base, s_emit;
 
     const int img = blockIdx.y;
-    int cell = blockIdx.x;
-    int l = 0;
-    while (l + 1 < P.nlevels && cell >= P.cell_begin[l + 1]) l++;
-    cell -= P.cell_begin[l];
+    const CellDesc cd = P.cells[blockIdx.x];
+    const int l = cd.level;
     const LevelDev& L = P.lv[l];
-    const int ci = cell / L.nColsEff, cj = cell - ci * L.nColsEff;
-    const int x0 = cj * L.wCell + 3, y0 = ci * L.hCell + 3;
-    const int x1 = (cj == L.nColsEff - 1) ? L.width - 3 : x0 + L.wCell;
-    const int y1 = (ci == L.nRowsEff - 1) ? L.height - 3 : y0 + L.hCell;
-    const int dw = x1 - x0, dh = y1 - y0;
+    const int x0 = cd.x0, y0 = cd.y0, dw = cd.dw, dh = cd.dh;
     if (dw <= 0 || dh <= 0) return;
     const int tw = dw + 6, th = dh + 6;
     const int tid = threadIdx.x;
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
     }
     const int npix = dw * dh;
     for (int i = tid; i < ((npix + 3) >> 2); i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0;
-    const unsigned m_dw = ((1u << 20) + dw - 1) / dw;
+    const unsigned m_dw = cd.m_dw;
     const uint8_t* T0 = tile + 3 * tp + dx + 3;            // pixel (0, 0) of the detection region
     const int iniTh = min(max(P.iniTh, 0), 255), minTh = min(max(P.minTh, 0), 255);
     const int rdx[16] = ORB_RING_DX, rdy[16] = ORB_RING_DY;
@@ -149,20 +150,50 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
     for (int round = 0; round < 2; round++) {
         if (tid == 0) { s_n1 = 0; s_n2 = 0; s_keep = 0; s_emit = 0; }
         __syncthreads();
-        // ---- pass 1: compass pre-test at threshold t, warp-compacted list of survivors
-        for (int i0 = 0; i0 < npix; i0 += FAST_THREADS) {
-            const int i = i0 + tid;
-            bool pass = false;
-            if (i < npix) {
-                const int y = fastdiv20(i, m_dw), x = i - y * dw;
-                const uint8_t* p = T0 + y * tp + x;
-                pass = fast16_pretest(p[0], p[3 * tp], p[3], p[-3 * tp], p[-3], t);
+        // ---- pass 1: compass pre-test at threshold t, four pixels (one aligned tile word) per thread with byte-SIMD compares;
+        //      warp-compacted list of survivors
+        {
+            const int c0 = dx + 3;                                     // tile column of region x = 0
+            const int wc0 = c0 >> 2, nwc = ((c0 + dw - 1) >> 2) - wc0 + 1;
+            const unsigned m_nwc = ((1u << 20) + nwc - 1) / nwc;
+            const uint32_t T4 = (uint32_t)t * 0x01010101u;
+            const int nitems = dh * nwc;
+            for (int it0 = 0; it0 < nitems; it0 += FAST_THREADS) {
+                const int it = it0 + tid;
+                uint32_t M = 0;
+                int ibase = 0;
+                if (it < nitems) {
+                    const int y = fastdiv20(it, m_nwc), wc = wc0 + (it - y * nwc);
+                    const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + (y + 3) * tp);
+                    const uint32_t C = row[wc], Cp = row[wc - 1], Cn = row[wc + 1];
+                    const uint32_t D = row[wc + 3 * nw], U = row[wc - 3 * nw];
+                    const uint32_t P12 = __byte_perm(Cp, C, 0x4321), P4 = __byte_perm(C, Cn, 0x6543);
+                    const uint32_t hi = __vaddus4(C, T4), lo = __vsubus4(C, T4);
+                    const uint32_t b0 = __vcmpgtu4(D, hi), b4 = __vcmpgtu4(P4, hi), b8 = __vcmpgtu4(U, hi), b12 = __vcmpgtu4(P12, hi);
+                    const uint32_t k0 = __vcmpgtu4(lo, D), k4 = __vcmpgtu4(lo, P4), k8 = __vcmpgtu4(lo, U), k12 = __vcmpgtu4(lo, P12);
+                    M = ((b0 | b8) & (b4 | b12)) | ((k0 | k8) & (k4 | k12));    // two ADJACENT compass pixels brighter, or two darker
+                    // bytes of this word that lie inside the detection region
+                    const int xlo = wc * 4 - c0;                                 // region x of byte 0
+                    uint32_t valid = 0xffffffffu;
+                    if (xlo < 0) valid <<= 8 * (-xlo);
+                    if (xlo + 3 >= dw) valid &= 0xffffffffu >> (8 * (xlo + 4 - dw));
+                    M &= valid & 0x01010101u;
+                    ibase = y * dw + xlo;
+                }
+                const int cnt = __popc(M);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+                const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+                int base = 0;
+                if (lane == 31 && wtot) base = atomicAdd(&s_n1, wtot);
+                base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+                while (M) {
+                    const int k = (__ffs(M) - 1) >> 3;
+                    list[base++] = (uint16_t)(ibase + k);
+                    M &= M - 1;
+                }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, pass);
-            int base = 0;
-            if (lane == 0 && m) base = atomicAdd(&s_n1, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass) list[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
         }
         __syncthreads();
         // ---- pass 2: exact corner score of the survivors
@@ -551,6 +582,7 @@ struct orbx {
     uint32_t* d_sel = nullptr;
     int* d_sel_count = nullptr;
     int* d_umax = nullptr;
+    CellDesc* d_cells = nullptr;
     orb_keypoint_t* d_kps = nullptr;   // output staging for the host API
     uint8_t* d_desc = nullptr;
     int* d_counts = nullptr;
@@ -577,7 +609,7 @@ static void orbx_free(orbx* e) {
     cudaSetDevice(e->device);
     for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
     cudaFree(e->d_levels); cudaFree(e->d_input); cudaFree(e->d_tables); cudaFree(e->d_cand); cudaFree(e->d_node_of);
-    cudaFree(e->d_cand_count); cudaFree(e->d_sel); cudaFree(e->d_sel_count); cudaFree(e->d_umax);
+    cudaFree(e->d_cand_count); cudaFree(e->d_sel); cudaFree(e->d_sel_count); cudaFree(e->d_umax); cudaFree(e->d_cells);
     cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_counts);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -613,6 +645,7 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
     size_t level_bytes = 0;           // per image, levels >= 1
     std::vector<size_t> level_off(nlevels, 0);
     int cells = 0, cand_total = 0, sel_total = 0, max_dw = 0, max_dh = 0, max_quota_l = 0;
+    std::vector<CellDesc> cell_table;
     for (int l = 0; l < nlevels; l++) {
         const orbgeo::Level& G = g.lv[l];
         LevelDev& L = P.lv[l];
@@ -638,6 +671,10 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
                     const int dw = std::max(x1 - x0, 0), dh = std::max(y1 - y0, 0);
                     cap += ((dw + 1) / 2) * ((dh + 1) / 2);
                     max_dw = std::max(max_dw, dw); max_dh = std::max(max_dh, dh);
+                    CellDesc cd;
+                    cd.x0 = (short)x0; cd.y0 = (short)y0; cd.dw = (short)dw; cd.dh = (short)dh; cd.level = l;
+                    cd.m_dw = dw > 0 ? ((1u << 20) + dw - 1) / dw : 0;
+                    cell_table.push_back(cd);
                 }
             L.cand_cap = cap;
             L.sel_cap = std::max(G.quota + 2, 4 * G.nIni);
@@ -662,6 +699,7 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
     alloc((void**)&e->d_sel, (size_t)sel_total * NI * sizeof(uint32_t));
     alloc((void**)&e->d_sel_count, NI * nlevels * sizeof(int));
     alloc((void**)&e->d_umax, 16 * sizeof(int));
+    alloc((void**)&e->d_cells, std::max<size_t>(cell_table.size(), 1) * sizeof(CellDesc));
     // resize tables
     std::vector<int> tabs;
     e->tab_off.assign((size_t)nlevels * 4, 0);
@@ -680,6 +718,8 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess && !tabs.empty()) ce = cudaMemcpy(e->d_tables, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (ce == cudaSuccess) ce = cudaMemcpy(e->d_umax, g.umax.data(), 16 * sizeof(int), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && !cell_table.empty()) ce = cudaMemcpy(e->d_cells, cell_table.data(), cell_table.size() * sizeof(CellDesc), cudaMemcpyHostToDevice);
+    P.cells = e->d_cells;
     if (ce != cudaSuccess) {
         int rc = orbhost::check_cuda(ce, "orbx_create allocations", __FILE__, __LINE__);
         orbx_free(e);
