@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
             const int c0 = dx + 3;                                     // tile column of region x = 0
             const int wc0 = c0 >> 2, nwc = ((c0 + dw - 1) >> 2) - wc0 + 1;
             const unsigned m_nwc = ((1u << 20) + nwc - 1) / nwc;
-            const uint32_t T4 = (uint32_t)t * 0x01010101u;
+            const uint32_t TH1 = (uint32_t)(t + 1) * 0x00010001u, TL1 = (uint32_t)(512 - t - 1) * 0x00010001u;
             const int nitems = dh * nwc;
             for (int it0 = 0; it0 < nitems; it0 += FAST_THREADS) {
                 const int it = it0 + tid;
@@ -168,10 +168,24 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
                     const uint32_t C = row[wc], Cp = row[wc - 1], Cn = row[wc + 1];
                     const uint32_t D = row[wc + 3 * nw], U = row[wc - 3 * nw];
                     const uint32_t P12 = __byte_perm(Cp, C, 0x4321), P4 = __byte_perm(C, Cn, 0x6543);
-                    const uint32_t hi = __vaddus4(C, T4), lo = __vsubus4(C, T4);
-                    const uint32_t b0 = __vcmpgtu4(D, hi), b4 = __vcmpgtu4(P4, hi), b8 = __vcmpgtu4(U, hi), b12 = __vcmpgtu4(P12, hi);
-                    const uint32_t k0 = __vcmpgtu4(lo, D), k4 = __vcmpgtu4(lo, P4), k8 = __vcmpgtu4(lo, U), k12 = __vcmpgtu4(lo, P12);
-                    M = ((b0 | b8) & (b4 | b12)) | ((k0 | k8) & (k4 | k12));    // two ADJACENT compass pixels brighter, or two darker
+                    // SWAR compare on 16-bit lanes (even / odd bytes): with a 512 bias, bit 9 of  p + 512 - (c + t + 1)  is set iff
+                    // p > c + t, and bit 9 of  (c + 512 - t - 1) - p  iff p < c - t  (no lane can borrow: all terms stay in [1, 766])
+                    const uint32_t LM = 0x00ff00ffu, B9 = 0x02000200u;
+                    const uint32_t Ce = C & LM, Co = (C >> 8) & LM;
+                    const uint32_t hie = Ce + TH1, hio = Co + TH1;             // c + t + 1
+                    const uint32_t loe = Ce + TL1, loo = Co + TL1;             // c + 512 - t - 1
+                    uint32_t be[4], bo[4], ke[4], ko[4];
+                    const uint32_t W4[4] = {D, P4, U, P12};
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t pe = W4[q] & LM, po = (W4[q] >> 8) & LM;
+                        be[q] = pe + B9 - hie; bo[q] = po + B9 - hio;
+                        ke[q] = loe - pe;      ko[q] = loo - po;
+                    }
+                    // two ADJACENT compass pixels brighter, or two darker
+                    const uint32_t Me = (((be[0] | be[2]) & (be[1] | be[3])) | ((ke[0] | ke[2]) & (ke[1] | ke[3]))) & B9;
+                    const uint32_t Mo = (((bo[0] | bo[2]) & (bo[1] | bo[3])) | ((ko[0] | ko[2]) & (ko[1] | ko[3]))) & B9;
+                    M = (Me >> 9) | (Mo >> 1);                                  // bit 8k of M <-> byte k of the word
                     // bytes of this word that lie inside the detection region
                     const int xlo = wc * 4 - c0;                                 // region x of byte 0
                     uint32_t valid = 0xffffffffu;
