@@ -221,7 +221,7 @@ __global__ void k_reset(BABatch A, int stopped0) {
 // ------------------------------------------------------------------------------------------------ k_lin
 __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
     __shared__ double red[BA_TE / 32];
-    __shared__ double s_rec[BA_TE * BA_REC], s_B[BA_TE * 18];
+    __shared__ double s_rec[BA_TE * BA_REC];     // records, then (same memory) the B blocks: 21.5 KB per CTA keeps 10 CTAs per SM
     const int b = blockIdx.x;
     const int p = A.blkE_prob[b];
     const BAState& S = A.state[p];
@@ -249,7 +249,6 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
             if (lvl) { A.err[0][2 * e] = l0; A.err[0][2 * e + 1] = l1; A.err[1][2 * e] = l0; A.err[1][2 * e + 1] = l1; }
         }
         double* R = s_rec + BA_REC * tid;       // staged in shared memory, written out coalesced below
-        double* Bm = s_B + 18 * tid;
         if (!lvl) {
             double er[2];
             if (S.round_start) {
@@ -303,15 +302,9 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
             R[6] = W; R[7] = -w * er[0] * wr; R[8] = -w * er[1] * wr;
 #pragma unroll
             for (int j = 0; j < 12; j++) R[9 + j] = Jp[j];
-#pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-                for (int cc = 0; cc < 3; cc++) Bm[r * 3 + cc] = W * (Jp[r] * Jl[cc] + Jp[6 + r] * Jl[3 + cc]);
         } else {
 #pragma unroll
             for (int j = 0; j < BA_REC; j++) R[j] = 0;
-#pragma unroll
-            for (int j = 0; j < 18; j++) Bm[j] = 0;
         }
     }
     const double cs = block_sum<BA_TE / 32>(chi, red);
@@ -323,7 +316,26 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
         double* gr = A.rec + (size_t)BA_REC * ebase;
         double* gb = A.B + 18 * (size_t)ebase;
         for (int i = tid; i < BA_REC * nv; i += BA_TE) gr[i] = s_rec[i];
-        for (int i = tid; i < 18 * nv; i += BA_TE) gb[i] = s_B[i];
+        // B_e = Jp^T W Jl from the staged record, written over it (level-1 edges: zero record -> zero block)
+        double Jl[6], Jp[12], W = 0;
+        if (valid) {
+            const double* R = s_rec + BA_REC * tid;
+#pragma unroll
+            for (int j = 0; j < 6; j++) Jl[j] = R[j];
+            W = R[6];
+#pragma unroll
+            for (int j = 0; j < 12; j++) Jp[j] = R[9 + j];
+        }
+        __syncthreads();
+        if (valid) {
+            double* Bm = s_rec + 18 * tid;
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int cc = 0; cc < 3; cc++) Bm[r * 3 + cc] = W * (Jp[r] * Jl[cc] + Jp[6 + r] * Jl[3 + cc]);
+        }
+        __syncthreads();
+        for (int i = tid; i < 18 * nv; i += BA_TE) gb[i] = s_rec[i];
     }
     if (b == P.blkE0 && tid == 0 && S.round_start) A.state[p].maxdiag_bits = 0ull;
 }
