@@ -462,7 +462,9 @@ __global__ void __launch_bounds__(BA_TT) k_trial_lm(BABatch A) {
 // ------------------------------------------------------------------------------------------------ k_pairs
 // warp per work item of a problem: items [0, nChunksMax) = chunk of <= BA_CH tuples of one pose pair -> partial 6x6 block of
 // sum Y_a B_b^T ; items [nChunksMax, nChunksMax + K) = free pose k -> Schur right-hand side bs_k = bp_k - sum_e Y_e bl.
+#define BA_STAGE_BYTES (32 * 144)   // one batch: 16 Y blocks + 16 B blocks
 __global__ void __launch_bounds__(128) k_pairs(BABatch A, const int* blkI_first) {
+    __shared__ __align__(16) unsigned char s_stage[4 * 2 * BA_STAGE_BYTES];   // per warp: two stages
     const int p = A.item_prob[blockIdx.x];
     const BAState& S = A.state[p];
     if (S.done) return;
@@ -474,32 +476,62 @@ __global__ void __launch_bounds__(128) k_pairs(BABatch A, const int* blkI_first)
         const int ch = P.chunk0 + item;
         const int2* T = A.tuples + P.tup0 + A.chunk_start[ch];
         const int len = A.chunk_len[ch];
-        // two lanes per tuple: lane parity h owns rows 3h..3h+2 of the 6x6 block (half the accumulators -> twice the occupancy);
-        // both lanes read the same B_b (one transaction), each reads its half of Y_a
-        const int h = lane & 1, slot = lane >> 1;
+        // Batches of 16 tuples: the 32 blocks of a batch (16 x Y_a, 16 x B_b, 144 B each) are copied global -> shared with
+        // cp.async, consecutive lanes fetching consecutive 16-byte pieces of a block (whole sectors per request, no register
+        // write-back), double-buffered per warp; then two lanes per tuple (lane parity h owns rows 3h..3h+2 of the 6x6 block)
+        // read them back conflict-free.
+        const int h = lane & 1, slot = lane >> 1, warp = threadIdx.x >> 5;
+        unsigned char* stage0 = s_stage + (size_t)warp * 2 * BA_STAGE_BYTES;
+        const int nbatch = (len + 15) >> 4;
+        auto issue = [&](int bidx, int stg) {
+            const int tl0 = bidx * 16;
+            int2 ab = make_int2(0, 0);
+            if (tl0 + (lane & 15) < len) ab = T[tl0 + (lane & 15)];
+            const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage0 + (size_t)stg * BA_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const int g = k * 32 + lane, rec = g / 9, part = g - rec * 9;
+                const int tl = rec & 15;
+                const int ex = __shfl_sync(0xffffffffu, ab.x, tl), ey = __shfl_sync(0xffffffffu, ab.y, tl);
+                const double* src = (rec < 16 ? A.Y + 18 * (size_t)ex : A.B + 18 * (size_t)ey) + 2 * part;
+                if (tl0 + tl < len) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * g), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
         double acc[18];
 #pragma unroll
         for (int i = 0; i < 18; i++) acc[i] = 0;
-        for (int t = slot; t < len; t += 16) {
-            const int2 ab = T[t];
-            const double* Yp = A.Y + 18 * (size_t)ab.x + 9 * h;
-            const double2* Bp = reinterpret_cast<const double2*>(A.B + 18 * (size_t)ab.y);
-            double y[9], bq[18];
-            if (h == 0) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) { const double2 a = reinterpret_cast<const double2*>(Yp)[i]; y[2 * i] = a.x; y[2 * i + 1] = a.y; }
-                y[8] = Yp[8];
+        issue(0, 0);
+        for (int bidx = 0; bidx < nbatch; bidx++) {
+            if (bidx + 1 < nbatch) {
+                issue(bidx + 1, (bidx + 1) & 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
             } else {
-                y[0] = Yp[0];
-#pragma unroll
-                for (int i = 0; i < 4; i++) { const double2 a = reinterpret_cast<const double2*>(Yp + 1)[i]; y[1 + 2 * i] = a.x; y[2 + 2 * i] = a.y; }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
+            __syncwarp();
+            if (bidx * 16 + slot < len) {
+                const unsigned char* stg = stage0 + (size_t)(bidx & 1) * BA_STAGE_BYTES;
+                const double* Yp = reinterpret_cast<const double*>(stg + 144 * slot) + 9 * h;
+                const double2* Bp = reinterpret_cast<const double2*>(stg + 144 * (16 + slot));
+                double y[9], bq[18];
+                if (h == 0) {
 #pragma unroll
-            for (int i = 0; i < 9; i++) { const double2 c = Bp[i]; bq[2 * i] = c.x; bq[2 * i + 1] = c.y; }
+                    for (int i = 0; i < 4; i++) { const double2 a = reinterpret_cast<const double2*>(Yp)[i]; y[2 * i] = a.x; y[2 * i + 1] = a.y; }
+                    y[8] = Yp[8];
+                } else {
+                    y[0] = Yp[0];
 #pragma unroll
-            for (int r = 0; r < 3; r++)
+                    for (int i = 0; i < 4; i++) { const double2 a = reinterpret_cast<const double2*>(Yp + 1)[i]; y[1 + 2 * i] = a.x; y[2 + 2 * i] = a.y; }
+                }
 #pragma unroll
-                for (int c = 0; c < 6; c++) acc[r * 6 + c] += y[r * 3] * bq[c * 3] + y[r * 3 + 1] * bq[c * 3 + 1] + y[r * 3 + 2] * bq[c * 3 + 2];
+                for (int i = 0; i < 9; i++) { const double2 c = Bp[i]; bq[2 * i] = c.x; bq[2 * i + 1] = c.y; }
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 6; c++) acc[r * 6 + c] += y[r * 3] * bq[c * 3] + y[r * 3 + 1] * bq[c * 3 + 1] + y[r * 3 + 2] * bq[c * 3 + 2];
+            }
+            __syncwarp();
         }
 #pragma unroll
         for (int i = 0; i < 18; i++) {
