@@ -307,33 +307,45 @@ def run_ours(args, rank, world, local_rank):
     ba_stats = opt.download_batch(out=h_ba)[3]
 
     # ---- end to end: pinned host images and host BA graphs in; keypoints / descriptors / matches / poses / points / outlier flags
-    #      out to pinned host memory, every step.  The BA graphs are double-buffered over two handles: while the device optimises the
-    #      windows of step i, the host flattens and uploads those of step i+1, and the results of step i are read during step i+1
-    #      (the last step's results are drained inside the timed region).
+    #      out to pinned host memory, every step.  Three streams: copies in (images + BA graphs), compute, copies out.  The BA graphs
+    #      are double-buffered over two handles: while the device optimises the windows of step i, the host flattens and uploads
+    #      step i+1, and the BA results of step i are read during step i+1 (the last step is drained inside the timed region).
     opts = [opt, opt2]
     for o in opts:
         o.set_copy_stream(copy_stream)       # uploads overlap with the other handle's run; runs share one compute stream
+    out_stream = torch.cuda.Stream(dev)      # device->host copies of keypoints / descriptors / matches
+    prev_out = [None]
 
     def e2e_step(i, first):
         o = opts[i % 2]
-        d_in[i % 2].copy_(host[i % 2], non_blocking=True)
+        with torch.cuda.stream(copy_stream):
+            d_in[i % 2].copy_(host[i % 2], non_blocking=True)
+            e_img = copy_stream.record_event()
+        o.upload(ba_prepared)                # flatten + host->device + index construction (copy stream)
+        stream.wait_event(e_img)
+        if prev_out[0] is not None:
+            stream.wait_event(prev_out[0])   # the previous step's results left the device before they are overwritten
         ext.extract_device(d_in[i % 2], d_kps, d_desc, d_cnt, stream=stream)
         mat.bruteforce_sets_device(d_desc, d_cnt, q_set, t_set, out=d_match, stream=stream)
-        h_cnt.copy_(d_cnt, non_blocking=True)
-        h_kps.copy_(d_kps, non_blocking=True)
-        h_desc.copy_(d_desc, non_blocking=True)
-        for hm, dm in zip(h_match, d_match):
-            hm.copy_(dm, non_blocking=True)
-        o.upload(ba_prepared)                # flatten + host->device + index construction
-        o.run()
+        e_em = stream.record_event()
+        o.run()                              # compute stream, after this handle's upload
+        with torch.cuda.stream(out_stream):
+            out_stream.wait_event(e_em)
+            h_cnt.copy_(d_cnt, non_blocking=True)
+            h_kps.copy_(d_kps, non_blocking=True)
+            h_desc.copy_(d_desc, non_blocking=True)
+            for hm, dm in zip(h_match, d_match):
+                hm.copy_(dm, non_blocking=True)
+            prev_out[0] = out_stream.record_event()
         r = 0
         if not first:
-            opts[(i - 1) % 2].download_batch(out=h_ba)     # results of the previous step's windows
+            opts[(i - 1) % 2].download_batch(out=h_ba)     # results of the previous step's windows (waits for that run only)
             r = int(h_ba[2].sum())
-        stream.synchronize()
+        prev_out[0].synchronize()
         return int(h_cnt.sum()) + r          # the step's results are read on the host
 
     def e2e_run(n):
+        prev_out[0] = None
         for i in range(n):
             e2e_step(i, i == 0)
         opts[(n - 1) % 2].download_batch(out=h_ba)

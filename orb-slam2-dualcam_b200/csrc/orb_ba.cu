@@ -863,8 +863,9 @@ struct orbba {
     int device = 0, max_problems = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // optional: uploads (host->device + index kernels) go here, runs wait for them
-    cudaEvent_t up_ev = nullptr;
+    cudaEvent_t up_ev = nullptr, done_ev = nullptr;   // upload finished / the enqueued LM steps finished
     bool up_pending = false;
+    cudaStream_t dl_stream = nullptr;        // device->host result copies (do not queue behind later work on the compute stream)
     int n = 0;
     BABatch A;                               // device pointers of the uploaded batch
     std::vector<BAProb> probs;
@@ -895,6 +896,8 @@ static void orbba_free(orbba* b) {
     if (b->h_flags) cudaFreeHost(b->h_flags);
     if (b->ev[0]) { cudaEventDestroy(b->ev[0]); cudaEventDestroy(b->ev[1]); }
     if (b->up_ev) cudaEventDestroy(b->up_ev);
+    if (b->done_ev) cudaEventDestroy(b->done_ev);
+    if (b->dl_stream) cudaStreamDestroy(b->dl_stream);
     for (cudaEvent_t e : b->kev) cudaEventDestroy(e);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
@@ -945,18 +948,19 @@ static int launch_steps(orbba* b, int steps) {
     k_stats<<<1, 256, 0, st>>>(A);
     b->launches += 2;
     ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaEventRecord(b->done_ev, st));
     return ORB_OK;
 }
 
 // waits for the enqueued steps; problems that needed more LM trials than were enqueued get further steps
 static int finish(orbba* b) {
     if (!b->pending) return ORB_OK;
-    ORB_CUDA(cudaStreamSynchronize(b->stream));
+    ORB_CUDA(cudaEventSynchronize(b->done_ev));      // only this handle's steps: later work on the same stream is not waited for
     int guard = 0;
     while (b->h_flags[1] > 0 && guard++ < 64) {
         int rc = launch_steps(b, 4);
         if (rc != ORB_OK) return rc;
-        ORB_CUDA(cudaStreamSynchronize(b->stream));
+        ORB_CUDA(cudaEventSynchronize(b->done_ev));
     }
     b->pending = false;
     return ORB_OK;
@@ -985,6 +989,8 @@ int orbba_create(orbba_t** out, int device, int max_problems) {
     if (ce == cudaSuccess) ce = cudaEventCreate(&b->ev[0]);
     if (ce == cudaSuccess) ce = cudaEventCreate(&b->ev[1]);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->up_ev, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->done_ev, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&b->dl_stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
     if (ce != cudaSuccess) { int rc = orbhost::check_cuda(ce, "orbba_create", __FILE__, __LINE__); orbba_free(b); return rc; }
     b->stream = b->own_stream;
@@ -1321,7 +1327,7 @@ int orbba_download_batch(orbba_t* b, double* poses_out, double* points_out, uint
     ORB_CUDA(cudaSetDevice(b->device));
     int rc = finish(b);
     if (rc != ORB_OK) return rc;
-    cudaStream_t st = b->stream;
+    cudaStream_t st = b->dl_stream;
     if (poses_out && b->Ptot) ORB_CUDA(cudaMemcpyAsync(poses_out, b->A.poses_out, sizeof(double) * 12 * b->Ptot, cudaMemcpyDeviceToHost, st));
     if (points_out && b->Ltot) ORB_CUDA(cudaMemcpyAsync(points_out, b->A.points_out, sizeof(double) * 3 * b->Ltot, cudaMemcpyDeviceToHost, st));
     if (edge_outlier && b->Etot) ORB_CUDA(cudaMemcpyAsync(edge_outlier, b->A.outlier, (size_t)b->Etot, cudaMemcpyDeviceToHost, st));
@@ -1345,7 +1351,7 @@ int orbba_download(orbba_t* b, int p, double* poses_out, double* points_out, uin
     int rc = finish(b);
     if (rc != ORB_OK) return rc;
     const BAProb& P = b->probs[p];
-    cudaStream_t st = b->stream;
+    cudaStream_t st = b->dl_stream;
     std::vector<uint8_t> tmp;
     if (poses_out && P.nP) ORB_CUDA(cudaMemcpyAsync(poses_out, b->A.poses_out + 12 * (size_t)P.p0, sizeof(double) * 12 * P.nP, cudaMemcpyDeviceToHost, st));
     if (points_out && P.nL) ORB_CUDA(cudaMemcpyAsync(points_out, b->A.points_out + 3 * (size_t)P.l0, sizeof(double) * 3 * P.nL, cudaMemcpyDeviceToHost, st));
