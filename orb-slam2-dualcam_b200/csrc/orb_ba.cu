@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
             R[6] = W; R[7] = -w * er[0] * wr; R[8] = -w * er[1] * wr;
 #pragma unroll
             for (int j = 0; j < 12; j++) R[9 + j] = Jp[j];
+            R[21] = 0;
         } else {
 #pragma unroll
             for (int j = 0; j < BA_REC; j++) R[j] = 0;
@@ -356,8 +357,9 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
         if (l < P.l0 + P.nL) {
             double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0, b0 = 0, b1 = 0, b2 = 0;
             for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
-                const double* R = A.rec + (size_t)BA_REC * e;
-                const double a0 = R[0], a1 = R[1], a2 = R[2], c0 = R[3], c1 = R[4], c2 = R[5], W = R[6], r0 = R[7], r1 = R[8];
+                const double2* R2 = reinterpret_cast<const double2*>(A.rec + (size_t)BA_REC * e);
+                const double2 q0 = R2[0], q1 = R2[1], q2 = R2[2], q3 = R2[3], q4 = R2[4];
+                const double a0 = q0.x, a1 = q0.y, a2 = q1.x, c0 = q1.y, c1 = q2.x, c2 = q2.y, W = q3.x, r0 = q3.y, r1 = q4.x;
                 h00 += (a0 * a0 + c0 * c0) * W; h01 += (a0 * a1 + c0 * c1) * W; h02 += (a0 * a2 + c0 * c2) * W;
                 h11 += (a1 * a1 + c1 * c1) * W; h12 += (a1 * a2 + c1 * c2) * W; h22 += (a2 * a2 + c2 * c2) * W;
                 b0 += a0 * r0 + c0 * r1; b1 += a1 * r0 + c1 * r1; b2 += a2 * r0 + c2 * r1;
@@ -390,11 +392,14 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
 #pragma unroll
     for (int i = 0; i < 6; i++) bb[i] = 0;
     for (int t = tid; t < cnt; t += BA_TP) {
-        const double* R = A.rec + (size_t)BA_REC * T[t].x;
-        const double W = R[6], r0 = R[7], r1 = R[8];
+        const double2* R2 = reinterpret_cast<const double2*>(A.rec + (size_t)BA_REC * T[t].x) + 3;   // doubles 6..21
+        double rr[16];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const double2 q = R2[i]; rr[2 * i] = q.x; rr[2 * i + 1] = q.y; }
+        const double W = rr[0], r0 = rr[1], r1 = rr[2];
         double a[6], c[6];
 #pragma unroll
-        for (int i = 0; i < 6; i++) { a[i] = R[9 + i]; c[i] = R[15 + i]; }
+        for (int i = 0; i < 6; i++) { a[i] = rr[3 + i]; c[i] = rr[9 + i]; }
         int u = 0;
 #pragma unroll
         for (int i = 0; i < 6; i++) {
@@ -430,9 +435,9 @@ __device__ __forceinline__ void landmark_dinv(const double* H, double lambda, do
     d[0] = c00 * id; d[1] = c01 * id; d[2] = c02 * id;
     d[3] = (m0 * m8 - m2 * m2) * id; d[4] = (m2 * m1 - m0 * m5) * id; d[5] = (m0 * m4 - m1 * m1) * id;
 }
-// thread per (edge, row r of the 6x3 block): Y_e[r] = B_e[r] Dinv, v_e[r] = Y_e[r] . bl   -- consecutive threads touch
-// consecutive 24-byte rows, so the B reads and Y writes are fully coalesced
-#define BA_TT 256
+// thread per (edge, pair of rows of the 6x3 block): Y_e[r] = B_e[r] Dinv, v_e[r] = Y_e[r] . bl -- consecutive threads touch
+// consecutive 48-byte row pairs with 128-bit accesses, so the B reads and Y writes are fully coalesced
+#define BA_TT 192
 __global__ void __launch_bounds__(BA_TT) k_trial_lm(BABatch A) {
     const int b = blockIdx.x;
     const int p = A.blkE_prob[b];
@@ -441,21 +446,28 @@ __global__ void __launch_bounds__(BA_TT) k_trial_lm(BABatch A) {
     const BAProb& P = A.prob[p];
     const double lambda = lambda_eff(S);
     const int ebase = P.e0 + (b - P.blkE0) * BA_TE;
-    const int nrows = 6 * min(BA_TE, P.e0 + P.nE - ebase);
-    for (int q = threadIdx.x; q < nrows; q += BA_TT) {
-        const int el = q / 6, r = q - el * 6;
+    const int nitems = 3 * min(BA_TE, P.e0 + P.nE - ebase);
+    for (int q = threadIdx.x; q < nitems; q += BA_TT) {
+        const int el = q / 3, rp = q - el * 3;
         const int e = ebase + el;
         if (A.pose_free[A.e_pose[e]] < 0) continue;
         const int l = A.e_pt[e];
         double d[6];
         landmark_dinv(A.Hll + 6 * (size_t)l, lambda, d);
-        const double* Br = A.B + 18 * (size_t)e + 3 * r;
-        const double x0 = Br[0], x1 = Br[1], x2 = Br[2];
-        const double y0 = x0 * d[0] + x1 * d[1] + x2 * d[2], y1 = x0 * d[1] + x1 * d[3] + x2 * d[4], y2 = x0 * d[2] + x1 * d[4] + x2 * d[5];
-        double* Yr = A.Y + 18 * (size_t)e + 3 * r;
-        Yr[0] = y0; Yr[1] = y1; Yr[2] = y2;
+        const double2* B2 = reinterpret_cast<const double2*>(A.B + 18 * (size_t)e + 6 * rp);
+        const double2 u0 = B2[0], u1 = B2[1], u2 = B2[2];
+        const double x[6] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y};
+        double y[6];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const double x0 = x[3 * r], x1 = x[3 * r + 1], x2 = x[3 * r + 2];
+            y[3 * r] = x0 * d[0] + x1 * d[1] + x2 * d[2]; y[3 * r + 1] = x0 * d[1] + x1 * d[3] + x2 * d[4]; y[3 * r + 2] = x0 * d[2] + x1 * d[4] + x2 * d[5];
+        }
+        double2* Y2 = reinterpret_cast<double2*>(A.Y + 18 * (size_t)e + 6 * rp);
+        Y2[0] = make_double2(y[0], y[1]); Y2[1] = make_double2(y[2], y[3]); Y2[2] = make_double2(y[4], y[5]);
         const double* bl = A.bl + 3 * (size_t)l;
-        A.v[6 * (size_t)e + r] = y0 * bl[0] + y1 * bl[1] + y2 * bl[2];
+        const double b0 = bl[0], b1 = bl[1], b2 = bl[2];
+        *reinterpret_cast<double2*>(A.v + 6 * (size_t)e + 2 * rp) = make_double2(y[0] * b0 + y[1] * b1 + y[2] * b2, y[3] * b0 + y[4] * b1 + y[5] * b2);
     }
 }
 
@@ -730,7 +742,10 @@ __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
             for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
                 const int kg = A.pose_free[A.e_pose[e]];
                 if (kg < 0) continue;
-                const double* Ym = A.Y + 18 * (size_t)e;
+                const double2* Y2 = reinterpret_cast<const double2*>(A.Y + 18 * (size_t)e);
+                double Ym[18];
+#pragma unroll
+                for (int i = 0; i < 9; i++) { const double2 q = Y2[i]; Ym[2 * i] = q.x; Ym[2 * i + 1] = q.y; }
                 const double* xp = A.xp + 6 * (size_t)kg;
 #pragma unroll
                 for (int r = 0; r < 6; r++) { x0 -= Ym[r * 3] * xp[r]; x1 -= Ym[r * 3 + 1] * xp[r]; x2 -= Ym[r * 3 + 2] * xp[r]; }

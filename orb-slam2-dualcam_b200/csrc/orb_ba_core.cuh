@@ -5,7 +5,7 @@
 #include <math.h>
 
 #define BA_CAM_STRIDE 47       // fx fy cx cy | ext quat xyzw | ext t | adj[36]
-#define BA_REC 21              // per-edge linearisation record: Jl[6] W r0 r1 Jp[12]
+#define BA_REC 22              // per-edge linearisation record: Jl[6] W r0 r1 Jp[12] pad (176 B: 16-byte aligned for 128-bit loads)
 
 // ------------------------------------------------------------------------------------------------ SE3 (unit quaternion xyzw + t)
 static __device__ __forceinline__ void q_rotate(const double* q, const double* v, double* o) {
