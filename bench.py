@@ -204,8 +204,8 @@ def ba_bytes(problems, stats):
         T = int((f_l * (f_l + 1) // 2).sum())
         C = K * (K + 1) // 2 + T // 256
         it, tr = st["iterations"], st["trials"]
-        tot["k_lin"] += it * (E * (12 + 16 + 8 + 16 + 168 + 144) + L * 24 + P * 56)
-        tot["k_build"] += it * (E * 72 + Ef * 120 + L * 72 + K * 336)
+        tot["k_lin"] += it * (E * (12 + 16 + 8 + 16 + 176 + 144) + L * 24 + P * 56)
+        tot["k_build"] += it * (E * 80 + Ef * 128 + L * 72 + K * 336)
         tot["k_trial_lm"] += tr * (Ef * (144 + 144 + 48) + L * 72)
         tot["k_pairs"] += tr * (Ef * (288 + 48) + T * 8 + C * 288 + K * 48)
         tot["k_solve"] += tr * (C * 288 + K * (336 + 104))

@@ -221,7 +221,7 @@ __global__ void k_reset(BABatch A, int stopped0) {
 // ------------------------------------------------------------------------------------------------ k_lin
 __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
     __shared__ double red[BA_TE / 32];
-    __shared__ double s_rec[BA_TE * BA_REC];     // records, then (same memory) the B blocks: 21.5 KB per CTA keeps 10 CTAs per SM
+    __shared__ __align__(16) double s_rec[BA_TE * BA_REC];     // records, then (same memory) the B blocks: 21.5 KB per CTA keeps 10 CTAs per SM
     const int b = blockIdx.x;
     const int p = A.blkE_prob[b];
     const BAState& S = A.state[p];
@@ -268,7 +268,12 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
                 // (-1/z * tmp) * J3, J3 = [-skew(p) | I], then * Adj_ext   (types_six_dof_expmap.cpp:136-153)
                 const double tJ[12] = {t02 * Y, t00 * Z - t02 * X, -t00 * Y, t00, 0, t02,
                                        -t11 * Z + t12 * Y, -t12 * X, t11 * X, 0, t11, t12};
-                const double* Ad = c + 11;
+                double Ad[36];
+                {
+                    const double2* A2 = reinterpret_cast<const double2*>(c + BA_CAM_ADJ);
+#pragma unroll
+                    for (int i = 0; i < 18; i++) { const double2 q = A2[i]; Ad[2 * i] = q.x; Ad[2 * i + 1] = q.y; }
+                }
 #pragma unroll
                 for (int i = 0; i < 2; i++)
 #pragma unroll
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
         const int nv = min(BA_TE, P.e0 + P.nE - ebase);
         double* gr = A.rec + (size_t)BA_REC * ebase;
         double* gb = A.B + 18 * (size_t)ebase;
-        for (int i = tid; i < BA_REC * nv; i += BA_TE) gr[i] = s_rec[i];
+        for (int i = tid; i < BA_REC / 2 * nv; i += BA_TE) reinterpret_cast<double2*>(gr)[i] = reinterpret_cast<const double2*>(s_rec)[i];
         // B_e = Jp^T W Jl from the staged record, written over it (level-1 edges: zero record -> zero block)
         double Jl[6], Jp[12], W = 0;
         if (valid) {
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
                 for (int cc = 0; cc < 3; cc++) Bm[r * 3 + cc] = W * (Jp[r] * Jl[cc] + Jp[6 + r] * Jl[3 + cc]);
         }
         __syncthreads();
-        for (int i = tid; i < 18 * nv; i += BA_TE) gb[i] = s_rec[i];
+        for (int i = tid; i < 9 * nv; i += BA_TE) reinterpret_cast<double2*>(gb)[i] = reinterpret_cast<const double2*>(s_rec)[i];
     }
     if (b == P.blkE0 && tid == 0 && S.round_start) A.state[p].maxdiag_bits = 0ull;
 }
@@ -1200,7 +1205,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
             const double nn = sqrt(Dc[4] * Dc[4] + Dc[5] * Dc[5] + Dc[6] * Dc[6] + Dc[7] * Dc[7]);
             for (int i = 4; i < 8; i++) Dc[i] /= nn;
             Dc[8] = T[3]; Dc[9] = T[7]; Dc[10] = T[11];
-            for (int i = 0; i < 36; i++) Dc[11 + i] = Q.cam_adj[36 * c + i];
+            for (int i = 0; i < 36; i++) Dc[BA_CAM_ADJ + i] = Q.cam_adj[36 * c + i];
         }
         for (int i = 0; i < P.nP; i++) {   // Converter::toSE3Quat + SE3Quat(R, t)
             const double* T = Q.poses + 12 * i;

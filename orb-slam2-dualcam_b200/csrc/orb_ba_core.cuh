@@ -4,7 +4,8 @@
 #pragma once
 #include <math.h>
 
-#define BA_CAM_STRIDE 47       // fx fy cx cy | ext quat xyzw | ext t | adj[36]
+#define BA_CAM_STRIDE 48       // fx fy cx cy | ext quat xyzw | ext t | pad | adj[36]   (adjoint 16-byte aligned at +12)
+#define BA_CAM_ADJ 12
 #define BA_REC 22              // per-edge linearisation record: Jl[6] W r0 r1 Jp[12] pad (176 B: 16-byte aligned for 128-bit loads)
 
 // ------------------------------------------------------------------------------------------------ SE3 (unit quaternion xyzw + t)

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(G_T) g_lin(GArgs A, int cur, int robust, doubl
     double Jp[12];
     if (A.pose_free[pi] >= 0) {
         const double tJ[12] = {t02 * Y, t00 * Z - t02 * X, -t00 * Y, t00, 0, t02, -t11 * Z + t12 * Y, -t12 * X, t11 * X, 0, t11, t12};
-        const double* Ad = c + 11;
+        const double* Ad = c + BA_CAM_ADJ;
 #pragma unroll
         for (int i = 0; i < 2; i++)
 #pragma unroll
@@ -547,7 +547,7 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
         const double nn = sqrt(Dc[4] * Dc[4] + Dc[5] * Dc[5] + Dc[6] * Dc[6] + Dc[7] * Dc[7]);
         for (int i = 4; i < 8; i++) Dc[i] /= nn;
         Dc[8] = T[3]; Dc[9] = T[7]; Dc[10] = T[11];
-        for (int i = 0; i < 36; i++) Dc[11 + i] = Q->cam_adj[36 * c + i];
+        for (int i = 0; i < 36; i++) Dc[BA_CAM_ADJ + i] = Q->cam_adj[36 * c + i];
     }
     for (int i = 0; i < nP; i++) {
         const double* T = Q->poses + 12 * i;
