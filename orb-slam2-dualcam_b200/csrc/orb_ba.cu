@@ -38,7 +38,7 @@
 #define BA_TL 128              // threads per landmark block
 #define BA_TP 128              // threads per pose block (k_build)
 #define BA_CH 256              // tuples per chunk (k_pairs)
-#define BA_TS 256              // threads of k_solve
+#define BA_TS 512              // threads of k_solve
 #define BA_HS_SMEM_N 156       // reduced camera system in shared memory up to 156 x 156 doubles (26 free poses)
 
 struct BAProb {                // static description of one problem inside the batch
@@ -595,12 +595,88 @@ __device__ void round_over(const BABatch& A, BAState& S, bool stopped) {
     }
 }
 
+// Assembles, factorises (LDL^T) and solves the reduced camera system of one problem in `Hs` (row stride ld = n | 1).  Inlined
+// twice by k_solve -- once with the shared-memory matrix, once with a global-memory one -- so that each copy uses the
+// loads / stores of its address space instead of generic ones.
+__device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P, const BAState& S, double* Hs, double* s_lcol, int* s_ok_p,
+                                              double lambda) {
+    const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ld = n | 1;                      // odd row stride: column accesses are bank-conflict free
+    // ---- assemble the reduced camera system: diag blocks Hpp + lambda I, minus the pair partial sums (fixed chunk order)
+    for (int r = warp; r < n; r += BA_TS / 32) {
+        const int kr = r / 6;
+        for (int c = lane; c < n; c += 32) {
+            const int kc = c / 6;
+            Hs[(size_t)r * ld + c] = kr == kc ? A.Hpp[36 * (size_t)(P.k0 + kr) + (r - 6 * kr) * 6 + (c - 6 * kc)] + (r == c ? lambda : 0.0) : 0.0;
+        }
+    }
+    __syncthreads();
+    {
+        const int nCh = S.nChunks;
+        // chunks of one pair are consecutive: thread (pair, entry) walks them in order
+        for (int w = tid; w < P.nPairs * 36; w += BA_TS) {
+            const int pid = w / 36, en = w - pid * 36;
+            const int cnt = A.pair_cnt[P.pair0 + pid];
+            if (cnt == 0) continue;
+            const int first = A.pair_fchunk[P.pair0 + pid];
+            const int nc = (cnt + BA_CH - 1) / BA_CH;
+            double s = 0;
+            for (int c = 0; c < nc && first + c < nCh; c++) s += A.partial[36 * (size_t)(P.chunk0 + first + c) + en];
+            int i1, i2;
+            pair_decode(pid, P.K, i1, i2);
+            const int r = en / 6, c = en - r * 6;
+            const size_t a = (size_t)(6 * i1 + r) * ld + 6 * i2 + c;
+            if (i1 != i2) { Hs[a] = -s; Hs[(size_t)(6 * i2 + c) * ld + 6 * i1 + r] = -s; }
+            else Hs[a] -= s;
+        }
+    }
+    if (tid == 0) *s_ok_p = 1;
+    __syncthreads();
+    // ---- LDL^T in place (lower triangle: L below the diagonal, D on it); right-looking, one column per step:
+    //      lcol[i] = L_ij, then row i of the trailing lower triangle -= L_ij * d_j * L_kj  (warp per row, lanes along the row)
+    for (int j = 0; j < n; j++) {
+        const double dj = Hs[(size_t)j * ld + j];
+        if (dj == 0.0 || !isfinite(dj)) { if (tid == 0) *s_ok_p = 0; break; }
+        for (int i = j + 1 + tid; i < n; i += BA_TS) { const double l = Hs[(size_t)i * ld + j] / dj; Hs[(size_t)i * ld + j] = l; s_lcol[i] = l; }
+        __syncthreads();
+        for (int i = j + 1 + warp; i < n; i += BA_TS / 32) {
+            const double li = s_lcol[i] * dj;
+            double* row = Hs + (size_t)i * ld;
+            for (int k = j + 1 + lane; k <= i; k += 32) row[k] -= li * s_lcol[k];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const bool ok = *s_ok_p != 0;
+    double* x = A.xp + 6 * (size_t)P.k0;
+    if (ok && warp == 0) {
+        const double* bs = A.bs + 6 * (size_t)P.k0;
+        double* xs = s_lcol;                   // the solve runs on the shared copy
+        for (int i = lane; i < n; i += 32) xs[i] = bs[i];
+        __syncwarp();
+        for (int j = 0; j < n; j++) {
+            const double xj = xs[j];
+            for (int i = j + 1 + lane; i < n; i += 32) xs[i] -= Hs[(size_t)i * ld + j] * xj;
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32) xs[i] /= Hs[(size_t)i * ld + i];
+        __syncwarp();
+        for (int j = n - 1; j >= 0; j--) {
+            const double xj = xs[j];
+            for (int i = lane; i < j; i += 32) xs[i] -= Hs[(size_t)j * ld + i] * xj;
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32) x[i] = xs[i];
+    }
+    return ok;
+}
+
 __global__ void __launch_bounds__(BA_TS) k_solve(BABatch A, int hs_smem_doubles) {
     extern __shared__ double sm_hs[];
     __shared__ double red[BA_TS / 32];
     __shared__ int s_go, s_ok;
     double* s_lcol = sm_hs + hs_smem_doubles;   // n doubles after the matrix
-    const int p = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p = blockIdx.x, tid = threadIdx.x;
     BAState& S = A.state[p];
     if (S.done) return;
     const BAProb& P = A.prob[p];
@@ -635,74 +711,10 @@ __global__ void __launch_bounds__(BA_TS) k_solve(BABatch A, int hs_smem_doubles)
     __syncthreads();
     if (!s_go) return;
     const double lambda = S.lambda;
-    const int ld = n | 1;                      // odd row stride: column accesses are bank-conflict free
-    double* Hs = n <= BA_HS_SMEM_N ? sm_hs : A.Hs + P.hs_off;
-    // ---- assemble the reduced camera system: diag blocks Hpp + lambda I, minus the pair partial sums (fixed chunk order)
-    for (int r = warp; r < n; r += BA_TS / 32) {
-        const int kr = r / 6;
-        for (int c = lane; c < n; c += 32) {
-            const int kc = c / 6;
-            Hs[(size_t)r * ld + c] = kr == kc ? A.Hpp[36 * (size_t)(P.k0 + kr) + (r - 6 * kr) * 6 + (c - 6 * kc)] + (r == c ? lambda : 0.0) : 0.0;
-        }
-    }
-    __syncthreads();
-    {
-        const int nCh = S.nChunks;
-        // chunks of one pair are consecutive: thread (pair, entry) walks them in order
-        for (int w = tid; w < P.nPairs * 36; w += BA_TS) {
-            const int pid = w / 36, en = w - pid * 36;
-            const int cnt = A.pair_cnt[P.pair0 + pid];
-            if (cnt == 0) continue;
-            const int first = A.pair_fchunk[P.pair0 + pid];
-            const int nc = (cnt + BA_CH - 1) / BA_CH;
-            double s = 0;
-            for (int c = 0; c < nc && first + c < nCh; c++) s += A.partial[36 * (size_t)(P.chunk0 + first + c) + en];
-            int i1, i2;
-            pair_decode(pid, P.K, i1, i2);
-            const int r = en / 6, c = en - r * 6;
-            const size_t a = (size_t)(6 * i1 + r) * ld + 6 * i2 + c;
-            if (i1 != i2) { Hs[a] = -s; Hs[(size_t)(6 * i2 + c) * ld + 6 * i1 + r] = -s; }
-            else Hs[a] -= s;
-        }
-    }
-    if (tid == 0) s_ok = 1;
-    __syncthreads();
-    // ---- LDL^T in place (lower triangle: L below the diagonal, D on it); right-looking, one column per step:
-    //      lcol[i] = L_ij, then row i of the trailing lower triangle -= L_ij * d_j * L_kj  (warp per row, lanes along the row)
-    for (int j = 0; j < n; j++) {
-        const double dj = Hs[(size_t)j * ld + j];
-        if (dj == 0.0 || !isfinite(dj)) { if (tid == 0) s_ok = 0; break; }
-        for (int i = j + 1 + tid; i < n; i += BA_TS) { const double l = Hs[(size_t)i * ld + j] / dj; Hs[(size_t)i * ld + j] = l; s_lcol[i] = l; }
-        __syncthreads();
-        for (int i = j + 1 + warp; i < n; i += BA_TS / 32) {
-            const double li = s_lcol[i] * dj;
-            double* row = Hs + (size_t)i * ld;
-            for (int k = j + 1 + lane; k <= i; k += 32) row[k] -= li * s_lcol[k];
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    const bool ok = s_ok != 0;
+    bool ok;
+    if (n <= BA_HS_SMEM_N) ok = solve_reduced(A, P, S, sm_hs, s_lcol, &s_ok, lambda);
+    else ok = solve_reduced(A, P, S, A.Hs + P.hs_off, s_lcol, &s_ok, lambda);
     double* x = A.xp + 6 * (size_t)P.k0;
-    if (ok && warp == 0) {
-        const double* bs = A.bs + 6 * (size_t)P.k0;
-        double* xs = s_lcol;                   // the solve runs on the shared copy
-        for (int i = lane; i < n; i += 32) xs[i] = bs[i];
-        __syncwarp();
-        for (int j = 0; j < n; j++) {
-            const double xj = xs[j];
-            for (int i = j + 1 + lane; i < n; i += 32) xs[i] -= Hs[(size_t)i * ld + j] * xj;
-            __syncwarp();
-        }
-        for (int i = lane; i < n; i += 32) xs[i] /= Hs[(size_t)i * ld + i];
-        __syncwarp();
-        for (int j = n - 1; j >= 0; j--) {
-            const double xj = xs[j];
-            for (int i = lane; i < j; i += 32) xs[i] -= Hs[(size_t)j * ld + i] * xj;
-            __syncwarp();
-        }
-        for (int i = lane; i < n; i += 32) x[i] = xs[i];
-    }
     if (!ok) for (int i = tid; i < n; i += BA_TS) x[i] = 0.0;   // g2o applies a stale x; the trial is rejected either way
     __syncthreads();
     // ---- trial poses: exp(x) * pose for free poses, copy for fixed ones;  pose part of computeScale()
