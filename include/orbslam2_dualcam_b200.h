@@ -324,6 +324,29 @@ int  orbba_stage_ms(orbba_t*, double* ms1, int* calls);
 int  orbba_kernel_ms(orbba_t*, double* ms6, int* steps);
 
 /* ------------------------------------------------------------------------------------------------
+ * Optimizer::PoseOptimization(pFrame) (src/Optimizer.cc:250-405): pose-only LM of one frame against the map points its keypoints hold,
+ * four rounds of optimize(10) with inlier / outlier re-classification.  Batched over frames (one per tracked sequence), one persistent
+ * CTA per frame.  The adaptor lists, in keypoint order, every keypoint i with mvpMapPoints[i] != NULL.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const double*  pose;         /* [12]        Frame::mTcw, row-major 3x4 (CV_32F widened) */
+    int32_t        n_obs;        /* nInitialCorrespondences */
+    const double*  Xw;           /* [n_obs][3]  MapPoint::GetWorldPos() */
+    const double*  obs;          /* [n_obs][2]  mvTotalKeysUn[i].pt */
+    const double*  inv_sigma2;   /* [n_obs]     mvInvLevelSigma2[octave] */
+    const int32_t* cam;          /* [n_obs]     keypointToCam[i] */
+    int32_t        n_cams;
+    const double*  cam_K;        /* [n_cams][4]  fx fy cx cy */
+    const double*  cam_ext;      /* [n_cams][12] mvExtrinsics[c] */
+    const double*  cam_adj;      /* [n_cams][36] mvExtAdj[c] */
+} orbpo_frame_t;
+/*   poses_out [n][12]: the pose SetPose() receives; outlier: mvbOutlier of the listed keypoints, frames concatenated [sum n_obs];
+ *   n_inliers [n]: the return value (nInitialCorrespondences - nBad; 0 and nothing touched below 3 correspondences);
+ *   lm_counts [n][2] (may be NULL): LM iterations and trials summed over the rounds.  HOST buffers, synchronous. */
+int  orbba_pose_optimization(orbba_t*, const orbpo_frame_t* frames, int n, double* poses_out, uint8_t* outlier, int32_t* n_inliers,
+                             int32_t* lm_counts);
+
+/* ------------------------------------------------------------------------------------------------
  * GlobalBundleAdjustemnt for large maps, on one GPU or landmark-partitioned over the GPUs of a node (BASELINE.json configs[4]:
  * 2000 key frames x 2 cameras, 200k map points).  One process per GPU; key-frame poses are replicated, rank r owns the map
  * points `index mod world == r` and their edges; per LM trial ONE NCCL all-reduce (sum, FP64) of the reduced camera system

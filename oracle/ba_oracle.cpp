@@ -440,6 +440,125 @@ struct BA {
     bool depthPositive(int e) const { double pc[3]; project(e, pc); return pc[2] > 0.0; }
 };
 
+// ---------------------------------------------------------------- pose-only optimisation (Optimizer::PoseOptimization)
+// One VertexSE3Expmap, unary EdgeSE3ProjectXYZOnlyPose edges (types_six_dof_expmap.cpp:200-255), BlockSolver_6_3 over
+// LinearSolverDense (6x6 Eigen::LDLT; restated as LDL^T without pivoting + positivity check), the same LM as above.
+struct PoseOnly {
+    SE3 pose;
+    int nE = 0;
+    std::vector<double> Xw, obs, info, err;
+    std::vector<int> eCam, level;
+    std::vector<Cam> cam;
+    bool robust = true;
+    double delta = 0, dsqr = 0, lambda = 0, ni = 2;
+    int nBad = 0, trials = 0, iterations = 0;
+    double H[36], b[6], x[6];
+
+    void project(int e, double pc[3]) const { double pr[3]; se3_map(pose, &Xw[3 * e], pr); se3_map(cam[eCam[e]].ext, pr, pc); }
+    void computeError(int e) {
+        double pc[3];
+        project(e, pc);
+        const Cam& c = cam[eCam[e]];
+        err[2 * e] = obs[2 * e] - (pc[0] / pc[2] * c.fx + c.cx);
+        err[2 * e + 1] = obs[2 * e + 1] - (pc[1] / pc[2] * c.fy + c.cy);
+    }
+    double chi2(int e) const { return (err[2 * e] * err[2 * e] + err[2 * e + 1] * err[2 * e + 1]) * info[e]; }
+    void computeActiveErrors() { for (int e = 0; e < nE; e++) if (level[e] == 0) computeError(e); }
+    double activeRobustChi2() const {
+        double chi = 0;
+        for (int e = 0; e < nE; e++) {
+            if (level[e]) continue;
+            const double c2 = chi2(e);
+            chi += (robust && c2 > dsqr) ? 2 * std::sqrt(c2) * delta - dsqr : c2;
+        }
+        return chi;
+    }
+    void buildSystem() {
+        for (double& v : H) v = 0;
+        for (double& v : b) v = 0;
+        for (int e = 0; e < nE; e++) {
+            if (level[e]) continue;
+            const Cam& c = cam[eCam[e]];
+            double pc[3];
+            project(e, pc);
+            const double X = pc[0], Y = pc[1], Z = pc[2];
+            const double tmp[6] = {c.fx, 0, -X / Z * c.fx, 0, c.fy, -Y / Z * c.fy};
+            const double J3[18] = {0, Z, -Y, 1, 0, 0, -Z, 0, X, 0, 1, 0, Y, -X, 0, 0, 0, 1};
+            double tJ[12], Jp[12];
+            for (int i = 0; i < 2; i++)
+                for (int j = 0; j < 6; j++) tJ[i * 6 + j] = (-1. / Z * tmp[i * 3]) * J3[j] + (-1. / Z * tmp[i * 3 + 1]) * J3[6 + j] + (-1. / Z * tmp[i * 3 + 2]) * J3[12 + j];
+            for (int i = 0; i < 2; i++)
+                for (int j = 0; j < 6; j++) {
+                    double s = 0;
+                    for (int k = 0; k < 6; k++) s += tJ[i * 6 + k] * c.adj[k * 6 + j];
+                    Jp[i * 6 + j] = s;
+                }
+            const double w = info[e];
+            double wr = 1;
+            if (robust) { const double c2 = chi2(e); if (c2 > dsqr) wr = delta / std::sqrt(c2); }
+            const double W = wr * w, r0 = -w * err[2 * e] * wr, r1 = -w * err[2 * e + 1] * wr;
+            for (int i = 0; i < 6; i++) {
+                b[i] += Jp[i] * r0 + Jp[6 + i] * r1;
+                for (int j = 0; j < 6; j++) H[i * 6 + j] += (Jp[i] * Jp[j] + Jp[6 + i] * Jp[6 + j]) * W;
+            }
+        }
+    }
+    bool solve() {
+        std::vector<double> A(36);
+        for (int i = 0; i < 36; i++) A[i] = H[i] + ((i % 7 == 0) ? lambda : 0.0);
+        for (double& v : x) v = 0;
+        return ldlt_solve(A, 6, b, x);
+    }
+    bool lmIteration(int iteration) {
+        computeActiveErrors();
+        double currentChi = activeRobustChi2(), tempChi = currentChi;
+        const double iniChi = currentChi;
+        buildSystem();
+        if (iteration == 0) {
+            double md = 0;
+            for (int j = 0; j < 6; j++) md = std::max(std::fabs(H[j * 7]), md);
+            lambda = 1e-5 * md; ni = 2; nBad = 0;
+        }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            const SE3 saved = pose;
+            const bool ok2 = solve();
+            pose = se3_mul(se3_exp(x), pose);
+            computeActiveErrors();
+            tempChi = activeRobustChi2();
+            if (!ok2) tempChi = std::numeric_limits<double>::max();
+            rho = currentChi - tempChi;
+            double scale = 0;
+            for (int j = 0; j < 6; j++) scale += x[j] * (lambda * x[j] + b[j]);
+            scale += 1e-3;
+            rho /= scale;
+            trials++;
+            if (rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1. - std::pow(2 * rho - 1, 3);
+                alpha = std::min(alpha, 2. / 3.);
+                lambda *= std::max(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+            } else {
+                lambda *= ni; ni *= 2;
+                pose = saved;
+            }
+            qmax++;
+        } while (rho < 0 && qmax < 10);
+        if (qmax == 10 || rho == 0) return false;
+        if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+        return nBad < 3;
+    }
+    void optimize(int its) {
+        bool any = false;
+        for (int e = 0; e < nE; e++) any |= level[e] == 0;
+        if (!any) return;                                  // "0 vertices to optimize"
+        bool ok = true;
+        for (int i = 0; i < its && ok; i++) { ok = lmIteration(i); iterations++; }
+    }
+};
+
 void load(BA& b, const orc_ba_problem_t* p, double huber_delta) {
     b.nP = p->n_poses; b.nL = p->n_points; b.nE = p->n_edges;
     b.pose.resize(b.nP); b.fixed.assign(p->pose_fixed, p->pose_fixed + b.nP);
@@ -534,6 +653,51 @@ int orc_ba_normal_equations(const orc_ba_problem_t* p, double huber_delta, doubl
     std::memcpy(Hll, b.Hll.data(), b.Hll.size() * 8); std::memcpy(bl, b.bl.data(), b.bl.size() * 8);
     std::memcpy(Hpl, b.Hpl.data(), b.Hpl.size() * 8);
     return (int)b.freePoses.size();
+}
+
+
+// Optimizer::PoseOptimization(pFrame)  src/Optimizer.cc:250-405.  One edge per keypoint that holds a map point (in keypoint
+// order).  Returns nInitialCorrespondences - nBad (0 when fewer than 3 correspondences: nothing is touched then);
+// outlier[e] = pFrame->mvbOutlier of the keypoint, pose_out = the pose SetPose() receives.
+int orc_pose_optimization(const double* pose12, int n, const double* Xw, const double* obs, const double* inv_sigma2, const int32_t* cam,
+                          int n_cams, const double* cam_K, const double* cam_ext, const double* cam_adj, double* pose_out, uint8_t* outlier,
+                          int32_t* lm_counts /* [2] iterations, trials; may be NULL */) {
+    for (int i = 0; i < 12; i++) pose_out[i] = pose12[i];
+    for (int e = 0; e < n; e++) outlier[e] = 0;
+    if (lm_counts) { lm_counts[0] = 0; lm_counts[1] = 0; }
+    if (n < 3) return 0;
+    PoseOnly P;
+    P.nE = n;
+    P.Xw.assign(Xw, Xw + 3 * (size_t)n); P.obs.assign(obs, obs + 2 * (size_t)n); P.info.assign(inv_sigma2, inv_sigma2 + n);
+    P.err.assign(2 * (size_t)n, 0); P.eCam.assign(cam, cam + n); P.level.assign(n, 0);
+    P.cam.resize(n_cams);
+    for (int c = 0; c < n_cams; c++) {
+        Cam& C = P.cam[c];
+        C.fx = cam_K[4 * c]; C.fy = cam_K[4 * c + 1]; C.cx = cam_K[4 * c + 2]; C.cy = cam_K[4 * c + 3];
+        C.ext = se3_from_Rt(cam_ext + 12 * c);
+        for (int i = 0; i < 36; i++) C.adj[i] = cam_adj[36 * c + i];
+    }
+    P.delta = (double)(float)std::sqrt(5.991); P.dsqr = P.delta * P.delta;   // const float deltaMono = sqrt(5.991)
+    const SE3 initial = se3_from_Rt(pose12);
+    P.pose = initial;
+    const float chi2Mono[4] = {5.991f, 5.991f, 5.991f, 5.991f};
+    int nBad = 0;
+    for (int it = 0; it < 4; it++) {
+        P.pose = initial;                                   // vSE3->setEstimate(toSE3Quat(pFrame->mTcw)): every round restarts
+        P.optimize(10);
+        nBad = 0;
+        for (int e = 0; e < n; e++) {
+            if (outlier[e]) P.computeError(e);
+            const float chi2 = (float)P.chi2(e);
+            if (chi2 > chi2Mono[it]) { outlier[e] = 1; P.level[e] = 1; nBad++; }
+            else { outlier[e] = 0; P.level[e] = 0; }
+        }
+        if (it == 2) P.robust = false;                      // e->setRobustKernel(0)
+        if (n < 10) break;                                  // optimizer.edges().size() < 10
+    }
+    se3_to_Rt(P.pose, pose_out);
+    if (lm_counts) { lm_counts[0] = P.iterations; lm_counts[1] = P.trials; }
+    return n - nBad;
 }
 
 }  // extern "C"

@@ -66,6 +66,7 @@ SIGNATURES = {
     "orbm_search_by_projection_last": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp, vp]),
     "orbm_search_by_bow": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp]),
     "orbm_is_in_frustum": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp]),
+    "orbba_pose_optimization": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp]),
     "orbba_dist_unique_id": (C.c_int, [vp]),
     "orbba_dist_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp]),
     "orbba_dist_destroy": (None, [vp]),

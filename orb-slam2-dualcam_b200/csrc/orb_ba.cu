@@ -998,6 +998,11 @@ static int finish(orbba* b) {
     return ORB_OK;
 }
 
+// accessors for orb_pose.cu (PoseOptimization shares the handle's device and stream)
+cudaStream_t orbba_stream_of(orbba* b) { return b->stream; }
+int orbba_device_of(orbba* b) { return b->device; }
+void orbba_count_launches(orbba* b, int n) { b->launches += n; }
+
 extern "C" {
 
 int orbba_create(orbba_t** out, int device, int max_problems) {

@@ -33,6 +33,11 @@ class StatsC(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class PoFrameC(C.Structure):
+    _fields_ = [("pose", C.c_void_p), ("n_obs", C.c_int32), ("Xw", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p), ("cam", C.c_void_p),
+                ("n_cams", C.c_int32), ("cam_K", C.c_void_p), ("cam_ext", C.c_void_p), ("cam_adj", C.c_void_p)]
+
+
 _KEYS = [("poses", np.float64), ("pose_fixed", np.uint8), ("points", np.float64), ("edge_pose", np.int32), ("edge_point", np.int32),
          ("edge_cam", np.int32), ("edge_obs", np.float64), ("edge_inv_sigma2", np.float64), ("cam_K", np.float64),
          ("cam_ext", np.float64), ("cam_adj", np.float64)]
@@ -82,6 +87,31 @@ class Optimizer:
         return poses, points, st.asdict()
 
     BundleAdjustment = GlobalBundleAdjustemnt
+
+    def PoseOptimization(self, frames):
+        """Optimizer::PoseOptimization(pFrame) (src/Optimizer.cc:250-405) for a batch of frames.
+        frames: list of dict(pose [12], Xw [n][3], obs [n][2], inv_sigma2 [n], cam [n], cam_K, cam_ext, cam_adj)
+        -> list of (pose [12], outlier bool [n], n_inliers, (lm_iterations, lm_trials))"""
+        single = isinstance(frames, dict)
+        frames = [frames] if single else list(frames)
+        arr = (PoFrameC * len(frames))()
+        keeps = []
+        for i, f in enumerate(frames):
+            k = dict(pose=np.ascontiguousarray(f["pose"], np.float64).reshape(12), Xw=np.ascontiguousarray(f["Xw"], np.float64), obs=np.ascontiguousarray(f["obs"], np.float64),
+                     inv_sigma2=np.ascontiguousarray(f["inv_sigma2"], np.float64), cam=np.ascontiguousarray(f["cam"], np.int32),
+                     cam_K=np.ascontiguousarray(f["cam_K"], np.float64), cam_ext=np.ascontiguousarray(f["cam_ext"], np.float64), cam_adj=np.ascontiguousarray(f["cam_adj"], np.float64))
+            keeps.append(k)
+            arr[i] = PoFrameC(pose=k["pose"].ctypes.data, n_obs=len(k["inv_sigma2"]), Xw=k["Xw"].ctypes.data, obs=k["obs"].ctypes.data, inv_sigma2=k["inv_sigma2"].ctypes.data,
+                              cam=k["cam"].ctypes.data, n_cams=k["cam_K"].shape[0], cam_K=k["cam_K"].ctypes.data, cam_ext=k["cam_ext"].ctypes.data, cam_adj=k["cam_adj"].ctypes.data)
+        n = len(frames)
+        tot = sum(a.n_obs for a in arr)
+        poses = np.zeros((n, 12)); outl = np.zeros(max(tot, 1), np.uint8); inl = np.zeros(n, np.int32); cnt = np.zeros((n, 2), np.int32)
+        check(lib().orbba_pose_optimization(self._h, C.addressof(arr), n, ptr(poses), ptr(outl), ptr(inl), ptr(cnt)))
+        res, off = [], 0
+        for i, a in enumerate(arr):
+            res.append((poses[i].copy(), outl[off:off + a.n_obs].astype(bool), int(inl[i]), (int(cnt[i, 0]), int(cnt[i, 1]))))
+            off += a.n_obs
+        return res[0] if single else res
 
     # ---- batched form
     @staticmethod

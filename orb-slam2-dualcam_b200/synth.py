@@ -427,3 +427,29 @@ def gba_problem(seed=0, n_kf=2000, n_points=200000, obs=8, outlier_frac=0.02, W=
                 edge_obs=np.ascontiguousarray(e_obs[order]), edge_inv_sigma2=inv_sigma2[octave][order].astype(np.float64),
                 cam_K=RIG_K.astype(np.float32).astype(np.float64), cam_ext=np.ascontiguousarray(ext.reshape(2, 12)), cam_adj=np.ascontiguousarray(adj.reshape(2, 36)),
                 gt_poses=gt.reshape(n_kf, 12), gt_points=X, planted_outlier=out[order])
+
+
+def pose_opt_frame(seed, n_obs=600, outlier_frac=0.15, W=640, H=480, pose_noise=(0.05, 1.5)):
+    """Optimizer::PoseOptimization input: a rig pose perturbed from the truth, map points seen by either camera of the rig,
+    octave-dependent pixel noise and gross outliers.  dict in the layout of orbpo_frame_t (+ gt_pose, planted)."""
+    rng = np.random.default_rng(seed)
+    ext, adj = rig_extrinsics()
+    R = _rodrigues(np.array([0.1, -0.2, 0.05])); t = np.array([0.3, -0.1, 0.5])
+    gt = np.concatenate([R, t[:, None]], 1)
+    cam = rng.integers(0, 2, n_obs)
+    u = rng.uniform(10, W - 10, n_obs); v = rng.uniform(10, H - 10, n_obs); d = rng.uniform(1.5, 15, n_obs)
+    K = RIG_K
+    pc = np.stack([(u - K[cam, 2]) / K[cam, 0] * d, (v - K[cam, 3]) / K[cam, 1] * d, d], 1)
+    pr = np.einsum("nji,nj->ni", ext[cam][:, :, :3], pc - ext[cam][:, :, 3])
+    Xw = (pr - t) @ R
+    octave = rng.integers(0, 8, n_obs)
+    noise = rng.normal(0, 1, (n_obs, 2)) * (1.2 ** octave)[:, None]
+    planted = rng.random(n_obs) < outlier_frac
+    noise[planted] += rng.choice([-25.0, 25.0], (int(planted.sum()), 2))
+    obs = (np.stack([u, v], 1) + noise).astype(np.float32).astype(np.float64)
+    dR = _rodrigues(rng.normal(0, np.deg2rad(pose_noise[1]) / np.sqrt(3), 3))
+    pose = np.concatenate([dR @ R, (dR @ t + rng.normal(0, pose_noise[0] / np.sqrt(3), 3))[:, None]], 1)
+    inv_sigma2 = (1.0 / (scale_factors(8).astype(np.float64) ** 2)).astype(np.float32).astype(np.float64)[octave]
+    return dict(pose=pose.astype(np.float32).astype(np.float64).reshape(12), Xw=Xw.astype(np.float32).astype(np.float64), obs=obs, inv_sigma2=inv_sigma2,
+                cam=cam.astype(np.int32), cam_K=RIG_K.astype(np.float32).astype(np.float64), cam_ext=np.ascontiguousarray(ext.reshape(2, 12)),
+                cam_adj=np.ascontiguousarray(adj.reshape(2, 36)), gt_pose=gt.reshape(12), planted=planted)

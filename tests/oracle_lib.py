@@ -296,3 +296,19 @@ def is_in_frustum(frame, pos, normal, max_dist, min_dist, cos_limit=0.5, for_all
     L.orc_is_in_frustum(C.addressof(qs), pos.ctypes.data, normal.ctypes.data, max_dist.ctypes.data, min_dist.ctypes.data, n, cos_limit, int(for_all),
                         out.ctypes.data, uvc.ctypes.data)
     return out, uvc
+
+
+def pose_optimization(f):
+    """Optimizer::PoseOptimization on the oracle -> (pose [12], outlier bool [n], n_inliers, (iterations, trials))"""
+    L = lib()
+    L.orc_pose_optimization.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 6
+    L.orc_pose_optimization.restype = C.c_int
+    k = dict(pose=np.ascontiguousarray(f["pose"], np.float64).reshape(12), Xw=np.ascontiguousarray(f["Xw"], np.float64), obs=np.ascontiguousarray(f["obs"], np.float64),
+             inv_sigma2=np.ascontiguousarray(f["inv_sigma2"], np.float64), cam=np.ascontiguousarray(f["cam"], np.int32),
+             cam_K=np.ascontiguousarray(f["cam_K"], np.float64), cam_ext=np.ascontiguousarray(f["cam_ext"], np.float64), cam_adj=np.ascontiguousarray(f["cam_adj"], np.float64))
+    n = len(k["inv_sigma2"])
+    pose = np.zeros(12); out = np.zeros(max(n, 1), np.uint8); cnt = np.zeros(2, np.int32)
+    r = L.orc_pose_optimization(k["pose"].ctypes.data, n, k["Xw"].ctypes.data, k["obs"].ctypes.data, k["inv_sigma2"].ctypes.data, k["cam"].ctypes.data,
+                                k["cam_K"].shape[0], k["cam_K"].ctypes.data, k["cam_ext"].ctypes.data, k["cam_adj"].ctypes.data, pose.ctypes.data,
+                                out.ctypes.data, cnt.ctypes.data)
+    return pose, out[:n].astype(bool), r, (int(cnt[0]), int(cnt[1]))
