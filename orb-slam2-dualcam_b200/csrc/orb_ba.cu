@@ -14,10 +14,10 @@
 // advanced by the last CTA of the step, so the host never reads anything back between steps.  Everything is FP64 and
 // every sum has one owner and a fixed order (no floating-point atomics): results are bit-reproducible.
 //
-//   k_lin       thread / edge       residual, 2x6 and 2x3 Jacobians, Huber weight, B_e = Jp^T W Jl          (per LM iteration)
-//   k_build     thread / landmark   Hll, bl ;  CTA / free pose: Hpp, bp                                      (per LM iteration)
-//   k_trial_lm  thread / landmark   Dinv = (Hll + lambda I)^-1, Dinv bl, Y_e = B_e Dinv, Y_e bl            (per trial)
-//   k_pairs     warp / chunk of (edge, edge) tuples of one pose pair: partial 6x6 of  sum Y_a B_b^T ; warp / pose: Schur rhs
+//   k_lin       thread / edge       residual, Huber weight; stores only the point in the camera frame + weights (64 B)   (per LM iteration)
+//   k_build     thread / landmark   Hll, bl ;  CTA / free pose: Hpp, bp  (Jacobians rebuilt from the 64-byte records)   (per LM iteration)
+//   k_pairs     warp / chunk of (edge, edge) tuples of one pose pair and camera pair: partial Schur product in "tJ space";
+//               warp / pose: Schur right-hand side                                                                      (per trial)
 //   k_solve     CTA / problem       reduced camera system in shared memory, LDL^T, pose increments, exp-map update
 //   k_back      thread / landmark   landmark increment, trial errors and chi2 of its edges; last CTA: LM decision
 // Blocks are laid out problem-major, so the CTAs resident at any time work on a handful of neighbouring problems and the
@@ -38,6 +38,7 @@
 #define BA_TL 128              // threads per landmark block
 #define BA_TP 128              // threads per pose block (k_build)
 #define BA_CH 256              // tuples per chunk (k_pairs)
+#define BA_MAXCC 16            // camera pairs per pose pair: rigs of up to 4 cameras
 #define BA_TS 512              // threads of k_solve
 #define BA_HS_SMEM_N 156       // reduced camera system in shared memory up to 156 x 156 doubles (26 free poses)
 
@@ -46,6 +47,7 @@ struct BAProb {                // static description of one problem inside the b
     int pair0, nPairs;         // K (K + 1) / 2 pair slots
     int chunk0, nChunksMax;    // chunk slots (upper bound)
     int item0, nItems;         // k_pairs work items: nChunksMax chunk warps + K pose warps
+    int rt0, CC, pc0, ut0;     // first (pose, camera) rotation, nC * nC, first (pair, camera pair) slot, first (free pose, camera) slot
     int blkE0, nbE, blkL0, nbL;
     long long tup0, eof0, hs_off;
 };
@@ -71,16 +73,21 @@ struct BABatch {               // kernel argument (by value)
     const int* pose_free;                       // [Ptot] global free index or -1
     const double *pose0, *pt0;
     const int *blkE_prob, *blkL_prob, *item_prob;
+    const int* free_pose;                       // [Ktot] global pose index of every free pose
     // index built on the device
     int* edge_of;                               // [landmark][free pose of the problem] -> edge or -1
-    int *pair_cnt, *pair_off, *pair_fchunk;      // per pair: tuples, first tuple, first chunk
+    int *pair_cnt, *pair_off;                    // per pair: tuples, first tuple
+    int *pc_cnt, *pc_off, *pc_fchunk, *pc_nchunk; // per (pair, camera pair): tuples, first tuple, first chunk, chunks
     int *chunk_pair, *chunk_start, *chunk_len;
     int2* tuples;
     // dynamic
     double *pose[2], *pt[2], *err[2];
     unsigned char* level;
-    double *rec, *B, *Y, *v;                    // per edge: 21 / 18 / 18 / 6
-    double *Hll, *bl, *Dinv, *db;               // per landmark: 6 / 3 / 6 / 3
+    double *er;                                 // per edge: X Y Z 1/Z W r0 r1 - (point in the camera frame, weights)
+    double *B, *Y, *v;                          // per edge and trial, tJ space: Bt (18), Yt (18), Yt bl (6)
+    double *RT;                                 // per (pose, camera): rotation of ext_c * pose (9)
+    double *ut_u, *ut_y;                        // per (free pose, camera): Schur rhs partial in tJ space (6), Adj_c x_k (6)
+    double *Hll, *bl;                           // per landmark: 6 / 3
     double *Hpp, *bp, *bs, *xp;                 // per free pose: 36 / 6 / 6 / 6
     double *partial;                            // per chunk: 36
     double *partE, *partL;                      // per edge block: chi, active ; per landmark block: chi, scale
@@ -133,7 +140,7 @@ __device__ __forceinline__ void pair_decode(int pid, int K, int& i, int& j) {
     while (rem >= K - i) { rem -= K - i; i++; }
     j = i + rem;
 }
-// warp per pose pair (i <= j): number of landmarks observed by both
+// warp per pose pair (i <= j): number of landmarks observed by both, per camera pair (camera of i's edge, camera of j's edge)
 __global__ void k_pair_count(BABatch A, const int* blkP_prob, const int* blkP_first) {
     const int p = blkP_prob[blockIdx.x];
     const BAProb P = A.prob[p];
@@ -142,37 +149,56 @@ __global__ void k_pair_count(BABatch A, const int* blkP_prob, const int* blkP_fi
     int i, j;
     pair_decode(pid, P.K, i, j);
     const int* T = A.edge_of + P.eof0;
-    int cnt = 0;
+    int cnt[BA_MAXCC];
+#pragma unroll
+    for (int q = 0; q < BA_MAXCC; q++) cnt[q] = 0;
     for (int l0 = 0; l0 < P.nL; l0 += 32) {
         const int l = l0 + lane;
-        const bool both = l < P.nL && T[(long long)l * P.K + i] >= 0 && T[(long long)l * P.K + j] >= 0;
-        cnt += __popc(__ballot_sync(0xffffffffu, both));
+        int a = -1, c = -1;
+        if (l < P.nL) { a = T[(long long)l * P.K + i]; c = T[(long long)l * P.K + j]; }
+        const bool both = a >= 0 && c >= 0;
+        const int combo = both ? (A.e_cam[a] - P.c0) * P.nC + (A.e_cam[c] - P.c0) : -1;
+#pragma unroll
+        for (int q = 0; q < BA_MAXCC; q++)
+            if (q < P.CC) cnt[q] += __popc(__ballot_sync(0xffffffffu, combo == q));
     }
-    if (lane == 0) A.pair_cnt[P.pair0 + pid] = cnt;
+    if (lane == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int q = 0; q < BA_MAXCC; q++)
+            if (q < P.CC) { A.pc_cnt[P.pc0 + pid * P.CC + q] = cnt[q]; tot += cnt[q]; }
+        A.pair_cnt[P.pair0 + pid] = tot;
+    }
 }
-// one thread per problem: tuple offsets of the pairs and the chunk table
+// one thread per problem: tuple offsets of the (pair, camera pair) slots and the chunk table
 __global__ void k_pair_scan(BABatch A) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= A.nProb) return;
     const BAProb P = A.prob[p];
     int off = 0, nc = 0;
     for (int pid = 0; pid < P.nPairs; pid++) {
-        const int c = A.pair_cnt[P.pair0 + pid];
         A.pair_off[P.pair0 + pid] = off;
-        A.pair_fchunk[P.pair0 + pid] = nc;
-        for (int s = 0; s < c; s += BA_CH) {
-            if (nc < P.nChunksMax) {
-                A.chunk_pair[P.chunk0 + nc] = pid;
-                A.chunk_start[P.chunk0 + nc] = off + s;
-                A.chunk_len[P.chunk0 + nc] = min(BA_CH, c - s);
+        for (int q = 0; q < P.CC; q++) {
+            const int pc = P.pc0 + pid * P.CC + q;
+            const int c = A.pc_cnt[pc];
+            A.pc_off[pc] = off;
+            A.pc_fchunk[pc] = nc;
+            for (int s = 0; s < c; s += BA_CH) {
+                if (nc < P.nChunksMax) {
+                    A.chunk_pair[P.chunk0 + nc] = pid * P.CC + q;
+                    A.chunk_start[P.chunk0 + nc] = off + s;
+                    A.chunk_len[P.chunk0 + nc] = min(BA_CH, c - s);
+                }
+                nc++;
             }
-            nc++;
+            A.pc_nchunk[pc] = nc - A.pc_fchunk[pc];
+            off += c;
         }
-        off += c;
     }
     A.state[p].nChunks = min(nc, P.nChunksMax);
     A.state[p].nTuples = off;
 }
+// tuples of a pair: grouped by camera pair, sorted by landmark inside a group
 __global__ void k_pair_fill(BABatch A, const int* blkP_prob, const int* blkP_first) {
     const int p = blkP_prob[blockIdx.x];
     const BAProb P = A.prob[p];
@@ -181,16 +207,24 @@ __global__ void k_pair_fill(BABatch A, const int* blkP_prob, const int* blkP_fir
     int i, j;
     pair_decode(pid, P.K, i, j);
     const int* T = A.edge_of + P.eof0;
-    int2* out = A.tuples + P.tup0 + A.pair_off[P.pair0 + pid];
-    int pos = 0;
+    int pos[BA_MAXCC];
+#pragma unroll
+    for (int q = 0; q < BA_MAXCC; q++) pos[q] = q < P.CC ? A.pc_off[P.pc0 + pid * P.CC + q] : 0;
+    int2* out = A.tuples + P.tup0;
     for (int l0 = 0; l0 < P.nL; l0 += 32) {
         const int l = l0 + lane;
         int a = -1, c = -1;
         if (l < P.nL) { a = T[(long long)l * P.K + i]; c = T[(long long)l * P.K + j]; }
         const bool both = a >= 0 && c >= 0;
-        const unsigned m = __ballot_sync(0xffffffffu, both);
-        if (both) out[pos + __popc(m & ((1u << lane) - 1))] = make_int2(a, c);
-        pos += __popc(m);
+        const int combo = both ? (A.e_cam[a] - P.c0) * P.nC + (A.e_cam[c] - P.c0) : -1;
+#pragma unroll
+        for (int q = 0; q < BA_MAXCC; q++) {
+            if (q < P.CC) {
+                const unsigned m = __ballot_sync(0xffffffffu, combo == q);
+                if (combo == q) out[pos[q] + __popc(m & ((1u << lane) - 1))] = make_int2(a, c);
+                pos[q] += __popc(m);
+            }
+        }
     }
 }
 
@@ -218,10 +252,45 @@ __global__ void k_reset(BABatch A, int stopped0) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ per-edge geometry
+// Nothing Jacobian-sized is stored per edge.  k_lin keeps only the point in the camera frame and the weights
+//     er[e] = { X, Y, Z, 1/Z, W, r0, r1, - }      (W = rho1 * invSigma2, r = -invSigma2 * e * rho1; all zero for a level-1 edge)
+// and every consumer rebuilds what it needs from them (FP64 flops are cheap next to 300 bytes per edge and launch):
+//     tJ_e (2x6) = -1/z * tmp * [-skew(p) | I]                       the pose Jacobian BEFORE the camera adjoint:  Jp_e = tJ_e * Adj_c
+//     Jl_e (2x3) = -1/z * tmp * R(ext_c * pose)                      (types_six_dof_expmap.cpp:136-159)
+// The 6x6 adjoint of a camera is the same for all its edges, so every sum over edges is formed in "tJ space" per camera (or per
+// camera pair) and the adjoint is applied once to the sum:  sum_e Jp_e^T X_e Jp'_e = Adj_c^T (sum_e tJ_e^T X_e tJ'_e) Adj_c'.
+__device__ __forceinline__ void edge_tj(double X, double Y, double Z, double iz, double fx, double fy, double* tJ, double* t4) {
+    const double t00 = -iz * fx, t02 = iz * iz * X * fx, t11 = -iz * fy, t12 = iz * iz * Y * fy;
+    t4[0] = t00; t4[1] = t02; t4[2] = t11; t4[3] = t12;
+    tJ[0] = t02 * Y; tJ[1] = t00 * Z - t02 * X; tJ[2] = -t00 * Y; tJ[3] = t00; tJ[4] = 0; tJ[5] = t02;
+    tJ[6] = -t11 * Z + t12 * Y; tJ[7] = -t12 * X; tJ[8] = t11 * X; tJ[9] = 0; tJ[10] = t11; tJ[11] = t12;
+}
+__device__ __forceinline__ void edge_jl(const double* t4, const double* R, double* Jl) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) { Jl[j] = t4[0] * R[j] + t4[1] * R[6 + j]; Jl[3 + j] = t4[2] * R[3 + j] + t4[3] * R[6 + j]; }
+}
+// (Hll + lambda I)^-1 of a landmark: cofactor inverse of the symmetric 3x3 (Eigen's fixed-size inverse in
+// BlockSolver::solve, block_solver.hpp:381-395).  d = {d00, d01, d02, d11, d12, d22}
+__device__ __forceinline__ void landmark_dinv(const double* H, double lambda, double* d) {
+    const double m0 = H[0] + lambda, m1 = H[1], m2 = H[2], m4 = H[3] + lambda, m5 = H[4], m8 = H[5] + lambda;
+    const double c00 = m4 * m8 - m5 * m5, c01 = m5 * m2 - m1 * m8, c02 = m1 * m5 - m4 * m2;
+    const double id = 1.0 / (m0 * c00 + m1 * c01 + m2 * c02);
+    d[0] = c00 * id; d[1] = c01 * id; d[2] = c02 * id;
+    d[3] = (m0 * m8 - m2 * m2) * id; d[4] = (m2 * m1 - m0 * m5) * id; d[5] = (m0 * m4 - m1 * m1) * id;
+}
+__device__ __forceinline__ void load8(const double* p, double* o) {   // 64-byte record, 16-byte aligned
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const double2 q = reinterpret_cast<const double2*>(p)[i]; o[2 * i] = q.x; o[2 * i + 1] = q.y; }
+}
+__device__ __forceinline__ void load6(const double* p, double* o) {   // 48-byte record, 16-byte aligned
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const double2 q = reinterpret_cast<const double2*>(p)[i]; o[2 * i] = q.x; o[2 * i + 1] = q.y; }
+}
+
 // ------------------------------------------------------------------------------------------------ k_lin
 __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
     __shared__ double red[BA_TE / 32];
-    __shared__ __align__(16) double s_rec[BA_TE * BA_REC];     // records, then (same memory) the B blocks: 21.5 KB per CTA keeps 10 CTAs per SM
     const int b = blockIdx.x;
     const int p = A.blkE_prob[b];
     const BAState& S = A.state[p];
@@ -233,14 +302,25 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
     const int cur = S.cur;
     const bool robust = S.round == 0 && A.delta > 0;
     const double delta = A.delta, dsqr = delta * delta;
+    if (b == P.blkE0) {   // rotation of (camera extrinsic * rig pose) for every (pose, camera) of the problem
+        for (int i = tid; i < P.nP * P.nC; i += BA_TE) {
+            const int pl = i / P.nC, cl = i - pl * P.nC;
+            const double* c = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + cl);
+            double q[4], Rm[9];
+            q_mul(c + 4, A.pose[cur] + 7 * (size_t)(P.p0 + pl), q);
+            q_normalize(q);
+            q_to_matrix(q, Rm);
+            double* o = A.RT + 9 * (size_t)(P.rt0 + i);
+#pragma unroll
+            for (int k = 0; k < 9; k++) o[k] = Rm[k];
+        }
+    }
     double chi = 0, act = 0;
     if (valid) {
         const double* c = A.cam + BA_CAM_STRIDE * (size_t)A.e_cam[e];
-        const int pi = A.e_pose[e];
-        const double* ps = A.pose[cur] + 7 * (size_t)pi;
         const double w = A.e_info[e];
         double pc[3];
-        edge_project(ps, A.pt[cur] + 3 * (size_t)A.e_pt[e], c, pc);
+        edge_project(A.pose[cur] + 7 * (size_t)A.e_pose[e], A.pt[cur] + 3 * (size_t)A.e_pt[e], c, pc);
         int lvl = A.level[e];
         if (S.mark) {   // e->chi2() > th || !e->isDepthPositive() -> level 1  (src/Optimizer.cc:598-613); chi2 from the errors computed last
             const double l0 = A.err[S.last][2 * e], l1 = A.err[S.last][2 * e + 1];
@@ -248,7 +328,7 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
             A.level[e] = (unsigned char)lvl;
             if (lvl) { A.err[0][2 * e] = l0; A.err[0][2 * e + 1] = l1; A.err[1][2 * e] = l0; A.err[1][2 * e + 1] = l1; }
         }
-        double* R = s_rec + BA_REC * tid;       // staged in shared memory, written out coalesced below
+        double2* R = reinterpret_cast<double2*>(A.er + 8 * (size_t)e);
         if (!lvl) {
             double er[2];
             if (S.round_start) {
@@ -260,89 +340,25 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
                 er[0] = A.err[cur][2 * e]; er[1] = A.err[cur][2 * e + 1];
             }
             act = 1;
-            const double X = pc[0], Y = pc[1], Z = pc[2], iz = -1. / Z;
-            const double t00 = iz * c[0], t02 = iz * (-X / Z * c[0]), t11 = iz * c[1], t12 = iz * (-Y / Z * c[1]);
-            double Jp[12];
-            const bool is_free = A.pose_free[pi] >= 0;
-            if (is_free) {
-                // (-1/z * tmp) * J3, J3 = [-skew(p) | I], then * Adj_ext   (types_six_dof_expmap.cpp:136-153)
-                const double tJ[12] = {t02 * Y, t00 * Z - t02 * X, -t00 * Y, t00, 0, t02,
-                                       -t11 * Z + t12 * Y, -t12 * X, t11 * X, 0, t11, t12};
-                double Ad[36];
-                {
-                    const double2* A2 = reinterpret_cast<const double2*>(c + BA_CAM_ADJ);
-#pragma unroll
-                    for (int i = 0; i < 18; i++) { const double2 q = A2[i]; Ad[2 * i] = q.x; Ad[2 * i + 1] = q.y; }
-                }
-#pragma unroll
-                for (int i = 0; i < 2; i++)
-#pragma unroll
-                    for (int j = 0; j < 6; j++) {
-                        double s = 0;
-#pragma unroll
-                        for (int k = 0; k < 6; k++) s += tJ[i * 6 + k] * Ad[k * 6 + j];
-                        Jp[i * 6 + j] = s;
-                    }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 12; i++) Jp[i] = 0;
-            }
-            double q[4], Rm[9], Jl[6];
-            q_mul(c + 4, ps, q);
-            q_normalize(q);
-            q_to_matrix(q, Rm);
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                Jl[j] = t00 * Rm[j] + t02 * Rm[6 + j];
-                Jl[3 + j] = t11 * Rm[3 + j] + t12 * Rm[6 + j];
-            }
             double wr = 1.0;
             if (robust) {
                 const double c2 = (er[0] * er[0] + er[1] * er[1]) * w;
                 if (c2 > dsqr) wr = delta / sqrt(c2);
             }
-            const double W = wr * w;
-#pragma unroll
-            for (int j = 0; j < 6; j++) R[j] = Jl[j];
-            R[6] = W; R[7] = -w * er[0] * wr; R[8] = -w * er[1] * wr;
-#pragma unroll
-            for (int j = 0; j < 12; j++) R[9 + j] = Jp[j];
-            R[21] = 0;
+            R[0] = make_double2(pc[0], pc[1]);
+            R[1] = make_double2(pc[2], 1.0 / pc[2]);
+            R[2] = make_double2(wr * w, -w * er[0] * wr);
+            R[3] = make_double2(-w * er[1] * wr, 0.0);
         } else {
-#pragma unroll
-            for (int j = 0; j < BA_REC; j++) R[j] = 0;
+            R[0] = make_double2(0.0, 0.0);
+            R[1] = make_double2(1.0, 1.0);
+            R[2] = make_double2(0.0, 0.0);
+            R[3] = make_double2(0.0, 0.0);
         }
     }
     const double cs = block_sum<BA_TE / 32>(chi, red);
-    const double as = block_sum<BA_TE / 32>(act, red);   // (the barriers inside also publish s_rec / s_B)
+    const double as = block_sum<BA_TE / 32>(act, red);
     if (tid == 0) { A.partE[2 * (size_t)b] = cs; A.partE[2 * (size_t)b + 1] = as; }
-    {
-        const int ebase = P.e0 + (b - P.blkE0) * BA_TE;
-        const int nv = min(BA_TE, P.e0 + P.nE - ebase);
-        double* gr = A.rec + (size_t)BA_REC * ebase;
-        double* gb = A.B + 18 * (size_t)ebase;
-        for (int i = tid; i < BA_REC / 2 * nv; i += BA_TE) reinterpret_cast<double2*>(gr)[i] = reinterpret_cast<const double2*>(s_rec)[i];
-        // B_e = Jp^T W Jl from the staged record, written over it (level-1 edges: zero record -> zero block)
-        double Jl[6], Jp[12], W = 0;
-        if (valid) {
-            const double* R = s_rec + BA_REC * tid;
-#pragma unroll
-            for (int j = 0; j < 6; j++) Jl[j] = R[j];
-            W = R[6];
-#pragma unroll
-            for (int j = 0; j < 12; j++) Jp[j] = R[9 + j];
-        }
-        __syncthreads();
-        if (valid) {
-            double* Bm = s_rec + 18 * tid;
-#pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-                for (int cc = 0; cc < 3; cc++) Bm[r * 3 + cc] = W * (Jp[r] * Jl[cc] + Jp[6 + r] * Jl[3 + cc]);
-        }
-        __syncthreads();
-        for (int i = tid; i < 9 * nv; i += BA_TE) reinterpret_cast<double2*>(gb)[i] = reinterpret_cast<const double2*>(s_rec)[i];
-    }
     if (b == P.blkE0 && tid == 0 && S.round_start) A.state[p].maxdiag_bits = 0ull;
 }
 
@@ -350,6 +366,7 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
 // blocks [0, nLandmarkBlocks): thread per landmark -> Hll, bl ;  blocks beyond: CTA per free pose -> Hpp, bp
 __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks, const int* pose_prob) {
     __shared__ double red[BA_TL / 32];
+    __shared__ double s_N[27];
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < nLandmarkBlocks) {
         const int b = blockIdx.x;
@@ -362,9 +379,13 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
         if (l < P.l0 + P.nL) {
             double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0, b0 = 0, b1 = 0, b2 = 0;
             for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
-                const double2* R2 = reinterpret_cast<const double2*>(A.rec + (size_t)BA_REC * e);
-                const double2 q0 = R2[0], q1 = R2[1], q2 = R2[2], q3 = R2[3], q4 = R2[4];
-                const double a0 = q0.x, a1 = q0.y, a2 = q1.x, c0 = q1.y, c1 = q2.x, c2 = q2.y, W = q3.x, r0 = q3.y, r1 = q4.x;
+                double r[8], t4[4], tJ[12], Jl[6];
+                load8(A.er + 8 * (size_t)e, r);
+                const int cg = A.e_cam[e];
+                const double* c = A.cam + BA_CAM_STRIDE * (size_t)cg;
+                edge_tj(r[0], r[1], r[2], r[3], c[0], c[1], tJ, t4);
+                edge_jl(t4, A.RT + 9 * (size_t)(P.rt0 + (A.e_pose[e] - P.p0) * P.nC + (cg - P.c0)), Jl);
+                const double a0 = Jl[0], a1 = Jl[1], a2 = Jl[2], c0 = Jl[3], c1 = Jl[4], c2 = Jl[5], W = r[4], r0 = r[5], r1 = r[6];
                 h00 += (a0 * a0 + c0 * c0) * W; h01 += (a0 * a1 + c0 * c1) * W; h02 += (a0 * a2 + c0 * c2) * W;
                 h11 += (a1 * a1 + c1 * c1) * W; h12 += (a1 * a2 + c1 * c2) * W; h22 += (a2 * a2 + c2 * c2) * W;
                 b0 += a0 * r0 + c0 * r1; b1 += a1 * r0 + c1 * r1; b2 += a2 * r0 + c2 * r1;
@@ -381,104 +402,132 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
         }
         return;
     }
-    // ---- pose part
+    // ---- pose part: per camera c, N_c = sum tJ^T W tJ and u_c = sum tJ^T r over the pose's edges seen by camera c (they are the
+    //      (c, c) slice of the diagonal pair's tuple list), then Hpp += Adj_c^T N_c Adj_c, bp += Adj_c^T u_c
     const int kg = blockIdx.x - nLandmarkBlocks;       // global free-pose index
     const int p = pose_prob[kg];
     const BAState& S = A.state[p];
     if (S.done || !S.need_build) return;
     const BAProb& P = A.prob[p];
     const int k = kg - P.k0;
-    const int pid = k * P.K - k * (k - 1) / 2;          // diagonal pair (k, k): its tuples (e, e) list the edges of pose k
-    const int2* T = A.tuples + P.tup0 + A.pair_off[P.pair0 + pid];
-    const int cnt = A.pair_cnt[P.pair0 + pid];
-    double h[21], bb[6];
+    const int pidd = k * P.K - k * (k - 1) / 2;         // diagonal pair (k, k)
+    double out = 0;                                     // thread t < 36: Hpp[t / 6][t % 6];  36 <= t < 42: bp[t - 36]
+    for (int cl = 0; cl < P.nC; cl++) {
+        const int pc = P.pc0 + pidd * P.CC + cl * P.nC + cl;
+        const int cnt = A.pc_cnt[pc];
+        if (cnt == 0) continue;                         // uniform over the CTA
+        const int2* T = A.tuples + P.tup0 + A.pc_off[pc];
+        const double* c = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + cl);
+        const double fx = c[0], fy = c[1];
+        double h[27];
 #pragma unroll
-    for (int i = 0; i < 21; i++) h[i] = 0;
+        for (int i = 0; i < 27; i++) h[i] = 0;
+        for (int t = tid; t < cnt; t += BA_TP) {
+            double r[8], t4[4], tJ[12];
+            load8(A.er + 8 * (size_t)T[t].x, r);
+            edge_tj(r[0], r[1], r[2], r[3], fx, fy, tJ, t4);
+            const double W = r[4], r0 = r[5], r1 = r[6];
+            int u = 0;
 #pragma unroll
-    for (int i = 0; i < 6; i++) bb[i] = 0;
-    for (int t = tid; t < cnt; t += BA_TP) {
-        const double2* R2 = reinterpret_cast<const double2*>(A.rec + (size_t)BA_REC * T[t].x) + 3;   // doubles 6..21
-        double rr[16];
+            for (int i = 0; i < 6; i++) {
+                h[21 + i] += tJ[i] * r0 + tJ[6 + i] * r1;
 #pragma unroll
-        for (int i = 0; i < 8; i++) { const double2 q = R2[i]; rr[2 * i] = q.x; rr[2 * i + 1] = q.y; }
-        const double W = rr[0], r0 = rr[1], r1 = rr[2];
-        double a[6], c[6];
-#pragma unroll
-        for (int i = 0; i < 6; i++) { a[i] = rr[3 + i]; c[i] = rr[9 + i]; }
-        int u = 0;
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            bb[i] += a[i] * r0 + c[i] * r1;
-#pragma unroll
-            for (int j = i; j < 6; j++) h[u++] += (a[i] * a[j] + c[i] * c[j]) * W;
+                for (int j = i; j < 6; j++) h[u++] += (tJ[i] * tJ[j] + tJ[6 + i] * tJ[6 + j]) * W;
+            }
         }
-    }
-    double md = 0;
-    double* H = A.Hpp + 36 * (size_t)kg;
-    int u = 0;
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-        const double s = block_sum<BA_TP / 32>(bb[i], red);
-        if (tid == 0) A.bp[6 * (size_t)kg + i] = s;
-#pragma unroll
-        for (int j = i; j < 6; j++) {
-            const double hv = block_sum<BA_TP / 32>(h[u++], red);
-            if (tid == 0) { H[i * 6 + j] = hv; H[j * 6 + i] = hv; }
-            if (i == j) md = fmax(md, fabs(hv));
+        for (int i = 0; i < 27; i++) { const double s = block_sum<BA_TP / 32>(h[i], red); if (tid == 0) s_N[i] = s; }
+        __syncthreads();
+        const double* Ad = c + BA_CAM_ADJ;
+        if (tid < 36) {
+            const int i = tid / 6, j = tid - 6 * i;
+            double s = 0;
+            for (int a = 0; a < 6; a++) {
+                double row = 0;                          // (N Adj)[a][j]
+                for (int q = 0; q < 6; q++) {
+                    const int lo = a < q ? a : q, hi = a < q ? q : a;
+                    row += s_N[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)] * Ad[q * 6 + j];
+                }
+                s += Ad[a * 6 + i] * row;
+            }
+            out += s;
+        } else if (tid < 42) {
+            const int i = tid - 36;
+            double s = 0;
+            for (int a = 0; a < 6; a++) s += Ad[a * 6 + i] * s_N[21 + a];
+            out += s;
         }
+        __syncthreads();
     }
-    if (tid == 0 && S.it == 0 && md > 0) atomicMax(&A.state[p].maxdiag_bits, (unsigned long long)__double_as_longlong(md));
+    if (tid < 36) {
+        A.Hpp[36 * (size_t)kg + tid] = out;
+        if (S.it == 0 && tid % 7 == 0 && fabs(out) > 0) atomicMax(&A.state[p].maxdiag_bits, (unsigned long long)__double_as_longlong(fabs(out)));
+    } else if (tid < 42) {
+        A.bp[6 * (size_t)kg + tid - 36] = out;
+    }
 }
 
-// ------------------------------------------------------------------------------------------------ k_trial_lm
-// (Hll + lambda I)^-1 of a landmark: cofactor inverse of the symmetric 3x3 (Eigen's fixed-size inverse in
-// BlockSolver::solve, block_solver.hpp:381-395).  d = {d00, d01, d02, d11, d12, d22}
-__device__ __forceinline__ void landmark_dinv(const double* H, double lambda, double* d) {
-    const double m0 = H[0] + lambda, m1 = H[1], m2 = H[2], m4 = H[3] + lambda, m5 = H[4], m8 = H[5] + lambda;
-    const double c00 = m4 * m8 - m5 * m5, c01 = m5 * m2 - m1 * m8, c02 = m1 * m5 - m4 * m2;
-    const double id = 1.0 / (m0 * c00 + m1 * c01 + m2 * c02);
-    d[0] = c00 * id; d[1] = c01 * id; d[2] = c02 * id;
-    d[3] = (m0 * m8 - m2 * m2) * id; d[4] = (m2 * m1 - m0 * m5) * id; d[5] = (m0 * m4 - m1 * m1) * id;
-}
-// thread per (edge, pair of rows of the 6x3 block): Y_e[r] = B_e[r] Dinv, v_e[r] = Y_e[r] . bl -- consecutive threads touch
-// consecutive 48-byte row pairs with 128-bit accesses, so the B reads and Y writes are fully coalesced
-#define BA_TT 192
-__global__ void __launch_bounds__(BA_TT) k_trial_lm(BABatch A) {
+// ------------------------------------------------------------------------------------------------ k_trial
+// thread per edge (per LM trial): the two 6x3 blocks the Schur products are made of, in tJ space (before the camera adjoints),
+//     Bt_e = tJ_e^T W_e Jl_e ,   Yt_e = Bt_e (Hll + lambda I)^-1 ,   v_e = Yt_e bl
+// rebuilt from the 64-byte edge record, staged in shared memory and written out coalesced.
+__global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
+    __shared__ __align__(16) double s_blk[BA_TE * 18];
     const int b = blockIdx.x;
     const int p = A.blkE_prob[b];
     const BAState& S = A.state[p];
     if (S.done) return;
     const BAProb& P = A.prob[p];
-    const double lambda = lambda_eff(S);
+    const int tid = threadIdx.x;
     const int ebase = P.e0 + (b - P.blkE0) * BA_TE;
-    const int nitems = 3 * min(BA_TE, P.e0 + P.nE - ebase);
-    for (int q = threadIdx.x; q < nitems; q += BA_TT) {
-        const int el = q / 3, rp = q - el * 3;
-        const int e = ebase + el;
-        if (A.pose_free[A.e_pose[e]] < 0) continue;
-        const int l = A.e_pt[e];
-        double d[6];
-        landmark_dinv(A.Hll + 6 * (size_t)l, lambda, d);
-        const double2* B2 = reinterpret_cast<const double2*>(A.B + 18 * (size_t)e + 6 * rp);
-        const double2 u0 = B2[0], u1 = B2[1], u2 = B2[2];
-        const double x[6] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y};
-        double y[6];
+    const int nv = min(BA_TE, P.e0 + P.nE - ebase);
+    const int e = ebase + tid;
+    const double lambda = lambda_eff(S);
+    double Bt[18], Yt[18];
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const double x0 = x[3 * r], x1 = x[3 * r + 1], x2 = x[3 * r + 2];
-            y[3 * r] = x0 * d[0] + x1 * d[1] + x2 * d[2]; y[3 * r + 1] = x0 * d[1] + x1 * d[3] + x2 * d[4]; y[3 * r + 2] = x0 * d[2] + x1 * d[4] + x2 * d[5];
+    for (int q = 0; q < 18; q++) { Bt[q] = 0; Yt[q] = 0; }
+    double vv[6] = {0, 0, 0, 0, 0, 0};
+    if (tid < nv && A.pose_free[A.e_pose[e]] >= 0) {
+        double r[8], t4[4], tJ[12], Jl[6], d[6];
+        load8(A.er + 8 * (size_t)e, r);
+        const int cg = A.e_cam[e], l = A.e_pt[e];
+        const double* c = A.cam + BA_CAM_STRIDE * (size_t)cg;
+        edge_tj(r[0], r[1], r[2], r[3], c[0], c[1], tJ, t4);
+        edge_jl(t4, A.RT + 9 * (size_t)(P.rt0 + (A.e_pose[e] - P.p0) * P.nC + (cg - P.c0)), Jl);
+        landmark_dinv(A.Hll + 6 * (size_t)l, lambda, d);
+        const double W = r[4];
+        const double b0 = A.bl[3 * (size_t)l], b1 = A.bl[3 * (size_t)l + 1], b2 = A.bl[3 * (size_t)l + 2];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const double x0 = W * (tJ[i] * Jl[0] + tJ[6 + i] * Jl[3]), x1 = W * (tJ[i] * Jl[1] + tJ[6 + i] * Jl[4]), x2 = W * (tJ[i] * Jl[2] + tJ[6 + i] * Jl[5]);
+            Bt[3 * i] = x0; Bt[3 * i + 1] = x1; Bt[3 * i + 2] = x2;
+            const double y0 = x0 * d[0] + x1 * d[1] + x2 * d[2], y1 = x0 * d[1] + x1 * d[3] + x2 * d[4], y2 = x0 * d[2] + x1 * d[4] + x2 * d[5];
+            Yt[3 * i] = y0; Yt[3 * i + 1] = y1; Yt[3 * i + 2] = y2;
+            vv[i] = y0 * b0 + y1 * b1 + y2 * b2;
         }
-        double2* Y2 = reinterpret_cast<double2*>(A.Y + 18 * (size_t)e + 6 * rp);
-        Y2[0] = make_double2(y[0], y[1]); Y2[1] = make_double2(y[2], y[3]); Y2[2] = make_double2(y[4], y[5]);
-        const double* bl = A.bl + 3 * (size_t)l;
-        const double b0 = bl[0], b1 = bl[1], b2 = bl[2];
-        *reinterpret_cast<double2*>(A.v + 6 * (size_t)e + 2 * rp) = make_double2(y[0] * b0 + y[1] * b1 + y[2] * b2, y[3] * b0 + y[4] * b1 + y[5] * b2);
     }
+    // coalesced write-out through shared memory: B, then Y, then v
+#pragma unroll
+    for (int q = 0; q < 18; q++) s_blk[18 * tid + q] = Bt[q];
+    __syncthreads();
+    for (int i = tid; i < 9 * nv; i += BA_TE) reinterpret_cast<double2*>(A.B + 18 * (size_t)ebase)[i] = reinterpret_cast<const double2*>(s_blk)[i];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 18; q++) s_blk[18 * tid + q] = Yt[q];
+    __syncthreads();
+    for (int i = tid; i < 9 * nv; i += BA_TE) reinterpret_cast<double2*>(A.Y + 18 * (size_t)ebase)[i] = reinterpret_cast<const double2*>(s_blk)[i];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 6; q++) s_blk[6 * tid + q] = vv[q];
+    __syncthreads();
+    for (int i = tid; i < 3 * nv; i += BA_TE) reinterpret_cast<double2*>(A.v + 6 * (size_t)ebase)[i] = reinterpret_cast<const double2*>(s_blk)[i];
 }
 
 // ------------------------------------------------------------------------------------------------ k_pairs
-// warp per work item of a problem: items [0, nChunksMax) = chunk of <= BA_CH tuples of one pose pair -> partial 6x6 block of
-// sum Y_a B_b^T ; items [nChunksMax, nChunksMax + K) = free pose k -> Schur right-hand side bs_k = bp_k - sum_e Y_e bl.
+// warp per work item of a problem.
+//   items [0, nChunksMax): a chunk of <= BA_CH (edge a, edge b) tuples of ONE pose pair (i, j) and ONE camera pair (ca, cb):
+//     partial 6x6 of  sum Yt_a Bt_b^T  (the Schur product before the camera adjoints, which k_solve applies once per camera pair)
+//   items [nChunksMax, nChunksMax + K): free pose k, per camera c:  u_(k,c) = sum_e v_e   (Schur right-hand side in tJ space)
 #define BA_STAGE_BYTES (32 * 144)   // one batch: 16 Y blocks + 16 B blocks
 __global__ void __launch_bounds__(128) k_pairs(BABatch A, const int* blkI_first) {
     __shared__ __align__(16) unsigned char s_stage[4 * 2 * BA_STAGE_BYTES];   // per warp: two stages
@@ -562,25 +611,28 @@ __global__ void __launch_bounds__(128) k_pairs(BABatch A, const int* blkI_first)
         }
     } else {
         const int k = item - P.nChunksMax;
-        const int kg = P.k0 + k;
-        const int pid = k * P.K - k * (k - 1) / 2;
-        const int2* T = A.tuples + P.tup0 + A.pair_off[P.pair0 + pid];
-        const int cnt = A.pair_cnt[P.pair0 + pid];
-        double cf[6];
+        const int pidd = k * P.K - k * (k - 1) / 2;
+        for (int cl = 0; cl < P.nC; cl++) {
+            const int pc = P.pc0 + pidd * P.CC + cl * P.nC + cl;
+            const int cnt = A.pc_cnt[pc];
+            const int2* T = A.tuples + P.tup0 + A.pc_off[pc];
+            double u[6];
 #pragma unroll
-        for (int i = 0; i < 6; i++) cf[i] = 0;
-        for (int t = lane; t < cnt; t += 32) {
-            const double* ve = A.v + 6 * (size_t)T[t].x;
+            for (int q = 0; q < 6; q++) u[q] = 0;
+            for (int t = lane; t < cnt; t += 32) {
+                double ve[6];
+                load6(A.v + 6 * (size_t)T[t].x, ve);
 #pragma unroll
-            for (int i = 0; i < 6; i++) cf[i] += ve[i];
-        }
+                for (int q = 0; q < 6; q++) u[q] += ve[q];
+            }
 #pragma unroll
-        for (int i = 0; i < 6; i++) cf[i] = warp_sum(cf[i]);
-        if (lane < 6) {
-            double vsel = cf[0];
+            for (int q = 0; q < 6; q++) u[q] = warp_sum(u[q]);
+            if (lane < 6) {
+                double vsel = u[0];
 #pragma unroll
-            for (int i = 1; i < 6; i++) if (lane == i) vsel = cf[i];
-            A.bs[6 * (size_t)kg + lane] = A.bp[6 * (size_t)kg + lane] - vsel;
+                for (int q = 1; q < 6; q++) if (lane == q) vsel = u[q];
+                A.ut_u[6 * (size_t)(P.ut0 + k * P.nC + cl) + lane] = vsel;
+            }
         }
     }
 }
@@ -599,10 +651,11 @@ __device__ void round_over(const BABatch& A, BAState& S, bool stopped) {
 // twice by k_solve -- once with the shared-memory matrix, once with a global-memory one -- so that each copy uses the
 // loads / stores of its address space instead of generic ones.
 __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P, const BAState& S, double* Hs, double* s_lcol, int* s_ok_p,
-                                              double lambda) {
+                                              double lambda, double* s_wscr) {
     const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ld = n | 1;                      // odd row stride: column accesses are bank-conflict free
-    // ---- assemble the reduced camera system: diag blocks Hpp + lambda I, minus the pair partial sums (fixed chunk order)
+    // ---- assemble the reduced camera system: diag blocks Hpp + lambda I, minus the Schur products.  The chunk partials hold
+    //      N = sum tJ_a^T S tJ_b per (pose pair, camera pair); the block of the pair is sum over camera pairs of Adj_ca^T N Adj_cb
     for (int r = warp; r < n; r += BA_TS / 32) {
         const int kr = r / 6;
         for (int c = lane; c < n; c += 32) {
@@ -612,23 +665,66 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
     }
     __syncthreads();
     {
+        // warp per pose pair: lanes own the 36 entries (lane, lane + 32) of N / tmp / the block; two 36-double scratch rows per warp
         const int nCh = S.nChunks;
-        // chunks of one pair are consecutive: thread (pair, entry) walks them in order
-        for (int w = tid; w < P.nPairs * 36; w += BA_TS) {
-            const int pid = w / 36, en = w - pid * 36;
-            const int cnt = A.pair_cnt[P.pair0 + pid];
-            if (cnt == 0) continue;
-            const int first = A.pair_fchunk[P.pair0 + pid];
-            const int nc = (cnt + BA_CH - 1) / BA_CH;
-            double s = 0;
-            for (int c = 0; c < nc && first + c < nCh; c++) s += A.partial[36 * (size_t)(P.chunk0 + first + c) + en];
+        double* wN = s_wscr + 72 * warp;
+        double* wT = wN + 36;
+        for (int pid = warp; pid < P.nPairs; pid += BA_TS / 32) {
+            if (A.pair_cnt[P.pair0 + pid] == 0) continue;
+            double blk0 = 0, blk1 = 0;                     // entries lane and lane + 32
+            for (int combo = 0; combo < P.CC; combo++) {
+                const int pc = P.pc0 + pid * P.CC + combo;
+                const int nc = A.pc_nchunk[pc], first = A.pc_fchunk[pc];
+                if (nc == 0) continue;
+                double n0 = 0, n1 = 0;
+                for (int c = 0; c < nc && first + c < nCh; c++) {
+                    const double* pp = A.partial + 36 * (size_t)(P.chunk0 + first + c);
+                    n0 += pp[lane];
+                    if (lane < 4) n1 += pp[32 + lane];
+                }
+                __syncwarp();
+                wN[lane] = n0;
+                if (lane < 4) wN[32 + lane] = n1;
+                __syncwarp();
+                const double* Aa = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + combo / P.nC) + BA_CAM_ADJ;
+                const double* Ab = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + combo % P.nC) + BA_CAM_ADJ;
+                for (int en = lane; en < 36; en += 32) {   // tmp = N Adj_cb
+                    const int a6 = en / 6, j6 = en - 6 * a6;
+                    double t = 0;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) t += wN[a6 * 6 + q] * Ab[q * 6 + j6];
+                    wT[en] = t;
+                }
+                __syncwarp();
+                for (int en = lane; en < 36; en += 32) {   // block += Adj_ca^T tmp
+                    const int i6 = en / 6, j6 = en - 6 * i6;
+                    double t = 0;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) t += Aa[q * 6 + i6] * wT[q * 6 + j6];
+                    if (en < 32) blk0 += t; else blk1 += t;
+                }
+            }
             int i1, i2;
             pair_decode(pid, P.K, i1, i2);
-            const int r = en / 6, c = en - r * 6;
-            const size_t a = (size_t)(6 * i1 + r) * ld + 6 * i2 + c;
-            if (i1 != i2) { Hs[a] = -s; Hs[(size_t)(6 * i2 + c) * ld + 6 * i1 + r] = -s; }
-            else Hs[a] -= s;
+            for (int en = lane; en < 36; en += 32) {
+                const int r = en / 6, c = en - 6 * r;
+                const double v = en < 32 ? blk0 : blk1;
+                const size_t a = (size_t)(6 * i1 + r) * ld + 6 * i2 + c;
+                if (i1 != i2) { Hs[a] = -v; Hs[(size_t)(6 * i2 + c) * ld + 6 * i1 + r] = -v; }
+                else Hs[a] -= v;
+            }
         }
+    }
+    // Schur right-hand side: bs_k = bp_k - sum_c Adj_c^T u_(k,c)
+    for (int i = tid; i < n; i += BA_TS) {
+        const int k = i / 6, c6 = i - 6 * k;
+        double sub = 0;
+        for (int cl = 0; cl < P.nC; cl++) {
+            const double* Ad = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + cl) + BA_CAM_ADJ;
+            const double* u = A.ut_u + 6 * (size_t)(P.ut0 + k * P.nC + cl);
+            for (int a = 0; a < 6; a++) sub += Ad[a * 6 + c6] * u[a];
+        }
+        A.bs[6 * (size_t)P.k0 + i] = A.bp[6 * (size_t)P.k0 + i] - sub;
     }
     if (tid == 0) *s_ok_p = 1;
     __syncthreads();
@@ -674,6 +770,7 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
 __global__ void __launch_bounds__(BA_TS) k_solve(BABatch A, int hs_smem_doubles) {
     extern __shared__ double sm_hs[];
     __shared__ double red[BA_TS / 32];
+    __shared__ double s_wscr[(BA_TS / 32) * 72];   // per warp: N and N Adj of the pair being assembled
     __shared__ int s_go, s_ok;
     double* s_lcol = sm_hs + hs_smem_doubles;   // n doubles after the matrix
     const int p = blockIdx.x, tid = threadIdx.x;
@@ -712,11 +809,18 @@ __global__ void __launch_bounds__(BA_TS) k_solve(BABatch A, int hs_smem_doubles)
     if (!s_go) return;
     const double lambda = S.lambda;
     bool ok;
-    if (n <= BA_HS_SMEM_N) ok = solve_reduced(A, P, S, sm_hs, s_lcol, &s_ok, lambda);
-    else ok = solve_reduced(A, P, S, A.Hs + P.hs_off, s_lcol, &s_ok, lambda);
+    if (n <= BA_HS_SMEM_N) ok = solve_reduced(A, P, S, sm_hs, s_lcol, &s_ok, lambda, s_wscr);
+    else ok = solve_reduced(A, P, S, A.Hs + P.hs_off, s_lcol, &s_ok, lambda, s_wscr);
     double* x = A.xp + 6 * (size_t)P.k0;
     if (!ok) for (int i = tid; i < n; i += BA_TS) x[i] = 0.0;   // g2o applies a stale x; the trial is rejected either way
     __syncthreads();
+    // y_(k,c) = Adj_c x_k : what the back-substitution needs of the pose increments (Jp x = tJ (Adj_c x))
+    for (int idx = tid; idx < P.K * P.nC * 6; idx += BA_TS) {
+        const int i6 = idx % 6, kc = idx / 6, cl = kc % P.nC, k = kc / P.nC;
+        const double* Ad = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + cl) + BA_CAM_ADJ + 6 * i6;
+        const double* xk = x + 6 * k;
+        A.ut_y[6 * (size_t)(P.ut0 + kc) + i6] = Ad[0] * xk[0] + Ad[1] * xk[1] + Ad[2] * xk[2] + Ad[3] * xk[3] + Ad[4] * xk[4] + Ad[5] * xk[5];
+    }
     // ---- trial poses: exp(x) * pose for free poses, copy for fixed ones;  pose part of computeScale()
     const int cur = S.cur;
     for (int i = tid; i < P.nP; i += BA_TS) {
@@ -752,21 +856,27 @@ __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
         const double delta = A.delta, dsqr = delta * delta;
         double x0 = 0, x1 = 0, x2 = 0;
         const double* bl = A.bl + 3 * (size_t)l;
-        if (S.solve_ok) {   // xl = Dinv (bl - sum B_e^T xp) = Dinv bl - sum Y_e^T xp   (block_solver.hpp:461-481)
-            double d[6];
-            landmark_dinv(A.Hll + 6 * (size_t)l, lambda, d);
-            x0 = d[0] * bl[0] + d[1] * bl[1] + d[2] * bl[2]; x1 = d[1] * bl[0] + d[3] * bl[1] + d[4] * bl[2]; x2 = d[2] * bl[0] + d[4] * bl[1] + d[5] * bl[2];
+        if (S.solve_ok) {   // xl = Dinv (bl - sum B_e^T xp),  B_e^T xp = Jl_e^T W_e tJ_e (Adj_c xp)   (block_solver.hpp:461-481)
+            double c0 = bl[0], c1 = bl[1], c2 = bl[2];
             for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
                 const int kg = A.pose_free[A.e_pose[e]];
                 if (kg < 0) continue;
-                const double2* Y2 = reinterpret_cast<const double2*>(A.Y + 18 * (size_t)e);
-                double Ym[18];
+                const int cg = A.e_cam[e];
+                const double* c = A.cam + BA_CAM_STRIDE * (size_t)cg;
+                double r[6], t4[4], tJ[12], Jl[6], y[6];
+                load6(A.er + 8 * (size_t)e, r);
+                load6(A.ut_y + 6 * (size_t)(P.ut0 + (kg - P.k0) * P.nC + (cg - P.c0)), y);
+                edge_tj(r[0], r[1], r[2], r[3], c[0], c[1], tJ, t4);
+                edge_jl(t4, A.RT + 9 * (size_t)(P.rt0 + (A.e_pose[e] - P.p0) * P.nC + (cg - P.c0)), Jl);
+                double s0 = 0, s1 = 0;
 #pragma unroll
-                for (int i = 0; i < 9; i++) { const double2 q = Y2[i]; Ym[2 * i] = q.x; Ym[2 * i + 1] = q.y; }
-                const double* xp = A.xp + 6 * (size_t)kg;
-#pragma unroll
-                for (int r = 0; r < 6; r++) { x0 -= Ym[r * 3] * xp[r]; x1 -= Ym[r * 3 + 1] * xp[r]; x2 -= Ym[r * 3 + 2] * xp[r]; }
+                for (int q = 0; q < 6; q++) { s0 += tJ[q] * y[q]; s1 += tJ[6 + q] * y[q]; }
+                s0 *= r[4]; s1 *= r[4];
+                c0 -= Jl[0] * s0 + Jl[3] * s1; c1 -= Jl[1] * s0 + Jl[4] * s1; c2 -= Jl[2] * s0 + Jl[5] * s1;
             }
+            double d[6];
+            landmark_dinv(A.Hll + 6 * (size_t)l, lambda, d);
+            x0 = d[0] * c0 + d[1] * c1 + d[2] * c2; x1 = d[1] * c0 + d[3] * c1 + d[4] * c2; x2 = d[2] * c0 + d[4] * c1 + d[5] * c2;
         }
         const double* po = A.pt[cur] + 3 * (size_t)l;
         double pn[3] = {po[0] + x0, po[1] + x1, po[2] + x2};
@@ -965,7 +1075,7 @@ static int launch_steps(orbba* b, int steps) {
         if (kv) cudaEventRecord(kv[1], st);
         k_build<<<b->nbL + b->Ktot, BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
         if (kv) cudaEventRecord(kv[2], st);
-        k_trial_lm<<<b->nbE, BA_TT, 0, st>>>(A);
+        k_trial<<<b->nbE, BA_TE, 0, st>>>(A);
         if (kv) cudaEventRecord(kv[3], st);
         if (b->nbI > 0) k_pairs<<<b->nbI, 128, 0, st>>>(A, b->d_blkI_first);
         if (kv) cudaEventRecord(kv[4], st);
@@ -1028,7 +1138,7 @@ int orbba_create(orbba_t** out, int device, int max_problems) {
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->up_ev, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->done_ev, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&b->dl_stream, cudaStreamNonBlocking);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
     if (ce != cudaSuccess) { int rc = orbhost::check_cuda(ce, "orbba_create", __FILE__, __LINE__); orbba_free(b); return rc; }
     b->stream = b->own_stream;
     *out = b;
@@ -1082,6 +1192,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         const int nP = Q.n_poses, nL = Q.n_points, nE = Q.n_edges, nC = Q.n_cams;
         char msg[256];
         if (nP < 0 || nL < 0 || nE < 0 || nC < 1) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d has negative sizes", p); errs[p] = msg; return; }
+        if (nC * nC > BA_MAXCC) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d has a rig of %d cameras (at most 4)", p, nC); errs[p] = msg; return; }
         if ((nP && (!Q.poses || !Q.pose_fixed)) || (nL && !Q.points) || (nE && (!Q.edge_pose || !Q.edge_point || !Q.edge_cam || !Q.edge_obs || !Q.edge_inv_sigma2)) ||
             !Q.cam_K || !Q.cam_ext || !Q.cam_adj) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d has a NULL array", p); errs[p] = msg; return; }
         std::vector<int>& pf = pose_free_local[p];
@@ -1127,6 +1238,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     for (int p = 0; p < n; p++) if (!errs[p].empty()) ORB_FAIL(ORB_E_INVALID, "%s", errs[p].c_str());
     // ---- pass 1b: offsets
     long long Etot = 0, Ltot = 0, Ptot = 0, Ctot = 0, Ktot = 0, pairTot = 0, tupTot = 0, chunkTot = 0, eofTot = 0, hsTot = 0, itemTot = 0;
+    long long rtTot = 0, pcTot = 0, utTot = 0;
     int nbE = 0, nbL = 0, nbP = 0, nbI = 0, max_n = 0;
     std::vector<int> bP0(n), bI0(n);
     for (int p = 0; p < n; p++) {
@@ -1137,7 +1249,10 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         P.e0 = (int)Etot; P.nE = nE; P.l0 = (int)Ltot; P.nL = nL; P.p0 = (int)Ptot; P.nP = nP; P.c0 = (int)Ctot; P.nC = nC;
         P.k0 = (int)Ktot; P.K = K; P.n = 6 * K;
         P.pair0 = (int)pairTot; P.nPairs = K * (K + 1) / 2;
-        P.chunk0 = (int)chunkTot; P.nChunksMax = P.nPairs + (int)(tup / BA_CH);
+        P.CC = nC * nC;
+        P.rt0 = (int)rtTot; P.pc0 = (int)pcTot; P.ut0 = (int)utTot;
+        rtTot += (long long)nP * nC; pcTot += (long long)P.nPairs * P.CC; utTot += (long long)K * nC;
+        P.chunk0 = (int)chunkTot; P.nChunksMax = P.nPairs * P.CC + (int)(tup / BA_CH);
         P.item0 = (int)itemTot; P.nItems = P.nChunksMax + K;
         P.blkE0 = nbE; P.nbE = std::max(1, (nE + BA_TE - 1) / BA_TE);
         P.blkL0 = nbL; P.nbL = std::max(1, (nL + BA_TL - 1) / BA_TL);
@@ -1148,7 +1263,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         if (P.n > BA_HS_SMEM_N) hsTot += (long long)P.n * (P.n | 1);
         nbE += P.nbE; nbL += P.nbL; nbP += (P.nPairs + 3) / 4; nbI += (P.nItems + 3) / 4;
         max_n = std::max(max_n, P.n);
-        if (Etot > 0x7fffffffLL || eofTot > 0x7fffffffLL * 4) ORB_FAIL(ORB_E_INVALID, "orbba_upload: batch too large");
+        if (Etot > 0x7fffffffLL || eofTot > 0x7fffffffLL * 4 || pcTot > 0x7fffffffLL || chunkTot > 0x7fffffffLL) ORB_FAIL(ORB_E_INVALID, "orbba_upload: batch too large");
     }
     // ---- layout: static (staged from the host) then device-only
     Layout L;
@@ -1158,16 +1273,19 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     const size_t o_ptoff = L.add(4 * (Ltot + 1)), o_pfree = L.add(4 * Ptot), o_pose0 = L.add(56 * Ptot), o_pt0 = L.add(24 * Ltot);
     const size_t o_blkE = L.add(4 * (size_t)nbE), o_blkL = L.add(4 * (size_t)nbL), o_item = L.add(4 * (size_t)std::max(nbI, 1));
     const size_t o_blkPp = L.add(4 * (size_t)std::max(nbP, 1)), o_blkPf = L.add(4 * (size_t)std::max(nbP, 1)), o_blkIf = L.add(4 * (size_t)std::max(nbI, 1));
-    const size_t o_poseprob = L.add(4 * (size_t)std::max<long long>(Ktot, 1));
+    const size_t o_poseprob = L.add(4 * (size_t)std::max<long long>(Ktot, 1)), o_freepose = L.add(4 * (size_t)std::max<long long>(Ktot, 1));
     const size_t static_bytes = L.add(0);
     const size_t o_state = L.add(sizeof(BAState) * n);
-    const size_t o_eof = L.add(4 * (size_t)eofTot), o_pcnt = L.add(4 * (size_t)pairTot), o_poff = L.add(4 * (size_t)pairTot), o_pfch = L.add(4 * (size_t)pairTot);
+    const size_t o_eof = L.add(4 * (size_t)eofTot), o_pcnt = L.add(4 * (size_t)pairTot), o_poff = L.add(4 * (size_t)pairTot);
+    const size_t o_pccnt = L.add(4 * (size_t)pcTot), o_pcoff = L.add(4 * (size_t)pcTot), o_pcfch = L.add(4 * (size_t)pcTot), o_pcnch = L.add(4 * (size_t)pcTot);
     const size_t o_cpair = L.add(4 * (size_t)chunkTot), o_cstart = L.add(4 * (size_t)chunkTot), o_clen = L.add(4 * (size_t)chunkTot);
     const size_t o_tup = L.add(8 * (size_t)tupTot);
     const size_t o_pose_a = L.add(56 * Ptot), o_pose_b = L.add(56 * Ptot), o_pt_a = L.add(24 * Ltot), o_pt_b = L.add(24 * Ltot);
     const size_t o_err_a = L.add(16 * Etot), o_err_b = L.add(16 * Etot), o_level = L.add(Etot);
-    const size_t o_rec = L.add(8 * BA_REC * (size_t)Etot), o_B = L.add(144 * (size_t)Etot), o_Y = L.add(144 * (size_t)Etot), o_v = L.add(48 * (size_t)Etot);
-    const size_t o_Hll = L.add(48 * Ltot), o_bl = L.add(24 * Ltot), o_Dinv = L.add(48 * Ltot), o_db = L.add(24 * Ltot);
+    const size_t o_B = L.add(144 * (size_t)Etot), o_Y = L.add(144 * (size_t)Etot), o_v = L.add(48 * (size_t)Etot);
+    const size_t o_er = L.add(64 * (size_t)Etot), o_RT = L.add(72 * (size_t)std::max<long long>(rtTot, 1));
+    const size_t o_utu = L.add(48 * (size_t)std::max<long long>(utTot, 1)), o_uty = L.add(48 * (size_t)std::max<long long>(utTot, 1));
+    const size_t o_Hll = L.add(48 * Ltot), o_bl = L.add(24 * Ltot);
     const size_t o_Hpp = L.add(288 * Ktot), o_bp = L.add(48 * Ktot), o_bs = L.add(48 * Ktot), o_xp = L.add(48 * Ktot);
     const size_t o_partial = L.add(288 * (size_t)chunkTot), o_partE = L.add(16 * (size_t)nbE), o_partL = L.add(16 * (size_t)nbL);
     const size_t o_Hs = L.add(8 * (size_t)hsTot);
@@ -1191,7 +1309,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     int *h_epose = (int*)(H + o_epose), *h_ept = (int*)(H + o_ept), *h_ecam = (int*)(H + o_ecam), *h_ptoff = (int*)(H + o_ptoff), *h_pfree = (int*)(H + o_pfree);
     double *h_eobs = (double*)(H + o_eobs), *h_einfo = (double*)(H + o_einfo), *h_cam = (double*)(H + o_cam), *h_pose0 = (double*)(H + o_pose0), *h_pt0 = (double*)(H + o_pt0);
     int *h_blkE = (int*)(H + o_blkE), *h_blkL = (int*)(H + o_blkL), *h_item = (int*)(H + o_item), *h_blkPp = (int*)(H + o_blkPp), *h_blkPf = (int*)(H + o_blkPf),
-        *h_blkIf = (int*)(H + o_blkIf), *h_poseprob = (int*)(H + o_poseprob);
+        *h_blkIf = (int*)(H + o_blkIf), *h_poseprob = (int*)(H + o_poseprob), *h_freepose = (int*)(H + o_freepose);
     parallel_for(n, [&](int p) {
         const int bP = bP0[p], bI = bI0[p];
         const orbba_problem_t& Q = problems[p];
@@ -1212,6 +1330,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         }
         for (int i = 0; i < P.nP; i++) h_pfree[P.p0 + i] = pose_free_local[p][i] >= 0 ? P.k0 + pose_free_local[p][i] : -1;
         for (int k = 0; k < P.K; k++) h_poseprob[P.k0 + k] = p;
+        for (int i = 0; i < P.nP; i++) if (pose_free_local[p][i] >= 0) h_freepose[P.k0 + pose_free_local[p][i]] = P.p0 + i;
         for (int c = 0; c < P.nC; c++) {
             double* Dc = h_cam + (size_t)BA_CAM_STRIDE * (P.c0 + c);
             for (int i = 0; i < 4; i++) Dc[i] = Q.cam_K[4 * c + i];
@@ -1253,13 +1372,16 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     A.pose0 = (const double*)(D + o_pose0); A.pt0 = (const double*)(D + o_pt0);
     A.blkE_prob = (const int*)(D + o_blkE); A.blkL_prob = (const int*)(D + o_blkL); A.item_prob = (const int*)(D + o_item);
     b->d_blkP_prob = (int*)(D + o_blkPp); b->d_blkP_first = (int*)(D + o_blkPf); b->d_blkI_first = (int*)(D + o_blkIf); b->d_pose_prob = (int*)(D + o_poseprob);
-    A.edge_of = (int*)(D + o_eof); A.pair_cnt = (int*)(D + o_pcnt); A.pair_off = (int*)(D + o_poff); A.pair_fchunk = (int*)(D + o_pfch);
+    A.edge_of = (int*)(D + o_eof); A.pair_cnt = (int*)(D + o_pcnt); A.pair_off = (int*)(D + o_poff);
+    A.pc_cnt = (int*)(D + o_pccnt); A.pc_off = (int*)(D + o_pcoff); A.pc_fchunk = (int*)(D + o_pcfch); A.pc_nchunk = (int*)(D + o_pcnch);
+    A.free_pose = (const int*)(D + o_freepose);
     A.chunk_pair = (int*)(D + o_cpair); A.chunk_start = (int*)(D + o_cstart); A.chunk_len = (int*)(D + o_clen);
     A.tuples = (int2*)(D + o_tup);
     A.pose[0] = (double*)(D + o_pose_a); A.pose[1] = (double*)(D + o_pose_b); A.pt[0] = (double*)(D + o_pt_a); A.pt[1] = (double*)(D + o_pt_b);
     A.err[0] = (double*)(D + o_err_a); A.err[1] = (double*)(D + o_err_b); A.level = D + o_level;
-    A.rec = (double*)(D + o_rec); A.B = (double*)(D + o_B); A.Y = (double*)(D + o_Y); A.v = (double*)(D + o_v);
-    A.Hll = (double*)(D + o_Hll); A.bl = (double*)(D + o_bl); A.Dinv = (double*)(D + o_Dinv); A.db = (double*)(D + o_db);
+    A.B = (double*)(D + o_B); A.Y = (double*)(D + o_Y); A.v = (double*)(D + o_v);
+    A.er = (double*)(D + o_er); A.RT = (double*)(D + o_RT); A.ut_u = (double*)(D + o_utu); A.ut_y = (double*)(D + o_uty);
+    A.Hll = (double*)(D + o_Hll); A.bl = (double*)(D + o_bl);
     A.Hpp = (double*)(D + o_Hpp); A.bp = (double*)(D + o_bp); A.bs = (double*)(D + o_bs); A.xp = (double*)(D + o_xp);
     A.partial = (double*)(D + o_partial); A.partE = (double*)(D + o_partE); A.partL = (double*)(D + o_partL); A.Hs = (double*)(D + o_Hs);
     A.poses_out = (double*)(D + o_poses_out); A.points_out = (double*)(D + o_points_out); A.outlier = D + o_outlier;
