@@ -365,8 +365,7 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
 // ------------------------------------------------------------------------------------------------ k_build
 // blocks [0, nLandmarkBlocks): thread per landmark -> Hll, bl ;  blocks beyond: CTA per free pose -> Hpp, bp
 __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks, const int* pose_prob) {
-    __shared__ double red[BA_TL / 32];
-    __shared__ double s_N[27];
+    __shared__ double s_N[27], s_W[(BA_TP / 32) * 27];
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < nLandmarkBlocks) {
         const int b = blockIdx.x;
@@ -435,8 +434,16 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
                 for (int j = i; j < 6; j++) h[u++] += (tJ[i] * tJ[j] + tJ[6 + i] * tJ[6 + j]) * W;
             }
         }
+        // fixed-order reduction: shuffle tree inside each warp, then the four warp sums in warp order
 #pragma unroll
-        for (int i = 0; i < 27; i++) { const double s = block_sum<BA_TP / 32>(h[i], red); if (tid == 0) s_N[i] = s; }
+        for (int i = 0; i < 27; i++) { const double s = warp_sum(h[i]); if ((tid & 31) == 0) s_W[(tid >> 5) * 27 + i] = s; }
+        __syncthreads();
+        if (tid < 27) {
+            double s = 0;
+#pragma unroll
+            for (int w = 0; w < BA_TP / 32; w++) s += s_W[w * 27 + tid];
+            s_N[tid] = s;
+        }
         __syncthreads();
         const double* Ad = c + BA_CAM_ADJ;
         if (tid < 36) {
