@@ -92,3 +92,39 @@ def test_degenerate_inputs():
     bad["edge_pose"][0] = 99
     with pytest.raises(OrbError):
         opt.LocalBundleAdjustment(bad)
+
+
+def test_batch_download_copy_stream_and_kernel_timing():
+    """orbba_download_batch == per-problem downloads; uploads on a copy stream; per-kernel timing of the LM step."""
+    import torch
+    ps = [synth.ba_problem(30 + i, n_kf=4 + i, n_points=120 + 30 * i) for i in range(4)]
+    opt = Optimizer(max_problems=4)
+    copy_stream = torch.cuda.Stream()
+    opt.set_copy_stream(copy_stream)
+    opt.profile(True)
+    opt.upload(opt.prepare(ps))
+    opt.run()
+    poses, points, outl, stats = opt.download_batch()
+    ms, steps = opt.kernel_ms()
+    assert steps >= 15 and set(ms) == {"k_lin", "k_build", "k_trial_lm", "k_pairs", "k_solve", "k_back"} and all(v >= 0 for v in ms.values())
+    oP = oL = oE = 0
+    for i, p in enumerate(ps):
+        a, b, c, st = opt.download(i)
+        nP, nL, nE = len(p["pose_fixed"]), len(p["points"]), len(p["edge_pose"])
+        assert np.array_equal(poses[oP:oP + nP], a) and np.array_equal(points[oL:oL + nL], b) and np.array_equal(outl[oE:oE + nE].astype(bool), c)
+        assert stats[i]["trials"] == st["trials"]
+        _check(p, (a, b, c, st), O.local_ba(p))
+        oP += nP; oL += nL; oE += nE
+    opt.set_copy_stream(None)
+
+
+def test_edges_not_grouped_by_landmark():
+    """the reference adds edges landmark by landmark; any other order is accepted and the outlier flags come back in caller order"""
+    p = synth.ba_problem(12, n_kf=5, n_points=150)
+    perm = np.random.default_rng(0).permutation(len(p["edge_pose"]))
+    q = dict(p)
+    for k in ("edge_pose", "edge_point", "edge_cam", "edge_obs", "edge_inv_sigma2"):
+        q[k] = np.ascontiguousarray(p[k][perm])
+    a = Optimizer().LocalBundleAdjustment(p)
+    b = Optimizer().LocalBundleAdjustment(q)
+    assert _pose_rel(b[0], a[0]) <= 1e-9 and np.array_equal(a[2][perm], b[2])      # (the order inside a landmark changes the rounding)
