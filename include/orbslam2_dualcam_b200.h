@@ -249,6 +249,12 @@ typedef struct {
 int  orbm_is_in_frustum(orbm_t*, const orbm_frustum_t* frame, const float* pos, const float* normal, const float* max_dist,
                         const float* min_dist, int n, float viewing_cos_limit, int for_all_cams, int32_t* out, float* uvc);
 
+/* Frame::UndistortKeyPoints(c) (src/Frame.cc:410-442): cv::undistortPoints(mat, mat, K, distCoef, Mat(), K) on the keypoint centres, every other
+ * field copied; a copy when distCoef[0] == 0.  K4 = fx fy cx cy, dist = k1 k2 p1 p2 [k3 ...] (n_dist <= 12).  kps_un may alias kps.  HOST buffers. */
+int  orbm_undistort_keypoints(orbm_t*, const orb_keypoint_t* kps, int n, const float* K4, const float* dist, int n_dist, orb_keypoint_t* kps_un);
+/* Frame::ComputeImageBounds(c) (src/Frame.cc:454-490): bounds = {mvMinX, mvMaxX, mvMinY, mvMaxY} from the undistorted image corners. */
+int  orbm_image_bounds(orbm_t*, int width, int height, const float* K4, const float* dist, int n_dist, float* bounds);
+
 /* ================================================================================================
  * BUNDLE ADJUSTMENT -- replaces Optimizer::LocalBundleAdjustment / BundleAdjustment / GlobalBundleAdjustemnt
  * (include/Optimizer.h:50-56, src/Optimizer.cc:62-248,407-696) together with the g2o machinery under them

@@ -5,6 +5,7 @@
 // /root/reference).  PARITY UNPINNED by the reference: it has no tests or fixtures for these functions.
 // Determinisations: the 3x3 * 3x1 float product of SearchByProjectionOnCam (cv::Mat operator*) is
 // evaluated left-to-right in FP32 without FMA; PredictScale's log() is evaluated in double.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -311,6 +312,47 @@ void orc_is_in_frustum(const orc_frustum_t* Q, const float* pos, const float* no
             uvc[3 * i] = u; uvc[3 * i + 1] = v; uvc[3 * i + 2] = viewCos;
             break;
         }
+    }
+}
+
+
+// Frame::UndistortKeyPoints / ComputeImageBounds (src/Frame.cc:410-442, 454-490) -> cv::undistortPoints(mat, mat, K, distCoef, Mat(), K).
+// OpenCV is not vendored in the reference; this restates cvUndistortPointsInternal (calib3d/undistort: normalise, 5 fixed-point
+// iterations of the inverse Brown model in double, re-project with P = K, round to float) and is PINNED bit-exactly against cv2 4.13
+// (tests/test_oracle_cv2.py, tests/golden/undistort.npz).
+void orc_undistort_points(const float* pts, int n, const float* K4, const float* dist, int n_dist, float* out) {
+    const double fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+    double k[14];
+    for (int i = 0; i < 14; i++) k[i] = i < n_dist ? (double)dist[i] : 0.0;
+    const double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; i++) {
+        const double u = pts[2 * i], v = pts[2 * i + 1];
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = fx * x + 0 * y + cx, yy = 0 * x + fy * y + cy, ww = 1. / (0 * x + 0 * y + 1.0);
+        out[2 * i] = (float)(xx * ww);
+        out[2 * i + 1] = (float)(yy * ww);
+    }
+}
+// bounds = {mvMinX, mvMaxX, mvMinY, mvMaxY}
+void orc_image_bounds(int width, int height, const float* K4, const float* dist, int n_dist, float* bounds) {
+    if (n_dist > 0 && dist[0] != 0.0f) {
+        const float c[8] = {0.f, 0.f, (float)width, 0.f, 0.f, (float)height, (float)width, (float)height};
+        float o[8];
+        orc_undistort_points(c, 4, K4, dist, n_dist, o);
+        bounds[0] = std::min(o[0], o[4]); bounds[1] = std::max(o[2], o[6]);
+        bounds[2] = std::min(o[1], o[3]); bounds[3] = std::max(o[5], o[7]);
+    } else {
+        bounds[0] = 0.f; bounds[1] = (float)width; bounds[2] = 0.f; bounds[3] = (float)height;
     }
 }
 

@@ -73,6 +73,8 @@ SIGNATURES = {
     "orbba_dist_launch_count": (C.c_longlong, [vp]),
     "orbba_dist_optimize": (C.c_int, [vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]),
     "orbba_dist_timing": (C.c_int, [vp, f64p, f64p, f64p]),
+    "orbm_undistort_keypoints": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
+    "orbm_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
     "orbm_bruteforce_sets_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp]),
 }
 

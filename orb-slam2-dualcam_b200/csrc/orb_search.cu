@@ -348,6 +348,32 @@ __global__ void __launch_bounds__(128) k_frustum(FrustumDev Q, const float* __re
     uvc[3 * i] = u_; uvc[3 * i + 1] = v_; uvc[3 * i + 2] = c_;
 }
 
+// ------------------------------------------------------------------------------------------------ undistort
+// cv::undistortPoints(mat, mat, K, distCoef, Mat(), K) as Frame::UndistortKeyPoints / ComputeImageBounds call it (src/Frame.cc:410-490):
+// cvUndistortPointsInternal restated -- FP64, no contraction (this file is built with -fmad=false), five fixed-point iterations.
+struct UndistDev { double fx, fy, cx, cy, k[12]; };
+__global__ void __launch_bounds__(128) k_undistort(UndistDev U, const float* __restrict__ in, int stride_floats, int n, float* __restrict__ out, int out_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double u = in[(size_t)i * stride_floats], v = in[(size_t)i * stride_floats + 1];
+    const double ifx = 1. / U.fx, ify = 1. / U.fy;
+    double x = (u - U.cx) * ifx, y = (v - U.cy) * ify;
+    const double x0 = x, y0 = y;
+    const double* k = U.k;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (icdist < 0) { x = (u - U.cx) * ifx; y = (v - U.cy) * ify; break; }
+        const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+        const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    const double xx = U.fx * x + 0 * y + U.cx, yy = 0 * x + U.fy * y + U.cy, ww = 1. / (0 * x + 0 * y + 1.0);
+    out[(size_t)i * out_stride] = (float)(xx * ww);
+    out[(size_t)i * out_stride + 1] = (float)(yy * ww);
+}
+
 // ================================================================================================ host side
 // The orbm handle (orb_match.cu) owns the stream; the scratch arena of the searches lives here, keyed by handle.
 struct orbm;
@@ -740,6 +766,57 @@ int orbm_is_in_frustum(orbm_t* m, const orbm_frustum_t* fr, const float* pos, co
     ORB_CUDA(cudaMemcpyAsync(uvc, A.d + o_uvc, 12 * (size_t)n, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
     orbm_count_launches(m, 1);
+    return ORB_OK;
+}
+
+
+static int undistort_run(orbm_t* m, const float* pts, int stride_floats, int n, const float* K4, const float* dist, int n_dist, float* out, int out_stride) {
+    UndistDev U;
+    U.fx = K4[0]; U.fy = K4[1]; U.cx = K4[2]; U.cy = K4[3];
+    for (int i = 0; i < 12; i++) U.k[i] = i < n_dist ? (double)dist[i] : 0.0;
+    const int device = orbm_device_of(m);
+    ORB_CUDA(cudaSetDevice(device));
+    cudaStream_t st = orbm_stream_of(m);
+    const size_t in_b = 4 * (size_t)n * stride_floats, out_b = 4 * (size_t)n * out_stride;
+    Arena& A = g_arena;
+    int rc = arena_reserve(A, device, ((in_b + 255) & ~(size_t)255) + out_b + 512, in_b + out_b + 512);
+    if (rc != ORB_OK) return rc;
+    uint8_t* d_out = A.d + ((in_b + 255) & ~(size_t)255);
+    memcpy(A.h, pts, in_b);
+    if (out != pts) memcpy(A.h + in_b, out, out_b);      // fields the kernel does not touch keep the caller's values
+    else memcpy(A.h + in_b, pts, out_b);
+    ORB_CUDA(cudaMemcpyAsync(A.d, A.h, in_b, cudaMemcpyHostToDevice, st));
+    ORB_CUDA(cudaMemcpyAsync(d_out, A.h + in_b, out_b, cudaMemcpyHostToDevice, st));
+    k_undistort<<<(n + 127) / 128, 128, 0, st>>>(U, (const float*)A.d, stride_floats, n, (float*)d_out, out_stride);
+    ORB_CUDA(cudaGetLastError());
+    ORB_CUDA(cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    orbm_count_launches(m, 1);
+    return ORB_OK;
+}
+
+int orbm_undistort_keypoints(orbm_t* m, const orb_keypoint_t* kps, int n, const float* K4, const float* dist, int n_dist, orb_keypoint_t* kps_un) {
+    if (!m) ORB_FAIL(ORB_E_INVALID, "orbm_undistort_keypoints: NULL handle");
+    if (n == 0) return ORB_OK;
+    if (!kps || !kps_un || !K4 || n < 0 || n_dist < 0 || n_dist > 12 || (n_dist && !dist)) ORB_FAIL(ORB_E_INVALID, "orbm_undistort_keypoints: bad argument");
+    if (kps_un != kps) memcpy(kps_un, kps, sizeof(orb_keypoint_t) * (size_t)n);
+    if (n_dist == 0 || dist[0] == 0.0f) return ORB_OK;                       // src/Frame.cc:414-418: no distortion -> copy
+    return undistort_run(m, &kps->x, 7, n, K4, dist, n_dist, &kps_un->x, 7);
+}
+
+int orbm_image_bounds(orbm_t* m, int width, int height, const float* K4, const float* dist, int n_dist, float* bounds) {
+    if (!m) ORB_FAIL(ORB_E_INVALID, "orbm_image_bounds: NULL handle");
+    if (!K4 || !bounds || n_dist < 0 || n_dist > 12 || (n_dist && !dist)) ORB_FAIL(ORB_E_INVALID, "orbm_image_bounds: bad argument");
+    if (n_dist > 0 && dist[0] != 0.0f) {
+        const float c[8] = {0.f, 0.f, (float)width, 0.f, 0.f, (float)height, (float)width, (float)height};
+        float o[8];
+        int rc = undistort_run(m, c, 2, 4, K4, dist, n_dist, o, 2);
+        if (rc != ORB_OK) return rc;
+        bounds[0] = std::min(o[0], o[4]); bounds[1] = std::max(o[2], o[6]);
+        bounds[2] = std::min(o[1], o[3]); bounds[3] = std::max(o[5], o[7]);
+    } else {
+        bounds[0] = 0.f; bounds[1] = (float)width; bounds[2] = 0.f; bounds[3] = (float)height;
+    }
     return ORB_OK;
 }
 

@@ -90,6 +90,21 @@ class ORBmatcher:
                                        ptr(out), ptr(uvc)))
         return out, uvc
 
+    def UndistortKeyPoints(self, kps, K4, dist):
+        """Frame::UndistortKeyPoints (src/Frame.cc:410-442): kps structured array (capi.KP_DTYPE) -> undistorted copy"""
+        kps = np.ascontiguousarray(kps, capi.KP_DTYPE)
+        K4 = np.ascontiguousarray(K4, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+        out = np.empty_like(kps)
+        check(lib().orbm_undistort_keypoints(self._h, ptr(kps), len(kps), ptr(K4), ptr(dist), len(dist), ptr(out)))
+        return out
+
+    def ComputeImageBounds(self, width, height, K4, dist):
+        """Frame::ComputeImageBounds (src/Frame.cc:454-490) -> float32 [4] = mvMinX, mvMaxX, mvMinY, mvMaxY"""
+        K4 = np.ascontiguousarray(K4, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+        b = np.zeros(4, np.float32)
+        check(lib().orbm_image_bounds(self._h, width, height, ptr(K4), ptr(dist), len(dist), ptr(b)))
+        return b
+
     def bruteforce(self, dq, nq, dt, nt):
         """dq uint8 [P][Q][32], nq int32 [P], dt uint8 [P][T][32], nt int32 [P] -> best_idx, best_d, second_d int32 [P][Q]
         (entries >= nq[p] hold -1 / 256 / 256)."""

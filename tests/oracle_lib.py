@@ -312,3 +312,24 @@ def pose_optimization(f):
                                 k["cam_K"].shape[0], k["cam_K"].ctypes.data, k["cam_ext"].ctypes.data, k["cam_adj"].ctypes.data, pose.ctypes.data,
                                 out.ctypes.data, cnt.ctypes.data)
     return pose, out[:n].astype(bool), r, (int(cnt[0]), int(cnt[1]))
+
+
+def undistort_points(pts, K4, dist):
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    K4 = np.ascontiguousarray(K4, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+    out = np.empty_like(pts)
+    L = lib()
+    L.orc_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_undistort_points.restype = None
+    L.orc_undistort_points(pts.ctypes.data, len(pts), K4.ctypes.data, dist.ctypes.data, len(dist), out.ctypes.data)
+    return out
+
+
+def image_bounds(width, height, K4, dist):
+    K4 = np.ascontiguousarray(K4, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+    b = np.zeros(4, np.float32)
+    L = lib()
+    L.orc_image_bounds.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_image_bounds.restype = None
+    L.orc_image_bounds(width, height, K4.ctypes.data, dist.ctypes.data, len(dist), b.ctypes.data)
+    return b
