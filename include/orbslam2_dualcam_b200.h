@@ -249,6 +249,64 @@ typedef struct {
 int  orbm_is_in_frustum(orbm_t*, const orbm_frustum_t* frame, const float* pos, const float* normal, const float* max_dist,
                         const float* min_dist, int n, float viewing_cos_limit, int for_all_cams, int32_t* out, float* uvc);
 
+/* ---- key-frame flavoured searches (SURVEY a14, a15 second half, f4).  The map mutations the reference performs inside some of these
+ * loops (AddMapPoint / Replace / AddObservation / UpdateConnections) stay with the caller; the library returns the decisions. ---- */
+typedef struct {                  /* candidate map points */
+    int32_t n;
+    const uint8_t* valid;         /* [n]     the caller's skip conditions: pMP && !isBad() && !sAlreadyFound.count(pMP) (resp. !IsInKeyFrame(pKF)) */
+    const float*   pos;           /* [n][3]  GetWorldPos() */
+    const float*   normal;        /* [n][3]  GetNormal(); may be NULL for the variants without the 60 degree test */
+    const float*   max_dist;      /* [n]     mfMaxDistance (GetMaxDistanceInvariance() / 1.2) */
+    const float*   min_dist;      /* [n]     mfMinDistance */
+    const uint8_t* desc;          /* [n][32] GetDescriptor() */
+    const float*   angle;         /* [n]     pKF->mvTotalKeysUn[i].angle; only read by the orientation check, may be NULL */
+} orbm_points_t;
+
+/* ORBmatcher::SearchByProjectionOnCam(pF, query, pKF, sAlreadyFound, th, ORBdist)  (relocalisation; src/ORBmatcher.cc:812-951).
+ *   view        Rsw / tsw / Ow of mvExtrinsics[c] * mTcw for every camera of pF, K, log scale factor (bounds are taken from F)
+ *   P           pKF->GetMapPointMatches(), index = global key point index of pKF
+ *   blocked     uint8 [totalN]  pF->mvpMapPoints[g] != NULL
+ *   kp_to_point int32 [totalN]  in/out: entry g is set to i when P[i] is written into pF->mvpMapPoints[g] (entries the orientation check
+ *               resets to NULL are left untouched) */
+int  orbm_search_by_projection_reloc(orbm_t*, const orbm_frame_t* F, const orbm_frustum_t* view, int cam, const orbm_points_t* P, float th,
+                                     int orb_dist, int check_orientation, const uint8_t* blocked, int32_t* kp_to_point, int32_t* nmatches);
+
+/* ORBmatcher::SearchByProjection(pKF, query, Scq_w, vpPoints, vpMatched, th)  (loop closing; src/ORBmatcher.cc:416-536).
+ *   view           slot `cam` holds the decomposed similarity: Rsw = Rcqw, tsw = tcqw, Ow = Ocqw (:431-435)
+ *   matched_local  uint8 [n_kp[cam]]  vpMatched[l] != NULL -- indexed by the CAMERA-LOCAL key point index, as the reference indexes it (:504, :523)
+ *   local_to_point int32 [n_kp[cam]]  in/out: entry l is set to i when vpMatched[l] = vpPoints[i]
+ *   kf_index_quirk 1 = KeyFrame::GetFeaturesInArea as upstream (window test on mvTotalKeysUn[camera-local index], src/KeyFrame.cc:757), 0 = the
+ *                  camera's own key point; identical for camera 0 */
+int  orbm_search_by_projection_sim3(orbm_t*, const orbm_frame_t* KF, const orbm_frustum_t* view, int cam, const orbm_points_t* P, int th,
+                                    int kf_index_quirk, const uint8_t* matched_local, int32_t* local_to_point, int32_t* nmatches);
+
+/* Search part of the three loops that mutate the map while they search: for every camera s of pKF and every map point i the key point with
+ * the smallest descriptor distance inside the projected window (global index, -1 if none) and that distance (256 if none);
+ * best_kp / best_dist are int32 [n_cams][n].  The caller applies the threshold and the Replace / AddMapPoint branch in the reference's order.
+ *   ORBM_KF_SEARCH     SearchByProjection(pKF, vpMapPoints, sAlreadyFound, th, ORBdist)       src/ORBmatcher.cc:693-775  (threshold ORBdist)
+ *   ORBM_KF_FUSE       Fuse(pKF, vpMapPoints, th)                                            src/ORBmatcher.cc:1431-1527 (threshold TH_LOW)
+ *   ORBM_KF_FUSE_SIM3  Fuse(pKF, Scw, vpPoints, th, vpReplacePoint); view = vRsw/vtsw/vOsw   src/ORBmatcher.cc:1560-1668 (threshold TH_LOW) */
+#define ORBM_KF_SEARCH    0
+#define ORBM_KF_FUSE      1
+#define ORBM_KF_FUSE_SIM3 2
+int  orbm_project_best(orbm_t*, const orbm_frame_t* KF, const orbm_frustum_t* view, const orbm_points_t* P, float th, int variant,
+                       int kf_index_quirk, int32_t* best_kp, int32_t* best_dist);
+
+/* ORBmatcher::SearchByBoWCrossCam(pKF1, c1, pKF2, c2, vpMatches12)  (src/ORBmatcher.cc:297-414).  mp_valid1 / mp_valid2 are indexed by the
+ * global key point index (pMP && !isBad()); matches12 int32 [K1->n_kp[c1]]: GLOBAL key point index of pKF2 whose map point is
+ * vpMatches12[idx1local], else -1.  (SearchByBoWCrossCam(pF, cF, pKF, cKF, ...) with cF != cKF is orbm_search_by_bow on one-camera sides.) */
+int  orbm_search_by_bow_kf(orbm_t*, const orbm_bowside_t* K1, int c1, const orbm_bowside_t* K2, int c2, const uint8_t* mp_valid1,
+                           const uint8_t* mp_valid2, float nnratio, int check_orientation, int32_t* matches12, int32_t* nmatches);
+
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, camS) + CheckDistEpipolarLine  (src/ORBmatcher.cc:1253-1427, 74-92).
+ *   kps1 / kps2  global undistorted key point arrays; has_mp1 / has_mp2 uint8 (global): GetMapPoint(g) != NULL
+ *   F12 float [9] row-major; C1sw = pKF1->GetCameraCenter(camS); R2sw, t2sw = pKF2->GetRotation / GetTranslation(camS); K2cam = fx fy cx cy of camS
+ *   matches12 int32 [K1->n_kp[cam]]: camera-local index in pKF2 or -1 (vMatchedPairs = the entries >= 0, both made global by the caller) */
+int  orbm_search_for_triangulation(orbm_t*, const orbm_bowside_t* K1, const orbm_bowside_t* K2, int cam, const orb_keypoint_t* kps1,
+                                   const orb_keypoint_t* kps2, const uint8_t* has_mp1, const uint8_t* has_mp2, const float* F12, const float* C1sw,
+                                   const float* R2sw, const float* t2sw, const float* K2cam, const float* scale_factors, int n_levels,
+                                   int check_orientation, int32_t* matches12, int32_t* nmatches);
+
 /* Frame::UndistortKeyPoints(c) (src/Frame.cc:410-442): cv::undistortPoints(mat, mat, K, distCoef, Mat(), K) on the keypoint centres, every other
  * field copied; a copy when distCoef[0] == 0.  K4 = fx fy cx cy, dist = k1 k2 p1 p2 [k3 ...] (n_dist <= 12).  kps_un may alias kps.  HOST buffers. */
 int  orbm_undistort_keypoints(orbm_t*, const orb_keypoint_t* kps, int n, const float* K4, const float* dist, int n_dist, orb_keypoint_t* kps_un);

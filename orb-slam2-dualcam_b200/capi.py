@@ -73,6 +73,11 @@ SIGNATURES = {
     "orbba_dist_launch_count": (C.c_longlong, [vp]),
     "orbba_dist_optimize": (C.c_int, [vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]),
     "orbba_dist_timing": (C.c_int, [vp, f64p, f64p, f64p]),
+    "orbm_search_by_projection_reloc": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
+    "orbm_search_by_projection_sim3": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]),
+    "orbm_project_best": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp]),
+    "orbm_search_by_bow_kf": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp]),
+    "orbm_search_for_triangulation": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
     "orbm_undistort_keypoints": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "orbm_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
     "orbm_bruteforce_sets_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp]),
@@ -99,6 +104,13 @@ class BowSideC(C.Structure):
 class FrustumC(C.Structure):
     _fields_ = [("n_cams", C.c_int32), ("n_levels", C.c_int32), ("Rsw", vp), ("tsw", vp), ("Ow", vp), ("K", vp), ("bounds", vp),
                 ("log_scale_factor", C.c_float)]
+
+
+KF_SEARCH, KF_FUSE, KF_FUSE_SIM3 = 0, 1, 2     # ORBM_KF_* variants of orbm_project_best
+
+
+class PointsC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("valid", vp), ("pos", vp), ("normal", vp), ("max_dist", vp), ("min_dist", vp), ("desc", vp), ("angle", vp)]
 
 
 def _c(a, dt):
@@ -132,6 +144,17 @@ def frustum_struct(q, cls=FrustumC):
     keep = dict(Rsw=_c(q["Rsw"], np.float32), tsw=_c(q["tsw"], np.float32), Ow=_c(q["Ow"], np.float32), K=_c(q["K"], np.float32),
                 bounds=_c(q["bounds"], np.float32))
     s = cls(n_cams=keep["Rsw"].shape[0], n_levels=int(q["n_levels"]), log_scale_factor=float(q["log_scale_factor"]), **{k: v.ctypes.data for k, v in keep.items()})
+    return s, keep
+
+
+def points_struct(p, cls=PointsC):
+    """dict(valid, pos, normal (opt), max_dist, min_dist, desc, angle (opt)) -> (struct, keep-alive)"""
+    keep = dict(valid=_c(p["valid"], np.uint8), pos=_c(p["pos"], np.float32), max_dist=_c(p["max_dist"], np.float32), min_dist=_c(p["min_dist"], np.float32),
+                desc=_c(p["desc"], np.uint8))
+    for k in ("normal", "angle"):
+        if p.get(k) is not None:
+            keep[k] = _c(p[k], np.float32)
+    s = cls(n=len(keep["valid"]), **{k: v.ctypes.data for k, v in keep.items()})
     return s, keep
 
 

@@ -42,6 +42,7 @@ struct FrameDev {
     const uint4* desc;         // 2 x uint4 per keypoint
     int* cell_off;             // [n_cams][GRID_CELLS + 1]
     int* cell_idx;             // [totalN] camera-local indices, camera c at first[c]
+    int kf_quirk;              // KeyFrame::GetFeaturesInArea as upstream: the window test reads mvTotalKeysUn[camera-LOCAL index] (src/KeyFrame.cc:757)
 };
 
 struct Query {                 // one window search
@@ -127,8 +128,9 @@ __global__ void __launch_bounds__(128) k_window_cands(FrameDev F, const Query* _
                     if (e < b) {
                         const int g = F.first[c] + idx[e];
                         const float4 k = F.kp[g];
+                        const float4 kpos = F.kf_quirk ? F.kp[idx[e]] : k;
                         const int oct = __float_as_int(k.w);
-                        pred = oct >= Q.minLevel && oct <= Q.maxLevel && fabsf(__fsub_rn(k.x, x)) < r && fabsf(__fsub_rn(k.y, y)) < r;
+                        pred = oct >= Q.minLevel && oct <= Q.maxLevel && fabsf(__fsub_rn(kpos.x, x)) < r && fabsf(__fsub_rn(kpos.y, y)) < r;
                         if (pred && FILL) {
                             const uint4 da = F.desc[2 * (size_t)g], db = F.desc[2 * (size_t)g + 1];
                             rec = ((uint32_t)hamming256(d, da, db) << 22) | ((uint32_t)oct << KP_BITS) | (uint32_t)g;
@@ -174,25 +176,171 @@ __global__ void __launch_bounds__(1024) k_scan(const int* __restrict__ cnt, int 
     if (threadIdx.x == 0) { off[n] = carry; *total = carry; }
 }
 
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t < v ? t : v;
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------ key-frame searches: projection
+// One thread per (camera, map point): the gates that precede the window search in SearchByProjectionOnCam(F, cam, KF, ...)
+// (src/ORBmatcher.cc:838-873), SearchByProjection(KF, MPs, ...) (:712-745), SearchByProjection(KF, query, Scw, ...) (:452-490),
+// Fuse (:1448-1484) and Fuse(Scw) (:1606-1643).  FP32 left to right, cv::norm / Mat::dot in double, as the oracle.
+enum { PS_DEPTH_POS = 1, PS_NORMALISE_FIRST = 2, PS_HALF_OPEN = 4, PS_VIEW_ANGLE = 8, PS_LEVEL_UP = 16, PS_CHI2 = 32 };
+struct ProjDev {
+    int n, n_levels, flags, cam0;            // query q: camera cam0 + q / n, map point q % n
+    float th, log_scale;
+    float R[MAX_CAMS][9], t[MAX_CAMS][3], Ow[MAX_CAMS][3], K[MAX_CAMS][4], b[MAX_CAMS][4];
+    float scale[16];
+    const uint8_t* valid; const float* pos; const float* normal; const float* max_dist; const float* min_dist; const uint4* desc; const float* angle;
+};
+__global__ void __launch_bounds__(128) k_project_queries(ProjDev P, int nq, Query* __restrict__ qs, int* __restrict__ q_seq, int* __restrict__ q_tag,
+                                                         uint8_t* __restrict__ q_obs, float* __restrict__ q_angle) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int i = q % P.n, c = P.cam0 + q / P.n;
+    Query Q;
+    Q.cam = c; Q.valid = 0; Q.u = Q.v = Q.r = 0.f; Q.minLevel = Q.maxLevel = 0; Q.tag = i; Q.obs_positive = 1; Q.angle = P.angle ? P.angle[i] : 0.f;
+    const uint4 da = P.desc[2 * (size_t)i], db = P.desc[2 * (size_t)i + 1];
+    Q.desc[0] = da.x; Q.desc[1] = da.y; Q.desc[2] = da.z; Q.desc[3] = da.w; Q.desc[4] = db.x; Q.desc[5] = db.y; Q.desc[6] = db.z; Q.desc[7] = db.w;
+    do {
+        if (!P.valid[i]) break;
+        const float* R = P.R[c];
+        const float P0 = P.pos[3 * (size_t)i], P1 = P.pos[3 * (size_t)i + 1], P2 = P.pos[3 * (size_t)i + 2];
+        const float X = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], P0), __fmul_rn(R[1], P1)), __fmul_rn(R[2], P2)), P.t[c][0]);
+        const float Y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], P0), __fmul_rn(R[4], P1)), __fmul_rn(R[5], P2)), P.t[c][1]);
+        const float Z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[6], P0), __fmul_rn(R[7], P1)), __fmul_rn(R[8], P2)), P.t[c][2]);
+        if ((P.flags & PS_DEPTH_POS) && Z < 0.0f) break;
+        const float invz = __fdiv_rn(1.0f, Z);
+        float u, v;
+        if (P.flags & PS_NORMALISE_FIRST) {
+            u = __fadd_rn(__fmul_rn(P.K[c][0], __fmul_rn(X, invz)), P.K[c][2]);
+            v = __fadd_rn(__fmul_rn(P.K[c][1], __fmul_rn(Y, invz)), P.K[c][3]);
+        } else {
+            u = __fadd_rn(__fmul_rn(__fmul_rn(P.K[c][0], X), invz), P.K[c][2]);
+            v = __fadd_rn(__fmul_rn(__fmul_rn(P.K[c][1], Y), invz), P.K[c][3]);
+        }
+        if (P.flags & PS_HALF_OPEN) { if (!(u >= P.b[c][0] && u < P.b[c][1] && v >= P.b[c][2] && v < P.b[c][3])) break; }
+        else { if (u < P.b[c][0] || u > P.b[c][1]) break; if (v < P.b[c][2] || v > P.b[c][3]) break; }
+        const float PO0 = __fsub_rn(P0, P.Ow[c][0]), PO1 = __fsub_rn(P1, P.Ow[c][1]), PO2 = __fsub_rn(P2, P.Ow[c][2]);
+        const float dist = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn((double)PO0, (double)PO0), __dmul_rn((double)PO1, (double)PO1)), __dmul_rn((double)PO2, (double)PO2)));
+        const float maxDistance = __fmul_rn(1.2f, P.max_dist[i]), minDistance = __fmul_rn(0.8f, P.min_dist[i]);
+        if (dist < minDistance || dist > maxDistance) break;
+        if (P.flags & PS_VIEW_ANGLE) {
+            const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)PO0, (double)P.normal[3 * (size_t)i]), __dmul_rn((double)PO1, (double)P.normal[3 * (size_t)i + 1])),
+                                         __dmul_rn((double)PO2, (double)P.normal[3 * (size_t)i + 2]));
+            if (dot < __dmul_rn(0.5, (double)dist)) break;
+        }
+        const float ratio = __fdiv_rn(P.max_dist[i], dist);                       // MapPoint::PredictScale  src/MapPoint.cc:423-455
+        int nScale = (int)ceil(log((double)ratio) / (double)P.log_scale);
+        if (nScale < 0) nScale = 0;
+        else if (nScale >= P.n_levels) nScale = P.n_levels - 1;
+        Q.valid = 1; Q.u = u; Q.v = v; Q.r = __fmul_rn(P.th, P.scale[nScale]);
+        Q.minLevel = nScale - 1; Q.maxLevel = (P.flags & PS_LEVEL_UP) ? nScale + 1 : nScale;
+    } while (false);
+    qs[q] = Q;
+    if (q_seq) { q_seq[q] = Q.valid ? 0 : -1; q_tag[q] = i; q_obs[q] = 1; q_angle[q] = Q.angle; }
+}
+
+// window search without claims: the key point with the smallest distance (first wins) for every query, one warp per query
+// (the inner loops of src/ORBmatcher.cc:753-775, 1492-1527, 1654-1668).  chi2: Fuse's pixel gate e2 * invSigma2[level] > 5.99 (:1510-1517).
+__global__ void __launch_bounds__(128) k_window_best(FrameDev F, const Query* __restrict__ qs, int nq, int chi2, int* __restrict__ best_kp,
+                                                     int* __restrict__ best_dist) {
+    const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const Query& Q = qs[q];
+    unsigned long long best = ~0ull;
+    if (Q.valid) {
+        const int c = Q.cam;
+        const float x = Q.u, y = Q.v, r = Q.r;
+        const int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, F.minX[c]), r), F.invW[c])));
+        const int x1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, F.minX[c]), r), F.invW[c])));
+        const int y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, F.minY[c]), r), F.invH[c])));
+        const int y1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, F.minY[c]), r), F.invH[c])));
+        if (x0 < GRID_COLS && x1 >= 0 && y0 < GRID_ROWS && y1 >= 0) {
+            uint32_t d[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) d[i] = Q.desc[i];
+            const int* off = F.cell_off + (size_t)c * (GRID_CELLS + 1);
+            const int* idx = F.cell_idx + F.first[c];
+            unsigned pos0 = 0;
+            for (int ix = x0; ix <= x1; ix++) {
+                const int a = off[ix * GRID_ROWS + y0], b = off[ix * GRID_ROWS + y1 + 1];
+                for (int e = a + lane; e < b; e += 32) {
+                    const int g = F.first[c] + idx[e];
+                    const float4 k = F.kp[g];
+                    const float4 kpos = F.kf_quirk ? F.kp[idx[e]] : k;
+                    const int oct = __float_as_int(k.w);
+                    if (!(fabsf(__fsub_rn(kpos.x, x)) < r && fabsf(__fsub_rn(kpos.y, y)) < r)) continue;
+                    if (oct < Q.minLevel || oct > Q.maxLevel) continue;
+                    if (chi2) {
+                        const float ex = __fsub_rn(x, k.x), ey = __fsub_rn(y, k.y);
+                        const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                        const float inv = __fdiv_rn(1.0f, __fmul_rn(F.scale[oct], F.scale[oct]));
+                        if ((double)__fmul_rn(e2, inv) > 5.99) continue;
+                    }
+                    const unsigned long long key = ((unsigned long long)hamming256(d, F.desc[2 * (size_t)g], F.desc[2 * (size_t)g + 1]) << 48) |
+                                                   ((unsigned long long)(pos0 + (unsigned)(e - a)) << 24) | (unsigned)g;
+                    best = key < best ? key : best;
+                }
+                pos0 += (unsigned)(b - a);
+            }
+        }
+    }
+    best = warp_min_u64(best);
+    if (lane == 0) { best_kp[q] = best == ~0ull ? -1 : (int)(best & KP_MASK); best_dist[q] = best == ~0ull ? 256 : (int)(best >> 48); }
+}
+
 // ------------------------------------------------------------------------------------------------ BoW candidates
-struct BowQuery { int gKF, f_begin, f_end, cam, firstF; float angle; };   // f_begin..f_end: range in the frame's idx array
+struct BowQuery { int gKF, f_begin, f_end, cam, firstF; float angle; };   // f_begin..f_end: range in the target side's idx array
+// gates of SearchForTriangulation (src/ORBmatcher.cc:1318-1335 + CheckDistEpipolarLine :74-92), evaluated per candidate
+struct TriDev { int on; float ex, ey; float F12[9]; float scale[16]; const float4* kp1; const float4* kp2; };
+#define REC_INVALID 0x3ffu
 __global__ void __launch_bounds__(128) k_bow_cands(const BowQuery* __restrict__ qs, int nq, const int* __restrict__ q_off, const uint4* __restrict__ descKF,
-                                                   const uint4* __restrict__ descF, const int* __restrict__ idxF, uint32_t* __restrict__ recs) {
+                                                   const uint4* __restrict__ descF, const int* __restrict__ idxF, uint32_t* __restrict__ recs,
+                                                   const uint8_t* __restrict__ t_skip, TriDev T) {
     const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= nq) return;
     const BowQuery Q = qs[q];
     const uint4 qa = descKF[2 * (size_t)Q.gKF], qb = descKF[2 * (size_t)Q.gKF + 1];
     const uint32_t d[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
     const int base = q_off[q];
+    float la = 0.f, lb = 0.f, lc = 0.f, den = 0.f;
+    if (T.on) {
+        const float4 k1 = T.kp1[Q.gKF];
+        la = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, T.F12[0]), __fmul_rn(k1.y, T.F12[3])), T.F12[6]);
+        lb = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, T.F12[1]), __fmul_rn(k1.y, T.F12[4])), T.F12[7]);
+        lc = __fadd_rn(__fadd_rn(__fmul_rn(k1.x, T.F12[2]), __fmul_rn(k1.y, T.F12[5])), T.F12[8]);
+        den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+    }
     for (int e = Q.f_begin + lane; e < Q.f_end; e += 32) {
         const int local = idxF[e];
         const size_t g = (size_t)Q.firstF + local;
-        recs[base + (e - Q.f_begin)] = ((uint32_t)hamming256(d, descF[2 * g], descF[2 * g + 1]) << 22) | (uint32_t)local;
+        uint32_t dist = (uint32_t)hamming256(d, descF[2 * g], descF[2 * g + 1]);
+        if (t_skip && t_skip[g]) dist = REC_INVALID;
+        if (T.on && dist != REC_INVALID) {
+            const float4 k2 = T.kp2[g];
+            const int oct = __float_as_int(k2.w);
+            const float dx = __fsub_rn(T.ex, k2.x), dy = __fsub_rn(T.ey, k2.y);
+            const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, k2.x), __fmul_rn(lb, k2.y)), lc);
+            bool ok = dist <= (uint32_t)ORBM_TH_LOW;
+            ok = ok && !(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.0f, T.scale[oct]));
+            ok = ok && den != 0.0f;
+            if (ok) {
+                const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                ok = (double)dsqr < __dmul_rn(3.84, (double)__fmul_rn(T.scale[oct], T.scale[oct]));
+            }
+            if (!ok) dist = REC_INVALID;
+        }
+        recs[base + (e - Q.f_begin)] = (dist << 22) | (uint32_t)local;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ resolve
-enum { MODE_MP = 0, MODE_LAST = 1, MODE_BOW = 2 };
+enum { MODE_MP = 0, MODE_LAST = 1, MODE_BOW = 2, MODE_BOW_KF = 3, MODE_TRI = 4 };
 struct ResolveArgs {
     int mode, nq, n_bits;            // n_bits: size of the claim bitmap (keypoints)
     const int* q_off;
@@ -209,16 +357,9 @@ struct ResolveArgs {
     int* m_kp; int* m_bin;           // match lists for the rotation check, per sequence slices of nq entries
     float nnratio;
     int check_ori;
+    int th_accept;                   // mode LAST: accept iff best <= th_accept (TH_HIGH, or the caller's ORBdist / TH_LOW in the key-frame variants)
 };
 
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
-        v = t < v ? t : v;
-    }
-    return v;
-}
 
 __global__ void __launch_bounds__(32) k_resolve(ResolveArgs R) {
     extern __shared__ unsigned s_claim[];          // bitmap over target keypoints
@@ -247,8 +388,11 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs R) {
         for (int pos = lane; pos < cnt; pos += 32) {
             const uint32_t rec = R.recs[off + pos];
             const uint32_t kp = rec & KP_MASK;
+            if ((rec >> 22) > 256u) continue;                          // masked / gated out by the candidate kernel
             if ((s_claim[kp >> 5] >> (kp & 31)) & 1u) continue;
-            const unsigned long long key = ((unsigned long long)(rec >> 22) << 48) | ((unsigned long long)pos << 24) | (rec & 0x3fffffu);
+            // SearchForTriangulation replaces the best on ties (`dist > bestDist` continues, :1323): the LAST candidate wins
+            const unsigned long long ord = R.mode == MODE_TRI ? (unsigned long long)(0xffffff - pos) : (unsigned long long)pos;
+            const unsigned long long key = ((unsigned long long)(rec >> 22) << 48) | (ord << 24) | (rec & 0x3fffffu);
             if (key < b1) { b2 = b1; b1 = key; } else if (key < b2) b2 = key;
         }
         const unsigned long long best = warp_min_u64(b1);
@@ -258,19 +402,23 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs R) {
         const int bd2 = second == NONE ? 256 : (int)(second >> 48), lvl2 = second == NONE ? -1 : (int)((second >> KP_BITS) & 31);
         bool accept;
         if (R.mode == MODE_MP) accept = bd <= ORBM_TH_HIGH && !(lvl == lvl2 && (float)bd > R.nnratio * (float)bd2);
-        else if (R.mode == MODE_LAST) accept = bd <= ORBM_TH_HIGH;
-        else accept = bd <= ORBM_TH_LOW && (float)bd < R.nnratio * (float)bd2;
+        else if (R.mode == MODE_LAST) accept = bd <= R.th_accept;
+        else if (R.mode == MODE_BOW) accept = bd <= ORBM_TH_LOW && (float)bd < R.nnratio * (float)bd2;
+        else if (R.mode == MODE_BOW_KF) accept = bd < ORBM_TH_LOW && (float)bd < R.nnratio * (float)bd2;      // strict, src/ORBmatcher.cc:363
+        else accept = true;                                                                                  // MODE_TRI: every gate is in the records
         if (!accept) continue;
+        const bool by_query = R.mode == MODE_BOW_KF || R.mode == MODE_TRI;      // vpMatches12 / vMatches12 are indexed by the query key point
+        const int oidx = by_query ? R.q_tag[q] : tbase + kp;
         if (lane == 0) {
-            R.out[tbase + kp] = R.q_tag[q];
-            const bool claim = R.mode == MODE_BOW ? true : (R.q_obs[q] != 0);
+            R.out[oidx] = by_query ? kp : R.q_tag[q];
+            const bool claim = R.mode >= MODE_BOW ? true : (R.q_obs[q] != 0);
             if (claim) s_claim[kp >> 5] |= 1u << (kp & 31); else s_claim[kp >> 5] &= ~(1u << (kp & 31));
             if (R.check_ori && R.mode != MODE_MP) {
                 float rot = __fsub_rn(R.q_angle[q], R.kp_angle[tbase + kp]);
                 if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
                 int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
                 if (bin == HISTO_LENGTH) bin = 0;
-                m_kp[nlist] = kp; m_bin[nlist] = bin;
+                m_kp[nlist] = oidx; m_bin[nlist] = bin;
                 s_hist[bin]++;
             }
         }
@@ -294,7 +442,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs R) {
         int removed = 0;
         for (int i = lane; i < nlist; i += 32) {
             const int bin = m_bin[i];
-            if (bin != ind1 && bin != ind2 && bin != ind3) { R.out[tbase + m_kp[i]] = -1; removed++; }
+            if (bin != ind1 && bin != ind2 && bin != ind3) { R.out[m_kp[i]] = -1; removed++; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
@@ -535,7 +683,7 @@ static int run_window_search(orbm_t* m, const orbm_frame_t* frame, std::vector<Q
         R.q_off = (const int*)(A.d + o_off); R.recs = recs; R.q_seq = (const int*)(A.d + o_seq); R.q_tag = (const int*)(A.d + o_tag);
         R.q_obs = A.d + o_obs; R.q_angle = (const float*)(A.d + o_qang); R.kp_angle = (const float*)(A.d + o_kang);
         R.seq_base = nullptr; R.blocked_in = A.d + o_blk; R.out = (int*)(A.d + o_out); R.seq_matches = (int*)(A.d + o_sm);
-        R.m_kp = (int*)(A.d + o_mkp); R.m_bin = (int*)(A.d + o_mbin); R.nnratio = nnratio; R.check_ori = check_ori;
+        R.m_kp = (int*)(A.d + o_mkp); R.m_bin = (int*)(A.d + o_mbin); R.nnratio = nnratio; R.check_ori = check_ori; R.th_accept = ORBM_TH_HIGH;
         k_resolve<<<n_seq, 32, ((totalN + 31) / 32 + 1) * 4, st>>>(R);
         launches++;
     }
@@ -640,58 +788,75 @@ int orbm_search_by_projection_last(orbm_t* m, const orbm_frame_t* cur, const flo
     return ORB_OK;
 }
 
-int orbm_search_by_bow(orbm_t* m, const orbm_bowside_t* F, const orbm_bowside_t* KF, const uint8_t* kf_mp_valid, float nnratio, int check_orientation,
-                       int map_scaled, int32_t* f_to_kf, int32_t* nmatches) {
-    if (!m) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_bow: NULL handle");
-    if (!F || !KF || !kf_mp_valid || !f_to_kf || F->n_cams != KF->n_cams || F->n_cams < 1 || F->n_cams > MAX_CAMS) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_bow: bad argument");
-    if (!F->n_kp || !KF->n_kp || !F->node_first || !KF->node_first) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_bow: NULL field");
-    const int C = F->n_cams;
-    std::vector<int> firstF(C + 1, 0), firstK(C + 1, 0);
-    for (int c = 0; c < C; c++) { firstF[c + 1] = firstF[c] + F->n_kp[c]; firstK[c + 1] = firstK[c] + KF->n_kp[c]; }
-    const int totF = firstF[C], totK = firstK[C];
-    if (totF > (int)KP_MASK) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_bow: too many keypoints");
-    for (int g = 0; g < totF; g++) f_to_kf[g] = -1;
-    // merge-join of the two feature vectors (src/ORBmatcher.cc:184-269): the queries in the reference's visiting order
+// merge-join of two DBoW2 feature vectors + sequential claims (src/ORBmatcher.cc:184-269, 323-391, 1288-1383): Q side = the loop's outer
+// features (queries), T side = inner features (targets).  pairs: (camera of Q, camera of T) per sequence; q_ok / t_skip are indexed globally.
+// out: MODE_BOW -> [totT] global target -> global query; MODE_BOW_KF / MODE_TRI (one sequence) -> [n_kp of Q camera] local query -> local target.
+struct BowJob {
+    const orbm_bowside_t* Q; const orbm_bowside_t* T;
+    int n_seq; int cq[MAX_CAMS], ct[MAX_CAMS];
+    const uint8_t* q_ok; int q_ok_invert;        // query i is searched iff (q_ok[i] != 0) != q_ok_invert
+    const uint8_t* t_skip;                       // may be NULL
+    int mode; float nnratio; int check_ori;
+    TriDev tri; const orb_keypoint_t* kps1; const orb_keypoint_t* kps2;
+};
+static int bow_join(orbm_t* m, const BowJob& J, const char* who, int32_t* out, int n_out, int* seq_matches) {
+    const orbm_bowside_t *Q = J.Q, *T = J.T;
+    if (!Q->n_kp || !T->n_kp || !Q->node_first || !T->node_first || Q->n_cams < 1 || Q->n_cams > MAX_CAMS || T->n_cams < 1 || T->n_cams > MAX_CAMS)
+        ORB_FAIL(ORB_E_INVALID, "%s: bad feature-vector side", who);
+    std::vector<int> firstQ(Q->n_cams + 1, 0), firstT(T->n_cams + 1, 0);
+    for (int c = 0; c < Q->n_cams; c++) firstQ[c + 1] = firstQ[c] + Q->n_kp[c];
+    for (int c = 0; c < T->n_cams; c++) firstT[c + 1] = firstT[c] + T->n_kp[c];
+    const int totQ = firstQ[Q->n_cams], totT = firstT[T->n_cams];
+    if (totT > (int)KP_MASK || totQ > (int)KP_MASK) ORB_FAIL(ORB_E_INVALID, "%s: too many keypoints", who);
+    if ((totQ && (!Q->desc || !Q->angle)) || (totT && (!T->desc || !T->angle))) ORB_FAIL(ORB_E_INVALID, "%s: NULL descriptors / angles", who);
+    for (int g = 0; g < n_out; g++) out[g] = -1;
     std::vector<BowQuery> qs;
     std::vector<int> q_off(1, 0), q_seq, q_tag;
     std::vector<float> q_ang;
-    for (int ic = 0; ic < C; ic++) {
-        if (ic != 0 && !map_scaled) continue;
-        int kf = KF->node_first[ic], kfEnd = KF->node_first[ic + 1], ff = F->node_first[ic], ffEnd = F->node_first[ic + 1];
-        while (kf != kfEnd && ff != ffEnd) {
-            if (KF->node_id[kf] == F->node_id[ff]) {
-                for (int a = KF->node_off[kf]; a < KF->node_off[kf + 1]; a++) {
-                    const int gKF = firstK[ic] + KF->idx[a];
-                    if (KF->idx[a] < 0 || KF->idx[a] >= KF->n_kp[ic]) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_bow: key-frame feature index out of range");
-                    if (!kf_mp_valid[gKF]) continue;
+    std::vector<int> seq_base(J.n_seq, 0);
+    int maxT = 0;
+    for (int sq = 0; sq < J.n_seq; sq++) {
+        const int cq = J.cq[sq], ct = J.ct[sq];
+        seq_base[sq] = firstT[ct];          // targets are camera-local in the records; angles / MODE_BOW outputs are global
+        maxT = std::max(maxT, T->n_kp[ct]);
+        int kq = Q->node_first[cq], kqEnd = Q->node_first[cq + 1], kt = T->node_first[ct], ktEnd = T->node_first[ct + 1];
+        while (kq != kqEnd && kt != ktEnd) {
+            if (Q->node_id[kq] == T->node_id[kt]) {
+                for (int a = Q->node_off[kq]; a < Q->node_off[kq + 1]; a++) {
+                    if (Q->idx[a] < 0 || Q->idx[a] >= Q->n_kp[cq]) ORB_FAIL(ORB_E_INVALID, "%s: feature index out of range", who);
+                    const int gQ = firstQ[cq] + Q->idx[a];
+                    if ((J.q_ok[gQ] != 0) == (J.q_ok_invert != 0)) continue;
                     BowQuery q;
-                    q.gKF = gKF; q.f_begin = F->node_off[ff]; q.f_end = F->node_off[ff + 1]; q.cam = ic; q.firstF = firstF[ic]; q.angle = KF->angle[gKF];
+                    q.gKF = gQ; q.f_begin = T->node_off[kt]; q.f_end = T->node_off[kt + 1]; q.cam = sq; q.firstF = firstT[ct]; q.angle = Q->angle[gQ];
                     qs.push_back(q);
                     q_off.push_back(q_off.back() + (q.f_end - q.f_begin));
-                    q_seq.push_back(ic); q_tag.push_back(gKF); q_ang.push_back(KF->angle[gKF]);
+                    q_seq.push_back(sq); q_tag.push_back(J.mode == MODE_BOW ? gQ : Q->idx[a]); q_ang.push_back(Q->angle[gQ]);
                 }
-                kf++; ff++;
-            } else if (KF->node_id[kf] < F->node_id[ff]) {
-                while (kf != kfEnd && KF->node_id[kf] < F->node_id[ff]) kf++;
+                kq++; kt++;
+            } else if (Q->node_id[kq] < T->node_id[kt]) {
+                while (kq != kqEnd && Q->node_id[kq] < T->node_id[kt]) kq++;          // lower_bound
             } else {
-                while (ff != ffEnd && F->node_id[ff] < KF->node_id[kf]) ff++;
+                while (kt != ktEnd && T->node_id[kt] < Q->node_id[kq]) kt++;
             }
         }
     }
     const int nq = (int)qs.size();
-    if (nmatches) *nmatches = 0;
+    for (int sq = 0; sq < J.n_seq; sq++) seq_matches[sq] = 0;
     if (nq == 0) return ORB_OK;
-    const int nIdxF = F->node_off[F->node_first[C]];
+    const int nIdxT = T->node_off[T->node_first[T->n_cams]];
+    for (int e = 0; e < nIdxT; e++) if (T->idx[e] < 0) ORB_FAIL(ORB_E_INVALID, "%s: feature index out of range", who);
     const int device = orbm_device_of(m);
     ORB_CUDA(cudaSetDevice(device));
     cudaStream_t st = orbm_stream_of(m);
+    const bool tri = J.tri.on != 0;
     Bump B;
     const size_t o_q = B.add(sizeof(BowQuery) * (size_t)nq), o_off = B.add(4 * (size_t)(nq + 1)), o_seq = B.add(4 * (size_t)nq), o_tag = B.add(4 * (size_t)nq),
-                 o_qang = B.add(4 * (size_t)nq), o_dK = B.add(32 * (size_t)totK), o_dF = B.add(32 * (size_t)totF), o_idx = B.add(4 * (size_t)std::max(nIdxF, 1)),
-                 o_fang = B.add(4 * (size_t)totF), o_base = B.add(4 * (size_t)C);
+                 o_qang = B.add(4 * (size_t)nq), o_dQ = B.add(32 * (size_t)totQ), o_dT = B.add(32 * (size_t)totT), o_idx = B.add(4 * (size_t)std::max(nIdxT, 1)),
+                 o_tang = B.add(4 * (size_t)totT), o_base = B.add(4 * (size_t)J.n_seq), o_skip = B.add(J.t_skip ? (size_t)totT : 0),
+                 o_k1 = B.add(tri ? 16 * (size_t)totQ : 0), o_k2 = B.add(tri ? 16 * (size_t)totT : 0);
     const size_t staged = B.add(0);
-    const size_t o_recs = B.add(4 * (size_t)std::max(q_off.back(), 1)), o_out = B.add(4 * (size_t)totF), o_sm = B.add(4 * (size_t)C),
-                 o_mkp = B.add(4 * (size_t)nq * C), o_mbin = B.add(4 * (size_t)nq * C);
+    const size_t o_recs = B.add(4 * (size_t)std::max(q_off.back(), 1)), o_out = B.add(4 * (size_t)std::max(n_out, 1)), o_sm = B.add(4 * (size_t)J.n_seq),
+                 o_mkp = B.add(4 * (size_t)nq * J.n_seq), o_mbin = B.add(4 * (size_t)nq * J.n_seq);
     const size_t total_bytes = B.add(0);
     Arena& A = g_arena;
     int rc = arena_reserve(A, device, total_bytes, staged);
@@ -701,36 +866,256 @@ int orbm_search_by_bow(orbm_t* m, const orbm_bowside_t* F, const orbm_bowside_t*
     memcpy(A.h + o_seq, q_seq.data(), 4 * (size_t)nq);
     memcpy(A.h + o_tag, q_tag.data(), 4 * (size_t)nq);
     memcpy(A.h + o_qang, q_ang.data(), 4 * (size_t)nq);
-    memcpy(A.h + o_dK, KF->desc, 32 * (size_t)totK);
-    memcpy(A.h + o_dF, F->desc, 32 * (size_t)totF);
-    if (nIdxF) memcpy(A.h + o_idx, F->idx, 4 * (size_t)nIdxF);
-    memcpy(A.h + o_fang, F->angle, 4 * (size_t)totF);
-    memcpy(A.h + o_base, firstF.data(), 4 * (size_t)C);
+    memcpy(A.h + o_dQ, Q->desc, 32 * (size_t)totQ);
+    memcpy(A.h + o_dT, T->desc, 32 * (size_t)totT);
+    if (nIdxT) memcpy(A.h + o_idx, T->idx, 4 * (size_t)nIdxT);
+    memcpy(A.h + o_tang, T->angle, 4 * (size_t)totT);
+    memcpy(A.h + o_base, seq_base.data(), 4 * (size_t)J.n_seq);
+    if (J.t_skip) memcpy(A.h + o_skip, J.t_skip, (size_t)totT);
+    TriDev TD = J.tri;
+    if (tri) {
+        float4* k1 = (float4*)(A.h + o_k1);
+        float4* k2 = (float4*)(A.h + o_k2);
+        for (int g = 0; g < totQ; g++) { float w; const int oct = J.kps1[g].octave; memcpy(&w, &oct, 4); k1[g] = make_float4(J.kps1[g].x, J.kps1[g].y, J.kps1[g].angle, w); }
+        for (int g = 0; g < totT; g++) { float w; const int oct = J.kps2[g].octave; memcpy(&w, &oct, 4); k2[g] = make_float4(J.kps2[g].x, J.kps2[g].y, J.kps2[g].angle, w); }
+        TD.kp1 = (const float4*)(A.d + o_k1); TD.kp2 = (const float4*)(A.d + o_k2);
+    }
     ORB_CUDA(cudaMemcpyAsync(A.d, A.h, staged, cudaMemcpyHostToDevice, st));
-    ORB_CUDA(cudaMemsetAsync(A.d + o_out, 0xff, 4 * (size_t)totF, st));
-    k_bow_cands<<<(nq + 3) / 4, 128, 0, st>>>((const BowQuery*)(A.d + o_q), nq, (const int*)(A.d + o_off), (const uint4*)(A.d + o_dK), (const uint4*)(A.d + o_dF),
-                                              (const int*)(A.d + o_idx), (uint32_t*)(A.d + o_recs));
+    ORB_CUDA(cudaMemsetAsync(A.d + o_out, 0xff, 4 * (size_t)std::max(n_out, 1), st));
+    k_bow_cands<<<(nq + 3) / 4, 128, 0, st>>>((const BowQuery*)(A.d + o_q), nq, (const int*)(A.d + o_off), (const uint4*)(A.d + o_dQ), (const uint4*)(A.d + o_dT),
+                                              (const int*)(A.d + o_idx), (uint32_t*)(A.d + o_recs), J.t_skip ? A.d + o_skip : nullptr, TD);
     ResolveArgs R;
     memset(&R, 0, sizeof(R));
-    int maxF = 0;
-    for (int c = 0; c < C; c++) maxF = std::max(maxF, F->n_kp[c]);
-    R.mode = MODE_BOW; R.nq = nq; R.n_bits = maxF;
+    R.mode = J.mode; R.nq = nq; R.n_bits = maxT;
     R.q_off = (const int*)(A.d + o_off); R.recs = (const uint32_t*)(A.d + o_recs); R.q_seq = (const int*)(A.d + o_seq); R.q_tag = (const int*)(A.d + o_tag);
-    R.q_obs = nullptr; R.q_angle = (const float*)(A.d + o_qang); R.kp_angle = (const float*)(A.d + o_fang); R.seq_base = (const int*)(A.d + o_base);
+    R.q_obs = nullptr; R.q_angle = (const float*)(A.d + o_qang); R.kp_angle = (const float*)(A.d + o_tang); R.seq_base = (const int*)(A.d + o_base);
     R.blocked_in = nullptr; R.out = (int*)(A.d + o_out); R.seq_matches = (int*)(A.d + o_sm); R.m_kp = (int*)(A.d + o_mkp); R.m_bin = (int*)(A.d + o_mbin);
-    R.nnratio = nnratio; R.check_ori = check_orientation != 0;
-    ORB_CUDA(cudaMemsetAsync(A.d + o_sm, 0, 4 * (size_t)C, st));
-    k_resolve<<<C, 32, ((maxF + 31) / 32 + 1) * 4, st>>>(R);
+    R.nnratio = J.nnratio; R.check_ori = J.check_ori != 0; R.th_accept = ORBM_TH_LOW;
+    ORB_CUDA(cudaMemsetAsync(A.d + o_sm, 0, 4 * (size_t)J.n_seq, st));
+    k_resolve<<<J.n_seq, 32, ((maxT + 31) / 32 + 1) * 4, st>>>(R);
     ORB_CUDA(cudaGetLastError());
-    std::vector<int> sm(C, 0);
-    ORB_CUDA(cudaMemcpyAsync(f_to_kf, A.d + o_out, 4 * (size_t)totF, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA(cudaMemcpyAsync(sm.data(), A.d + o_sm, 4 * (size_t)C, cudaMemcpyDeviceToHost, st));
+    if (n_out) ORB_CUDA(cudaMemcpyAsync(out, A.d + o_out, 4 * (size_t)n_out, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(seq_matches, A.d + o_sm, 4 * (size_t)J.n_seq, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
     orbm_count_launches(m, 2);
+    return ORB_OK;
+}
+
+int orbm_search_by_bow(orbm_t* m, const orbm_bowside_t* F, const orbm_bowside_t* KF, const uint8_t* kf_mp_valid, float nnratio, int check_orientation,
+                       int map_scaled, int32_t* f_to_kf, int32_t* nmatches) {
+    if (!m) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_bow: NULL handle");
+    if (!F || !KF || !kf_mp_valid || !f_to_kf || F->n_cams != KF->n_cams || F->n_cams < 1 || F->n_cams > MAX_CAMS) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_bow: bad argument");
+    if (!F->n_kp || !KF->n_kp) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_bow: NULL field");
+    BowJob J;
+    memset(&J, 0, sizeof(J));
+    J.Q = KF; J.T = F; J.q_ok = kf_mp_valid; J.mode = MODE_BOW; J.nnratio = nnratio; J.check_ori = check_orientation;
+    int totF = 0;
+    for (int c = 0; c < F->n_cams; c++) {
+        totF += F->n_kp[c];
+        if (c != 0 && !map_scaled) continue;
+        J.cq[J.n_seq] = c; J.ct[J.n_seq] = c; J.n_seq++;
+    }
+    int sm[MAX_CAMS];
+    const int rc = bow_join(m, J, "orbm_search_by_bow", f_to_kf, totF, sm);
+    if (rc != ORB_OK) return rc;
     int tot = 0;
-    for (int c = 0; c < C; c++) if (c == 0 || map_scaled) tot += sm[c];
+    for (int sq = 0; sq < J.n_seq; sq++) tot += sm[sq];
     if (nmatches) *nmatches = tot;
     return ORB_OK;
+}
+
+int orbm_search_by_bow_kf(orbm_t* m, const orbm_bowside_t* K1, int c1, const orbm_bowside_t* K2, int c2, const uint8_t* mp_valid1, const uint8_t* mp_valid2,
+                          float nnratio, int check_orientation, int32_t* matches12, int32_t* nmatches) {
+    if (!m) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_bow_kf: NULL handle");
+    if (!K1 || !K2 || !mp_valid1 || !mp_valid2 || !matches12 || !K1->n_kp || !K2->n_kp || c1 < 0 || c1 >= K1->n_cams || c2 < 0 || c2 >= K2->n_cams)
+        ORB_FAIL(ORB_E_INVALID, "orbm_search_by_bow_kf: bad argument");
+    int tot2 = 0, first2 = 0;
+    for (int c = 0; c < K2->n_cams && c < MAX_CAMS; c++) { if (c < c2) first2 += K2->n_kp[c]; tot2 += K2->n_kp[c]; }
+    std::vector<uint8_t> skip((size_t)std::max(tot2, 1));
+    for (int g = 0; g < tot2; g++) skip[g] = mp_valid2[g] ? 0 : 1;
+    BowJob J;
+    memset(&J, 0, sizeof(J));
+    J.Q = K1; J.T = K2; J.q_ok = mp_valid1; J.t_skip = skip.data(); J.mode = MODE_BOW_KF; J.nnratio = nnratio; J.check_ori = check_orientation;
+    J.n_seq = 1; J.cq[0] = c1; J.ct[0] = c2;
+    int sm[MAX_CAMS];
+    const int n1 = K1->n_kp[c1];
+    const int rc = bow_join(m, J, "orbm_search_by_bow_kf", matches12, n1, sm);
+    if (rc != ORB_OK) return rc;
+    for (int i = 0; i < n1; i++) if (matches12[i] >= 0) matches12[i] += first2;       // GetGlobalIdxByLocal(bestIdx2local, c2)  :367
+    if (nmatches) *nmatches = sm[0];
+    return ORB_OK;
+}
+
+int orbm_search_for_triangulation(orbm_t* m, const orbm_bowside_t* K1, const orbm_bowside_t* K2, int cam, const orb_keypoint_t* kps1,
+                                  const orb_keypoint_t* kps2, const uint8_t* has_mp1, const uint8_t* has_mp2, const float* F12, const float* C1sw,
+                                  const float* R2sw, const float* t2sw, const float* K2cam, const float* scale_factors, int n_levels,
+                                  int check_orientation, int32_t* matches12, int32_t* nmatches) {
+    if (!m) ORB_FAIL(ORB_E_INVALID, "orbm_search_for_triangulation: NULL handle");
+    if (!K1 || !K2 || !kps1 || !kps2 || !has_mp1 || !has_mp2 || !F12 || !C1sw || !R2sw || !t2sw || !K2cam || !scale_factors || !matches12 || !K1->n_kp ||
+        !K2->n_kp || cam < 0 || cam >= K1->n_cams || cam >= K2->n_cams || n_levels < 1 || n_levels > 16)
+        ORB_FAIL(ORB_E_INVALID, "orbm_search_for_triangulation: bad argument");
+    int tot2 = 0;
+    for (int c = 0; c < K2->n_cams && c < MAX_CAMS; c++) tot2 += K2->n_kp[c];
+    for (int g = 0; g < tot2; g++) if (kps2[g].octave < 0 || kps2[g].octave >= n_levels) ORB_FAIL(ORB_E_INVALID, "orbm_search_for_triangulation: octave out of range");
+    BowJob J;
+    memset(&J, 0, sizeof(J));
+    J.Q = K1; J.T = K2; J.q_ok = has_mp1; J.q_ok_invert = 1; J.t_skip = has_mp2; J.mode = MODE_TRI; J.check_ori = check_orientation;
+    J.n_seq = 1; J.cq[0] = cam; J.ct[0] = cam; J.kps1 = kps1; J.kps2 = kps2;
+    // epipole of camera 1 in image 2 (:1261-1268), FP32 left to right
+    volatile float C0 = R2sw[0] * C1sw[0]; C0 = C0 + R2sw[1] * C1sw[1]; C0 = C0 + R2sw[2] * C1sw[2]; C0 = C0 + t2sw[0];
+    volatile float C1 = R2sw[3] * C1sw[0]; C1 = C1 + R2sw[4] * C1sw[1]; C1 = C1 + R2sw[5] * C1sw[2]; C1 = C1 + t2sw[1];
+    volatile float C2 = R2sw[6] * C1sw[0]; C2 = C2 + R2sw[7] * C1sw[1]; C2 = C2 + R2sw[8] * C1sw[2]; C2 = C2 + t2sw[2];
+    const float invz = 1.0f / C2;
+    volatile float ex = K2cam[0] * C0; ex = ex * invz; ex = ex + K2cam[2];
+    volatile float ey = K2cam[1] * C1; ey = ey * invz; ey = ey + K2cam[3];
+    J.tri.on = 1; J.tri.ex = ex; J.tri.ey = ey;
+    memcpy(J.tri.F12, F12, 36);
+    for (int l = 0; l < n_levels; l++) J.tri.scale[l] = scale_factors[l];
+    int sm[MAX_CAMS];
+    const int rc = bow_join(m, J, "orbm_search_for_triangulation", matches12, K1->n_kp[cam], sm);
+    if (rc != ORB_OK) return rc;
+    if (nmatches) *nmatches = sm[0];
+    return ORB_OK;
+}
+
+// ---- key-frame flavoured projection searches.  claims == true: project -> count -> scan -> fill -> sequential resolve (one camera);
+// claims == false: project -> best key point per (camera, map point), no interaction between map points.
+static int run_projected(orbm_t* m, const orbm_frame_t* frame, const orbm_frustum_t* view, const orbm_points_t* P, const char* who, int cam0, int n_cam_run,
+                         float th, int flags, int kf_quirk, bool claims, int th_accept, int check_ori, const uint8_t* blocked /* global, claims only */,
+                         int32_t* out /* claims: [totalN] */, int32_t* nmatches, int32_t* best_kp, int32_t* best_dist) {
+    int rc = check_frame(frame, who);
+    if (rc != ORB_OK) return rc;
+    if (!view || !P || !view->Rsw || !view->tsw || !view->Ow || !view->K || view->n_cams != frame->n_cams) ORB_FAIL(ORB_E_INVALID, "%s: bad view", who);
+    if (P->n < 0 || (P->n && (!P->valid || !P->pos || !P->max_dist || !P->min_dist || !P->desc))) ORB_FAIL(ORB_E_INVALID, "%s: NULL map-point field", who);
+    if (P->n && (flags & PS_VIEW_ANGLE) && !P->normal) ORB_FAIL(ORB_E_INVALID, "%s: map-point normals are required", who);
+    if (P->n && check_ori && !P->angle) ORB_FAIL(ORB_E_INVALID, "%s: map-point key point angles are required for the orientation check", who);
+    if (cam0 < 0 || cam0 + n_cam_run > frame->n_cams) ORB_FAIL(ORB_E_INVALID, "%s: camera out of range", who);
+    const int n = P->n, nq = n * n_cam_run;
+    int totalN = 0;
+    for (int c = 0; c < frame->n_cams; c++) totalN += frame->n_kp[c];
+    if (nmatches) *nmatches = 0;
+    if (!claims) for (int q = 0; q < nq; q++) { best_kp[q] = -1; best_dist[q] = 256; }
+    if (n == 0 || totalN == 0) return ORB_OK;
+    const int device = orbm_device_of(m);
+    ORB_CUDA(cudaSetDevice(device));
+    cudaStream_t st = orbm_stream_of(m);
+    Bump B;
+    const size_t o_kp = B.add(16 * (size_t)totalN), o_desc = B.add(32 * (size_t)totalN), o_kang = B.add(4 * (size_t)totalN), o_blk = B.add((size_t)totalN);
+    const size_t o_pv = B.add((size_t)n), o_pp = B.add(12 * (size_t)n), o_pn = B.add(12 * (size_t)n), o_pmax = B.add(4 * (size_t)n), o_pmin = B.add(4 * (size_t)n),
+                 o_pd = B.add(32 * (size_t)n), o_pa = B.add(4 * (size_t)n);
+    const size_t staged = B.add(0);
+    const size_t o_q = B.add(sizeof(Query) * (size_t)nq), o_seq = B.add(4 * (size_t)nq), o_tag = B.add(4 * (size_t)nq), o_obs = B.add((size_t)nq), o_qang = B.add(4 * (size_t)nq);
+    const size_t o_celloff = B.add(4 * (size_t)frame->n_cams * (GRID_CELLS + 1)), o_cellidx = B.add(4 * (size_t)totalN);
+    const size_t o_cnt = B.add(4 * (size_t)(nq + 1)), o_off = B.add(4 * (size_t)(nq + 1)), o_out = B.add(4 * (size_t)totalN);
+    const size_t o_sm = B.add(4), o_mkp = B.add(4 * (size_t)nq), o_mbin = B.add(4 * (size_t)nq), o_bkp = B.add(4 * (size_t)nq), o_bd = B.add(4 * (size_t)nq);
+    const size_t total_bytes = B.add(0);
+    Arena& A = g_arena;
+    rc = arena_reserve(A, device, total_bytes, staged);
+    if (rc != ORB_OK) return rc;
+    FrameDev F;
+    stage_frame(frame, F, A.h + o_kp, A.h + o_desc);
+    F.kp = (const float4*)(A.d + o_kp); F.desc = (const uint4*)(A.d + o_desc);
+    F.cell_off = (int*)(A.d + o_celloff); F.cell_idx = (int*)(A.d + o_cellidx); F.kf_quirk = kf_quirk != 0;
+    for (int g = 0; g < totalN; g++) ((float*)(A.h + o_kang))[g] = frame->kps_un[g].angle;
+    if (blocked) memcpy(A.h + o_blk, blocked, (size_t)totalN); else memset(A.h + o_blk, 0, (size_t)totalN);
+    memcpy(A.h + o_pv, P->valid, (size_t)n); memcpy(A.h + o_pp, P->pos, 12 * (size_t)n);
+    if (P->normal) memcpy(A.h + o_pn, P->normal, 12 * (size_t)n);
+    memcpy(A.h + o_pmax, P->max_dist, 4 * (size_t)n); memcpy(A.h + o_pmin, P->min_dist, 4 * (size_t)n); memcpy(A.h + o_pd, P->desc, 32 * (size_t)n);
+    if (P->angle) memcpy(A.h + o_pa, P->angle, 4 * (size_t)n);
+    ProjDev D;
+    memset(&D, 0, sizeof(D));
+    D.n = n; D.n_levels = frame->n_levels; D.flags = flags; D.cam0 = cam0; D.th = th; D.log_scale = view->log_scale_factor;
+    for (int c = 0; c < frame->n_cams; c++) {
+        memcpy(D.R[c], view->Rsw + 9 * c, 36); memcpy(D.t[c], view->tsw + 3 * c, 12); memcpy(D.Ow[c], view->Ow + 3 * c, 12);
+        memcpy(D.K[c], view->K + 4 * c, 16); memcpy(D.b[c], frame->bounds + 4 * c, 16);
+    }
+    for (int l = 0; l < frame->n_levels; l++) D.scale[l] = frame->scale_factors[l];
+    D.valid = A.d + o_pv; D.pos = (const float*)(A.d + o_pp); D.normal = P->normal ? (const float*)(A.d + o_pn) : nullptr;
+    D.max_dist = (const float*)(A.d + o_pmax); D.min_dist = (const float*)(A.d + o_pmin); D.desc = (const uint4*)(A.d + o_pd);
+    D.angle = P->angle ? (const float*)(A.d + o_pa) : nullptr;
+    ORB_CUDA(cudaMemcpyAsync(A.d, A.h, staged, cudaMemcpyHostToDevice, st));
+    const size_t gsm = (GRID_CELLS + 1) * 4 + 2 * 32768;
+    ORB_CUDA(cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    k_grid_build<<<frame->n_cams, 256, gsm, st>>>(F);
+    Query* dq = (Query*)(A.d + o_q);
+    k_project_queries<<<(nq + 127) / 128, 128, 0, st>>>(D, nq, dq, claims ? (int*)(A.d + o_seq) : nullptr, (int*)(A.d + o_tag), A.d + o_obs, (float*)(A.d + o_qang));
+    int launches = 2;
+    if (!claims) {
+        k_window_best<<<(nq + 3) / 4, 128, 0, st>>>(F, dq, nq, (flags & PS_CHI2) != 0, (int*)(A.d + o_bkp), (int*)(A.d + o_bd));
+        ORB_CUDA(cudaGetLastError());
+        ORB_CUDA(cudaMemcpyAsync(best_kp, A.d + o_bkp, 4 * (size_t)nq, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaMemcpyAsync(best_dist, A.d + o_bd, 4 * (size_t)nq, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+        orbm_count_launches(m, launches + 1);
+        return ORB_OK;
+    }
+    ORB_CUDA(cudaMemsetAsync(A.d + o_out, 0xff, 4 * (size_t)totalN, st));
+    ORB_CUDA(cudaMemsetAsync(A.d + o_sm, 0, 4, st));
+    k_window_cands<false><<<(nq + 3) / 4, 128, 0, st>>>(F, dq, nq, (int*)(A.d + o_cnt), nullptr, nullptr);
+    k_scan<<<1, 1024, 0, st>>>((const int*)(A.d + o_cnt), nq, (int*)(A.d + o_off), A.d_total);
+    launches += 2;
+    ORB_CUDA(cudaStreamSynchronize(st));
+    const int total = *A.h_total;
+    rc = recs_reserve(A, 4 * (size_t)std::max(total, 1));
+    if (rc != ORB_OK) return rc;
+    uint32_t* recs = (uint32_t*)A.recs;
+    if (total > 0) { k_window_cands<true><<<(nq + 3) / 4, 128, 0, st>>>(F, dq, nq, nullptr, (const int*)(A.d + o_off), recs); launches++; }
+    ResolveArgs R;
+    memset(&R, 0, sizeof(R));
+    R.mode = MODE_LAST; R.nq = nq; R.n_bits = totalN;
+    R.q_off = (const int*)(A.d + o_off); R.recs = recs; R.q_seq = (const int*)(A.d + o_seq); R.q_tag = (const int*)(A.d + o_tag);
+    R.q_obs = A.d + o_obs; R.q_angle = (const float*)(A.d + o_qang); R.kp_angle = (const float*)(A.d + o_kang);
+    R.seq_base = nullptr; R.blocked_in = A.d + o_blk; R.out = (int*)(A.d + o_out); R.seq_matches = (int*)(A.d + o_sm);
+    R.m_kp = (int*)(A.d + o_mkp); R.m_bin = (int*)(A.d + o_mbin); R.nnratio = 0.f; R.check_ori = check_ori != 0; R.th_accept = th_accept;
+    k_resolve<<<1, 32, ((totalN + 31) / 32 + 1) * 4, st>>>(R);
+    launches++;
+    ORB_CUDA(cudaGetLastError());
+    std::vector<int> res((size_t)totalN);
+    int nm = 0;
+    ORB_CUDA(cudaMemcpyAsync(res.data(), A.d + o_out, 4 * (size_t)totalN, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaMemcpyAsync(&nm, A.d + o_sm, 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA(cudaStreamSynchronize(st));
+    orbm_count_launches(m, launches);
+    for (int g = 0; g < totalN; g++) if (res[g] >= 0) out[g] = res[g];
+    if (nmatches) *nmatches = nm;
+    return ORB_OK;
+}
+
+int orbm_search_by_projection_reloc(orbm_t* m, const orbm_frame_t* F, const orbm_frustum_t* view, int cam, const orbm_points_t* P, float th, int orb_dist,
+                                    int check_orientation, const uint8_t* blocked, int32_t* kp_to_point, int32_t* nmatches) {
+    if (!m) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_projection_reloc: NULL handle");
+    if (!blocked || !kp_to_point) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_projection_reloc: bad argument");
+    return run_projected(m, F, view, P, "orbm_search_by_projection_reloc", cam, 1, th, PS_LEVEL_UP, 0, true, orb_dist, check_orientation, blocked, kp_to_point,
+                         nmatches, nullptr, nullptr);
+}
+
+int orbm_search_by_projection_sim3(orbm_t* m, const orbm_frame_t* KF, const orbm_frustum_t* view, int cam, const orbm_points_t* P, int th, int kf_index_quirk,
+                                   const uint8_t* matched_local, int32_t* local_to_point, int32_t* nmatches) {
+    if (!m) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_projection_sim3: NULL handle");
+    if (!KF || !KF->n_kp || !matched_local || !local_to_point || cam < 0 || cam >= KF->n_cams) ORB_FAIL(ORB_E_INVALID, "orbm_search_by_projection_sim3: bad argument");
+    int first = 0, totalN = 0;
+    for (int c = 0; c < KF->n_cams && c < MAX_CAMS; c++) { if (c < cam) first += KF->n_kp[c]; totalN += KF->n_kp[c]; }
+    // the reference indexes vpMatched with the camera-local key point index (src/ORBmatcher.cc:504, 523): expand to the global layout and back
+    std::vector<uint8_t> blocked((size_t)std::max(totalN, 1), 0);
+    std::vector<int32_t> out((size_t)std::max(totalN, 1), -1);
+    for (int l = 0; l < KF->n_kp[cam]; l++) blocked[first + l] = matched_local[l];
+    const int rc = run_projected(m, KF, view, P, "orbm_search_by_projection_sim3", cam, 1, (float)th, PS_DEPTH_POS | PS_NORMALISE_FIRST | PS_HALF_OPEN | PS_VIEW_ANGLE,
+                                 kf_index_quirk, true, ORBM_TH_LOW, 0, blocked.data(), out.data(), nmatches, nullptr, nullptr);
+    if (rc != ORB_OK) return rc;
+    for (int l = 0; l < KF->n_kp[cam]; l++) if (out[first + l] >= 0) local_to_point[l] = out[first + l];
+    return ORB_OK;
+}
+
+int orbm_project_best(orbm_t* m, const orbm_frame_t* KF, const orbm_frustum_t* view, const orbm_points_t* P, float th, int variant, int kf_index_quirk,
+                      int32_t* best_kp, int32_t* best_dist) {
+    if (!m) ORB_FAIL(ORB_E_INVALID, "orbm_project_best: NULL handle");
+    if (!KF || !best_kp || !best_dist) ORB_FAIL(ORB_E_INVALID, "orbm_project_best: bad argument");
+    int flags;
+    if (variant == ORBM_KF_SEARCH) flags = PS_LEVEL_UP;
+    else if (variant == ORBM_KF_FUSE) flags = PS_DEPTH_POS | PS_NORMALISE_FIRST | PS_HALF_OPEN | PS_VIEW_ANGLE | PS_CHI2;
+    else if (variant == ORBM_KF_FUSE_SIM3) flags = PS_DEPTH_POS | PS_NORMALISE_FIRST | PS_HALF_OPEN | PS_VIEW_ANGLE;
+    else ORB_FAIL(ORB_E_INVALID, "orbm_project_best: unknown variant %d", variant);
+    return run_projected(m, KF, view, P, "orbm_project_best", 0, KF->n_cams, th, flags, kf_index_quirk, false, 0, 0, nullptr, nullptr, nullptr, best_kp, best_dist);
 }
 
 int orbm_is_in_frustum(orbm_t* m, const orbm_frustum_t* fr, const float* pos, const float* normal, const float* max_dist, const float* min_dist, int n,

@@ -78,6 +78,70 @@ class ORBmatcher:
                                        ptr(out), C.addressof(n)))
         return n.value, out
 
+    def SearchByProjectionReloc(self, F, view, cam, points, th, ORBdist, blocked, kp_to_point=None):
+        """ORBmatcher::SearchByProjectionOnCam(pF, query, pKF, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:812-951).
+        points: dict(valid, pos, max_dist, min_dist, desc, angle) over pKF's key points -> (nmatches, kp_to_point int32 [totalN])"""
+        fs, fk = capi.frame_struct(F)
+        vs, vk = capi.frustum_struct(view)
+        ps, pk = capi.points_struct(points)
+        blocked = np.ascontiguousarray(blocked, np.uint8)
+        out = np.full(len(blocked), -1, np.int32) if kp_to_point is None else kp_to_point
+        n = C.c_int32()
+        check(lib().orbm_search_by_projection_reloc(self._h, C.addressof(fs), C.addressof(vs), int(cam), C.addressof(ps), float(th), int(ORBdist),
+                                                    int(self.mbCheckOrientation), ptr(blocked), ptr(out), C.addressof(n)))
+        return n.value, out
+
+    def SearchByProjectionSim3(self, KF, view, cam, points, th, matched_local, kf_index_quirk=True):
+        """ORBmatcher::SearchByProjection(pKF, query, Scq_w, vpPoints, vpMatched, th) (src/ORBmatcher.cc:416-536).
+        view slot `cam` = the decomposed similarity -> (nmatches, local_to_point int32 [n_kp[cam]])"""
+        fs, fk = capi.frame_struct(KF)
+        vs, vk = capi.frustum_struct(view)
+        ps, pk = capi.points_struct(points)
+        matched_local = np.ascontiguousarray(matched_local, np.uint8)
+        out = np.full(len(matched_local), -1, np.int32)
+        n = C.c_int32()
+        check(lib().orbm_search_by_projection_sim3(self._h, C.addressof(fs), C.addressof(vs), int(cam), C.addressof(ps), int(th), int(kf_index_quirk),
+                                                   ptr(matched_local), ptr(out), C.addressof(n)))
+        return n.value, out
+
+    def ProjectBest(self, KF, view, points, th, variant, kf_index_quirk=True):
+        """search part of SearchByProjection(pKF, vpMapPoints, sFound, th, ORBdist) / Fuse / Fuse(Scw) (src/ORBmatcher.cc:693-775, 1431-1527,
+        1560-1668): variant in capi.KF_SEARCH / KF_FUSE / KF_FUSE_SIM3 -> (best_kp, best_dist) int32 [n_cams][n]"""
+        fs, fk = capi.frame_struct(KF)
+        vs, vk = capi.frustum_struct(view)
+        ps, pk = capi.points_struct(points)
+        shape = (len(fk["n_kp"]), len(pk["valid"]))
+        bk = np.full(shape, -1, np.int32); bd = np.full(shape, 256, np.int32)
+        check(lib().orbm_project_best(self._h, C.addressof(fs), C.addressof(vs), C.addressof(ps), float(th), int(variant), int(kf_index_quirk), ptr(bk), ptr(bd)))
+        return bk, bd
+
+    def SearchByBoWKF(self, K1, c1, K2, c2, mp_valid1, mp_valid2):
+        """ORBmatcher::SearchByBoWCrossCam(pKF1, c1, pKF2, c2, vpMatches12) (src/ORBmatcher.cc:297-414)
+        -> (nmatches, matches12 int32 [n_kp1[c1]] = global key point index in KF2 or -1)"""
+        s1, k1 = capi.bowside_struct(K1)
+        s2, k2 = capi.bowside_struct(K2)
+        v1 = np.ascontiguousarray(mp_valid1, np.uint8); v2 = np.ascontiguousarray(mp_valid2, np.uint8)
+        out = np.full(int(k1["n_kp"][c1]), -1, np.int32)
+        n = C.c_int32()
+        check(lib().orbm_search_by_bow_kf(self._h, C.addressof(s1), int(c1), C.addressof(s2), int(c2), ptr(v1), ptr(v2), self.mfNNratio,
+                                          int(self.mbCheckOrientation), ptr(out), C.addressof(n)))
+        return n.value, out
+
+    def SearchForTriangulation(self, K1, K2, cam, kps1, kps2, has_mp1, has_mp2, F12, C1sw, R2sw, t2sw, K2cam, scale_factors):
+        """ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, camS) (src/ORBmatcher.cc:1253-1427)
+        -> (nmatches, matches12 int32 [n_kp1[cam]] = camera-local index in KF2 or -1)"""
+        s1, k1 = capi.bowside_struct(K1)
+        s2, k2 = capi.bowside_struct(K2)
+        kps1 = np.ascontiguousarray(kps1, capi.KP_DTYPE); kps2 = np.ascontiguousarray(kps2, capi.KP_DTYPE)
+        h1 = np.ascontiguousarray(has_mp1, np.uint8); h2 = np.ascontiguousarray(has_mp2, np.uint8)
+        F12, C1sw, R2sw, t2sw, K2cam, sf = (np.ascontiguousarray(a, np.float32) for a in (F12, C1sw, R2sw, t2sw, K2cam, scale_factors))
+        out = np.full(int(k1["n_kp"][cam]), -1, np.int32)
+        n = C.c_int32()
+        check(lib().orbm_search_for_triangulation(self._h, C.addressof(s1), C.addressof(s2), int(cam), ptr(kps1), ptr(kps2), ptr(h1), ptr(h2), ptr(F12),
+                                                  ptr(C1sw), ptr(R2sw), ptr(t2sw), ptr(K2cam), ptr(sf), len(sf), int(self.mbCheckOrientation), ptr(out),
+                                                  C.addressof(n)))
+        return n.value, out
+
     def isInFrustum(self, frame, pos, normal, max_dist, min_dist, viewingCosLimit=0.5, bForAllCam=True):
         """Frame::isInFrustum + MapPoint::PredictScale for n map points (src/Frame.cc:244-312, src/MapPoint.cc:440-455).
         -> (out int32 [n][3] = in_view, cam, level ; uvc float32 [n][3] = u, v, viewCos)"""

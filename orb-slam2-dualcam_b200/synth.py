@@ -344,7 +344,7 @@ def bow_scene(seed, n_kp=(1000, 900), n_nodes=90, p_flip=0.05, frac_valid=0.6):
         ka = rng.normal(75.0, 3, n) % 360
         bad = rng.random(n) < 0.1
         ka[bad] = rng.uniform(0, 360, bad.sum())
-        kdesc.append(d); knodes.append(nodes); fdesc.append(fd); fnodes.append(fn); kang.append(ka); fang.append(rng.normal(30.0, 3, nf) % 360)
+        kdesc.append(d); knodes.append(nodes); fdesc.append(fd); fnodes.append(fn); kang.append(ka); fang.append(rng.normal(30.0 + 100.0 * c, 3, nf) % 360)
     KF = dict(n_kp=np.array(n_kp, np.int32), desc=np.concatenate(kdesc), angle=np.concatenate(kang).astype(np.float32), **csr(knodes))
     F = dict(n_kp=np.array([len(x) for x in fdesc], np.int32), desc=np.concatenate(fdesc), angle=np.concatenate(fang).astype(np.float32), **csr(fnodes))
     valid = (rng.random(int(sum(n_kp))) < frac_valid).astype(np.uint8)
@@ -453,3 +453,133 @@ def pose_opt_frame(seed, n_obs=600, outlier_frac=0.15, W=640, H=480, pose_noise=
     return dict(pose=pose.astype(np.float32).astype(np.float64).reshape(12), Xw=Xw.astype(np.float32).astype(np.float64), obs=obs, inv_sigma2=inv_sigma2,
                 cam=cam.astype(np.int32), cam_K=RIG_K.astype(np.float32).astype(np.float64), cam_ext=np.ascontiguousarray(ext.reshape(2, 12)),
                 cam_adj=np.ascontiguousarray(adj.reshape(2, 36)), gt_pose=gt.reshape(12), planted=planted)
+
+
+# ------------------------------------------------------------------------------------------------ key-frame flavoured searches
+def _csr(nodes_per_cam):
+    """per-camera node id of every feature -> DBoW2::FeatureVector flattened to CSR (node ids ascending, camera-local indices ascending)"""
+    node_first, node_id, node_off, idx = [0], [], [0], []
+    for nodes in nodes_per_cam:
+        for nid in np.unique(nodes):
+            node_id.append(int(nid)); idx.extend(np.flatnonzero(nodes == nid).tolist()); node_off.append(len(idx))
+        node_first.append(len(node_id))
+    return dict(node_first=np.array(node_first, np.int32), node_id=np.array(node_id, np.int32), node_off=np.array(node_off, np.int32),
+                idx=np.array(idx, np.int32))
+
+
+def _rig_view(Rcw, tcw, W, H, n_levels):
+    ext, _ = rig_extrinsics()
+    Rsw = np.zeros((2, 9), np.float32); tsw = np.zeros((2, 3), np.float32); Ow = np.zeros((2, 3), np.float32)
+    for c in range(2):
+        R = ext[c, :, :3] @ Rcw; t = ext[c, :, :3] @ tcw + ext[c, :, 3]
+        Rsw[c] = R.reshape(9); tsw[c] = t; Ow[c] = -R.T @ t
+    return dict(Rsw=Rsw, tsw=tsw, Ow=Ow, K=RIG_K.astype(np.float32), bounds=np.tile(np.array([0, W, 0, H], np.float32), (2, 1)), n_levels=n_levels,
+                log_scale_factor=np.float32(np.log(np.float32(1.2))))
+
+
+def kf_projection_scene(seed, n_kp=(1000, 900), n_stray=300, W=640, H=480, n_levels=8, p_flip=0.06, pix_noise=1.5, frac_invalid=0.1):
+    """A dual key frame (or frame), its per-camera view and candidate map points for the projection searches of relocalisation /
+    loop closing / fusion: most points are back-projections of key points (noisy descriptor copy, scale range consistent with the
+    key point's octave, normal along the viewing ray), some are strays anywhere around the rig.
+    -> (frame, view, points, blocked uint8 [totalN])"""
+    rng = np.random.default_rng(seed)
+    frame = search_frame(seed, n_kp, W, H, n_levels, clustered=False)
+    view = _rig_view(_rodrigues(np.array([0.015, -0.03, 0.01])), np.array([0.05, -0.02, 0.08]), W, H, n_levels)
+    first = np.concatenate([[0], np.cumsum(n_kp)])
+    total = int(first[-1])
+    kps = frame["kps_un"]
+    pos, normal, maxd, mind, desc, ang = [], [], [], [], [], []
+    for c in range(len(n_kp)):
+        R = view["Rsw"][c].reshape(3, 3).astype(np.float64); t = view["tsw"][c].astype(np.float64); K = view["K"][c].astype(np.float64)
+        pick = rng.permutation(n_kp[c])[: int(n_kp[c] * 0.7)] + first[c]
+        n = len(pick)
+        d = rng.uniform(2, 20, n)
+        u = kps["x"][pick] + rng.normal(0, pix_noise, n); v = kps["y"][pick] + rng.normal(0, pix_noise, n)
+        pc = np.stack([(u - K[2]) / K[0] * d, (v - K[3]) / K[1] * d, d], 1)
+        Xw = (pc - t) @ R
+        O = view["Ow"][c].astype(np.float64)
+        dist = np.linalg.norm(Xw - O, axis=1)
+        lvl = kps["octave"][pick] + rng.choice([-1, 0, 0, 0, 1], n) - rng.uniform(0.1, 0.9, n)
+        pos.append(Xw); maxd.append(dist * 1.2 ** lvl); mind.append(dist * 1.2 ** lvl / 1.2 ** (n_levels - 1))
+        nr = (Xw - O) / dist[:, None] + rng.normal(0, 0.5, (n, 3))
+        normal.append(nr / np.linalg.norm(nr, axis=1, keepdims=True))
+        desc.append(random_descriptors(seed * 13 + c, n, p_flip, frame["desc"][pick]))
+        a = (kps["angle"][pick] + 20.0 + rng.normal(0, 2, n)) % 360
+        bad = rng.random(n) < 0.12
+        a[bad] = rng.uniform(0, 360, bad.sum())
+        ang.append(a)
+    Xs = rng.uniform([-20, -10, -10], [20, 10, 30], (n_stray, 3))
+    ds = np.linalg.norm(Xs - view["Ow"][0], axis=1)
+    pos.append(Xs); maxd.append(ds * rng.uniform(0.7, 3.0, n_stray)); mind.append(maxd[-1] / 1.2 ** (n_levels - 1))
+    nr = rng.normal(0, 1, (n_stray, 3)); normal.append(nr / np.linalg.norm(nr, axis=1, keepdims=True))
+    desc.append(random_descriptors(seed * 17, n_stray)); ang.append(rng.uniform(0, 360, n_stray))
+    N = sum(len(p) for p in pos)
+    perm = rng.permutation(N)
+    points = dict(valid=(rng.random(N) >= frac_invalid).astype(np.uint8), pos=np.concatenate(pos)[perm].astype(np.float32),
+                  normal=np.concatenate(normal)[perm].astype(np.float32), max_dist=np.concatenate(maxd)[perm].astype(np.float32),
+                  min_dist=np.concatenate(mind)[perm].astype(np.float32), desc=np.ascontiguousarray(np.concatenate(desc)[perm]),
+                  angle=np.concatenate(ang)[perm].astype(np.float32))
+    blocked = (rng.random(total) < 0.15).astype(np.uint8)
+    return frame, view, points, blocked
+
+
+def triangulation_scene(seed, n=900, cam=0, W=640, H=480, n_levels=8, n_nodes=80, p_flip=0.05):
+    """SearchForTriangulation inputs: two dual key frames seeing the same 3-D points from two poses, key points = projections + noise,
+    shared vocabulary nodes for true correspondences, the fundamental matrix F12 of camera `cam` (LocalMapping::ComputeF12 layout:
+    x1^T F12 x2 = 0) and the quantities of the epipole.  -> dict"""
+    rng = np.random.default_rng(seed)
+    va = _rig_view(_rodrigues(np.array([0.0, 0.02, 0.0])), np.array([0.0, 0.0, 0.0]), W, H, n_levels)
+    vb = _rig_view(_rodrigues(np.array([0.01, -0.04, 0.005])), np.array([-0.6, 0.05, 0.1]), W, H, n_levels)
+    sides, kps_all, nodes_all, has_all = [], [], [], []
+    K = RIG_K.astype(np.float32)
+    # points in front of camera `cam` of key frame 1
+    R1 = va["Rsw"][cam].reshape(3, 3).astype(np.float64); t1 = va["tsw"][cam].astype(np.float64)
+    R2 = vb["Rsw"][cam].reshape(3, 3).astype(np.float64); t2 = vb["tsw"][cam].astype(np.float64)
+    uv = rng.uniform([10, 10], [W - 10, H - 10], (n, 2)); d = rng.uniform(3, 25, n)
+    pc1 = np.stack([(uv[:, 0] - K[cam, 2]) / K[cam, 0] * d, (uv[:, 1] - K[cam, 3]) / K[cam, 1] * d, d], 1)
+    Xw = (pc1 - t1) @ R1
+    pc2 = Xw @ R2.T + t2
+    uv2 = np.stack([K[cam, 0] * pc2[:, 0] / pc2[:, 2] + K[cam, 2], K[cam, 1] * pc2[:, 1] / pc2[:, 2] + K[cam, 3]], 1)
+    node = rng.integers(0, n_nodes, n) * 5 + 2
+    base = random_descriptors(seed * 41, n)
+    out = {}
+    for which, (uvk, nk) in enumerate(((uv, n), (uv2, n))):
+        per_cam_k, per_cam_d, per_cam_nodes = [], [], []
+        for c in range(2):
+            if c == cam:
+                m = nk + nk // 4
+                k = np.zeros(m, KP_DTYPE)
+                k["x"][:nk] = uvk[:, 0] + rng.normal(0, 0.7, nk); k["y"][:nk] = uvk[:, 1] + rng.normal(0, 0.7, nk)
+                off = rng.random(nk) < 0.15                       # off the epipolar line
+                k["y"][:nk][off] += rng.uniform(8, 40, off.sum())
+                k["x"][nk:] = rng.uniform(0, W, m - nk); k["y"][nk:] = rng.uniform(0, H, m - nk)
+                k["octave"] = rng.integers(0, n_levels, m)
+                k["angle"][:nk] = ((40.0 if which == 0 else 10.0) + rng.normal(0, 3, nk)) % 360
+                wild = rng.random(nk) < 0.1
+                k["angle"][:nk][wild] = rng.uniform(0, 360, wild.sum())
+                k["angle"][nk:] = rng.uniform(0, 360, m - nk)
+                dd = np.concatenate([random_descriptors(seed * 43 + which, nk, p_flip, base), random_descriptors(seed * 47 + which, m - nk)])
+                nn = np.concatenate([node, rng.integers(0, n_nodes + 4, m - nk) * 5 + 2])
+                stray = rng.random(m) < 0.05
+                nn[stray] = rng.integers(0, n_nodes, stray.sum()) * 5 + 2
+                order = rng.permutation(m)                          # features are not stored in correspondence order
+                k, dd, nn = k[order], dd[order], nn[order]
+            else:
+                m = 300
+                k = np.zeros(m, KP_DTYPE)
+                k["x"] = rng.uniform(0, W, m); k["y"] = rng.uniform(0, H, m); k["octave"] = rng.integers(0, n_levels, m); k["angle"] = rng.uniform(0, 360, m)
+                dd = random_descriptors(seed * 53 + which + c, m); nn = rng.integers(0, n_nodes, m) * 5 + 2
+            k["class_id"] = -1
+            per_cam_k.append(k); per_cam_d.append(dd); per_cam_nodes.append(nn)
+        kk = np.concatenate(per_cam_k)
+        side = dict(n_kp=np.array([len(x) for x in per_cam_k], np.int32), desc=np.concatenate(per_cam_d), angle=kk["angle"].astype(np.float32), **_csr(per_cam_nodes))
+        out[f"K{which + 1}"] = side; out[f"kps{which + 1}"] = kk
+        out[f"has_mp{which + 1}"] = (rng.random(len(kk)) < 0.3).astype(np.uint8)
+    # F12 = K1^-T [t12]x R12 K2^-1 with R12 = R1 R2^T, t12 = -R12 t2 + t1   (src/LocalMapping.cc ComputeF12)
+    R12 = R1 @ R2.T; t12 = -R12 @ t2 + t1
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    Km = np.array([[K[cam, 0], 0, K[cam, 2]], [0, K[cam, 1], K[cam, 3]], [0, 0, 1]], np.float64)
+    out["F12"] = (np.linalg.inv(Km).T @ tx @ R12 @ np.linalg.inv(Km)).astype(np.float32).reshape(9)
+    out["C1sw"] = va["Ow"][cam]; out["R2sw"] = vb["Rsw"][cam]; out["t2sw"] = vb["tsw"][cam]; out["K2cam"] = K[cam]
+    out["scale_factors"] = scale_factors(n_levels); out["cam"] = cam
+    return out

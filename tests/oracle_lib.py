@@ -333,3 +333,73 @@ def image_bounds(width, height, K4, dist):
     L.orc_image_bounds.restype = None
     L.orc_image_bounds(width, height, K4.ctypes.data, dist.ctypes.data, len(dist), b.ctypes.data)
     return b
+
+
+# ---- key-frame flavoured searches (oracle/match_kf_oracle.cpp)
+def search_by_projection_reloc(F, view, cam, points, th, ORBdist, blocked, check_ori=True):
+    cp = _capi()
+    fs, fk = cp.frame_struct(F); vs, vk = cp.frustum_struct(view); ps, pk = cp.points_struct(points)
+    blocked = np.ascontiguousarray(blocked, np.uint8)
+    out = np.full(len(blocked), -1, np.int32)
+    L = lib()
+    L.orc_search_by_projection_reloc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_search_by_projection_reloc.restype = C.c_int
+    n = L.orc_search_by_projection_reloc(C.addressof(fs), C.addressof(vs), cam, C.addressof(ps), th, ORBdist, int(check_ori), blocked.ctypes.data, out.ctypes.data)
+    return n, out
+
+
+def search_by_projection_sim3(KF, view, cam, points, th, matched_local, kf_quirk=True):
+    cp = _capi()
+    fs, fk = cp.frame_struct(KF); vs, vk = cp.frustum_struct(view); ps, pk = cp.points_struct(points)
+    matched_local = np.ascontiguousarray(matched_local, np.uint8)
+    out = np.full(len(matched_local), -1, np.int32)
+    L = lib()
+    L.orc_search_by_projection_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_search_by_projection_sim3.restype = C.c_int
+    n = L.orc_search_by_projection_sim3(C.addressof(fs), C.addressof(vs), cam, C.addressof(ps), th, int(kf_quirk), matched_local.ctypes.data, out.ctypes.data)
+    return n, out
+
+
+def project_best(KF, view, points, th, variant, kf_quirk=True):
+    """variant 0: SearchByProjection(KF, MPs, ...) ; 1: Fuse ; 2: Fuse(Scw)"""
+    cp = _capi()
+    fs, fk = cp.frame_struct(KF); vs, vk = cp.frustum_struct(view); ps, pk = cp.points_struct(points)
+    shape = (len(fk["n_kp"]), len(pk["valid"]))
+    bk = np.zeros(shape, np.int32); bd = np.zeros(shape, np.int32)
+    L = lib()
+    if variant == 0:
+        L.orc_search_kf_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_search_kf_points.restype = None
+        L.orc_search_kf_points(C.addressof(fs), C.addressof(vs), C.addressof(ps), th, int(kf_quirk), bk.ctypes.data, bd.ctypes.data)
+    else:
+        L.orc_fuse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_fuse.restype = None
+        L.orc_fuse(C.addressof(fs), C.addressof(vs), C.addressof(ps), th, int(variant == 2), int(kf_quirk), bk.ctypes.data, bd.ctypes.data)
+    return bk, bd
+
+
+def search_by_bow_kf(K1, c1, K2, c2, mp_valid1, mp_valid2, nnratio=0.7, check_ori=True):
+    cp = _capi()
+    s1, k1 = cp.bowside_struct(K1); s2, k2 = cp.bowside_struct(K2)
+    v1 = np.ascontiguousarray(mp_valid1, np.uint8); v2 = np.ascontiguousarray(mp_valid2, np.uint8)
+    out = np.full(int(k1["n_kp"][c1]), -1, np.int32)
+    L = lib()
+    L.orc_search_by_bow_kf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+    L.orc_search_by_bow_kf.restype = C.c_int
+    n = L.orc_search_by_bow_kf(C.addressof(s1), c1, C.addressof(s2), c2, v1.ctypes.data, v2.ctypes.data, nnratio, int(check_ori), out.ctypes.data)
+    return n, out
+
+
+def search_for_triangulation(K1, K2, cam, kps1, kps2, has_mp1, has_mp2, F12, C1sw, R2sw, t2sw, K2cam, scale_factors, check_ori=True):
+    cp = _capi()
+    s1, k1 = cp.bowside_struct(K1); s2, k2 = cp.bowside_struct(K2)
+    kps1 = np.ascontiguousarray(kps1, cp.KP_DTYPE); kps2 = np.ascontiguousarray(kps2, cp.KP_DTYPE)
+    h1 = np.ascontiguousarray(has_mp1, np.uint8); h2 = np.ascontiguousarray(has_mp2, np.uint8)
+    F12, C1sw, R2sw, t2sw, K2cam, sf = (np.ascontiguousarray(a, np.float32) for a in (F12, C1sw, R2sw, t2sw, K2cam, scale_factors))
+    out = np.full(int(k1["n_kp"][cam]), -1, np.int32)
+    L = lib()
+    L.orc_search_for_triangulation.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_void_p]
+    L.orc_search_for_triangulation.restype = C.c_int
+    n = L.orc_search_for_triangulation(C.addressof(s1), C.addressof(s2), cam, kps1.ctypes.data, kps2.ctypes.data, h1.ctypes.data, h2.ctypes.data, F12.ctypes.data,
+                                       C1sw.ctypes.data, R2sw.ctypes.data, t2sw.ctypes.data, K2cam.ctypes.data, sf.ctypes.data, int(check_ori), out.ctypes.data)
+    return n, out
