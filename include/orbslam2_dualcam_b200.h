@@ -314,6 +314,35 @@ int  orbm_undistort_keypoints(orbm_t*, const orb_keypoint_t* kps, int n, const f
 int  orbm_image_bounds(orbm_t*, int width, int height, const float* K4, const float* dist, int n_dist, float* bounds);
 
 /* ================================================================================================
+ * BAG OF WORDS -- replaces ORBVocabulary::transform as Frame::ComputeBoW / KeyFrame::ComputeBoW call it (src/Frame.cc:393-408,
+ * Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1149-1227, 1249-1292): the producer of the DBoW2::FeatureVector that orbm_search_by_bow*
+ * and orbm_search_for_triangulation consume, and of the BowVector of the key-frame database.  TF_IDF weighting and L1 normalisation,
+ * i.e. the ORB vocabulary's header "10 6 0 0".
+ * ================================================================================================ */
+typedef struct orbv orbv_t;
+
+/* The node table of TemplatedVocabulary::loadFromTextFile (:1362-1447): row 0 is the root (ignored), row i >= 1 is line i of the text
+ * file: parent id, leaf flag, 32 descriptor bytes, weight.  Word ids are assigned to the leaves in file order, children keep file order. */
+int  orbv_create(orbv_t** out, int device, int k, int L, int n_nodes, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc,
+                 const double* weight);
+void orbv_destroy(orbv_t*);
+int  orbv_set_stream(orbv_t*, void* cuda_stream);
+int  orbv_words(const orbv_t*);
+long long orbv_launch_count(const orbv_t*);
+
+/* transform(features, v, fv, levelsup) for n_sets descriptor sets at once (one set = the descriptors of one camera image; set s is rows
+ * set_off[s] .. set_off[s+1] of desc, at most 8192 rows).  HOST buffers, synchronous.  All per-feature outputs are laid out like desc:
+ *   word_id, node_id int32 [n]   per feature: word, and ancestor at level L - levelsup (may be NULL)
+ *   bow_ids int32 / bow_vals double [n], n_words int32 [n_sets]
+ *                                BowVector of set s = entries set_off[s] .. + n_words[s]: word ids ascending, L1-normalised tf-idf values
+ *   fv_node int32 [n], fv_off int32 [n + n_sets], fv_idx int32 [n], n_fv_nodes int32 [n_sets]
+ *                                FeatureVector of set s: node ids fv_node[set_off[s] ..+ n_fv_nodes[s]] ascending; node j owns the features
+ *                                fv_idx[set_off[s] + o[j] .. set_off[s] + o[j+1]) with o = fv_off + set_off[s] + s  (set-local indices, ascending)
+ * Features whose word has weight 0 (stopped words) appear in neither vector. */
+int  orbv_transform(orbv_t*, const uint8_t* desc, const int32_t* set_off, int n_sets, int levelsup, int32_t* word_id, int32_t* node_id,
+                    int32_t* bow_ids, double* bow_vals, int32_t* n_words, int32_t* fv_node, int32_t* fv_off, int32_t* fv_idx, int32_t* n_fv_nodes);
+
+/* ================================================================================================
  * BUNDLE ADJUSTMENT -- replaces Optimizer::LocalBundleAdjustment / BundleAdjustment / GlobalBundleAdjustemnt
  * (include/Optimizer.h:50-56, src/Optimizer.cc:62-248,407-696) together with the g2o machinery under them
  * (dual-camera EdgeSE3ProjectXYZ, Huber kernel, BlockSolver_6_3 Schur complement, Levenberg-Marquardt).

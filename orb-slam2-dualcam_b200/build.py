@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "liborbslam2_dualcam_b200.so")
-SOURCES = ["orb_common.cu", "orb_extract.cu", "orb_match.cu", "orb_search.cu", "orb_ba.cu", "orb_gba.cu", "orb_pose.cu"]
+SOURCES = ["orb_common.cu", "orb_extract.cu", "orb_match.cu", "orb_search.cu", "orb_bow.cu", "orb_ba.cu", "orb_gba.cu", "orb_pose.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 # integer / bit-exact float paths: no FMA contraction; the FP64 bundle adjustment (1e-5 parity budget) keeps FMA

@@ -78,6 +78,12 @@ SIGNATURES = {
     "orbm_project_best": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp]),
     "orbm_search_by_bow_kf": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp]),
     "orbm_search_for_triangulation": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+    "orbv_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "orbv_destroy": (None, [vp]),
+    "orbv_set_stream": (C.c_int, [vp, vp]),
+    "orbv_words": (C.c_int, [vp]),
+    "orbv_launch_count": (C.c_longlong, [vp]),
+    "orbv_transform": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "orbm_undistort_keypoints": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp]),
     "orbm_image_bounds": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
     "orbm_bruteforce_sets_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp]),

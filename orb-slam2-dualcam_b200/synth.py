@@ -583,3 +583,45 @@ def triangulation_scene(seed, n=900, cam=0, W=640, H=480, n_levels=8, n_nodes=80
     out["C1sw"] = va["Ow"][cam]; out["R2sw"] = vb["Rsw"][cam]; out["t2sw"] = vb["tsw"][cam]; out["K2cam"] = K[cam]
     out["scale_factors"] = scale_factors(n_levels); out["cam"] = cam
     return out
+
+
+# ------------------------------------------------------------------------------------------------ vocabulary
+def vocabulary(seed, k=10, L=3, p_flip=0.12, frac_stopped=0.02, ragged=False):
+    """A synthetic DBoW2 vocabulary tree in the layout of ORBvoc.txt (rows in creation order of the hierarchical k-means: the k children
+    of a node are created together, then each child is expanded): child descriptors are noisy copies of their parent's, leaf weights
+    are idf-like positive doubles, a few words are stopped (weight 0).  ragged: some inner nodes have fewer than k children."""
+    rng = np.random.default_rng(seed)
+    parent, leaf, desc, weight = [0], [0], [np.zeros(32, np.uint8)], [0.0]
+
+    def expand(pid, pdesc, level):
+        nk = k if not ragged else int(rng.integers(2, k + 1))
+        base = rng.integers(0, 256, (nk, 32), dtype=np.uint8) if level == 1 else random_descriptors(int(rng.integers(1 << 30)), nk, p_flip, np.tile(pdesc, (nk, 1)))
+        ids = []
+        for j in range(nk):
+            ids.append(len(parent))
+            parent.append(pid); desc.append(base[j])
+            is_leaf = level == L
+            leaf.append(1 if is_leaf else 0)
+            weight.append(0.0 if (not is_leaf or rng.random() < frac_stopped) else float(rng.uniform(0.5, 9.0)))
+        if level < L:
+            for j, nid in enumerate(ids):
+                expand(nid, base[j], level + 1)
+
+    expand(0, None, 1)
+    return dict(k=k, L=L, parent=np.array(parent, np.int32), is_leaf=np.array(leaf, np.uint8), desc=np.stack(desc), weight=np.array(weight, np.float64))
+
+
+def vocabulary_text(voc):
+    """the same vocabulary as the lines of an ORBvoc.txt-style file (TemplatedVocabulary::saveToTextFile)"""
+    lines = [f"{voc['k']} {voc['L']} 0 0"]
+    for i in range(1, len(voc["parent"])):
+        lines.append(f"{voc['parent'][i]} {int(voc['is_leaf'][i])} " + " ".join(str(int(b)) for b in voc["desc"][i]) + f" {float(voc['weight'][i])!r}")
+    return lines
+
+
+def vocabulary_features(seed, voc, n, p_flip=0.06):
+    """descriptors that are noisy copies of random leaf descriptors (so that words repeat inside an image)"""
+    rng = np.random.default_rng(seed)
+    leaves = np.flatnonzero(voc["is_leaf"])
+    pick = leaves[rng.integers(0, max(len(leaves) // 3, 1), n)]
+    return random_descriptors(seed + 1, n, p_flip, voc["desc"][pick])

@@ -403,3 +403,46 @@ def search_for_triangulation(K1, K2, cam, kps1, kps2, has_mp1, has_mp2, F12, C1s
     n = L.orc_search_for_triangulation(C.addressof(s1), C.addressof(s2), cam, kps1.ctypes.data, kps2.ctypes.data, h1.ctypes.data, h2.ctypes.data, F12.ctypes.data,
                                        C1sw.ctypes.data, R2sw.ctypes.data, t2sw.ctypes.data, K2cam.ctypes.data, sf.ctypes.data, int(check_ori), out.ctypes.data)
     return n, out
+
+
+# ---- DBoW2 transform (oracle/bow_oracle.cpp)
+class Vocabulary:
+    def __init__(self, voc):
+        L = lib()
+        L.orc_vocab_create.restype = C.c_void_p
+        L.orc_vocab_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._k = [np.ascontiguousarray(voc["parent"], np.int32), np.ascontiguousarray(voc["is_leaf"], np.uint8), np.ascontiguousarray(voc["desc"], np.uint8),
+                   np.ascontiguousarray(voc["weight"], np.float64)]
+        self._h = L.orc_vocab_create(int(voc["k"]), int(voc["L"]), len(self._k[0]), *[a.ctypes.data for a in self._k])
+        assert self._h, "bad vocabulary"
+
+    def __del__(self):
+        L = lib()
+        L.orc_vocab_destroy.argtypes = [C.c_void_p]
+        L.orc_vocab_destroy.restype = None
+        if getattr(self, "_h", None):
+            L.orc_vocab_destroy(self._h)
+            self._h = None
+
+    def transform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        word = np.zeros(n, np.int32); node = np.zeros(n, np.int32); ids = np.zeros(n, np.int32); vals = np.zeros(n, np.float64)
+        fvn = np.zeros(n, np.int32); fvo = np.zeros(n + 1, np.int32); fvi = np.zeros(n, np.int32)
+        nw = C.c_int32(); nf = C.c_int32()
+        L = lib()
+        L.orc_vocab_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 9
+        L.orc_vocab_transform.restype = C.c_int
+        L.orc_vocab_transform(self._h, desc.ctypes.data, n, levelsup, word.ctypes.data, node.ctypes.data, ids.ctypes.data, vals.ctypes.data, C.addressof(nw),
+                              fvn.ctypes.data, fvo.ctypes.data, fvi.ctypes.data, C.addressof(nf))
+        return dict(word_id=word, node_id=node, bow_ids=ids[:nw.value], bow_vals=vals[:nw.value], fv_node=fvn[:nf.value], fv_off=fvo[:nf.value + 1],
+                    fv_idx=fvi[:fvo[nf.value]])
+
+
+def bow_score_l1(a, b):
+    L = lib()
+    L.orc_bow_score_l1.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_bow_score_l1.restype = C.c_double
+    i1, v1 = np.ascontiguousarray(a[0], np.int32), np.ascontiguousarray(a[1], np.float64)
+    i2, v2 = np.ascontiguousarray(b[0], np.int32), np.ascontiguousarray(b[1], np.float64)
+    return L.orc_bow_score_l1(i1.ctypes.data, v1.ctypes.data, len(i1), i2.ctypes.data, v2.ctypes.data, len(i2))

@@ -15,7 +15,7 @@ HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))
 def declared_symbols():
     txt = open(HEADER).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(orb[xmb]?a?_[a-z_0-9]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(orb[xmbv]?a?_[a-z_0-9]+)\s*\(", txt)))
 
 
 def test_header_symbols_are_exported_and_bound():
@@ -52,6 +52,9 @@ def test_create_fails_loudly_without_gpu():
         orb.ORBmatcher()
     with pytest.raises(orb.OrbError):
         orb.Optimizer()
+    with pytest.raises(orb.OrbError) as e:
+        orb.ORBVocabulary(orb.synth.vocabulary(0, k=3, L=2))
+    assert e.value.code == capi.ORB_E_NO_DEVICE
 
 
 def test_null_handles_are_rejected():
