@@ -208,8 +208,8 @@ def ba_bytes(problems, stats):
         C = K * (K + 1) // 2 * nC * nC + T // 256
         tot["k_lin"] += it * (E * (12 + 16 + 8 + 16 + 64) + L * 24 + P * 56)                 # ids, obs, info, err -> 64-byte edge record
         tot["k_build"] += it * (E * (64 + 8) + Ef * (64 + 8) + L * 72 + K * 336)              # records read once per landmark part and once per pose part
-        tot["k_trial_lm"] += tr * (Ef * (64 + 12 + 144 + 144 + 48) + L * 72)                  # k_trial: record -> Bt, Yt, v
-        tot["k_pairs"] += tr * (Ef * (288 + 48) + T * 8 + C * 288 + K * nC * 48)              # every Yt / Bt block read once
+        tot["k_trial_lm"] += tr * (Ef * (64 + 12 + 128 + 48) + L * 72)                        # k_trial: record -> {X Y Z 1/Z V VD} (128 B), v
+        tot["k_pairs"] += tr * (Ef * (128 + 48) + T * 8 + C * 288 + K * nC * 48)              # every 128-byte edge record read once
         tot["k_solve"] += tr * (C * 288 + K * (336 + 104) + K * nC * 96)
         tot["k_back"] += tr * (Ef * (64 + 12) + L * (96 + 24) + E * (36 + 16))
     return tot

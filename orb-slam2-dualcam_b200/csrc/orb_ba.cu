@@ -84,7 +84,7 @@ struct BABatch {               // kernel argument (by value)
     double *pose[2], *pt[2], *err[2];
     unsigned char* level;
     double *er;                                 // per edge: X Y Z 1/Z W r0 r1 - (point in the camera frame, weights)
-    double *B, *Y, *v;                          // per edge and trial, tJ space: Bt (18), Yt (18), Yt bl (6)
+    double *yr, *v;                             // per edge and trial: X Y Z 1/Z VD[6] - - (12), Yt bl in tJ space (6)
     double *RT;                                 // per (pose, camera): rotation of ext_c * pose (9)
     double *ut_u, *ut_y;                        // per (free pose, camera): Schur rhs partial in tJ space (6), Adj_c x_k (6)
     double *Hll, *bl;                           // per landmark: 6 / 3
@@ -475,11 +475,17 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
 }
 
 // ------------------------------------------------------------------------------------------------ k_trial
-// thread per edge (per LM trial): the two 6x3 blocks the Schur products are made of, in tJ space (before the camera adjoints),
-//     Bt_e = tJ_e^T W_e Jl_e ,   Yt_e = Bt_e (Hll + lambda I)^-1 ,   v_e = Yt_e bl
-// rebuilt from the 64-byte edge record, staged in shared memory and written out coalesced.
+// thread per edge (per LM trial).  The 6x3 block of an edge in tJ space factors through the 2-d residual:
+//     Bt_e = tJ_e^T W_e Jl_e = U_e V_e            U_e = tJ_e^T (6x2, a function of X Y Z 1/Z and the camera),  V_e = W_e Jl_e (2x3)
+//     Yt_e = Bt_e (Hll + lambda I)^-1 = U_e VD_e   VD_e = V_e D_l (2x3)
+// so the Schur product of a tuple is  Yt_a Bt_b^T = U_a (VD_a V_b^T) U_b^T  and only VD_e (6 doubles) has to be materialised per trial:
+//     yr[e] = { X, Y, Z, 1/Z, V_e[6], VD_e[6] }  (128 bytes = 4 sectors; a tuple gathers 80 bytes of each of its two edges:
+//              X..1/Z + VD of edge a, X..1/Z + V of edge b, three sectors each)
+//     v[e]  = Yt_e bl = U_e (VD_e bl)
+// staged in shared memory and written out coalesced.
+#define BA_YR 16
 __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
-    __shared__ __align__(16) double s_blk[BA_TE * 18];
+    __shared__ __align__(16) double s_blk[BA_TE * BA_YR];
     const int b = blockIdx.x;
     const int p = A.blkE_prob[b];
     const BAState& S = A.state[p];
@@ -490,9 +496,9 @@ __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
     const int nv = min(BA_TE, P.e0 + P.nE - ebase);
     const int e = ebase + tid;
     const double lambda = lambda_eff(S);
-    double Bt[18], Yt[18];
+    double yr[BA_YR];
 #pragma unroll
-    for (int q = 0; q < 18; q++) { Bt[q] = 0; Yt[q] = 0; }
+    for (int q = 0; q < BA_YR; q++) yr[q] = 0;
     double vv[6] = {0, 0, 0, 0, 0, 0};
     if (tid < nv && A.pose_free[A.e_pose[e]] >= 0) {
         double r[8], t4[4], tJ[12], Jl[6], d[6];
@@ -504,25 +510,24 @@ __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
         landmark_dinv(A.Hll + 6 * (size_t)l, lambda, d);
         const double W = r[4];
         const double b0 = A.bl[3 * (size_t)l], b1 = A.bl[3 * (size_t)l + 1], b2 = A.bl[3 * (size_t)l + 2];
+        yr[0] = r[0]; yr[1] = r[1]; yr[2] = r[2]; yr[3] = r[3];
+        double w[2];
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
-            const double x0 = W * (tJ[i] * Jl[0] + tJ[6 + i] * Jl[3]), x1 = W * (tJ[i] * Jl[1] + tJ[6 + i] * Jl[4]), x2 = W * (tJ[i] * Jl[2] + tJ[6 + i] * Jl[5]);
-            Bt[3 * i] = x0; Bt[3 * i + 1] = x1; Bt[3 * i + 2] = x2;
+        for (int k = 0; k < 2; k++) {
+            const double x0 = W * Jl[3 * k], x1 = W * Jl[3 * k + 1], x2 = W * Jl[3 * k + 2];
             const double y0 = x0 * d[0] + x1 * d[1] + x2 * d[2], y1 = x0 * d[1] + x1 * d[3] + x2 * d[4], y2 = x0 * d[2] + x1 * d[4] + x2 * d[5];
-            Yt[3 * i] = y0; Yt[3 * i + 1] = y1; Yt[3 * i + 2] = y2;
-            vv[i] = y0 * b0 + y1 * b1 + y2 * b2;
+            yr[4 + 3 * k] = x0; yr[5 + 3 * k] = x1; yr[6 + 3 * k] = x2;
+            yr[10 + 3 * k] = y0; yr[11 + 3 * k] = y1; yr[12 + 3 * k] = y2;
+            w[k] = y0 * b0 + y1 * b1 + y2 * b2;
         }
+#pragma unroll
+        for (int i = 0; i < 6; i++) vv[i] = tJ[i] * w[0] + tJ[6 + i] * w[1];
     }
-    // coalesced write-out through shared memory: B, then Y, then v
+    // coalesced write-out through shared memory: yr, then v
 #pragma unroll
-    for (int q = 0; q < 18; q++) s_blk[18 * tid + q] = Bt[q];
+    for (int q = 0; q < BA_YR; q++) s_blk[BA_YR * tid + q] = yr[q];
     __syncthreads();
-    for (int i = tid; i < 9 * nv; i += BA_TE) reinterpret_cast<double2*>(A.B + 18 * (size_t)ebase)[i] = reinterpret_cast<const double2*>(s_blk)[i];
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 18; q++) s_blk[18 * tid + q] = Yt[q];
-    __syncthreads();
-    for (int i = tid; i < 9 * nv; i += BA_TE) reinterpret_cast<double2*>(A.Y + 18 * (size_t)ebase)[i] = reinterpret_cast<const double2*>(s_blk)[i];
+    for (int i = tid; i < (BA_YR / 2) * nv; i += BA_TE) reinterpret_cast<double2*>(A.yr + BA_YR * (size_t)ebase)[i] = reinterpret_cast<const double2*>(s_blk)[i];
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < 6; q++) s_blk[6 * tid + q] = vv[q];
@@ -533,11 +538,16 @@ __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
 // ------------------------------------------------------------------------------------------------ k_pairs
 // warp per work item of a problem.
 //   items [0, nChunksMax): a chunk of <= BA_CH (edge a, edge b) tuples of ONE pose pair (i, j) and ONE camera pair (ca, cb):
-//     partial 6x6 of  sum Yt_a Bt_b^T  (the Schur product before the camera adjoints, which k_solve applies once per camera pair)
+//     partial 6x6 of  sum Yt_a Bt_b^T = sum U_a (VD_a V_b^T) U_b^T  (the Schur product before the camera adjoints, which k_solve
+//     applies once per camera pair).  Per tuple 80 bytes of yr[a] and 80 bytes of yr[b] are gathered; U_a and U_b are rebuilt from
+//     X Y Z 1/Z with the chunk's constants (intrinsics of ca / cb).
 //   items [nChunksMax, nChunksMax + K): free pose k, per camera c:  u_(k,c) = sum_e v_e   (Schur right-hand side in tJ space)
-#define BA_STAGE_BYTES (32 * 144)   // one batch: 16 Y blocks + 16 B blocks
-__global__ void __launch_bounds__(128) k_pairs(BABatch A, const int* blkI_first) {
-    __shared__ __align__(16) unsigned char s_stage[4 * 2 * BA_STAGE_BYTES];   // per warp: two stages
+#define BA_STAGE_A (16 * 80)
+#define BA_STAGE_BYTES (2 * BA_STAGE_A)          // one batch of 16 tuples
+#define BA_NSTAGE 3
+__global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_first) {
+    __shared__ __align__(16) unsigned char s_stage[4 * BA_NSTAGE * BA_STAGE_BYTES];   // per warp: BA_NSTAGE stages
+    __shared__ int2 s_tup[4 * BA_CH];                                                  // per warp: the chunk's tuple list
     const int p = A.item_prob[blockIdx.x];
     const BAState& S = A.state[p];
     if (S.done) return;
@@ -549,24 +559,37 @@ __global__ void __launch_bounds__(128) k_pairs(BABatch A, const int* blkI_first)
         const int ch = P.chunk0 + item;
         const int2* T = A.tuples + P.tup0 + A.chunk_start[ch];
         const int len = A.chunk_len[ch];
-        // Batches of 16 tuples: the 32 blocks of a batch (16 x Y_a, 16 x B_b, 144 B each) are copied global -> shared with
-        // cp.async, consecutive lanes fetching consecutive 16-byte pieces of a block (whole sectors per request, no register
-        // write-back), double-buffered per warp; then two lanes per tuple (lane parity h owns rows 3h..3h+2 of the 6x6 block)
-        // read them back conflict-free.
+        // chunk constants
+        const int pcq = A.chunk_pair[ch], q = pcq % P.CC, ca = q / P.nC, cb = q - ca * P.nC;
+        const double fxa = A.cam[BA_CAM_STRIDE * (size_t)(P.c0 + ca)], fya = A.cam[BA_CAM_STRIDE * (size_t)(P.c0 + ca) + 1];
+        const double fxb = A.cam[BA_CAM_STRIDE * (size_t)(P.c0 + cb)], fyb = A.cam[BA_CAM_STRIDE * (size_t)(P.c0 + cb) + 1];
+        // Batches of 16 tuples: the pieces of a batch (16 x 80 B of yr[a], 16 x 80 B of yr[b]) are copied global -> shared with
+        // cp.async (16 bytes per request, whole sectors, no register write-back), double-buffered per warp; then two lanes per tuple
+        // (lane parity h owns rows 3h..3h+2 of the 6x6 block) read them back conflict-free (8-byte reads, stride 80 bytes).
         const int h = lane & 1, slot = lane >> 1, warp = threadIdx.x >> 5;
-        unsigned char* stage0 = s_stage + (size_t)warp * 2 * BA_STAGE_BYTES;
+        unsigned char* stage0 = s_stage + (size_t)warp * BA_NSTAGE * BA_STAGE_BYTES;
         const int nbatch = (len + 15) >> 4;
+        // the tuple list first (one exposed latency per chunk instead of one per batch)
+        int2* tup = s_tup + warp * BA_CH;
+        {
+            const unsigned tdst = (unsigned)__cvta_generic_to_shared(tup);
+            for (int t = lane; t < len; t += 32) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tdst + 8u * t), "l"(T + t) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+        }
         auto issue = [&](int bidx, int stg) {
             const int tl0 = bidx * 16;
             int2 ab = make_int2(0, 0);
-            if (tl0 + (lane & 15) < len) ab = T[tl0 + (lane & 15)];
+            if (tl0 + (lane & 15) < len) ab = tup[tl0 + (lane & 15)];
             const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage0 + (size_t)stg * BA_STAGE_BYTES);
 #pragma unroll
-            for (int k = 0; k < 9; k++) {
-                const int g = k * 32 + lane, rec = g / 9, part = g - rec * 9;
-                const int tl = rec & 15;
+            for (int k = 0; k < 5; k++) {
+                const int g = k * 32 + lane;                      // 160 pieces of 16 bytes: 16 x 5 of edge a, 16 x 5 of edge b
+                const int side = g >= 80, gg = g - 80 * side, tl = gg / 5, part = gg - tl * 5;
                 const int ex = __shfl_sync(0xffffffffu, ab.x, tl), ey = __shfl_sync(0xffffffffu, ab.y, tl);
-                const double* src = (rec < 16 ? A.Y + 18 * (size_t)ex : A.B + 18 * (size_t)ey) + 2 * part;
+                // edge a: doubles 0..3 and 10..15 (VD); edge b: doubles 0..9 (V)
+                const double* src = A.yr + BA_YR * (size_t)(side ? ey : ex) + 2 * part + ((!side && part >= 2) ? 6 : 0);
                 if (tl0 + tl < len) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * g), "l"(src) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -574,35 +597,49 @@ __global__ void __launch_bounds__(128) k_pairs(BABatch A, const int* blkI_first)
         double acc[18];
 #pragma unroll
         for (int i = 0; i < 18; i++) acc[i] = 0;
-        issue(0, 0);
+        // prefetch distance BA_NSTAGE - 1: every iteration commits exactly one (possibly empty) group
+#pragma unroll
+        for (int k = 0; k < BA_NSTAGE - 1; k++) {
+            if (k < nbatch) issue(k, k); else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         for (int bidx = 0; bidx < nbatch; bidx++) {
-            if (bidx + 1 < nbatch) {
-                issue(bidx + 1, (bidx + 1) & 1);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
+            if (bidx + BA_NSTAGE - 1 < nbatch) issue(bidx + BA_NSTAGE - 1, (bidx + BA_NSTAGE - 1) % BA_NSTAGE);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(BA_NSTAGE - 1) : "memory");
             __syncwarp();
             if (bidx * 16 + slot < len) {
-                const unsigned char* stg = stage0 + (size_t)(bidx & 1) * BA_STAGE_BYTES;
-                const double* Yp = reinterpret_cast<const double*>(stg + 144 * slot) + 9 * h;
-                const double2* Bp = reinterpret_cast<const double2*>(stg + 144 * (16 + slot));
-                double y[9], bq[18];
-                if (h == 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) { const double2 a = reinterpret_cast<const double2*>(Yp)[i]; y[2 * i] = a.x; y[2 * i + 1] = a.y; }
-                    y[8] = Yp[8];
-                } else {
-                    y[0] = Yp[0];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) { const double2 a = reinterpret_cast<const double2*>(Yp + 1)[i]; y[1 + 2 * i] = a.x; y[2 + 2 * i] = a.y; }
+                const unsigned char* stg = stage0 + (size_t)(bidx % BA_NSTAGE) * BA_STAGE_BYTES;
+                const double* ya = reinterpret_cast<const double*>(stg + 80 * slot);
+                const double* eb = reinterpret_cast<const double*>(stg + BA_STAGE_A + 80 * slot);
+                // U_a: my three rows of tJ_a^T
+                double ua0[3], ua1[3];
+                {
+                    const double X = ya[0], Y = ya[1], Z = ya[2], iz = ya[3];
+                    const double t00 = -iz * fxa, t02 = iz * iz * X * fxa, t11 = -iz * fya, t12 = iz * iz * Y * fya;
+                    if (h == 0) {
+                        ua0[0] = t02 * Y; ua0[1] = t00 * Z - t02 * X; ua0[2] = -t00 * Y;
+                        ua1[0] = -t11 * Z + t12 * Y; ua1[1] = -t12 * X; ua1[2] = t11 * X;
+                    } else {
+                        ua0[0] = t00; ua0[1] = 0; ua0[2] = t02;
+                        ua1[0] = 0; ua1[1] = t11; ua1[2] = t12;
+                    }
                 }
+                const double Xb = eb[0], Yb = eb[1], Zb = eb[2], izb = eb[3];
+                const double s00 = -izb * fxb, s02 = izb * izb * Xb * fxb, s11 = -izb * fyb, s12 = izb * izb * Yb * fyb;
+                double m00 = 0, m01 = 0, m10 = 0, m11 = 0;        // M = VD_a V_b^T (2x2)
 #pragma unroll
-                for (int i = 0; i < 9; i++) { const double2 c = Bp[i]; bq[2 * i] = c.x; bq[2 * i + 1] = c.y; }
+                for (int c = 0; c < 3; c++) {
+                    const double v0 = eb[4 + c], v1 = eb[7 + c], d0 = ya[4 + c], d1 = ya[7 + c];
+                    m00 += d0 * v0; m01 += d0 * v1; m10 += d1 * v0; m11 += d1 * v1;
+                }
+                const double b0[6] = {s02 * Yb, s00 * Zb - s02 * Xb, -s00 * Yb, s00, 0, s02};
+                const double b1[6] = {-s11 * Zb + s12 * Yb, -s12 * Xb, s11 * Xb, 0, s11, s12};
 #pragma unroll
-                for (int r = 0; r < 3; r++)
+                for (int r = 0; r < 3; r++) {
+                    const double t0 = ua0[r] * m00 + ua1[r] * m10, t1 = ua0[r] * m01 + ua1[r] * m11;
 #pragma unroll
-                    for (int c = 0; c < 6; c++) acc[r * 6 + c] += y[r * 3] * bq[c * 3] + y[r * 3 + 1] * bq[c * 3 + 1] + y[r * 3 + 2] * bq[c * 3 + 2];
+                    for (int c = 0; c < 6; c++) acc[r * 6 + c] += t0 * b0[c] + t1 * b1[c];
+                }
             }
             __syncwarp();
         }
@@ -1289,7 +1326,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     const size_t o_tup = L.add(8 * (size_t)tupTot);
     const size_t o_pose_a = L.add(56 * Ptot), o_pose_b = L.add(56 * Ptot), o_pt_a = L.add(24 * Ltot), o_pt_b = L.add(24 * Ltot);
     const size_t o_err_a = L.add(16 * Etot), o_err_b = L.add(16 * Etot), o_level = L.add(Etot);
-    const size_t o_B = L.add(144 * (size_t)Etot), o_Y = L.add(144 * (size_t)Etot), o_v = L.add(48 * (size_t)Etot);
+    const size_t o_yr = L.add(8 * BA_YR * (size_t)Etot), o_v = L.add(48 * (size_t)Etot);
     const size_t o_er = L.add(64 * (size_t)Etot), o_RT = L.add(72 * (size_t)std::max<long long>(rtTot, 1));
     const size_t o_utu = L.add(48 * (size_t)std::max<long long>(utTot, 1)), o_uty = L.add(48 * (size_t)std::max<long long>(utTot, 1));
     const size_t o_Hll = L.add(48 * Ltot), o_bl = L.add(24 * Ltot);
@@ -1386,7 +1423,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     A.tuples = (int2*)(D + o_tup);
     A.pose[0] = (double*)(D + o_pose_a); A.pose[1] = (double*)(D + o_pose_b); A.pt[0] = (double*)(D + o_pt_a); A.pt[1] = (double*)(D + o_pt_b);
     A.err[0] = (double*)(D + o_err_a); A.err[1] = (double*)(D + o_err_b); A.level = D + o_level;
-    A.B = (double*)(D + o_B); A.Y = (double*)(D + o_Y); A.v = (double*)(D + o_v);
+    A.yr = (double*)(D + o_yr); A.v = (double*)(D + o_v);
     A.er = (double*)(D + o_er); A.RT = (double*)(D + o_RT); A.ut_u = (double*)(D + o_utu); A.ut_y = (double*)(D + o_uty);
     A.Hll = (double*)(D + o_Hll); A.bl = (double*)(D + o_bl);
     A.Hpp = (double*)(D + o_Hpp); A.bp = (double*)(D + o_bp); A.bs = (double*)(D + o_bs); A.xp = (double*)(D + o_xp);
