@@ -47,6 +47,7 @@ struct BAProb {                // static description of one problem inside the b
     int pair0, nPairs;         // K (K + 1) / 2 pair slots
     int chunk0, nChunksMax;    // chunk slots (upper bound)
     int item0, nItems;         // k_pairs work items: nChunksMax chunk warps + K pose warps
+    int blkI0;                 // first k_pairs block of the problem
     int rt0, CC, pc0, ut0;     // first (pose, camera) rotation, nC * nC, first (pair, camera pair) slot, first (free pose, camera) slot
     int blkE0, nbE, blkL0, nbL;
     long long tup0, eof0, hs_off;
@@ -79,6 +80,7 @@ struct BABatch {               // kernel argument (by value)
     int *pair_cnt, *pair_off;                    // per pair: tuples, first tuple
     int *pc_cnt, *pc_off, *pc_fchunk, *pc_nchunk; // per (pair, camera pair): tuples, first tuple, first chunk, chunks
     int *chunk_pair, *chunk_start, *chunk_len;
+    int4* item_rec;                             // per k_pairs warp (block * 4 + warp), two int4: {problem, first tuple (absolute), tuples, chunk} {camera a, camera b, -, -}
     int2* tuples;
     // dynamic
     double *pose[2], *pt[2], *err[2];
@@ -188,6 +190,9 @@ __global__ void k_pair_scan(BABatch A) {
                     A.chunk_pair[P.chunk0 + nc] = pid * P.CC + q;
                     A.chunk_start[P.chunk0 + nc] = off + s;
                     A.chunk_len[P.chunk0 + nc] = min(BA_CH, c - s);
+                    int4* rec = A.item_rec + 2 * ((size_t)P.blkI0 * 4 + nc);      // everything the chunk's warp needs, in one 32-byte read
+                    rec[0] = make_int4(p, (int)(P.tup0 + off + s), min(BA_CH, c - s), P.chunk0 + nc);
+                    rec[1] = make_int4(P.c0 + q / P.nC, P.c0 + q % P.nC, 0, 0);
                 }
                 nc++;
             }
@@ -544,25 +549,20 @@ __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
 //   items [nChunksMax, nChunksMax + K): free pose k, per camera c:  u_(k,c) = sum_e v_e   (Schur right-hand side in tJ space)
 #define BA_STAGE_A (16 * 80)
 #define BA_STAGE_BYTES (2 * BA_STAGE_A)          // one batch of 16 tuples
-#define BA_NSTAGE 3
+#define BA_NSTAGE 4
 __global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_first) {
     __shared__ __align__(16) unsigned char s_stage[4 * BA_NSTAGE * BA_STAGE_BYTES];   // per warp: BA_NSTAGE stages
     __shared__ int2 s_tup[4 * BA_CH];                                                  // per warp: the chunk's tuple list
-    const int p = A.item_prob[blockIdx.x];
-    const BAState& S = A.state[p];
-    if (S.done) return;
-    const BAProb& P = A.prob[p];
-    const int item = (blockIdx.x - blkI_first[blockIdx.x]) * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (item >= P.nItems) return;
-    if (item < P.nChunksMax) {
-        if (item >= S.nChunks) return;
-        const int ch = P.chunk0 + item;
-        const int2* T = A.tuples + P.tup0 + A.chunk_start[ch];
-        const int len = A.chunk_len[ch];
-        // chunk constants
-        const int pcq = A.chunk_pair[ch], q = pcq % P.CC, ca = q / P.nC, cb = q - ca * P.nC;
-        const double fxa = A.cam[BA_CAM_STRIDE * (size_t)(P.c0 + ca)], fya = A.cam[BA_CAM_STRIDE * (size_t)(P.c0 + ca) + 1];
-        const double fxb = A.cam[BA_CAM_STRIDE * (size_t)(P.c0 + cb)], fyb = A.cam[BA_CAM_STRIDE * (size_t)(P.c0 + cb) + 1];
+    const int lane = threadIdx.x & 31;
+    const int4 rec0 = A.item_rec[2 * ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5))], rec1 = A.item_rec[2 * ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5)) + 1];
+    if (rec0.z > 0) {
+        // chunk item: the record replaces the chain block -> problem -> chunk table -> camera (one dependent read instead of three)
+        const int len = rec0.z, ch = rec0.w;
+        const int2* T = A.tuples + rec0.y;
+        const int done = A.state[rec0.x].done;
+        const double fxa = A.cam[BA_CAM_STRIDE * (size_t)rec1.x], fya = A.cam[BA_CAM_STRIDE * (size_t)rec1.x + 1];
+        const double fxb = A.cam[BA_CAM_STRIDE * (size_t)rec1.y], fyb = A.cam[BA_CAM_STRIDE * (size_t)rec1.y + 1];
+        if (done) return;
         // Batches of 16 tuples: the pieces of a batch (16 x 80 B of yr[a], 16 x 80 B of yr[b]) are copied global -> shared with
         // cp.async (16 bytes per request, whole sectors, no register write-back), double-buffered per warp; then two lanes per tuple
         // (lane parity h owns rows 3h..3h+2 of the 6x6 block) read them back conflict-free (8-byte reads, stride 80 bytes).
@@ -632,13 +632,18 @@ __global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_fir
                     const double v0 = eb[4 + c], v1 = eb[7 + c], d0 = ya[4 + c], d1 = ya[7 + c];
                     m00 += d0 * v0; m01 += d0 * v1; m10 += d1 * v0; m11 += d1 * v1;
                 }
-                const double b0[6] = {s02 * Yb, s00 * Zb - s02 * Xb, -s00 * Yb, s00, 0, s02};
-                const double b1[6] = {-s11 * Zb + s12 * Yb, -s12 * Xb, s11 * Xb, 0, s11, s12};
+                // U_b = tJ_b^T: columns b0 (x residual) and b1 (y residual); b0[4] = b1[3] = 0
+                const double b00 = s02 * Yb, b01 = s00 * Zb - s02 * Xb, b02 = -s00 * Yb, b10 = -s11 * Zb + s12 * Yb, b11 = -s12 * Xb, b12 = s11 * Xb;
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
                     const double t0 = ua0[r] * m00 + ua1[r] * m10, t1 = ua0[r] * m01 + ua1[r] * m11;
-#pragma unroll
-                    for (int c = 0; c < 6; c++) acc[r * 6 + c] += t0 * b0[c] + t1 * b1[c];
+                    double* a = acc + 6 * r;              // two chained FMAs per entry (no separate add), the structural zeros skipped
+                    a[0] = fma(t1, b10, fma(t0, b00, a[0]));
+                    a[1] = fma(t1, b11, fma(t0, b01, a[1]));
+                    a[2] = fma(t1, b12, fma(t0, b02, a[2]));
+                    a[3] = fma(t0, s00, a[3]);
+                    a[4] = fma(t1, s11, a[4]);
+                    a[5] = fma(t1, s12, fma(t0, s02, a[5]));
                 }
             }
             __syncwarp();
@@ -654,6 +659,12 @@ __global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_fir
             for (int i = 0; i < 18; i++) out[i] = acc[i];
         }
     } else {
+        const int p = A.item_prob[blockIdx.x];
+        const BAState& S = A.state[p];
+        if (S.done) return;
+        const BAProb& P = A.prob[p];
+        const int item = (blockIdx.x - blkI_first[blockIdx.x]) * 4 + (threadIdx.x >> 5);
+        if (item < P.nChunksMax || item >= P.nItems) return;
         const int k = item - P.nChunksMax;
         const int pidd = k * P.K - k * (k - 1) / 2;
         for (int cl = 0; cl < P.nC; cl++) {
@@ -1301,13 +1312,13 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         P.blkE0 = nbE; P.nbE = std::max(1, (nE + BA_TE - 1) / BA_TE);
         P.blkL0 = nbL; P.nbL = std::max(1, (nL + BA_TL - 1) / BA_TL);
         P.tup0 = tupTot; P.eof0 = eofTot; P.hs_off = hsTot;
-        bP0[p] = nbP; bI0[p] = nbI;
+        bP0[p] = nbP; bI0[p] = nbI; P.blkI0 = nbI;
         Etot += nE; Ltot += nL; Ptot += nP; Ctot += nC; Ktot += K; pairTot += P.nPairs; tupTot += tup; chunkTot += P.nChunksMax;
         itemTot += P.nItems; eofTot += (long long)nL * K;
         if (P.n > BA_HS_SMEM_N) hsTot += (long long)P.n * (P.n | 1);
         nbE += P.nbE; nbL += P.nbL; nbP += (P.nPairs + 3) / 4; nbI += (P.nItems + 3) / 4;
         max_n = std::max(max_n, P.n);
-        if (Etot > 0x7fffffffLL || eofTot > 0x7fffffffLL * 4 || pcTot > 0x7fffffffLL || chunkTot > 0x7fffffffLL) ORB_FAIL(ORB_E_INVALID, "orbba_upload: batch too large");
+        if (Etot > 0x7fffffffLL || eofTot > 0x7fffffffLL * 4 || pcTot > 0x7fffffffLL || chunkTot > 0x7fffffffLL || tupTot > 0x7fffffffLL) ORB_FAIL(ORB_E_INVALID, "orbba_upload: batch too large");
     }
     // ---- layout: static (staged from the host) then device-only
     Layout L;
@@ -1323,6 +1334,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     const size_t o_eof = L.add(4 * (size_t)eofTot), o_pcnt = L.add(4 * (size_t)pairTot), o_poff = L.add(4 * (size_t)pairTot);
     const size_t o_pccnt = L.add(4 * (size_t)pcTot), o_pcoff = L.add(4 * (size_t)pcTot), o_pcfch = L.add(4 * (size_t)pcTot), o_pcnch = L.add(4 * (size_t)pcTot);
     const size_t o_cpair = L.add(4 * (size_t)chunkTot), o_cstart = L.add(4 * (size_t)chunkTot), o_clen = L.add(4 * (size_t)chunkTot);
+    const size_t o_irec = L.add(32 * 4 * (size_t)std::max(nbI, 1));
     const size_t o_tup = L.add(8 * (size_t)tupTot);
     const size_t o_pose_a = L.add(56 * Ptot), o_pose_b = L.add(56 * Ptot), o_pt_a = L.add(24 * Ltot), o_pt_b = L.add(24 * Ltot);
     const size_t o_err_a = L.add(16 * Etot), o_err_b = L.add(16 * Etot), o_level = L.add(Etot);
@@ -1420,6 +1432,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     A.pc_cnt = (int*)(D + o_pccnt); A.pc_off = (int*)(D + o_pcoff); A.pc_fchunk = (int*)(D + o_pcfch); A.pc_nchunk = (int*)(D + o_pcnch);
     A.free_pose = (const int*)(D + o_freepose);
     A.chunk_pair = (int*)(D + o_cpair); A.chunk_start = (int*)(D + o_cstart); A.chunk_len = (int*)(D + o_clen);
+    A.item_rec = (int4*)(D + o_irec);
     A.tuples = (int2*)(D + o_tup);
     A.pose[0] = (double*)(D + o_pose_a); A.pose[1] = (double*)(D + o_pose_b); A.pt[0] = (double*)(D + o_pt_a); A.pt[1] = (double*)(D + o_pt_b);
     A.err[0] = (double*)(D + o_err_a); A.err[1] = (double*)(D + o_err_b); A.level = D + o_level;
@@ -1437,6 +1450,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     cudaStream_t st = b->copy_stream ? b->copy_stream : b->stream;
     ORB_CUDA(cudaMemcpyAsync(D, H, static_bytes, cudaMemcpyHostToDevice, st));
     ORB_CUDA(cudaMemsetAsync(D + o_state, 0, sizeof(BAState) * n, st));
+    ORB_CUDA(cudaMemsetAsync(D + o_irec, 0, 32 * 4 * (size_t)std::max(nbI, 1), st));
     if (eofTot) ORB_CUDA(cudaMemsetAsync(D + o_eof, 0xff, 4 * (size_t)eofTot, st));
     k_edge_of<<<nbE, BA_TE, 0, st>>>(A);
     if (nbP > 0) {
