@@ -37,7 +37,7 @@
 #define BA_TE 128              // threads per edge block
 #define BA_TL 128              // threads per landmark block
 #define BA_TP 128              // threads per pose block (k_build)
-#define BA_CH 256              // tuples per chunk (k_pairs)
+#define BA_CH 512              // tuples per chunk (k_pairs)
 #define BA_MAXCC 16            // camera pairs per pose pair: rigs of up to 4 cameras
 #define BA_TS 512              // threads of k_solve
 #define BA_HS_SMEM_N 156       // reduced camera system in shared memory up to 156 x 156 doubles (26 free poses)
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
 //   items [nChunksMax, nChunksMax + K): free pose k, per camera c:  u_(k,c) = sum_e v_e   (Schur right-hand side in tJ space)
 #define BA_STAGE_A (16 * 80)
 #define BA_STAGE_BYTES (2 * BA_STAGE_A)          // one batch of 16 tuples
-#define BA_NSTAGE 4
+#define BA_NSTAGE 3
 __global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_first) {
     __shared__ __align__(16) unsigned char s_stage[4 * BA_NSTAGE * BA_STAGE_BYTES];   // per warp: BA_NSTAGE stages
     __shared__ int2 s_tup[4 * BA_CH];                                                  // per warp: the chunk's tuple list
