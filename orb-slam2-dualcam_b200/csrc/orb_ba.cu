@@ -76,7 +76,7 @@ struct BABatch {               // kernel argument (by value)
     const int *blkE_prob, *blkL_prob, *item_prob;
     const int* free_pose;                       // [Ktot] global pose index of every free pose
     // index built on the device
-    int* edge_of;                               // [landmark][free pose of the problem] -> edge or -1
+    int* edge_of;                               // [free pose of the problem][landmark] -> edge or -1 (pose-major: the pair kernels read it coalesced)
     int *pair_cnt, *pair_off;                    // per pair: tuples, first tuple
     int *pc_cnt, *pc_off, *pc_fchunk, *pc_nchunk; // per (pair, camera pair): tuples, first tuple, first chunk, chunks
     int *chunk_pair, *chunk_start, *chunk_len;
@@ -134,7 +134,7 @@ __global__ void k_edge_of(BABatch A) {
     const int e = P.e0 + (b - P.blkE0) * BA_TE + threadIdx.x;
     if (e >= P.e0 + P.nE) return;
     const int k = A.pose_free[A.e_pose[e]];
-    if (k >= 0) A.edge_of[P.eof0 + (long long)(A.e_pt[e] - P.l0) * P.K + (k - P.k0)] = e;
+    if (k >= 0) A.edge_of[P.eof0 + (long long)(k - P.k0) * P.nL + (A.e_pt[e] - P.l0)] = e;
 }
 __device__ __forceinline__ void pair_decode(int pid, int K, int& i, int& j) {
     i = 0;
@@ -157,7 +157,7 @@ __global__ void k_pair_count(BABatch A, const int* blkP_prob, const int* blkP_fi
     for (int l0 = 0; l0 < P.nL; l0 += 32) {
         const int l = l0 + lane;
         int a = -1, c = -1;
-        if (l < P.nL) { a = T[(long long)l * P.K + i]; c = T[(long long)l * P.K + j]; }
+        if (l < P.nL) { a = T[(long long)i * P.nL + l]; c = T[(long long)j * P.nL + l]; }
         const bool both = a >= 0 && c >= 0;
         const int combo = both ? (A.e_cam[a] - P.c0) * P.nC + (A.e_cam[c] - P.c0) : -1;
 #pragma unroll
@@ -219,7 +219,7 @@ __global__ void k_pair_fill(BABatch A, const int* blkP_prob, const int* blkP_fir
     for (int l0 = 0; l0 < P.nL; l0 += 32) {
         const int l = l0 + lane;
         int a = -1, c = -1;
-        if (l < P.nL) { a = T[(long long)l * P.K + i]; c = T[(long long)l * P.K + j]; }
+        if (l < P.nL) { a = T[(long long)i * P.nL + l]; c = T[(long long)j * P.nL + l]; }
         const bool both = a >= 0 && c >= 0;
         const int combo = both ? (A.e_cam[a] - P.c0) * P.nC + (A.e_cam[c] - P.c0) : -1;
 #pragma unroll
