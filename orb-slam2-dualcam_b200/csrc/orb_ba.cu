@@ -484,8 +484,8 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
 //     Bt_e = tJ_e^T W_e Jl_e = U_e V_e            U_e = tJ_e^T (6x2, a function of X Y Z 1/Z and the camera),  V_e = W_e Jl_e (2x3)
 //     Yt_e = Bt_e (Hll + lambda I)^-1 = U_e VD_e   VD_e = V_e D_l (2x3)
 // so the Schur product of a tuple is  Yt_a Bt_b^T = U_a (VD_a V_b^T) U_b^T  and only VD_e (6 doubles) has to be materialised per trial:
-//     yr[e] = { X, Y, Z, 1/Z, V_e[6], VD_e[6] }  (128 bytes = 4 sectors; a tuple gathers 80 bytes of each of its two edges:
-//              X..1/Z + VD of edge a, X..1/Z + V of edge b, three sectors each)
+//     yr[e] = { X/Z, Y/Z, 1/Z, -, V_e[6], VD_e[6] }  (128 bytes = 4 sectors; a tuple gathers 80 bytes of each of its two edges:
+//              the three ratios + VD of edge a, the three ratios + V of edge b, three sectors each)
 //     v[e]  = Yt_e bl = U_e (VD_e bl)
 // staged in shared memory and written out coalesced.
 #define BA_YR 16
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
         landmark_dinv(A.Hll + 6 * (size_t)l, lambda, d);
         const double W = r[4];
         const double b0 = A.bl[3 * (size_t)l], b1 = A.bl[3 * (size_t)l + 1], b2 = A.bl[3 * (size_t)l + 2];
-        yr[0] = r[0]; yr[1] = r[1]; yr[2] = r[2]; yr[3] = r[3];
+        yr[0] = r[0] * r[3]; yr[1] = r[1] * r[3]; yr[2] = r[3];      // x/z, y/z, 1/z: U_e = [fx u0 | fy u1] with u0, u1 polynomials in these three
         double w[2];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
@@ -563,6 +563,7 @@ __global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_fir
         const double fxa = A.cam[BA_CAM_STRIDE * (size_t)rec1.x], fya = A.cam[BA_CAM_STRIDE * (size_t)rec1.x + 1];
         const double fxb = A.cam[BA_CAM_STRIDE * (size_t)rec1.y], fyb = A.cam[BA_CAM_STRIDE * (size_t)rec1.y + 1];
         if (done) return;
+        const double f00 = fxa * fxb, f01 = fxa * fyb, f10 = fya * fxb, f11 = fya * fyb;
         // Batches of 16 tuples: the pieces of a batch (16 x 80 B of yr[a], 16 x 80 B of yr[b]) are copied global -> shared with
         // cp.async (16 bytes per request, whole sectors, no register write-back), double-buffered per warp; then two lanes per tuple
         // (lane parity h owns rows 3h..3h+2 of the 6x6 block) read them back conflict-free (8-byte reads, stride 80 bytes).
@@ -611,39 +612,39 @@ __global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_fir
                 const unsigned char* stg = stage0 + (size_t)(bidx % BA_NSTAGE) * BA_STAGE_BYTES;
                 const double* ya = reinterpret_cast<const double*>(stg + 80 * slot);
                 const double* eb = reinterpret_cast<const double*>(stg + BA_STAGE_A + 80 * slot);
-                // U_a: my three rows of tJ_a^T
+                // tJ_e^T = [fx u0 | fy u1] with  u0 = (xy, -(1 + x^2), y, -w, 0, xw),  u1 = (1 + y^2, -xy, -x, 0, -w, yw),  x = X/Z, y = Y/Z, w = 1/Z
+                // (types_six_dof_expmap.cpp:136-153 with Z * (1/Z) = 1); the focal lengths are folded into M.
                 double ua0[3], ua1[3];
                 {
-                    const double X = ya[0], Y = ya[1], Z = ya[2], iz = ya[3];
-                    const double t00 = -iz * fxa, t02 = iz * iz * X * fxa, t11 = -iz * fya, t12 = iz * iz * Y * fya;
+                    const double x = ya[0], y = ya[1], w = ya[2];
                     if (h == 0) {
-                        ua0[0] = t02 * Y; ua0[1] = t00 * Z - t02 * X; ua0[2] = -t00 * Y;
-                        ua1[0] = -t11 * Z + t12 * Y; ua1[1] = -t12 * X; ua1[2] = t11 * X;
+                        const double xy = x * y;
+                        ua0[0] = xy; ua0[1] = -fma(x, x, 1.0); ua0[2] = y;
+                        ua1[0] = fma(y, y, 1.0); ua1[1] = -xy; ua1[2] = -x;
                     } else {
-                        ua0[0] = t00; ua0[1] = 0; ua0[2] = t02;
-                        ua1[0] = 0; ua1[1] = t11; ua1[2] = t12;
+                        ua0[0] = -w; ua0[1] = 0; ua0[2] = x * w;
+                        ua1[0] = 0; ua1[1] = -w; ua1[2] = y * w;
                     }
                 }
-                const double Xb = eb[0], Yb = eb[1], Zb = eb[2], izb = eb[3];
-                const double s00 = -izb * fxb, s02 = izb * izb * Xb * fxb, s11 = -izb * fyb, s12 = izb * izb * Yb * fyb;
-                double m00 = 0, m01 = 0, m10 = 0, m11 = 0;        // M = VD_a V_b^T (2x2)
+                double m00 = 0, m01 = 0, m10 = 0, m11 = 0;        // M = diag(f_a) VD_a V_b^T diag(f_b) (2x2)
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const double v0 = eb[4 + c], v1 = eb[7 + c], d0 = ya[4 + c], d1 = ya[7 + c];
                     m00 += d0 * v0; m01 += d0 * v1; m10 += d1 * v0; m11 += d1 * v1;
                 }
-                // U_b = tJ_b^T: columns b0 (x residual) and b1 (y residual); b0[4] = b1[3] = 0
-                const double b00 = s02 * Yb, b01 = s00 * Zb - s02 * Xb, b02 = -s00 * Yb, b10 = -s11 * Zb + s12 * Yb, b11 = -s12 * Xb, b12 = s11 * Xb;
+                m00 *= f00; m01 *= f01; m10 *= f10; m11 *= f11;
+                const double xb = eb[0], yb = eb[1], wb = eb[2];
+                const double xyb = xb * yb, b01 = -fma(xb, xb, 1.0), b10 = fma(yb, yb, 1.0), xwb = xb * wb, ywb = yb * wb;
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
                     const double t0 = ua0[r] * m00 + ua1[r] * m10, t1 = ua0[r] * m01 + ua1[r] * m11;
-                    double* a = acc + 6 * r;              // two chained FMAs per entry (no separate add), the structural zeros skipped
-                    a[0] = fma(t1, b10, fma(t0, b00, a[0]));
-                    a[1] = fma(t1, b11, fma(t0, b01, a[1]));
-                    a[2] = fma(t1, b12, fma(t0, b02, a[2]));
-                    a[3] = fma(t0, s00, a[3]);
-                    a[4] = fma(t1, s11, a[4]);
-                    a[5] = fma(t1, s12, fma(t0, s02, a[5]));
+                    double* a = acc + 6 * r;              // two chained FMAs per entry, the structural zeros of u0 / u1 skipped
+                    a[0] = fma(t1, b10, fma(t0, xyb, a[0]));
+                    a[1] = fma(t1, -xyb, fma(t0, b01, a[1]));
+                    a[2] = fma(t1, -xb, fma(t0, yb, a[2]));
+                    a[3] = fma(t0, -wb, a[3]);
+                    a[4] = fma(t1, -wb, a[4]);
+                    a[5] = fma(t1, ywb, fma(t0, xwb, a[5]));
                 }
             }
             __syncwarp();
