@@ -579,19 +579,26 @@ __global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_fir
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
         }
+        // piece g = k * 32 + lane of a batch (160 pieces of 16 bytes: 16 x 5 of edge a, then 16 x 5 of edge b); what does not depend on
+        // the batch is fixed per lane here: tuple slot, which edge of the tuple, offset inside the 128-byte record
+        int p_tl[5], p_src[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int g = k * 32 + lane, side = g >= 80, gg = g - 80 * side, tl = gg / 5, part = gg - tl * 5;
+            p_tl[k] = tl | (side << 8);
+            p_src[k] = 2 * part + ((!side && part >= 2) ? 6 : 0);        // edge a: doubles 0..3 and 10..15 (VD); edge b: doubles 0..9 (V)
+        }
         auto issue = [&](int bidx, int stg) {
             const int tl0 = bidx * 16;
-            int2 ab = make_int2(0, 0);
-            if (tl0 + (lane & 15) < len) ab = tup[tl0 + (lane & 15)];
-            const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage0 + (size_t)stg * BA_STAGE_BYTES);
+            const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage0 + (size_t)stg * BA_STAGE_BYTES) + 16u * lane;
 #pragma unroll
             for (int k = 0; k < 5; k++) {
-                const int g = k * 32 + lane;                      // 160 pieces of 16 bytes: 16 x 5 of edge a, 16 x 5 of edge b
-                const int side = g >= 80, gg = g - 80 * side, tl = gg / 5, part = gg - tl * 5;
-                const int ex = __shfl_sync(0xffffffffu, ab.x, tl), ey = __shfl_sync(0xffffffffu, ab.y, tl);
-                // edge a: doubles 0..3 and 10..15 (VD); edge b: doubles 0..9 (V)
-                const double* src = A.yr + BA_YR * (size_t)(side ? ey : ex) + 2 * part + ((!side && part >= 2) ? 6 : 0);
-                if (tl0 + tl < len) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * g), "l"(src) : "memory");
+                const int tl = p_tl[k] & 0xff;
+                if (tl0 + tl < len) {
+                    const int2 ab = tup[tl0 + tl];
+                    const double* src = A.yr + BA_YR * (size_t)((p_tl[k] >> 8) ? ab.y : ab.x) + p_src[k];
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 512u * k), "l"(src) : "memory");
+                }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
