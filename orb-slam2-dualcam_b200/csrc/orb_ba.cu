@@ -489,8 +489,9 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
 //     v[e]  = Yt_e bl = U_e (VD_e bl)
 // staged in shared memory and written out coalesced.
 #define BA_YR 16
+#define BA_YRS 18                 // row stride of the record in k_trial's staging buffer
 __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
-    __shared__ __align__(16) double s_blk[BA_TE * BA_YR];
+    __shared__ __align__(16) double s_blk[BA_TE * BA_YRS];
     const int b = blockIdx.x;
     const int p = A.blkE_prob[b];
     const BAState& S = A.state[p];
@@ -528,11 +529,13 @@ __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
 #pragma unroll
         for (int i = 0; i < 6; i++) vv[i] = tJ[i] * w[0] + tJ[6 + i] * w[1];
     }
-    // coalesced write-out through shared memory: yr, then v
+    // coalesced write-out through shared memory: yr, then v.  Rows of 18 doubles (a 128-byte row stride would put every lane on the
+    // same banks): 16-byte stores by the owner, 16-byte reads by consecutive lanes, both at most 2-way conflicted
 #pragma unroll
-    for (int q = 0; q < BA_YR; q++) s_blk[BA_YR * tid + q] = yr[q];
+    for (int q = 0; q < BA_YR / 2; q++) reinterpret_cast<double2*>(s_blk + BA_YRS * tid)[q] = make_double2(yr[2 * q], yr[2 * q + 1]);
     __syncthreads();
-    for (int i = tid; i < (BA_YR / 2) * nv; i += BA_TE) reinterpret_cast<double2*>(A.yr + BA_YR * (size_t)ebase)[i] = reinterpret_cast<const double2*>(s_blk)[i];
+    for (int i = tid; i < (BA_YR / 2) * nv; i += BA_TE)
+        reinterpret_cast<double2*>(A.yr + BA_YR * (size_t)ebase)[i] = reinterpret_cast<const double2*>(s_blk + BA_YRS * (i >> 3))[i & 7];
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < 6; q++) s_blk[6 * tid + q] = vv[q];
