@@ -369,10 +369,13 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
 
 // ------------------------------------------------------------------------------------------------ k_build
 // blocks [0, nLandmarkBlocks): thread per landmark -> Hll, bl ;  blocks beyond: CTA per free pose -> Hpp, bp
+// Two instantiations, launched back to back: the landmark part needs half the registers of the pose part, and as one kernel it ran at
+// the pose part's occupancy (126 registers, 16 warps per SM).
+template <int PART>
 __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks, const int* pose_prob) {
     __shared__ double s_N[27], s_W[(BA_TP / 32) * 27];
     const int tid = threadIdx.x;
-    if ((int)blockIdx.x < nLandmarkBlocks) {
+    if (PART == 0) {
         const int b = blockIdx.x;
         const int p = A.blkL_prob[b];
         const BAState& S = A.state[p];
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
     }
     // ---- pose part: per camera c, N_c = sum tJ^T W tJ and u_c = sum tJ^T r over the pose's edges seen by camera c (they are the
     //      (c, c) slice of the diagonal pair's tuple list), then Hpp += Adj_c^T N_c Adj_c, bp += Adj_c^T u_c
-    const int kg = blockIdx.x - nLandmarkBlocks;       // global free-pose index
+    const int kg = blockIdx.x;                         // global free-pose index
     const int p = pose_prob[kg];
     const BAState& S = A.state[p];
     if (S.done || !S.need_build) return;
@@ -1139,7 +1142,8 @@ static int launch_steps(orbba* b, int steps) {
         if (kv) cudaEventRecord(kv[0], st);
         k_lin<<<b->nbE, BA_TE, 0, st>>>(A);
         if (kv) cudaEventRecord(kv[1], st);
-        k_build<<<b->nbL + b->Ktot, BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
+        k_build<0><<<b->nbL, BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
+        if (b->Ktot > 0) k_build<1><<<b->Ktot, BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
         if (kv) cudaEventRecord(kv[2], st);
         k_trial<<<b->nbE, BA_TE, 0, st>>>(A);
         if (kv) cudaEventRecord(kv[3], st);
@@ -1149,7 +1153,7 @@ static int launch_steps(orbba* b, int steps) {
         if (kv) cudaEventRecord(kv[5], st);
         k_back<<<b->nbL, BA_TL, 0, st>>>(A);
         if (kv) { cudaEventRecord(kv[6], st); b->kev_steps++; }
-        b->launches += 5 + (b->nbI > 0);
+        b->launches += 5 + (b->nbI > 0) + (b->Ktot > 0);
     }
     b->h_flags[1] = 0;
     k_final<<<b->nbE, BA_TE, 0, st>>>(A);
