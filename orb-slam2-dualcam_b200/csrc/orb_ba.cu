@@ -925,9 +925,11 @@ __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
         const double delta = A.delta, dsqr = delta * delta;
         double x0 = 0, x1 = 0, x2 = 0;
         const double* bl = A.bl + 3 * (size_t)l;
+        const int e_begin = A.pt_off[l], e_end = A.pt_off[l + 1];
         if (S.solve_ok) {   // xl = Dinv (bl - sum B_e^T xp),  B_e^T xp = Jl_e^T W_e tJ_e (Adj_c xp)   (block_solver.hpp:461-481)
             double c0 = bl[0], c1 = bl[1], c2 = bl[2];
-            for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
+#pragma unroll 2
+            for (int e = e_begin; e < e_end; e++) {
                 const int kg = A.pose_free[A.e_pose[e]];
                 if (kg < 0) continue;
                 const int cg = A.e_cam[e];
@@ -952,14 +954,31 @@ __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
         double* pw = A.pt[cur ^ 1] + 3 * (size_t)l;
         pw[0] = pn[0]; pw[1] = pn[1]; pw[2] = pn[2];
         sc = x0 * (lambda * x0 + bl[0]) + x1 * (lambda * x1 + bl[1]) + x2 * (lambda * x2 + bl[2]);
-        for (int e = A.pt_off[l]; e < A.pt_off[l + 1]; e++) {
-            if (A.level[e]) continue;
-            const double* c = A.cam + BA_CAM_STRIDE * (size_t)A.e_cam[e];
+        // software pipeline: the ids / observation / weight of edge e + 1 are fetched before edge e is evaluated (the error store of
+        // edge e would otherwise fence the loads of the next iteration: the pointers of BABatch are not restrict-qualified)
+        const unsigned char* __restrict__ lvl_ = A.level;
+        const int* __restrict__ ecam_ = A.e_cam;
+        const int* __restrict__ epose_ = A.e_pose;
+        const double2* __restrict__ obs_ = reinterpret_cast<const double2*>(A.e_obs);
+        const double* __restrict__ info_ = A.e_info;
+        double2* __restrict__ errw_ = reinterpret_cast<double2*>(A.err[cur ^ 1]);
+        int n_lv = 0, n_cam = 0, n_pose = 0;
+        double2 n_obs = make_double2(0.0, 0.0);
+        double n_info = 0;
+        if (e_begin < e_end) { n_lv = lvl_[e_begin]; n_cam = ecam_[e_begin]; n_pose = epose_[e_begin]; n_obs = obs_[e_begin]; n_info = info_[e_begin]; }
+        for (int e = e_begin; e < e_end; e++) {
+            const int lv = n_lv, cg = n_cam, pg = n_pose;
+            const double2 ob = n_obs;
+            const double w = n_info;
+            if (e + 1 < e_end) { n_lv = lvl_[e + 1]; n_cam = ecam_[e + 1]; n_pose = epose_[e + 1]; n_obs = obs_[e + 1]; n_info = info_[e + 1]; }
+            if (lv) continue;
+            const double* c = A.cam + BA_CAM_STRIDE * (size_t)cg;
             double pc[3], er[2];
-            edge_project(A.pose[cur ^ 1] + 7 * (size_t)A.e_pose[e], pn, c, pc);
-            edge_error(pc, c, A.e_obs + 2 * (size_t)e, er);
-            A.err[cur ^ 1][2 * e] = er[0]; A.err[cur ^ 1][2 * e + 1] = er[1];
-            const double c2 = (er[0] * er[0] + er[1] * er[1]) * A.e_info[e];
+            const double o2[2] = {ob.x, ob.y};
+            edge_project(A.pose[cur ^ 1] + 7 * (size_t)pg, pn, c, pc);
+            edge_error(pc, c, o2, er);
+            errw_[e] = make_double2(er[0], er[1]);
+            const double c2 = (er[0] * er[0] + er[1] * er[1]) * w;
             chi += robust ? huber_rho0(c2, delta, dsqr) : c2;
         }
     }
