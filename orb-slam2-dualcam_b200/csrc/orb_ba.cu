@@ -40,7 +40,7 @@
 #define BA_CH 512              // tuples per chunk (k_pairs)
 #define BA_MAXCC 16            // camera pairs per pose pair: rigs of up to 4 cameras
 #define BA_TS 512              // threads of k_solve
-#define BA_HS_SMEM_N 156       // reduced camera system in shared memory up to 156 x 156 doubles (26 free poses)
+#define BA_HS_SMEM_N 228       // reduced camera system (packed lower triangle) in shared memory up to 228 x 228 doubles (38 free poses)
 
 struct BAProb {                // static description of one problem inside the batch
     int e0, nE, l0, nL, p0, nP, c0, nC, k0, K, n;
@@ -716,20 +716,21 @@ __device__ void round_over(const BABatch& A, BAState& S, bool stopped) {
     }
 }
 
-// Assembles, factorises (LDL^T) and solves the reduced camera system of one problem in `Hs` (row stride ld = n | 1).  Inlined
+// Assembles, factorises (LDL^T) and solves the reduced camera system of one problem in `Hs` (packed lower triangle).  Inlined
 // twice by k_solve -- once with the shared-memory matrix, once with a global-memory one -- so that each copy uses the
 // loads / stores of its address space instead of generic ones.
 __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P, const BAState& S, double* Hs, double* s_lcol, int* s_ok_p,
                                               double lambda, double* s_wscr) {
     const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ld = n | 1;                      // odd row stride: column accesses are bank-conflict free
+    // packed lower triangle, row i at i (i + 1) / 2: half the shared memory of a square matrix, so two CTAs (problems) share an SM
+#define HS_AT(i, j) Hs[(size_t)(i) * ((i) + 1) / 2 + (j)]
     // ---- assemble the reduced camera system: diag blocks Hpp + lambda I, minus the Schur products.  The chunk partials hold
     //      N = sum tJ_a^T S tJ_b per (pose pair, camera pair); the block of the pair is sum over camera pairs of Adj_ca^T N Adj_cb
     for (int r = warp; r < n; r += BA_TS / 32) {
         const int kr = r / 6;
-        for (int c = lane; c < n; c += 32) {
+        for (int c = lane; c <= r; c += 32) {
             const int kc = c / 6;
-            Hs[(size_t)r * ld + c] = kr == kc ? A.Hpp[36 * (size_t)(P.k0 + kr) + (r - 6 * kr) * 6 + (c - 6 * kc)] + (r == c ? lambda : 0.0) : 0.0;
+            HS_AT(r, c) = kr == kc ? A.Hpp[36 * (size_t)(P.k0 + kr) + (r - 6 * kr) * 6 + (c - 6 * kc)] + (r == c ? lambda : 0.0) : 0.0;
         }
     }
     __syncthreads();
@@ -778,9 +779,8 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
             for (int en = lane; en < 36; en += 32) {
                 const int r = en / 6, c = en - 6 * r;
                 const double v = en < 32 ? blk0 : blk1;
-                const size_t a = (size_t)(6 * i1 + r) * ld + 6 * i2 + c;
-                if (i1 != i2) { Hs[a] = -v; Hs[(size_t)(6 * i2 + c) * ld + 6 * i1 + r] = -v; }
-                else Hs[a] -= v;
+                if (i1 != i2) HS_AT(6 * i2 + c, 6 * i1 + r) = -v;          // i1 < i2: the block lies above the diagonal, its transpose below
+                else if (c <= r) HS_AT(6 * i1 + r, 6 * i1 + c) -= v;
             }
         }
     }
@@ -800,13 +800,13 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
     // ---- LDL^T in place (lower triangle: L below the diagonal, D on it); right-looking, one column per step:
     //      lcol[i] = L_ij, then row i of the trailing lower triangle -= L_ij * d_j * L_kj  (warp per row, lanes along the row)
     for (int j = 0; j < n; j++) {
-        const double dj = Hs[(size_t)j * ld + j];
+        const double dj = HS_AT(j, j);
         if (dj == 0.0 || !isfinite(dj)) { if (tid == 0) *s_ok_p = 0; break; }
-        for (int i = j + 1 + tid; i < n; i += BA_TS) { const double l = Hs[(size_t)i * ld + j] / dj; Hs[(size_t)i * ld + j] = l; s_lcol[i] = l; }
+        for (int i = j + 1 + tid; i < n; i += BA_TS) { const double l = HS_AT(i, j) / dj; HS_AT(i, j) = l; s_lcol[i] = l; }
         __syncthreads();
         for (int i = j + 1 + warp; i < n; i += BA_TS / 32) {
             const double li = s_lcol[i] * dj;
-            double* row = Hs + (size_t)i * ld;
+            double* row = &HS_AT(i, 0);
             for (int k = j + 1 + lane; k <= i; k += 32) row[k] -= li * s_lcol[k];
         }
         __syncthreads();
@@ -821,14 +821,14 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
         __syncwarp();
         for (int j = 0; j < n; j++) {
             const double xj = xs[j];
-            for (int i = j + 1 + lane; i < n; i += 32) xs[i] -= Hs[(size_t)i * ld + j] * xj;
+            for (int i = j + 1 + lane; i < n; i += 32) xs[i] -= HS_AT(i, j) * xj;
             __syncwarp();
         }
-        for (int i = lane; i < n; i += 32) xs[i] /= Hs[(size_t)i * ld + i];
+        for (int i = lane; i < n; i += 32) xs[i] /= HS_AT(i, i);
         __syncwarp();
         for (int j = n - 1; j >= 0; j--) {
             const double xj = xs[j];
-            for (int i = lane; i < j; i += 32) xs[i] -= Hs[(size_t)j * ld + i] * xj;
+            for (int i = lane; i < j; i += 32) xs[i] -= HS_AT(j, i) * xj;
             __syncwarp();
         }
         for (int i = lane; i < n; i += 32) x[i] = xs[i];
@@ -1154,7 +1154,7 @@ static int launch_steps(orbba* b, int steps) {
     const BABatch& A = b->A;
     cudaStream_t st = b->stream;
     const int hs_n = b->max_n <= BA_HS_SMEM_N ? b->max_n : BA_HS_SMEM_N;   // problems above the limit keep their matrix in global memory
-    const int hs_doubles = hs_n * (hs_n | 1);
+    const int hs_doubles = (hs_n * (hs_n + 1) / 2 + 1) & ~1;
     const size_t smem = ((size_t)hs_doubles + std::max(b->max_n, 1)) * sizeof(double);
     for (int s = 0; s < steps; s++) {
         cudaEvent_t* kv = (b->profile && b->kev_steps < BA_KEV_STEPS && !b->kev.empty()) ? &b->kev[(size_t)7 * b->kev_steps] : nullptr;

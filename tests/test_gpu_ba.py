@@ -30,8 +30,9 @@ def _check(p, got, ref):
 
 
 @pytest.mark.parametrize("kw", [dict(seed=1, n_kf=6, n_points=120), dict(seed=2, n_kf=10, n_points=600, n_fixed_extra=3),
-                                dict(seed=5, n_kf=3, n_points=40, outlier_frac=0.2), dict(seed=6, n_kf=30, n_points=800)],
-                         ids=["small", "fixed_extra", "many_outliers", "hs_in_global_memory"])
+                                dict(seed=5, n_kf=3, n_points=40, outlier_frac=0.2), dict(seed=6, n_kf=30, n_points=800),
+                                dict(seed=7, n_kf=42, n_points=1000)],
+                         ids=["small", "fixed_extra", "many_outliers", "large_window_in_shared_memory", "hs_in_global_memory"])
 def test_local_ba_vs_oracle(kw):
     p = synth.ba_problem(**kw)
     opt = Optimizer()
