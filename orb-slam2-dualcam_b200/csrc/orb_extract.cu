@@ -59,17 +59,19 @@ struct ExtractParams {
 };
 
 // ------------------------------------------------------------------------------------------------ pyramid
-// cv::resize(INTER_LINEAR, 8UC1) as called at src/ORBextractor.cc:1120.  One thread = 4 destination pixels of one row.
+// cv::resize(INTER_LINEAR, 8UC1) as called at src/ORBextractor.cc:1120.  One thread = 4 consecutive destination pixels of one row.
 __global__ void __launch_bounds__(128) resize_level_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                                                            unsigned long long sstride, uint8_t* __restrict__ dst, int dw, int dh,
                                                            int dpitch, unsigned long long dstride, const int* __restrict__ xofs,
                                                            const int* __restrict__ ialpha /* 2 x int16 packed */,
                                                            const int* __restrict__ yofs, const int* __restrict__ ibeta) {
-    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int dy = blockIdx.y;
-    if (dx0 >= dw) return;
-    const uint8_t* S = src + (unsigned long long)blockIdx.z * sstride;
-    uint8_t* D = dst + (unsigned long long)blockIdx.z * dstride + (size_t)dy * dpitch;
+    // items (row, group of 4 pixels) are numbered row-major over the whole level, so no lane idles at the end of a row
+    const int nx4 = (dw + 3) >> 2;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= nx4 * dh) return;
+    const int dy = item / nx4, dx0 = (item - dy * nx4) * 4;
+    const uint8_t* S = src + (unsigned long long)blockIdx.y * sstride;
+    uint8_t* D = dst + (unsigned long long)blockIdx.y * dstride + (size_t)dy * dpitch;
     const int sy = yofs[dy];
     const int r0 = min(max(sy, 0), sh - 1), r1 = min(max(sy + 1, 0), sh - 1);
     const int bpk = ibeta[dy];
@@ -834,7 +836,7 @@ int orbx_extract_device(orbx_t* e, const uint8_t* d_imgs, int frames, size_t row
     for (int l = 1; l < L; l++) {
         const LevelDev& S = P.lv[l - 1];
         const LevelDev& D = P.lv[l];
-        dim3 grid((D.w + 4 * 128 - 1) / (4 * 128), D.h, NI);
+        dim3 grid((((D.w + 3) / 4) * D.h + 127) / 128, NI);
         const int* T = e->d_tables;
         resize_level_kernel<<<grid, 128, 0, st>>>(P.base[l - 1], S.w, S.h, S.pitch, S.img_stride, const_cast<uint8_t*>(P.base[l]), D.w, D.h,
                                                   D.pitch, D.img_stride, T + e->tab_off[l * 4 + 0], T + e->tab_off[l * 4 + 1],
