@@ -76,7 +76,7 @@ struct BABatch {               // kernel argument (by value)
     const int *blkE_prob, *blkL_prob, *item_prob;
     const int* free_pose;                       // [Ktot] global pose index of every free pose
     // index built on the device
-    int* edge_of;                               // [free pose of the problem][landmark] -> edge or -1 (pose-major: the pair kernels read it coalesced)
+    int* edge_of;                               // [free pose of the problem][landmark] -> edge << 2 | camera, or -1 (pose-major: the pair kernels read it coalesced)
     int *pair_cnt, *pair_off;                    // per pair: tuples, first tuple
     int *pc_cnt, *pc_off, *pc_fchunk, *pc_nchunk; // per (pair, camera pair): tuples, first tuple, first chunk, chunks
     int *chunk_pair, *chunk_start, *chunk_len;
@@ -134,7 +134,7 @@ __global__ void k_edge_of(BABatch A) {
     const int e = P.e0 + (b - P.blkE0) * BA_TE + threadIdx.x;
     if (e >= P.e0 + P.nE) return;
     const int k = A.pose_free[A.e_pose[e]];
-    if (k >= 0) A.edge_of[P.eof0 + (long long)(k - P.k0) * P.nL + (A.e_pt[e] - P.l0)] = e;
+    if (k >= 0) A.edge_of[P.eof0 + (long long)(k - P.k0) * P.nL + (A.e_pt[e] - P.l0)] = (e << 2) | (A.e_cam[e] - P.c0);   // edge and its camera (rigs of <= 4 cameras)
 }
 __device__ __forceinline__ void pair_decode(int pid, int K, int& i, int& j) {
     i = 0;
@@ -159,7 +159,7 @@ __global__ void k_pair_count(BABatch A, const int* blkP_prob, const int* blkP_fi
         int a = -1, c = -1;
         if (l < P.nL) { a = T[(long long)i * P.nL + l]; c = T[(long long)j * P.nL + l]; }
         const bool both = a >= 0 && c >= 0;
-        const int combo = both ? (A.e_cam[a] - P.c0) * P.nC + (A.e_cam[c] - P.c0) : -1;
+        const int combo = both ? (a & 3) * P.nC + (c & 3) : -1;
 #pragma unroll
         for (int q = 0; q < BA_MAXCC; q++)
             if (q < P.CC) cnt[q] += __popc(__ballot_sync(0xffffffffu, combo == q));
@@ -221,12 +221,12 @@ __global__ void k_pair_fill(BABatch A, const int* blkP_prob, const int* blkP_fir
         int a = -1, c = -1;
         if (l < P.nL) { a = T[(long long)i * P.nL + l]; c = T[(long long)j * P.nL + l]; }
         const bool both = a >= 0 && c >= 0;
-        const int combo = both ? (A.e_cam[a] - P.c0) * P.nC + (A.e_cam[c] - P.c0) : -1;
+        const int combo = both ? (a & 3) * P.nC + (c & 3) : -1;
 #pragma unroll
         for (int q = 0; q < BA_MAXCC; q++) {
             if (q < P.CC) {
                 const unsigned m = __ballot_sync(0xffffffffu, combo == q);
-                if (combo == q) out[pos[q] + __popc(m & ((1u << lane) - 1))] = make_int2(a, c);
+                if (combo == q) out[pos[q] + __popc(m & ((1u << lane) - 1))] = make_int2(a >> 2, c >> 2);
                 pos[q] += __popc(m);
             }
         }
@@ -1352,7 +1352,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         if (P.n > BA_HS_SMEM_N) hsTot += (long long)P.n * (P.n | 1);
         nbE += P.nbE; nbL += P.nbL; nbP += (P.nPairs + 3) / 4; nbI += (P.nItems + 3) / 4;
         max_n = std::max(max_n, P.n);
-        if (Etot > 0x7fffffffLL || eofTot > 0x7fffffffLL * 4 || pcTot > 0x7fffffffLL || chunkTot > 0x7fffffffLL || tupTot > 0x7fffffffLL) ORB_FAIL(ORB_E_INVALID, "orbba_upload: batch too large");
+        if (Etot > 0x1fffffffLL || eofTot > 0x7fffffffLL * 4 || pcTot > 0x7fffffffLL || chunkTot > 0x7fffffffLL || tupTot > 0x7fffffffLL) ORB_FAIL(ORB_E_INVALID, "orbba_upload: batch too large");
     }
     // ---- layout: static (staged from the host) then device-only
     Layout L;
