@@ -455,6 +455,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
+        # the ranks of a node share its host cores: split them for the library's host-side flattening of the BA graphs
+        os.environ.setdefault("ORB_HOST_THREADS", str(max(2, (os.cpu_count() or 16) // max(world, 1))))
         run_ours(args, rank, world, local_rank)
 
 

@@ -1137,7 +1137,9 @@ namespace {
 // runs fn(0..n-1) on up to 16 host threads (problems are independent); inline for a single item
 template <class F>
 void parallel_for(int n, F fn) {
-    const int nt = std::min({n, 16, (int)std::max(1u, std::thread::hardware_concurrency())});
+    // host threads for validation / flattening: ORB_HOST_THREADS (e.g. cores / ranks when several processes share a node), else up to 16
+    static const int cap = []() { const char* e = getenv("ORB_HOST_THREADS"); const int v = e ? atoi(e) : 0; return v > 0 ? std::min(v, 64) : 16; }();
+    const int nt = std::min({n, cap, (int)std::max(1u, std::thread::hardware_concurrency())});
     if (nt <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
     std::atomic<int> next(0);
     std::vector<std::thread> ts;
