@@ -80,6 +80,7 @@ struct BABatch {               // kernel argument (by value)
     int *pair_cnt, *pair_off;                    // per pair: tuples, first tuple
     int *pc_cnt, *pc_off, *pc_fchunk, *pc_nchunk; // per (pair, camera pair): tuples, first tuple, first chunk, chunks
     int *chunk_pair, *chunk_start, *chunk_len;
+    int* pairs_counter;                         // work-queue head of the persistent k_pairs
     int4* item_rec;                             // per k_pairs warp (block * 4 + warp), two int4: {problem, first tuple (absolute), tuples, chunk} {camera a, camera b, -, -}
     int2* tuples;
     // dynamic
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
 __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
     __shared__ __align__(16) double s_blk[BA_TE * BA_YRS];
     const int b = blockIdx.x;
+    if (b == 0 && threadIdx.x == 0) *A.pairs_counter = 0;       // work queue of the k_pairs launch that follows
     const int p = A.blkE_prob[b];
     const BAState& S = A.state[p];
     if (S.done) return;
@@ -556,151 +558,175 @@ __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
 #define BA_STAGE_A (16 * 80)
 #define BA_STAGE_BYTES (2 * BA_STAGE_A)          // one batch of 16 tuples
 #define BA_NSTAGE 3
-__global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_first) {
+// Persistent warps: the grid holds as many CTAs as fit the device, every warp walks the item list with a fixed stride (which warp computes a
+// chunk does not change its result).  While a chunk is being reduced, the record of the warp's next item is already in registers and the
+// next chunk's tuple list is on its way to shared memory, so only the first item of a warp pays the start-up round trips.
+__global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_first, int n_items) {
     __shared__ __align__(16) unsigned char s_stage[4 * BA_NSTAGE * BA_STAGE_BYTES];   // per warp: BA_NSTAGE stages
     __shared__ int2 s_tup[4 * BA_CH];                                                  // per warp: the chunk's tuple list
-    const int lane = threadIdx.x & 31;
-    const int4 rec0 = A.item_rec[2 * ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5))], rec1 = A.item_rec[2 * ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5)) + 1];
-    if (rec0.z > 0) {
-        // chunk item: the record replaces the chain block -> problem -> chunk table -> camera (one dependent read instead of three)
-        const int len = rec0.z, ch = rec0.w;
-        const int2* T = A.tuples + rec0.y;
-        const int done = A.state[rec0.x].done;
-        const double fxa = A.cam[BA_CAM_STRIDE * (size_t)rec1.x], fya = A.cam[BA_CAM_STRIDE * (size_t)rec1.x + 1];
-        const double fxb = A.cam[BA_CAM_STRIDE * (size_t)rec1.y], fyb = A.cam[BA_CAM_STRIDE * (size_t)rec1.y + 1];
-        if (done) return;
-        const double f00 = fxa * fxb, f01 = fxa * fyb, f10 = fya * fxb, f11 = fya * fyb;
-        // Batches of 16 tuples: the pieces of a batch (16 x 80 B of yr[a], 16 x 80 B of yr[b]) are copied global -> shared with
-        // cp.async (16 bytes per request, whole sectors, no register write-back), double-buffered per warp; then two lanes per tuple
-        // (lane parity h owns rows 3h..3h+2 of the 6x6 block) read them back conflict-free (8-byte reads, stride 80 bytes).
-        const int h = lane & 1, slot = lane >> 1, warp = threadIdx.x >> 5;
-        unsigned char* stage0 = s_stage + (size_t)warp * BA_NSTAGE * BA_STAGE_BYTES;
-        const int nbatch = (len + 15) >> 4;
-        // the tuple list first (one exposed latency per chunk instead of one per batch)
-        int2* tup = s_tup + warp * BA_CH;
-        {
-            const unsigned tdst = (unsigned)__cvta_generic_to_shared(tup);
-            for (int t = lane; t < len; t += 32) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tdst + 8u * t), "l"(T + t) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = lane & 1, slot = lane >> 1;
+    unsigned char* stage0 = s_stage + (size_t)warp * BA_NSTAGE * BA_STAGE_BYTES;
+    int2* tup = s_tup + warp * BA_CH;
+    // piece g = k * 32 + lane of a batch (160 pieces of 16 bytes: 16 x 5 of edge a, then 16 x 5 of edge b); what does not depend on
+    // the batch is fixed per lane here: tuple slot, which edge of the tuple, offset inside the 128-byte record
+    int p_tl[5], p_src[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int g = k * 32 + lane, side = g >= 80, gg = g - 80 * side, tl = gg / 5, part = gg - tl * 5;
+        p_tl[k] = tl | (side << 8);
+        p_src[k] = 2 * part + ((!side && part >= 2) ? 6 : 0);        // edge a: doubles 0..3 and 10..15 (VD); edge b: doubles 0..9 (V)
+    }
+    auto stage_tuples = [&](const int4& r) {                          // one cp.async group: the tuple list of chunk record r
+        const int2* T = A.tuples + r.y;
+        const unsigned tdst = (unsigned)__cvta_generic_to_shared(tup);
+        for (int t = lane; t < r.z; t += 32) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tdst + 8u * t), "l"(T + t) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // dynamic item queue (the counter is zeroed by k_trial, which precedes this kernel in every step)
+    auto grab = [&]() { int v = 0; if (lane == 0) v = atomicAdd(A.pairs_counter, 1); return __shfl_sync(0xffffffffu, v, 0); };
+    int it = grab();
+    int4 rec0 = make_int4(0, 0, 0, 0), rec1 = rec0;
+    if (it < n_items) { rec0 = A.item_rec[2 * (size_t)it]; rec1 = A.item_rec[2 * (size_t)it + 1]; }
+    bool tup_ready = false;                                           // the tuple list of the current item is already (being) staged
+    int nxt = it;
+    for (; it < n_items; it = nxt) {
+        nxt = grab();
+        int4 nx0 = make_int4(0, 0, 0, 0), nx1 = nx0;
+        if (nxt < n_items) { nx0 = A.item_rec[2 * (size_t)nxt]; nx1 = A.item_rec[2 * (size_t)nxt + 1]; }
+        const int4 r0 = rec0, r1 = rec1;
+        rec0 = nx0; rec1 = nx1;
+        if (r0.z > 0) {
+            // chunk item: a <= BA_CH-tuple chunk of one (pose pair, camera pair); the record holds {problem, first tuple, tuples, chunk}
+            const int len = r0.z, ch = r0.w;
+            const int done = A.state[r0.x].done;
+            const double fxa = A.cam[BA_CAM_STRIDE * (size_t)r1.x], fya = A.cam[BA_CAM_STRIDE * (size_t)r1.x + 1];
+            const double fxb = A.cam[BA_CAM_STRIDE * (size_t)r1.y], fyb = A.cam[BA_CAM_STRIDE * (size_t)r1.y + 1];
+            if (!tup_ready) stage_tuples(r0);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
-        }
-        // piece g = k * 32 + lane of a batch (160 pieces of 16 bytes: 16 x 5 of edge a, then 16 x 5 of edge b); what does not depend on
-        // the batch is fixed per lane here: tuple slot, which edge of the tuple, offset inside the 128-byte record
-        int p_tl[5], p_src[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            const int g = k * 32 + lane, side = g >= 80, gg = g - 80 * side, tl = gg / 5, part = gg - tl * 5;
-            p_tl[k] = tl | (side << 8);
-            p_src[k] = 2 * part + ((!side && part >= 2) ? 6 : 0);        // edge a: doubles 0..3 and 10..15 (VD); edge b: doubles 0..9 (V)
-        }
-        auto issue = [&](int bidx, int stg) {
-            const int tl0 = bidx * 16;
-            const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage0 + (size_t)stg * BA_STAGE_BYTES) + 16u * lane;
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                const int tl = p_tl[k] & 0xff;
-                if (tl0 + tl < len) {
-                    const int2 ab = tup[tl0 + tl];
-                    const double* src = A.yr + BA_YR * (size_t)((p_tl[k] >> 8) ? ab.y : ab.x) + p_src[k];
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 512u * k), "l"(src) : "memory");
-                }
+            tup_ready = false;
+            const bool next_chunk = nx0.z > 0;
+            if (done) {
+                if (next_chunk) { stage_tuples(nx0); tup_ready = true; }
+                continue;
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        double acc[18];
+            const double f00 = fxa * fxb, f01 = fxa * fyb, f10 = fya * fxb, f11 = fya * fyb;
+            // Batches of 16 tuples: the pieces of a batch (16 x 80 B per side) are copied global -> shared with cp.async (16 bytes per
+            // request, whole sectors, no register write-back), BA_NSTAGE stages per warp; then two lanes per tuple (lane parity h owns rows
+            // 3h..3h+2 of the 6x6 block) read them back conflict-free (8-byte reads, stride 80 bytes).
+            const int nbatch = (len + 15) >> 4;
+            auto issue = [&](int bidx, int stg) {
+                const int tl0 = bidx * 16;
+                const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage0 + (size_t)stg * BA_STAGE_BYTES) + 16u * lane;
 #pragma unroll
-        for (int i = 0; i < 18; i++) acc[i] = 0;
-        // prefetch distance BA_NSTAGE - 1: every iteration commits exactly one (possibly empty) group
-#pragma unroll
-        for (int k = 0; k < BA_NSTAGE - 1; k++) {
-            if (k < nbatch) issue(k, k); else asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        for (int bidx = 0; bidx < nbatch; bidx++) {
-            if (bidx + BA_NSTAGE - 1 < nbatch) issue(bidx + BA_NSTAGE - 1, (bidx + BA_NSTAGE - 1) % BA_NSTAGE);
-            else asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group %0;" ::"n"(BA_NSTAGE - 1) : "memory");
-            __syncwarp();
-            if (bidx * 16 + slot < len) {
-                const unsigned char* stg = stage0 + (size_t)(bidx % BA_NSTAGE) * BA_STAGE_BYTES;
-                const double* ya = reinterpret_cast<const double*>(stg + 80 * slot);
-                const double* eb = reinterpret_cast<const double*>(stg + BA_STAGE_A + 80 * slot);
-                // tJ_e^T = [fx u0 | fy u1] with  u0 = (xy, -(1 + x^2), y, -w, 0, xw),  u1 = (1 + y^2, -xy, -x, 0, -w, yw),  x = X/Z, y = Y/Z, w = 1/Z
-                // (types_six_dof_expmap.cpp:136-153 with Z * (1/Z) = 1); the focal lengths are folded into M.
-                double ua0[3], ua1[3];
-                {
-                    const double x = ya[0], y = ya[1], w = ya[2];
-                    if (h == 0) {
-                        const double xy = x * y;
-                        ua0[0] = xy; ua0[1] = -fma(x, x, 1.0); ua0[2] = y;
-                        ua1[0] = fma(y, y, 1.0); ua1[1] = -xy; ua1[2] = -x;
-                    } else {
-                        ua0[0] = -w; ua0[1] = 0; ua0[2] = x * w;
-                        ua1[0] = 0; ua1[1] = -w; ua1[2] = y * w;
+                for (int k = 0; k < 5; k++) {
+                    const int tl = p_tl[k] & 0xff;
+                    if (tl0 + tl < len) {
+                        const int2 ab = tup[tl0 + tl];
+                        const double* src = A.yr + BA_YR * (size_t)((p_tl[k] >> 8) ? ab.y : ab.x) + p_src[k];
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 512u * k), "l"(src) : "memory");
                     }
                 }
-                double m00 = 0, m01 = 0, m10 = 0, m11 = 0;        // M = diag(f_a) VD_a V_b^T diag(f_b) (2x2)
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            double acc[18];
 #pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const double v0 = eb[4 + c], v1 = eb[7 + c], d0 = ya[4 + c], d1 = ya[7 + c];
-                    m00 += d0 * v0; m01 += d0 * v1; m10 += d1 * v0; m11 += d1 * v1;
-                }
-                m00 *= f00; m01 *= f01; m10 *= f10; m11 *= f11;
-                const double xb = eb[0], yb = eb[1], wb = eb[2];
-                const double xyb = xb * yb, b01 = -fma(xb, xb, 1.0), b10 = fma(yb, yb, 1.0), xwb = xb * wb, ywb = yb * wb;
+            for (int i = 0; i < 18; i++) acc[i] = 0;
+            // prefetch distance BA_NSTAGE - 1: every iteration commits exactly one (possibly empty) group
 #pragma unroll
-                for (int r = 0; r < 3; r++) {
-                    const double t0 = ua0[r] * m00 + ua1[r] * m10, t1 = ua0[r] * m01 + ua1[r] * m11;
-                    double* a = acc + 6 * r;              // two chained FMAs per entry, the structural zeros of u0 / u1 skipped
-                    a[0] = fma(t1, b10, fma(t0, xyb, a[0]));
-                    a[1] = fma(t1, -xyb, fma(t0, b01, a[1]));
-                    a[2] = fma(t1, -xb, fma(t0, yb, a[2]));
-                    a[3] = fma(t0, -wb, a[3]);
-                    a[4] = fma(t1, -wb, a[4]);
-                    a[5] = fma(t1, ywb, fma(t0, xwb, a[5]));
-                }
+            for (int k = 0; k < BA_NSTAGE - 1; k++) {
+                if (k < nbatch) issue(k, k); else asm volatile("cp.async.commit_group;" ::: "memory");
             }
-            __syncwarp();
-        }
-#pragma unroll
-        for (int i = 0; i < 18; i++) {
-#pragma unroll
-            for (int o = 16; o > 1; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-        }
-        if (lane < 2) {
-            double* out = A.partial + 36 * (size_t)ch + 18 * h;
-#pragma unroll
-            for (int i = 0; i < 18; i++) out[i] = acc[i];
-        }
-    } else {
-        const int p = A.item_prob[blockIdx.x];
-        const BAState& S = A.state[p];
-        if (S.done) return;
-        const BAProb& P = A.prob[p];
-        const int item = (blockIdx.x - blkI_first[blockIdx.x]) * 4 + (threadIdx.x >> 5);
-        if (item < P.nChunksMax || item >= P.nItems) return;
-        const int k = item - P.nChunksMax;
-        const int pidd = k * P.K - k * (k - 1) / 2;
-        for (int cl = 0; cl < P.nC; cl++) {
-            const int pc = P.pc0 + pidd * P.CC + cl * P.nC + cl;
-            const int cnt = A.pc_cnt[pc];
-            const int2* T = A.tuples + P.tup0 + A.pc_off[pc];
-            double u[6];
-#pragma unroll
-            for (int q = 0; q < 6; q++) u[q] = 0;
-            for (int t = lane; t < cnt; t += 32) {
-                double ve[6];
-                load6(A.v + 6 * (size_t)T[t].x, ve);
-#pragma unroll
-                for (int q = 0; q < 6; q++) u[q] += ve[q];
+            for (int bidx = 0; bidx < nbatch; bidx++) {
+                if (bidx + BA_NSTAGE - 1 < nbatch) issue(bidx + BA_NSTAGE - 1, (bidx + BA_NSTAGE - 1) % BA_NSTAGE);
+                else asm volatile("cp.async.commit_group;" ::: "memory");
+                // once the last batch has been issued nobody reads the tuple list any more: fetch the next chunk's (one more group in flight)
+                if (next_chunk && !tup_ready && bidx + BA_NSTAGE - 1 >= nbatch - 1) { __syncwarp(); stage_tuples(nx0); tup_ready = true; }
+                if (tup_ready) asm volatile("cp.async.wait_group %0;" ::"n"(BA_NSTAGE) : "memory");
+                else asm volatile("cp.async.wait_group %0;" ::"n"(BA_NSTAGE - 1) : "memory");
+                __syncwarp();
+                if (bidx * 16 + slot < len) {
+                    const unsigned char* stg = stage0 + (size_t)(bidx % BA_NSTAGE) * BA_STAGE_BYTES;
+                    const double* ya = reinterpret_cast<const double*>(stg + 80 * slot);
+                    const double* eb = reinterpret_cast<const double*>(stg + BA_STAGE_A + 80 * slot);
+                    // tJ_e^T = [fx u0 | fy u1] with  u0 = (xy, -(1 + x^2), y, -w, 0, xw),  u1 = (1 + y^2, -xy, -x, 0, -w, yw),  x = X/Z, y = Y/Z, w = 1/Z
+                    // (types_six_dof_expmap.cpp:136-153 with Z * (1/Z) = 1); the focal lengths are folded into M.
+                    double ua0[3], ua1[3];
+                    {
+                        const double x = ya[0], y = ya[1], w = ya[2];
+                        if (h == 0) {
+                            const double xy = x * y;
+                            ua0[0] = xy; ua0[1] = -fma(x, x, 1.0); ua0[2] = y;
+                            ua1[0] = fma(y, y, 1.0); ua1[1] = -xy; ua1[2] = -x;
+                        } else {
+                            ua0[0] = -w; ua0[1] = 0; ua0[2] = x * w;
+                            ua1[0] = 0; ua1[1] = -w; ua1[2] = y * w;
+                        }
+                    }
+                    double m00 = 0, m01 = 0, m10 = 0, m11 = 0;        // M = diag(f_a) VD_a V_b^T diag(f_b) (2x2)
+    #pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const double v0 = eb[4 + c], v1 = eb[7 + c], d0 = ya[4 + c], d1 = ya[7 + c];
+                        m00 += d0 * v0; m01 += d0 * v1; m10 += d1 * v0; m11 += d1 * v1;
+                    }
+                    m00 *= f00; m01 *= f01; m10 *= f10; m11 *= f11;
+                    const double xb = eb[0], yb = eb[1], wb = eb[2];
+                    const double xyb = xb * yb, b01 = -fma(xb, xb, 1.0), b10 = fma(yb, yb, 1.0), xwb = xb * wb, ywb = yb * wb;
+    #pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        const double t0 = ua0[r] * m00 + ua1[r] * m10, t1 = ua0[r] * m01 + ua1[r] * m11;
+                        double* a = acc + 6 * r;              // two chained FMAs per entry, the structural zeros of u0 / u1 skipped
+                        a[0] = fma(t1, b10, fma(t0, xyb, a[0]));
+                        a[1] = fma(t1, -xyb, fma(t0, b01, a[1]));
+                        a[2] = fma(t1, -xb, fma(t0, yb, a[2]));
+                        a[3] = fma(t0, -wb, a[3]);
+                        a[4] = fma(t1, -wb, a[4]);
+                        a[5] = fma(t1, ywb, fma(t0, xwb, a[5]));
+                    }
+                }
+                __syncwarp();
             }
 #pragma unroll
-            for (int q = 0; q < 6; q++) u[q] = warp_sum(u[q]);
-            if (lane < 6) {
-                double vsel = u[0];
+            for (int i = 0; i < 18; i++) {
 #pragma unroll
-                for (int q = 1; q < 6; q++) if (lane == q) vsel = u[q];
-                A.ut_u[6 * (size_t)(P.ut0 + k * P.nC + cl) + lane] = vsel;
+                for (int o = 16; o > 1; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+            }
+            if (lane < 2) {
+                double* out = A.partial + 36 * (size_t)ch + 18 * h;
+#pragma unroll
+                for (int i = 0; i < 18; i++) out[i] = acc[i];
+            }
+        } else {
+            const int p = A.item_prob[it >> 2];
+            const BAState& S = A.state[p];
+            if (S.done) continue;
+            const BAProb& P = A.prob[p];
+            const int item = ((it >> 2) - blkI_first[it >> 2]) * 4 + (it & 3);
+            if (item < P.nChunksMax || item >= P.nItems) continue;
+            const int k = item - P.nChunksMax;
+            const int pidd = k * P.K - k * (k - 1) / 2;
+            for (int cl = 0; cl < P.nC; cl++) {
+                const int pc = P.pc0 + pidd * P.CC + cl * P.nC + cl;
+                const int cnt = A.pc_cnt[pc];
+                const int2* T = A.tuples + P.tup0 + A.pc_off[pc];
+                double u[6];
+    #pragma unroll
+                for (int q = 0; q < 6; q++) u[q] = 0;
+                for (int t = lane; t < cnt; t += 32) {
+                    double ve[6];
+                    load6(A.v + 6 * (size_t)T[t].x, ve);
+    #pragma unroll
+                    for (int q = 0; q < 6; q++) u[q] += ve[q];
+                }
+    #pragma unroll
+                for (int q = 0; q < 6; q++) u[q] = warp_sum(u[q]);
+                if (lane < 6) {
+                    double vsel = u[0];
+    #pragma unroll
+                    for (int q = 1; q < 6; q++) if (lane == q) vsel = u[q];
+                    A.ut_u[6 * (size_t)(P.ut0 + k * P.nC + cl) + lane] = vsel;
+                }
             }
         }
     }
@@ -1104,6 +1130,7 @@ struct orbba {
     uint8_t* h_stage = nullptr; size_t stage_cap = 0;   // pinned staging of the static arrays
     int *d_blkP_prob = nullptr, *d_blkP_first = nullptr, *d_blkI_first = nullptr, *d_pose_prob = nullptr;
     int nbE = 0, nbL = 0, nbP = 0, nbI = 0, Ktot = 0, max_n = 0;
+    int pairs_grid = 148 * 4;          // resident CTAs of the persistent k_pairs (set from the occupancy calculator at create)
     long long Etot = 0, Ltot = 0, Ptot = 0;
     int* h_flags = nullptr;                  // pinned + mapped: [0] stop flag, [1] active problems after the last step
     int* d_flags = nullptr;
@@ -1168,7 +1195,7 @@ static int launch_steps(orbba* b, int steps) {
         if (kv) cudaEventRecord(kv[2], st);
         k_trial<<<b->nbE, BA_TE, 0, st>>>(A);
         if (kv) cudaEventRecord(kv[3], st);
-        if (b->nbI > 0) k_pairs<<<b->nbI, 128, 0, st>>>(A, b->d_blkI_first);
+        if (b->nbI > 0) k_pairs<<<std::min(b->nbI, b->pairs_grid), 128, 0, st>>>(A, b->d_blkI_first, b->nbI * 4);
         if (kv) cudaEventRecord(kv[4], st);
         k_solve<<<b->n, BA_TS, smem, st>>>(A, hs_doubles);
         if (kv) cudaEventRecord(kv[5], st);
@@ -1230,6 +1257,11 @@ int orbba_create(orbba_t** out, int device, int max_problems) {
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&b->done_ev, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&b->dl_stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+    if (ce == cudaSuccess) {
+        int per_sm = 0;
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs, 128, 0);
+        if (ce == cudaSuccess) b->pairs_grid = std::max(1, per_sm) * prop.multiProcessorCount;
+    }
     if (ce != cudaSuccess) { int rc = orbhost::check_cuda(ce, "orbba_create", __FILE__, __LINE__); orbba_free(b); return rc; }
     b->stream = b->own_stream;
     *out = b;
@@ -1370,7 +1402,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     const size_t o_eof = L.add(4 * (size_t)eofTot), o_pcnt = L.add(4 * (size_t)pairTot), o_poff = L.add(4 * (size_t)pairTot);
     const size_t o_pccnt = L.add(4 * (size_t)pcTot), o_pcoff = L.add(4 * (size_t)pcTot), o_pcfch = L.add(4 * (size_t)pcTot), o_pcnch = L.add(4 * (size_t)pcTot);
     const size_t o_cpair = L.add(4 * (size_t)chunkTot), o_cstart = L.add(4 * (size_t)chunkTot), o_clen = L.add(4 * (size_t)chunkTot);
-    const size_t o_irec = L.add(32 * 4 * (size_t)std::max(nbI, 1));
+    const size_t o_irec = L.add(32 * 4 * (size_t)std::max(nbI, 1)), o_pcount = L.add(256);
     const size_t o_tup = L.add(8 * (size_t)tupTot);
     const size_t o_pose_a = L.add(56 * Ptot), o_pose_b = L.add(56 * Ptot), o_pt_a = L.add(24 * Ltot), o_pt_b = L.add(24 * Ltot);
     const size_t o_err_a = L.add(16 * Etot), o_err_b = L.add(16 * Etot), o_level = L.add(Etot);
@@ -1468,7 +1500,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     A.pc_cnt = (int*)(D + o_pccnt); A.pc_off = (int*)(D + o_pcoff); A.pc_fchunk = (int*)(D + o_pcfch); A.pc_nchunk = (int*)(D + o_pcnch);
     A.free_pose = (const int*)(D + o_freepose);
     A.chunk_pair = (int*)(D + o_cpair); A.chunk_start = (int*)(D + o_cstart); A.chunk_len = (int*)(D + o_clen);
-    A.item_rec = (int4*)(D + o_irec);
+    A.item_rec = (int4*)(D + o_irec); A.pairs_counter = (int*)(D + o_pcount);
     A.tuples = (int2*)(D + o_tup);
     A.pose[0] = (double*)(D + o_pose_a); A.pose[1] = (double*)(D + o_pose_b); A.pt[0] = (double*)(D + o_pt_a); A.pt[1] = (double*)(D + o_pt_b);
     A.err[0] = (double*)(D + o_err_a); A.err[1] = (double*)(D + o_err_b); A.level = D + o_level;
