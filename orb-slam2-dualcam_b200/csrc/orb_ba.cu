@@ -768,9 +768,11 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
         for (int pid = warp; pid < P.nPairs; pid += BA_TS / 32) {
             if (A.pair_cnt[P.pair0 + pid] == 0) continue;
             double blk0 = 0, blk1 = 0;                     // entries lane and lane + 32
+            // chunk ranges of all camera pairs first (lane q holds camera pair q), so that their reads are in flight together
+            int my_nc = 0, my_first = 0;
+            if (lane < P.CC) { my_nc = A.pc_nchunk[P.pc0 + pid * P.CC + lane]; my_first = A.pc_fchunk[P.pc0 + pid * P.CC + lane]; }
             for (int combo = 0; combo < P.CC; combo++) {
-                const int pc = P.pc0 + pid * P.CC + combo;
-                const int nc = A.pc_nchunk[pc], first = A.pc_fchunk[pc];
+                const int nc = __shfl_sync(0xffffffffu, my_nc, combo), first = __shfl_sync(0xffffffffu, my_first, combo);
                 if (nc == 0) continue;
                 double n0 = 0, n1 = 0;
                 for (int c = 0; c < nc && first + c < nCh; c++) {
