@@ -252,8 +252,8 @@ def run_ours(args, rank, world, local_rank):
             torch.empty((nEt,), dtype=torch.uint8).pin_memory())
     # (Running LocalBA on a second stream next to extract + match was measured and is slower: 124 ms vs 81 ms per step, the two
     # working sets evict each other from L2.  One compute stream.)
-    stream = torch.cuda.Stream(dev)          # every kernel and event of the timed regions goes through this stream
-    copy_stream = torch.cuda.Stream(dev)     # end-to-end leg: BA uploads (host->device + index kernels), see below
+    stream = torch.cuda.Stream(dev, priority=-1)   # every kernel and event of the timed regions goes through this (high-priority) stream
+    copy_stream = torch.cuda.Stream(dev)     # end-to-end leg: BA uploads (host->device + index kernels, which yield to the compute stream), see below
     torch.cuda.set_stream(stream)
     opt.set_stream(stream)
     opt.upload(ba_prepared)                  # device-resident leg: the windows are uploaded (and indexed) once
