@@ -193,7 +193,7 @@ def run_reference(args, rank, world):
 def ba_bytes(problems, stats):
     """Algorithmic bytes of every BA kernel summed over the launches that do work: per problem, k_lin / k_build run
     once per LM iteration, the other four once per LM trial."""
-    tot = dict.fromkeys(["k_lin", "k_build", "k_trial_lm", "k_pairs", "k_solve", "k_back"], 0.0)
+    tot = dict.fromkeys(["k_lin", "k_build", "k_land", "k_pairs", "k_solve", "k_back"], 0.0)
     for p, st in zip(problems, stats):
         E, L = len(p["edge_pose"]), len(p["points"])
         free = p["pose_fixed"] == 0
@@ -208,7 +208,7 @@ def ba_bytes(problems, stats):
         C = K * (K + 1) // 2 * nC * nC + T // 256
         tot["k_lin"] += it * (E * (12 + 16 + 8 + 16 + 64) + L * 24 + P * 56)                 # ids, obs, info, err -> 64-byte edge record
         tot["k_build"] += it * (E * (64 + 8) + Ef * (64 + 8) + L * 72 + K * 336)              # records read once per landmark part and once per pose part
-        tot["k_trial_lm"] += tr * (Ef * (64 + 12 + 128 + 48) + L * 72)                        # k_trial: record -> {X Y Z 1/Z V VD} (128 B), v
+        tot["k_land"] += tr * (Ef * (64 + 12 + 128 + 48) + L * 72)                        # k_trial: record -> {X Y Z 1/Z V VD} (128 B), v
         tot["k_pairs"] += tr * (Ef * (128 + 48) + T * 8 + C * 288 + K * nC * 48)              # every 128-byte edge record read once
         tot["k_solve"] += tr * (C * 288 + K * (336 + 104) + K * nC * 96)
         tot["k_back"] += tr * (Ef * (64 + 12) + L * (96 + 24) + E * (36 + 16))

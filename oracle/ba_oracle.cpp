@@ -624,7 +624,7 @@ int orc_local_ba(const orc_ba_problem_t* p, int its1, int its2, double huber_del
     return 0;
 }
 
-// Optimizer::BundleAdjustment src/Optimizer.cc:70-248 (single optimize(nIterations); Huber sqrt(5.991) if robust; no outlier pass)
+// Optimizer::BundleAdjustment src/Optimizer.cc:70-248 (single optimize(nIterations); Huber thHuber2D = sqrt(3.99) if robust, :108; no outlier pass)
 int orc_global_ba(const orc_ba_problem_t* p, int iterations, double huber_delta, const volatile uint8_t* stop,
                   double* poses_out, double* points_out, orc_ba_stats_t* stats) {
     if (!p) return -1;

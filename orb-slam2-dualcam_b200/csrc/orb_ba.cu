@@ -14,10 +14,13 @@
 // advanced by the last CTA of the step, so the host never reads anything back between steps.  Everything is FP64 and
 // every sum has one owner and a fixed order (no floating-point atomics): results are bit-reproducible.
 //
-//   k_lin       thread / edge       residual, Huber weight; stores only the point in the camera frame + weights (64 B)   (per LM iteration)
-//   k_build     thread / landmark   Hll, bl ;  CTA / free pose: Hpp, bp  (Jacobians rebuilt from the 64-byte records)   (per LM iteration)
-//   k_pairs     warp / chunk of (edge, edge) tuples of one pose pair and camera pair: partial Schur product in "tJ space";
-//               warp / pose: Schur right-hand side                                                                      (per trial)
+//   k_lin, k_build   only on the first step of a round (Huber round, plain round): robust chi2 of the round's first estimate,
+//               outlier marking, and max |diag H| for computeLambdaInit -- exit at once on every other step
+//   k_land      CTA / group of whole landmarks (<= 128 edges): linearisation of every edge (residual, Huber weight, Jl), the
+//               landmark blocks Hll, bl, (Hll + lambda I)^-1, and per edge the 128-byte record {x y 1/z W V VD} + {r, VD bl};
+//               nothing Jacobian-sized is written, the per-edge intermediates never leave the SM                          (per trial)
+//   k_pairs     warp / chunk of (edge, edge) tuples of one pose pair and camera pair: partial Schur product in "tJ space"
+//               (the diagonal pairs carry Hpp with them: U (VD V^T - W I) U^T); warp / pose: bp and the Schur right-hand side  (per trial)
 //   k_solve     CTA / problem       reduced camera system in shared memory, LDL^T, pose increments, exp-map update
 //   k_back      thread / landmark   landmark increment, trial errors and chi2 of its edges; last CTA: LM decision
 // Blocks are laid out problem-major, so the CTAs resident at any time work on a handful of neighbouring problems and the
@@ -35,6 +38,8 @@
 #include "orb_ba_core.cuh"
 
 #define BA_TE 128              // threads per edge block
+#define BA_TG 128              // threads (= edge slots) per landmark-group block (k_land, k_back)
+#define BA_TAB 16              // (pose, camera) table entry: R[9] t[3] fx fy cx cy
 #define BA_TL 128              // threads per landmark block
 #define BA_TP 128              // threads per pose block (k_build)
 #define BA_CH 512              // tuples per chunk (k_pairs)
@@ -50,6 +55,7 @@ struct BAProb {                // static description of one problem inside the b
     int blkI0;                 // first k_pairs block of the problem
     int rt0, CC, pc0, ut0;     // first (pose, camera) rotation, nC * nC, first (pair, camera pair) slot, first (free pose, camera) slot
     int blkE0, nbE, blkL0, nbL;
+    int blkG0, nbG;            // landmark-group blocks of k_land
     long long tup0, eof0, hs_off;
 };
 
@@ -74,6 +80,7 @@ struct BABatch {               // kernel argument (by value)
     const int* pose_free;                       // [Ptot] global free index or -1
     const double *pose0, *pt0;
     const int *blkE_prob, *blkL_prob, *item_prob;
+    const int *blkG_prob, *blkG_l0, *blkG_nl;  // k_land block -> problem, first landmark (global), landmarks (whole landmarks, <= BA_TG edges; a landmark with more gets a block of its own)
     const int* free_pose;                       // [Ktot] global pose index of every free pose
     // index built on the device
     int* edge_of;                               // [free pose of the problem][landmark] -> edge << 2 | camera, or -1 (pose-major: the pair kernels read it coalesced)
@@ -87,12 +94,13 @@ struct BABatch {               // kernel argument (by value)
     double *pose[2], *pt[2], *err[2];
     unsigned char* level;
     double *er;                                 // per edge: X Y Z 1/Z W r0 r1 - (point in the camera frame, weights)
-    double *yr, *v;                             // per edge and trial: X Y Z 1/Z VD[6] - - (12), Yt bl in tJ space (6)
-    double *RT;                                 // per (pose, camera): rotation of ext_c * pose (9)
-    double *ut_u, *ut_y;                        // per (free pose, camera): Schur rhs partial in tJ space (6), Adj_c x_k (6)
+    double *yr, *rw;                            // per edge and trial: {x y 1/z W V[6] VD[6]} (16), {r0 r1 (VD bl)0 (VD bl)1} (4)
+    double *tab[2];                             // per estimate buffer and (pose, camera): [R | t] of ext_c * pose and the intrinsics (BA_TAB doubles, one 128-byte line)
+    double *ut_u, *ut_b, *ut_y;                 // per (free pose, camera): Schur rhs partial / bp partial in tJ space (6 each), Adj_c x_k (6)
+    int* rs_flag;                               // != 0: some problem starts a round on this step (k_lin / k_build have work)
     double *Hll, *bl;                           // per landmark: 6 / 3
     double *Hpp, *bp, *bs, *xp;                 // per free pose: 36 / 6 / 6 / 6
-    double *partial;                            // per chunk: 36
+    double *partial, *prhs;                     // per chunk: 36 ; per chunk of a diagonal pair: bp and Schur rhs partials in tJ space (6 + 6)
     double *partE, *partL;                      // per edge block: chi, active ; per landmark block: chi, scale
     double* Hs;                                 // reduced systems that do not fit in shared memory
     // outputs
@@ -179,7 +187,9 @@ __global__ void k_pair_scan(BABatch A) {
     if (p >= A.nProb) return;
     const BAProb P = A.prob[p];
     int off = 0, nc = 0;
-    for (int pid = 0; pid < P.nPairs; pid++) {
+    int pi = 0, pj = 0;                                    // the pair (pi <= pj) of slot pid
+    for (int pid = 0; pid < P.nPairs; pid++, pj++) {
+        if (pj == P.K) { pi++; pj = pi; }
         A.pair_off[P.pair0 + pid] = off;
         for (int q = 0; q < P.CC; q++) {
             const int pc = P.pc0 + pid * P.CC + q;
@@ -193,7 +203,7 @@ __global__ void k_pair_scan(BABatch A) {
                     A.chunk_len[P.chunk0 + nc] = min(BA_CH, c - s);
                     int4* rec = A.item_rec + 2 * ((size_t)P.blkI0 * 4 + nc);      // everything the chunk's warp needs, in one 32-byte read
                     rec[0] = make_int4(p, (int)(P.tup0 + off + s), min(BA_CH, c - s), P.chunk0 + nc);
-                    rec[1] = make_int4(P.c0 + q / P.nC, P.c0 + q % P.nC, 0, 0);
+                    rec[1] = make_int4(P.c0 + q / P.nC, P.c0 + q % P.nC, pi == pj, P.rt0 + (A.free_pose[P.k0 + pj] - P.p0) * P.nC + q % P.nC);   // .z: diagonal pair (its tuples are (e, e): Hpp rides along); .w: projection-table entry of (pose j, camera b)
                 }
                 nc++;
             }
@@ -234,6 +244,47 @@ __global__ void k_pair_fill(BABatch A, const int* blkP_prob, const int* blkP_fir
     }
 }
 
+// The projection of every edge goes through a per-(pose, camera) table: T = ext_c * pose as [R | t] plus the camera intrinsics
+// (se3quat.h:104-128 composition, then toRotationMatrix), 16 doubles = one 128-byte line.  One definition of the reprojection and of
+// the residual for every kernel of this file, so that they all produce the same bits.  R is also the factor of
+// Jl = -1/z tmp R(ext_c pose) (types_six_dof_expmap.cpp:155-159).  tab[b] always belongs to pose[b].
+__device__ __forceinline__ void tab_entry(const double* cam, const double* pose7, double* o) {
+    double q[4], Rm[9], t[3];
+    q_mul(cam + 4, pose7, q);
+    q_normalize(q);
+    q_to_matrix(q, Rm);
+    se3_map(cam + 4, pose7 + 4, t);
+#pragma unroll
+    for (int k = 0; k < 9; k++) o[k] = Rm[k];
+    o[9] = t[0]; o[10] = t[1]; o[11] = t[2];
+    o[12] = cam[0]; o[13] = cam[1]; o[14] = cam[2]; o[15] = cam[3];
+}
+__device__ __forceinline__ void tab_project(const double* T, const double* X, double* pc) {
+    pc[0] = fma(T[0], X[0], fma(T[1], X[1], fma(T[2], X[2], T[9])));
+    pc[1] = fma(T[3], X[0], fma(T[4], X[1], fma(T[5], X[2], T[10])));
+    pc[2] = fma(T[6], X[0], fma(T[7], X[1], fma(T[8], X[2], T[11])));
+}
+__device__ __forceinline__ void tab_error(const double* pc, const double* K4, double ox, double oy, double* e2) {   // K4 = fx fy cx cy
+    e2[0] = ox - fma(pc[0] / pc[2], K4[0], K4[2]);
+    e2[1] = oy - fma(pc[1] / pc[2], K4[1], K4[3]);
+}
+__device__ __forceinline__ void write_tab(const BABatch& A, const BAProb& P, const double* pose, double* tab, int tid, int nthreads) {
+    for (int i = tid; i < P.nP * P.nC; i += nthreads) {
+        const int pl = i / P.nC, cl = i - pl * P.nC;
+        double o[BA_TAB];
+        tab_entry(A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + cl), pose + 7 * (size_t)(P.p0 + pl), o);
+        double2* d = reinterpret_cast<double2*>(tab + BA_TAB * (size_t)(P.rt0 + i));
+#pragma unroll
+        for (int k = 0; k < BA_TAB / 2; k++) d[k] = make_double2(o[2 * k], o[2 * k + 1]);
+    }
+}
+// [R | t] of an entry: six 128-bit gathers.  The intrinsics are read from the camera block instead (a window has two or three cameras,
+// so those loads are broadcasts, while the table entries of a warp's edges lie in up to 32 different lines)
+__device__ __forceinline__ void load_tab(const double* T, double* o) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const double2 v = reinterpret_cast<const double2*>(T)[k]; o[2 * k] = v.x; o[2 * k + 1] = v.y; }
+}
+
 // ------------------------------------------------------------------------------------------------ reset
 __global__ void k_reset(BABatch A, int stopped0) {
     const int b = blockIdx.x;
@@ -247,6 +298,8 @@ __global__ void k_reset(BABatch A, int stopped0) {
     // poses / points: strided over the problem's edge blocks (at least one block exists per problem)
     for (int i = lb * BA_TE + tid; i < 7 * P.nP; i += P.nbE * BA_TE) { const double v = A.pose0[7 * (size_t)P.p0 + i]; A.pose[0][7 * (size_t)P.p0 + i] = v; A.pose[1][7 * (size_t)P.p0 + i] = v; }
     for (int i = lb * BA_TE + tid; i < 3 * P.nL; i += P.nbE * BA_TE) { const double v = A.pt0[3 * (size_t)P.l0 + i]; A.pt[0][3 * (size_t)P.l0 + i] = v; A.pt[1][3 * (size_t)P.l0 + i] = v; }
+    if (lb == 0) { write_tab(A, P, A.pose0, A.tab[0], tid, BA_TE); write_tab(A, P, A.pose0, A.tab[1], tid, BA_TE); }
+    if (b == 0 && tid == 0) *A.rs_flag = 1;
     if (lb == 0 && tid == 0) {
         BAState& S = A.state[p];
         const int nChunks = S.nChunks, nTuples = S.nTuples;
@@ -297,10 +350,11 @@ __device__ __forceinline__ void load6(const double* p, double* o) {   // 48-byte
 // ------------------------------------------------------------------------------------------------ k_lin
 __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
     __shared__ double red[BA_TE / 32];
+    if (*A.rs_flag == 0) return;                      // no problem starts a round on this step
     const int b = blockIdx.x;
     const int p = A.blkE_prob[b];
     const BAState& S = A.state[p];
-    if (S.done || !S.need_build) return;
+    if (S.done || !S.round_start) return;
     const BAProb& P = A.prob[p];
     const int tid = threadIdx.x;
     const int e = P.e0 + (b - P.blkE0) * BA_TE + tid;
@@ -308,25 +362,12 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
     const int cur = S.cur;
     const bool robust = S.round == 0 && A.delta > 0;
     const double delta = A.delta, dsqr = delta * delta;
-    if (b == P.blkE0) {   // rotation of (camera extrinsic * rig pose) for every (pose, camera) of the problem
-        for (int i = tid; i < P.nP * P.nC; i += BA_TE) {
-            const int pl = i / P.nC, cl = i - pl * P.nC;
-            const double* c = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + cl);
-            double q[4], Rm[9];
-            q_mul(c + 4, A.pose[cur] + 7 * (size_t)(P.p0 + pl), q);
-            q_normalize(q);
-            q_to_matrix(q, Rm);
-            double* o = A.RT + 9 * (size_t)(P.rt0 + i);
-#pragma unroll
-            for (int k = 0; k < 9; k++) o[k] = Rm[k];
-        }
-    }
     double chi = 0, act = 0;
     if (valid) {
-        const double* c = A.cam + BA_CAM_STRIDE * (size_t)A.e_cam[e];
+        const double* T = A.tab[cur] + BA_TAB * (size_t)(P.rt0 + (A.e_pose[e] - P.p0) * P.nC + (A.e_cam[e] - P.c0));
         const double w = A.e_info[e];
         double pc[3];
-        edge_project(A.pose[cur] + 7 * (size_t)A.e_pose[e], A.pt[cur] + 3 * (size_t)A.e_pt[e], c, pc);
+        tab_project(T, A.pt[cur] + 3 * (size_t)A.e_pt[e], pc);
         int lvl = A.level[e];
         if (S.mark) {   // e->chi2() > th || !e->isDepthPositive() -> level 1  (src/Optimizer.cc:598-613); chi2 from the errors computed last
             const double l0 = A.err[S.last][2 * e], l1 = A.err[S.last][2 * e + 1];
@@ -338,7 +379,7 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
         if (!lvl) {
             double er[2];
             if (S.round_start) {
-                edge_error(pc, c, A.e_obs + 2 * (size_t)e, er);
+                tab_error(pc, A.cam + BA_CAM_STRIDE * (size_t)A.e_cam[e], A.e_obs[2 * (size_t)e], A.e_obs[2 * (size_t)e + 1], er);
                 A.err[cur][2 * e] = er[0]; A.err[cur][2 * e + 1] = er[1];
                 const double c2 = (er[0] * er[0] + er[1] * er[1]) * w;
                 chi = robust ? huber_rho0(c2, delta, dsqr) : c2;
@@ -376,11 +417,12 @@ template <int PART>
 __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks, const int* pose_prob) {
     __shared__ double s_N[27], s_W[(BA_TP / 32) * 27];
     const int tid = threadIdx.x;
+    if (*A.rs_flag == 0) return;                      // only the first step of a round needs max |diag H| (computeLambdaInit)
     if (PART == 0) {
         const int b = blockIdx.x;
         const int p = A.blkL_prob[b];
         const BAState& S = A.state[p];
-        if (S.done || !S.need_build) return;
+        if (S.done || !S.round_start) return;
         const BAProb& P = A.prob[p];
         const int l = P.l0 + (b - P.blkL0) * BA_TL + tid;
         double md = 0;
@@ -392,7 +434,7 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
                 const int cg = A.e_cam[e];
                 const double* c = A.cam + BA_CAM_STRIDE * (size_t)cg;
                 edge_tj(r[0], r[1], r[2], r[3], c[0], c[1], tJ, t4);
-                edge_jl(t4, A.RT + 9 * (size_t)(P.rt0 + (A.e_pose[e] - P.p0) * P.nC + (cg - P.c0)), Jl);
+                edge_jl(t4, A.tab[S.cur] + BA_TAB * (size_t)(P.rt0 + (A.e_pose[e] - P.p0) * P.nC + (cg - P.c0)), Jl);
                 const double a0 = Jl[0], a1 = Jl[1], a2 = Jl[2], c0 = Jl[3], c1 = Jl[4], c2 = Jl[5], W = r[4], r0 = r[5], r1 = r[6];
                 h00 += (a0 * a0 + c0 * c0) * W; h01 += (a0 * a1 + c0 * c1) * W; h02 += (a0 * a2 + c0 * c2) * W;
                 h11 += (a1 * a1 + c1 * c1) * W; h12 += (a1 * a2 + c1 * c2) * W; h22 += (a2 * a2 + c2 * c2) * W;
@@ -415,7 +457,7 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
     const int kg = blockIdx.x;                         // global free-pose index
     const int p = pose_prob[kg];
     const BAState& S = A.state[p];
-    if (S.done || !S.need_build) return;
+    if (S.done || !S.round_start) return;
     const BAProb& P = A.prob[p];
     const int k = kg - P.k0;
     const int pidd = k * P.K - k * (k - 1) / 2;         // diagonal pair (k, k)
@@ -483,69 +525,180 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
     }
 }
 
-// ------------------------------------------------------------------------------------------------ k_trial
-// thread per edge (per LM trial).  The 6x3 block of an edge in tJ space factors through the 2-d residual:
-//     Bt_e = tJ_e^T W_e Jl_e = U_e V_e            U_e = tJ_e^T (6x2, a function of X Y Z 1/Z and the camera),  V_e = W_e Jl_e (2x3)
-//     Yt_e = Bt_e (Hll + lambda I)^-1 = U_e VD_e   VD_e = V_e D_l (2x3)
-// so the Schur product of a tuple is  Yt_a Bt_b^T = U_a (VD_a V_b^T) U_b^T  and only VD_e (6 doubles) has to be materialised per trial:
-//     yr[e] = { X/Z, Y/Z, 1/Z, -, V_e[6], VD_e[6] }  (128 bytes = 4 sectors; a tuple gathers 80 bytes of each of its two edges:
-//              the three ratios + VD of edge a, the three ratios + V of edge b, three sectors each)
-//     v[e]  = Yt_e bl = U_e (VD_e bl)
-// staged in shared memory and written out coalesced.
+// ------------------------------------------------------------------------------------------------ k_land
+// One CTA = a group of WHOLE landmarks with at most BA_TG edges between them (edges are stored grouped by landmark), one LM trial.
+// Everything that is local to a landmark happens here without leaving the SM:
+//   phase A  thread / edge      reprojection at pose[cur], pt[cur]; residual (the errors of the accepted estimate, err[cur]); Huber
+//                               weight; Jl = -1/z tmp R(ext_c pose) (types_six_dof_expmap.cpp:136-159); the edge's terms of Hll, bl
+//   phase B  thread / landmark  Hll, bl summed in edge order (fixed order, no atomics); D = (Hll + lambda I)^-1, D bl
+//   phase C  thread / edge      the 6x3 block of an edge in tJ space factors through the 2-d residual:
+//                                   Bt_e = tJ_e^T W_e Jl_e = U_e V_e          U_e = tJ_e^T (6x2, polynomials in x = X/Z, y = Y/Z, w = 1/Z),  V_e = W_e Jl_e (2x3)
+//                                   Yt_e = Bt_e D = U_e VD_e                  VD_e = V_e D (2x3)
+//                               so the Schur product of a tuple is U_a (VD_a V_b^T) U_b^T and the per-edge record is
+//                                   yr[e] = { x, y, w, W, V[6], VD[6] }   (128 bytes = 4 sectors; k_pairs gathers x y w W + VD of edge a and
+//                                                                           x y w W + V of edge b, three sectors each; k_back reads x y w W + V)
+//                                   rw[e] = { r0, r1, (VD bl)0, (VD bl)1 } (bp and the Schur right-hand side, summed per pose in k_pairs)
+//                               staged in shared memory and written out coalesced.
+// A landmark observed by more than BA_TG key frames has a block of its own (`big` path: strided loops and block reductions).
 #define BA_YR 16
-#define BA_YRS 18                 // row stride of the record in k_trial's staging buffer
-__global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
-    __shared__ __align__(16) double s_blk[BA_TE * BA_YRS];
-    const int b = blockIdx.x;
-    if (b == 0 && threadIdx.x == 0) *A.pairs_counter = 0;       // work queue of the k_pairs launch that follows
-    const int p = A.blkE_prob[b];
+#define BA_YRS 18                 // row stride of the record in the staging buffer (a 128-byte stride would put every lane on the same banks)
+
+struct EdgeLin { double x, y, iz, W, r0, r1, Jl[6]; bool free_pose; };
+
+// linearisation of edge e at the accepted estimate (level-1 edges and their zero weights included)
+__device__ __forceinline__ void edge_lin(const BABatch& A, const BAProb& P, int e, int cur, bool robust, double delta, double dsqr,
+                                         const double* tb, int ts, EdgeLin& L) {
+    const int pg = A.e_pose[e], cg = A.e_cam[e];
+    double T[12], pc[3];
+    const double* K4 = A.cam + BA_CAM_STRIDE * (size_t)cg;
+    load_tab(tb + ts * ((pg - P.p0) * P.nC + (cg - P.c0)), T);
+    tab_project(T, A.pt[cur] + 3 * (size_t)A.e_pt[e], pc);
+    L.free_pose = A.pose_free[pg] >= 0;
+    if (A.level[e]) {                                     // removed from the optimisation (src/Optimizer.cc:598-613): contributes nothing
+        L.x = 0; L.y = 0; L.iz = 1; L.W = 0; L.r0 = 0; L.r1 = 0;
+#pragma unroll
+        for (int j = 0; j < 6; j++) L.Jl[j] = 0;
+        return;
+    }
+    const double w = A.e_info[e];
+    const double2 er = reinterpret_cast<const double2*>(A.err[cur])[e];
+    double wr = 1.0;
+    if (robust) {
+        const double c2 = (er.x * er.x + er.y * er.y) * w;
+        if (c2 > dsqr) wr = delta / sqrt(c2);
+    }
+    const double iz = 1.0 / pc[2];
+    L.x = pc[0] * iz; L.y = pc[1] * iz; L.iz = iz; L.W = wr * w; L.r0 = -w * er.x * wr; L.r1 = -w * er.y * wr;
+    const double t00 = -iz * K4[0], t02 = iz * iz * pc[0] * K4[0], t11 = -iz * K4[1], t12 = iz * iz * pc[1] * K4[1];
+    const double t4[4] = {t00, t02, t11, t12};
+    edge_jl(t4, T, L.Jl);
+}
+__device__ __forceinline__ void edge_terms(const EdgeLin& L, double* t9) {   // Jl^T W Jl (upper triangle) and Jl^T r
+    const double a0 = L.Jl[0], a1 = L.Jl[1], a2 = L.Jl[2], c0 = L.Jl[3], c1 = L.Jl[4], c2 = L.Jl[5], W = L.W;
+    t9[0] = (a0 * a0 + c0 * c0) * W; t9[1] = (a0 * a1 + c0 * c1) * W; t9[2] = (a0 * a2 + c0 * c2) * W;
+    t9[3] = (a1 * a1 + c1 * c1) * W; t9[4] = (a1 * a2 + c1 * c2) * W; t9[5] = (a2 * a2 + c2 * c2) * W;
+    t9[6] = a0 * L.r0 + c0 * L.r1; t9[7] = a1 * L.r0 + c1 * L.r1; t9[8] = a2 * L.r0 + c2 * L.r1;
+}
+// d9 = { D (6, symmetric), D bl (3) } -> the record of the edge
+__device__ __forceinline__ void edge_record(const EdgeLin& L, const double* d9, double* yr, double* rw) {
+    yr[0] = L.x; yr[1] = L.y; yr[2] = L.iz; yr[3] = L.free_pose ? L.W : 0.0;
+    rw[0] = L.r0; rw[1] = L.r1;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        double x0 = L.W * L.Jl[3 * k], x1 = L.W * L.Jl[3 * k + 1], x2 = L.W * L.Jl[3 * k + 2];
+        if (!L.free_pose) { x0 = 0; x1 = 0; x2 = 0; }     // no pose block: the edge is in no tuple, k_back skips it
+        yr[4 + 3 * k] = x0; yr[5 + 3 * k] = x1; yr[6 + 3 * k] = x2;
+        yr[10 + 3 * k] = x0 * d9[0] + x1 * d9[1] + x2 * d9[2];
+        yr[11 + 3 * k] = x0 * d9[1] + x1 * d9[3] + x2 * d9[4];
+        yr[12 + 3 * k] = x0 * d9[2] + x1 * d9[4] + x2 * d9[5];
+        rw[2 + k] = x0 * d9[6] + x1 * d9[7] + x2 * d9[8];
+    }
+}
+
+__global__ void __launch_bounds__(BA_TG, 7) k_land(BABatch A) {
+    __shared__ __align__(16) double s_blk[BA_TG * BA_YRS];   // phase A: 9 terms per edge; phase C: record staging
+    __shared__ __align__(16) double s_lm[BA_TG * 9];         // per landmark of the group: D (6), D bl (3)
+    __shared__ double red[BA_TG / 32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (b == 0 && tid == 0) { *A.pairs_counter = 0; *A.rs_flag = 0; }   // work queue of the k_pairs launch that follows; k_lin / k_build are done with the flag
+    const int p = A.blkG_prob[b];
     const BAState& S = A.state[p];
     if (S.done) return;
     const BAProb& P = A.prob[p];
-    const int tid = threadIdx.x;
-    const int ebase = P.e0 + (b - P.blkE0) * BA_TE;
-    const int nv = min(BA_TE, P.e0 + P.nE - ebase);
-    const int e = ebase + tid;
+    const int l0 = A.blkG_l0[b], nl = A.blkG_nl[b];
+    const int e0 = A.pt_off[l0], ne = A.pt_off[l0 + nl] - e0;
+    const int cur = S.cur;
     const double lambda = lambda_eff(S);
-    double yr[BA_YR];
+    const bool robust = S.round == 0 && A.delta > 0;
+    const double delta = A.delta, dsqr = delta * delta;
+    // the (pose, camera) table is gathered straight from global memory (one 128-byte line per edge, L1 / L2 hits): a per-CTA copy in
+    // shared memory was measured slower (the kernel is bound by LSU wavefronts, and the copy adds 40 lines per 128 edges)
+    const int ts = BA_TAB;
+    const double* tb = A.tab[cur] + BA_TAB * (size_t)P.rt0;
+    if (ne <= BA_TG) {
+        // ---- phase A
+        EdgeLin L;
+        const int e = e0 + tid;
+        if (tid < ne) {
+            edge_lin(A, P, e, cur, robust, delta, dsqr, tb, ts, L);
+            double t9[9];
+            edge_terms(L, t9);
 #pragma unroll
-    for (int q = 0; q < BA_YR; q++) yr[q] = 0;
-    double vv[6] = {0, 0, 0, 0, 0, 0};
-    if (tid < nv && A.pose_free[A.e_pose[e]] >= 0) {
-        double r[8], t4[4], tJ[12], Jl[6], d[6];
-        load8(A.er + 8 * (size_t)e, r);
-        const int cg = A.e_cam[e], l = A.e_pt[e];
-        const double* c = A.cam + BA_CAM_STRIDE * (size_t)cg;
-        edge_tj(r[0], r[1], r[2], r[3], c[0], c[1], tJ, t4);
-        edge_jl(t4, A.RT + 9 * (size_t)(P.rt0 + (A.e_pose[e] - P.p0) * P.nC + (cg - P.c0)), Jl);
-        landmark_dinv(A.Hll + 6 * (size_t)l, lambda, d);
-        const double W = r[4];
-        const double b0 = A.bl[3 * (size_t)l], b1 = A.bl[3 * (size_t)l + 1], b2 = A.bl[3 * (size_t)l + 2];
-        yr[0] = r[0] * r[3]; yr[1] = r[1] * r[3]; yr[2] = r[3];      // x/z, y/z, 1/z: U_e = [fx u0 | fy u1] with u0, u1 polynomials in these three
-        double w[2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const double x0 = W * Jl[3 * k], x1 = W * Jl[3 * k + 1], x2 = W * Jl[3 * k + 2];
-            const double y0 = x0 * d[0] + x1 * d[1] + x2 * d[2], y1 = x0 * d[1] + x1 * d[3] + x2 * d[4], y2 = x0 * d[2] + x1 * d[4] + x2 * d[5];
-            yr[4 + 3 * k] = x0; yr[5 + 3 * k] = x1; yr[6 + 3 * k] = x2;
-            yr[10 + 3 * k] = y0; yr[11 + 3 * k] = y1; yr[12 + 3 * k] = y2;
-            w[k] = y0 * b0 + y1 * b1 + y2 * b2;
+            for (int q = 0; q < 9; q++) s_blk[9 * tid + q] = t9[q];
         }
+        __syncthreads();
+        // ---- phase B
+        if (tid < nl) {
+            const int l = l0 + tid;
+            double h[9];
 #pragma unroll
-        for (int i = 0; i < 6; i++) vv[i] = tJ[i] * w[0] + tJ[6 + i] * w[1];
+            for (int q = 0; q < 9; q++) h[q] = 0;
+            for (int i = A.pt_off[l] - e0; i < A.pt_off[l + 1] - e0; i++) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) h[q] += s_blk[9 * i + q];
+            }
+            double* H = A.Hll + 6 * (size_t)l;
+#pragma unroll
+            for (int q = 0; q < 6; q++) H[q] = h[q];
+            A.bl[3 * (size_t)l] = h[6]; A.bl[3 * (size_t)l + 1] = h[7]; A.bl[3 * (size_t)l + 2] = h[8];
+            double d[6];
+            landmark_dinv(h, lambda, d);
+            double* o = s_lm + 9 * tid;
+#pragma unroll
+            for (int q = 0; q < 6; q++) o[q] = d[q];
+            o[6] = d[0] * h[6] + d[1] * h[7] + d[2] * h[8]; o[7] = d[1] * h[6] + d[3] * h[7] + d[4] * h[8]; o[8] = d[2] * h[6] + d[4] * h[7] + d[5] * h[8];
+        }
+        __syncthreads();
+        // ---- phase C
+        double yr[BA_YR], rw[4];
+        if (tid < ne) {
+            edge_record(L, s_lm + 9 * (A.e_pt[e] - l0), yr, rw);
+#pragma unroll
+            for (int q = 0; q < BA_YR / 2; q++) reinterpret_cast<double2*>(s_blk + BA_YRS * tid)[q] = make_double2(yr[2 * q], yr[2 * q + 1]);
+        }
+        __syncthreads();
+        for (int i = tid; i < (BA_YR / 2) * ne; i += BA_TG)
+            reinterpret_cast<double2*>(A.yr + BA_YR * (size_t)e0)[i] = reinterpret_cast<const double2*>(s_blk + BA_YRS * (i >> 3))[i & 7];
+        if (tid < ne) {
+            double2* o = reinterpret_cast<double2*>(A.rw + 4 * (size_t)e);
+            o[0] = make_double2(rw[0], rw[1]); o[1] = make_double2(rw[2], rw[3]);
+        }
+        return;
     }
-    // coalesced write-out through shared memory: yr, then v.  Rows of 18 doubles (a 128-byte row stride would put every lane on the
-    // same banks): 16-byte stores by the owner, 16-byte reads by consecutive lanes, both at most 2-way conflicted
+    // ---- a single landmark with more than BA_TG edges (nl == 1)
+    double h[9];
 #pragma unroll
-    for (int q = 0; q < BA_YR / 2; q++) reinterpret_cast<double2*>(s_blk + BA_YRS * tid)[q] = make_double2(yr[2 * q], yr[2 * q + 1]);
-    __syncthreads();
-    for (int i = tid; i < (BA_YR / 2) * nv; i += BA_TE)
-        reinterpret_cast<double2*>(A.yr + BA_YR * (size_t)ebase)[i] = reinterpret_cast<const double2*>(s_blk + BA_YRS * (i >> 3))[i & 7];
-    __syncthreads();
+    for (int q = 0; q < 9; q++) h[q] = 0;
+    for (int i = tid; i < ne; i += BA_TG) {
+        EdgeLin L;
+        edge_lin(A, P, e0 + i, cur, robust, delta, dsqr, tb, ts, L);
+        double t9[9];
+        edge_terms(L, t9);
 #pragma unroll
-    for (int q = 0; q < 6; q++) s_blk[6 * tid + q] = vv[q];
-    __syncthreads();
-    for (int i = tid; i < 3 * nv; i += BA_TE) reinterpret_cast<double2*>(A.v + 6 * (size_t)ebase)[i] = reinterpret_cast<const double2*>(s_blk)[i];
+        for (int q = 0; q < 9; q++) h[q] += t9[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 9; q++) h[q] = block_sum<BA_TG / 32>(h[q], red);
+    if (tid == 0) {
+        double* H = A.Hll + 6 * (size_t)l0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) H[q] = h[q];
+        A.bl[3 * (size_t)l0] = h[6]; A.bl[3 * (size_t)l0 + 1] = h[7]; A.bl[3 * (size_t)l0 + 2] = h[8];
+    }
+    double d9[9];
+    landmark_dinv(h, lambda, d9);
+    d9[6] = d9[0] * h[6] + d9[1] * h[7] + d9[2] * h[8]; d9[7] = d9[1] * h[6] + d9[3] * h[7] + d9[4] * h[8]; d9[8] = d9[2] * h[6] + d9[4] * h[7] + d9[5] * h[8];
+    for (int i = tid; i < ne; i += BA_TG) {
+        EdgeLin L;
+        edge_lin(A, P, e0 + i, cur, robust, delta, dsqr, tb, ts, L);
+        double yr[BA_YR], rw[4];
+        edge_record(L, d9, yr, rw);
+        double2* o = reinterpret_cast<double2*>(A.yr + BA_YR * (size_t)(e0 + i));
+#pragma unroll
+        for (int q = 0; q < BA_YR / 2; q++) o[q] = make_double2(yr[2 * q], yr[2 * q + 1]);
+        double2* o2 = reinterpret_cast<double2*>(A.rw + 4 * (size_t)(e0 + i));
+        o2[0] = make_double2(rw[0], rw[1]); o2[1] = make_double2(rw[2], rw[3]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ k_pairs
@@ -553,29 +706,39 @@ __global__ void __launch_bounds__(BA_TE) k_trial(BABatch A) {
 //   items [0, nChunksMax): a chunk of <= BA_CH (edge a, edge b) tuples of ONE pose pair (i, j) and ONE camera pair (ca, cb):
 //     partial 6x6 of  sum Yt_a Bt_b^T = sum U_a (VD_a V_b^T) U_b^T  (the Schur product before the camera adjoints, which k_solve
 //     applies once per camera pair).  Per tuple 80 bytes of yr[a] and 80 bytes of yr[b] are gathered; U_a and U_b are rebuilt from
-//     X Y Z 1/Z with the chunk's constants (intrinsics of ca / cb).
-//   items [nChunksMax, nChunksMax + K): free pose k, per camera c:  u_(k,c) = sum_e v_e   (Schur right-hand side in tJ space)
-#define BA_STAGE_A (16 * 80)
-#define BA_STAGE_BYTES (2 * BA_STAGE_A)          // one batch of 16 tuples
+//     x y w with the chunk's constants (intrinsics of ca / cb).  The tuples of a diagonal pair (i, i) are (e, e), one per edge of
+//     pose i: there the 2x2 core is VD_e V_e^T - W_e I, i.e. the chunk sum is (Schur product) - Hpp_i in tJ space, so that the pose
+//     block Hpp = sum tJ^T W tJ (block_solver.hpp:100-134 via constructQuadraticForm) needs no pass of its own.
+//   items [nChunksMax, nChunksMax + K): free pose k, per camera c:  sum_e U_e r_e (bp) and sum_e U_e (VD_e bl) (Schur right-hand
+//     side), both in tJ space
+#define BA_STAGE_A (16 * 80)                     // edge a of 16 tuples: x y w W VD[6]
+#define BA_STAGE_BYTES (BA_STAGE_A + 16 * 32)    // + edge b: x y w W  (diagonal pairs: r0 r1 (VD bl)0 (VD bl)1 of the same edge)
 #define BA_NSTAGE 3
-// Persistent warps: the grid holds as many CTAs as fit the device, every warp walks the item list with a fixed stride (which warp computes a
-// chunk does not change its result).  While a chunk is being reduced, the record of the warp's next item is already in registers and the
+// Persistent warps: the grid holds as many CTAs as fit the device, every warp pulls items from a queue (which warp computes a chunk
+// does not change its result).  While a chunk is being reduced, the record of the warp's next item is already in registers and the
 // next chunk's tuple list is on its way to shared memory, so only the first item of a warp pays the start-up round trips.
-__global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_first, int n_items) {
+// (A tensor-core form of the batch -- operand columns A_t = U'_a M^_t, B_t = U'_b exchanged through shared memory and summed with
+// mma.sync.m8n8k4.f64, DMMA.884 -- was measured at the same chunk size: 14.1 instead of 13.4 ms per 15 launches.  The FP64 FMA pipe and the
+// DMMA path have the same peak on B200, tools/microbench.cu: 62 / 64 FMA per clock and SM; the kernel is bound by LSU wavefronts -- one
+// per gathered sector plus the shared-memory reads -- and the operand exchange adds three per tuple.)
+__global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, int n_items) {
     __shared__ __align__(16) unsigned char s_stage[4 * BA_NSTAGE * BA_STAGE_BYTES];   // per warp: BA_NSTAGE stages
     __shared__ int2 s_tup[4 * BA_CH];                                                  // per warp: the chunk's tuple list
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane & 1, slot = lane >> 1;
     unsigned char* stage0 = s_stage + (size_t)warp * BA_NSTAGE * BA_STAGE_BYTES;
     int2* tup = s_tup + warp * BA_CH;
-    // piece g = k * 32 + lane of a batch (160 pieces of 16 bytes: 16 x 5 of edge a, then 16 x 5 of edge b); what does not depend on
-    // the batch is fixed per lane here: tuple slot, which edge of the tuple, offset inside the 128-byte record
-    int p_tl[5], p_src[5];
+    // piece g = k * 32 + lane of a batch (112 pieces of 16 bytes: 16 x 5 of edge a, then 16 x 2 of edge b); what does not depend on
+    // the batch is fixed per lane here: tuple slot, which edge of the tuple, offset inside the 128-byte record.  Edge a brings three
+    // sectors (x y w W | VD), edge b ONE (x y w W): V_b = W Jl_b is rebuilt from them and the rotation of (pose j, camera b), which
+    // is a constant of the chunk -- four L2 sectors per tuple instead of six (the kernel is bound by the L2 gathers).
+    int p_tl[4], p_src[4];
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
-        const int g = k * 32 + lane, side = g >= 80, gg = g - 80 * side, tl = gg / 5, part = gg - tl * 5;
-        p_tl[k] = tl | (side << 8);
-        p_src[k] = 2 * part + ((!side && part >= 2) ? 6 : 0);        // edge a: doubles 0..3 and 10..15 (VD); edge b: doubles 0..9 (V)
+    for (int k = 0; k < 4; k++) {
+        const int g = k * 32 + lane, side = g >= 80;
+        const int tl = side ? (g - 80) >> 1 : g / 5, part = side ? (g - 80) & 1 : g - 5 * (g / 5);
+        p_tl[k] = g < 112 ? (tl | (side << 8)) : 0xffff;
+        p_src[k] = side ? 2 * part : (part < 2 ? 2 * part : 6 + 2 * part);     // edge a: doubles 0..3 and 10..15 (VD); edge b: doubles 0..3
     }
     auto stage_tuples = [&](const int4& r) {                          // one cp.async group: the tuple list of chunk record r
         const int2* T = A.tuples + r.y;
@@ -583,7 +746,7 @@ __global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_fir
         for (int t = lane; t < r.z; t += 32) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tdst + 8u * t), "l"(T + t) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // dynamic item queue (the counter is zeroed by k_trial, which precedes this kernel in every step)
+    // dynamic item queue (the counter is zeroed by k_land, which precedes this kernel in every step)
     auto grab = [&]() { int v = 0; if (lane == 0) v = atomicAdd(A.pairs_counter, 1); return __shfl_sync(0xffffffffu, v, 0); };
     int it = grab();
     int4 rec0 = make_int4(0, 0, 0, 0), rec1 = rec0;
@@ -596,137 +759,136 @@ __global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_fir
         if (nxt < n_items) { nx0 = A.item_rec[2 * (size_t)nxt]; nx1 = A.item_rec[2 * (size_t)nxt + 1]; }
         const int4 r0 = rec0, r1 = rec1;
         rec0 = nx0; rec1 = nx1;
-        if (r0.z > 0) {
-            // chunk item: a <= BA_CH-tuple chunk of one (pose pair, camera pair); the record holds {problem, first tuple, tuples, chunk}
-            const int len = r0.z, ch = r0.w;
-            const int done = A.state[r0.x].done;
-            const double fxa = A.cam[BA_CAM_STRIDE * (size_t)r1.x], fya = A.cam[BA_CAM_STRIDE * (size_t)r1.x + 1];
-            const double fxb = A.cam[BA_CAM_STRIDE * (size_t)r1.y], fyb = A.cam[BA_CAM_STRIDE * (size_t)r1.y + 1];
-            if (!tup_ready) stage_tuples(r0);
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (r0.z <= 0) continue;                                      // unused chunk slot
+        // chunk item: a <= BA_CH-tuple chunk of one (pose pair, camera pair); the record holds {problem, first tuple, tuples, chunk}
+        const int len = r0.z, ch = r0.w;
+        const int done = A.state[r0.x].done;
+        const bool diag = r1.z != 0;
+        const double fxa = A.cam[BA_CAM_STRIDE * (size_t)r1.x], fya = A.cam[BA_CAM_STRIDE * (size_t)r1.x + 1];
+        const double fxb = A.cam[BA_CAM_STRIDE * (size_t)r1.y], fyb = A.cam[BA_CAM_STRIDE * (size_t)r1.y + 1];
+        // R(ext_cb * pose_j) at the accepted estimate: Jl_b = -1/z tmp R (types_six_dof_expmap.cpp:155-159)
+        const double* Rb = A.tab[A.state[r0.x].cur] + BA_TAB * (size_t)r1.w;
+        double Rm[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) Rm[q] = Rb[q];
+        if (!tup_ready) stage_tuples(r0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        tup_ready = false;
+        const bool next_chunk = nx0.z > 0;
+        if (done) {
+            if (next_chunk) { stage_tuples(nx0); tup_ready = true; }
+            continue;
+        }
+        // the focal lengths of U = [fx u0 | fy u1] are folded into the 2x2 core; V_b = W_b Jl_b carries those of Jl_b itself
+        const double f00 = fxa * fxb * fxb, f01 = fxa * fyb * fyb, f10 = fya * fxb * fxb, f11 = fya * fyb * fyb;
+        // Batches of 16 tuples: the pieces of a batch (16 x 80 B per side) are copied global -> shared with cp.async (16 bytes per
+        // request, whole sectors, no register write-back), BA_NSTAGE stages per warp.
+        const int nbatch = (len + 15) >> 4;
+        auto issue = [&](int bidx, int stg) {
+            const int tl0 = bidx * 16;
+            const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage0 + (size_t)stg * BA_STAGE_BYTES) + 16u * lane;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int tl = p_tl[k] & 0xff;
+                if (p_tl[k] != 0xffff && tl0 + tl < len) {
+                    const int2 ab = tup[tl0 + tl];
+                    const double* src = A.yr + BA_YR * (size_t)((p_tl[k] >> 8) ? ab.y : ab.x) + p_src[k];
+                    // diagonal pair (a == b): the second half carries {r, VD bl} of the same edge instead
+                    if (diag && (p_tl[k] >> 8)) src = A.rw + 4 * (size_t)ab.x + p_src[k];
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 512u * k), "l"(src) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        double acc[18];
+#pragma unroll
+        for (int i = 0; i < 18; i++) acc[i] = 0;
+        double ub[3] = {0, 0, 0}, uu[3] = {0, 0, 0};      // diagonal pairs: rows 3h..3h+2 of sum U_e r_e (bp) and sum U_e (VD_e bl) (Schur rhs)
+        // prefetch distance BA_NSTAGE - 1: every iteration commits exactly one (possibly empty) group
+#pragma unroll
+        for (int k = 0; k < BA_NSTAGE - 1; k++) {
+            if (k < nbatch) issue(k, k); else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int bidx = 0; bidx < nbatch; bidx++) {
+            if (bidx + BA_NSTAGE - 1 < nbatch) issue(bidx + BA_NSTAGE - 1, (bidx + BA_NSTAGE - 1) % BA_NSTAGE);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            // once the last batch has been issued nobody reads the tuple list any more: fetch the next chunk's (one more group in flight)
+            if (next_chunk && !tup_ready && bidx + BA_NSTAGE - 1 >= nbatch - 1) { __syncwarp(); stage_tuples(nx0); tup_ready = true; }
+            if (tup_ready) asm volatile("cp.async.wait_group %0;" ::"n"(BA_NSTAGE) : "memory");
+            else asm volatile("cp.async.wait_group %0;" ::"n"(BA_NSTAGE - 1) : "memory");
             __syncwarp();
-            tup_ready = false;
-            const bool next_chunk = nx0.z > 0;
-            if (done) {
-                if (next_chunk) { stage_tuples(nx0); tup_ready = true; }
-                continue;
-            }
-            const double f00 = fxa * fxb, f01 = fxa * fyb, f10 = fya * fxb, f11 = fya * fyb;
-            // Batches of 16 tuples: the pieces of a batch (16 x 80 B per side) are copied global -> shared with cp.async (16 bytes per
-            // request, whole sectors, no register write-back), BA_NSTAGE stages per warp; then two lanes per tuple (lane parity h owns rows
-            // 3h..3h+2 of the 6x6 block) read them back conflict-free (8-byte reads, stride 80 bytes).
-            const int nbatch = (len + 15) >> 4;
-            auto issue = [&](int bidx, int stg) {
-                const int tl0 = bidx * 16;
-                const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage0 + (size_t)stg * BA_STAGE_BYTES) + 16u * lane;
-#pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    const int tl = p_tl[k] & 0xff;
-                    if (tl0 + tl < len) {
-                        const int2 ab = tup[tl0 + tl];
-                        const double* src = A.yr + BA_YR * (size_t)((p_tl[k] >> 8) ? ab.y : ab.x) + p_src[k];
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 512u * k), "l"(src) : "memory");
+            // two lanes per tuple: lane parity h owns rows 3h..3h+2 of the 6x6 block
+            if (bidx * 16 + slot < len) {
+                const unsigned char* stg = stage0 + (size_t)(bidx % BA_NSTAGE) * BA_STAGE_BYTES;
+                const double* ya = reinterpret_cast<const double*>(stg + 80 * slot);
+                const double* eb = reinterpret_cast<const double*>(stg + BA_STAGE_A + 32 * slot);
+                const double* ebx = diag ? ya : eb;               // x y w W of edge b
+                // tJ_e^T = [fx u0 | fy u1] with  u0 = (xy, -(1 + x^2), y, -w, 0, xw),  u1 = (1 + y^2, -xy, -x, 0, -w, yw),  x = X/Z, y = Y/Z, w = 1/Z
+                // (types_six_dof_expmap.cpp:136-153 with Z * (1/Z) = 1); the focal lengths are folded into M.
+                double ua0[3], ua1[3];
+                {
+                    const double x = ya[0], y = ya[1], w = ya[2];
+                    if (h == 0) {
+                        const double xy = x * y;
+                        ua0[0] = xy; ua0[1] = -fma(x, x, 1.0); ua0[2] = y;
+                        ua1[0] = fma(y, y, 1.0); ua1[1] = -xy; ua1[2] = -x;
+                    } else {
+                        ua0[0] = -w; ua0[1] = 0; ua0[2] = x * w;
+                        ua1[0] = 0; ua1[1] = -w; ua1[2] = y * w;
                     }
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            };
-            double acc[18];
+                const double xb = ebx[0], yb = ebx[1], wb = ebx[2];
+                const double sb = ebx[3] * wb;                     // V_b = W_b Jl_b = W_b w_b diag(f_b) [x_b R_2 - R_0 ; y_b R_2 - R_1]
+                double m00 = 0, m01 = 0, m10 = 0, m11 = 0;        // M = diag(f_a) VD_a V_b^T diag(f_b) (2x2)
 #pragma unroll
-            for (int i = 0; i < 18; i++) acc[i] = 0;
-            // prefetch distance BA_NSTAGE - 1: every iteration commits exactly one (possibly empty) group
-#pragma unroll
-            for (int k = 0; k < BA_NSTAGE - 1; k++) {
-                if (k < nbatch) issue(k, k); else asm volatile("cp.async.commit_group;" ::: "memory");
-            }
-            for (int bidx = 0; bidx < nbatch; bidx++) {
-                if (bidx + BA_NSTAGE - 1 < nbatch) issue(bidx + BA_NSTAGE - 1, (bidx + BA_NSTAGE - 1) % BA_NSTAGE);
-                else asm volatile("cp.async.commit_group;" ::: "memory");
-                // once the last batch has been issued nobody reads the tuple list any more: fetch the next chunk's (one more group in flight)
-                if (next_chunk && !tup_ready && bidx + BA_NSTAGE - 1 >= nbatch - 1) { __syncwarp(); stage_tuples(nx0); tup_ready = true; }
-                if (tup_ready) asm volatile("cp.async.wait_group %0;" ::"n"(BA_NSTAGE) : "memory");
-                else asm volatile("cp.async.wait_group %0;" ::"n"(BA_NSTAGE - 1) : "memory");
-                __syncwarp();
-                if (bidx * 16 + slot < len) {
-                    const unsigned char* stg = stage0 + (size_t)(bidx % BA_NSTAGE) * BA_STAGE_BYTES;
-                    const double* ya = reinterpret_cast<const double*>(stg + 80 * slot);
-                    const double* eb = reinterpret_cast<const double*>(stg + BA_STAGE_A + 80 * slot);
-                    // tJ_e^T = [fx u0 | fy u1] with  u0 = (xy, -(1 + x^2), y, -w, 0, xw),  u1 = (1 + y^2, -xy, -x, 0, -w, yw),  x = X/Z, y = Y/Z, w = 1/Z
-                    // (types_six_dof_expmap.cpp:136-153 with Z * (1/Z) = 1); the focal lengths are folded into M.
-                    double ua0[3], ua1[3];
-                    {
-                        const double x = ya[0], y = ya[1], w = ya[2];
-                        if (h == 0) {
-                            const double xy = x * y;
-                            ua0[0] = xy; ua0[1] = -fma(x, x, 1.0); ua0[2] = y;
-                            ua1[0] = fma(y, y, 1.0); ua1[1] = -xy; ua1[2] = -x;
-                        } else {
-                            ua0[0] = -w; ua0[1] = 0; ua0[2] = x * w;
-                            ua1[0] = 0; ua1[1] = -w; ua1[2] = y * w;
-                        }
-                    }
-                    double m00 = 0, m01 = 0, m10 = 0, m11 = 0;        // M = diag(f_a) VD_a V_b^T diag(f_b) (2x2)
-    #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const double v0 = eb[4 + c], v1 = eb[7 + c], d0 = ya[4 + c], d1 = ya[7 + c];
-                        m00 += d0 * v0; m01 += d0 * v1; m10 += d1 * v0; m11 += d1 * v1;
-                    }
-                    m00 *= f00; m01 *= f01; m10 *= f10; m11 *= f11;
-                    const double xb = eb[0], yb = eb[1], wb = eb[2];
-                    const double xyb = xb * yb, b01 = -fma(xb, xb, 1.0), b10 = fma(yb, yb, 1.0), xwb = xb * wb, ywb = yb * wb;
-    #pragma unroll
-                    for (int r = 0; r < 3; r++) {
-                        const double t0 = ua0[r] * m00 + ua1[r] * m10, t1 = ua0[r] * m01 + ua1[r] * m11;
-                        double* a = acc + 6 * r;              // two chained FMAs per entry, the structural zeros of u0 / u1 skipped
-                        a[0] = fma(t1, b10, fma(t0, xyb, a[0]));
-                        a[1] = fma(t1, -xyb, fma(t0, b01, a[1]));
-                        a[2] = fma(t1, -xb, fma(t0, yb, a[2]));
-                        a[3] = fma(t0, -wb, a[3]);
-                        a[4] = fma(t1, -wb, a[4]);
-                        a[5] = fma(t1, ywb, fma(t0, xwb, a[5]));
-                    }
+                for (int c = 0; c < 3; c++) {
+                    const double v0 = fma(xb, Rm[6 + c], -Rm[c]), v1 = fma(yb, Rm[6 + c], -Rm[3 + c]), d0 = ya[4 + c], d1 = ya[7 + c];
+                    m00 += d0 * v0; m01 += d0 * v1; m10 += d1 * v0; m11 += d1 * v1;
                 }
-                __syncwarp();
+                m00 *= sb * f00; m01 *= sb * f01; m10 *= sb * f10; m11 *= sb * f11;
+                if (diag) {
+                    const double Wf = ya[3];
+                    m00 -= Wf * fxa * fxa; m11 -= Wf * fya * fya;   // U_e (VD_e V_e^T - W_e I) U_e^T: the pose block rides along
+                    const double a0 = fxa * eb[0], a1 = fya * eb[1], c0 = fxa * eb[2], c1 = fya * eb[3];
+#pragma unroll
+                    for (int r = 0; r < 3; r++) { ub[r] += ua0[r] * a0 + ua1[r] * a1; uu[r] += ua0[r] * c0 + ua1[r] * c1; }
+                }
+                const double xyb = xb * yb, b01 = -fma(xb, xb, 1.0), b10 = fma(yb, yb, 1.0), xwb = xb * wb, ywb = yb * wb;
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const double t0 = ua0[r] * m00 + ua1[r] * m10, t1 = ua0[r] * m01 + ua1[r] * m11;
+                    double* a = acc + 6 * r;              // two chained FMAs per entry, the structural zeros of u0 / u1 skipped
+                    a[0] = fma(t1, b10, fma(t0, xyb, a[0]));
+                    a[1] = fma(t1, -xyb, fma(t0, b01, a[1]));
+                    a[2] = fma(t1, -xb, fma(t0, yb, a[2]));
+                    a[3] = fma(t0, -wb, a[3]);
+                    a[4] = fma(t1, -wb, a[4]);
+                    a[5] = fma(t1, ywb, fma(t0, xwb, a[5]));
+                }
             }
+            __syncwarp();
+        }
 #pragma unroll
-            for (int i = 0; i < 18; i++) {
+        for (int i = 0; i < 18; i++) {
 #pragma unroll
-                for (int o = 16; o > 1; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+            for (int o = 16; o > 1; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        }
+        if (lane < 2) {
+            double* out = A.partial + 36 * (size_t)ch + 18 * h;
+#pragma unroll
+            for (int i = 0; i < 18; i++) out[i] = acc[i];
+        }
+        if (diag) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+#pragma unroll
+                for (int o = 16; o > 1; o >>= 1) { ub[i] += __shfl_xor_sync(0xffffffffu, ub[i], o); uu[i] += __shfl_xor_sync(0xffffffffu, uu[i], o); }
             }
             if (lane < 2) {
-                double* out = A.partial + 36 * (size_t)ch + 18 * h;
+                double* out = A.prhs + 12 * (size_t)ch + 3 * h;
 #pragma unroll
-                for (int i = 0; i < 18; i++) out[i] = acc[i];
-            }
-        } else {
-            const int p = A.item_prob[it >> 2];
-            const BAState& S = A.state[p];
-            if (S.done) continue;
-            const BAProb& P = A.prob[p];
-            const int item = ((it >> 2) - blkI_first[it >> 2]) * 4 + (it & 3);
-            if (item < P.nChunksMax || item >= P.nItems) continue;
-            const int k = item - P.nChunksMax;
-            const int pidd = k * P.K - k * (k - 1) / 2;
-            for (int cl = 0; cl < P.nC; cl++) {
-                const int pc = P.pc0 + pidd * P.CC + cl * P.nC + cl;
-                const int cnt = A.pc_cnt[pc];
-                const int2* T = A.tuples + P.tup0 + A.pc_off[pc];
-                double u[6];
-    #pragma unroll
-                for (int q = 0; q < 6; q++) u[q] = 0;
-                for (int t = lane; t < cnt; t += 32) {
-                    double ve[6];
-                    load6(A.v + 6 * (size_t)T[t].x, ve);
-    #pragma unroll
-                    for (int q = 0; q < 6; q++) u[q] += ve[q];
-                }
-    #pragma unroll
-                for (int q = 0; q < 6; q++) u[q] = warp_sum(u[q]);
-                if (lane < 6) {
-                    double vsel = u[0];
-    #pragma unroll
-                    for (int q = 1; q < 6; q++) if (lane == q) vsel = u[q];
-                    A.ut_u[6 * (size_t)(P.ut0 + k * P.nC + cl) + lane] = vsel;
-                }
+                for (int i = 0; i < 3; i++) { out[i] = ub[i]; out[6 + i] = uu[i]; }
             }
         }
     }
@@ -737,6 +899,7 @@ __global__ void __launch_bounds__(128, 4) k_pairs(BABatch A, const int* blkI_fir
 __device__ void round_over(const BABatch& A, BAState& S, bool stopped) {
     if (S.round == 0 && A.its2 >= 0 && !stopped) {
         S.round = 1; S.it = 0; S.mark = 1; S.round_start = 1; S.need_build = 1; S.lambda_pending = 1;
+        *A.rs_flag = 1;                               // the next step's k_lin / k_build have work (k_land of this step has already cleared the flag)
     } else {
         S.done = 1;
     }
@@ -753,10 +916,8 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
     // ---- assemble the reduced camera system: diag blocks Hpp + lambda I, minus the Schur products.  The chunk partials hold
     //      N = sum tJ_a^T S tJ_b per (pose pair, camera pair); the block of the pair is sum over camera pairs of Adj_ca^T N Adj_cb
     for (int r = warp; r < n; r += BA_TS / 32) {
-        const int kr = r / 6;
         for (int c = lane; c <= r; c += 32) {
-            const int kc = c / 6;
-            HS_AT(r, c) = kr == kc ? A.Hpp[36 * (size_t)(P.k0 + kr) + (r - 6 * kr) * 6 + (c - 6 * kc)] + (r == c ? lambda : 0.0) : 0.0;
+            HS_AT(r, c) = r == c ? lambda : 0.0;     // Hpp arrives with the diagonal pairs' partials (k_pairs)
         }
     }
     __syncthreads();
@@ -812,16 +973,27 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
             }
         }
     }
-    // Schur right-hand side: bs_k = bp_k - sum_c Adj_c^T u_(k,c)
+    // bp_k = sum_c Adj_c^T b_(k,c) and the Schur right-hand side bs_k = bp_k - sum_c Adj_c^T u_(k,c); b_(k,c) and u_(k,c) are the sums of
+    // the right-hand-side partials of the chunks of the diagonal pair (k, k), camera pair (c, c)
     for (int i = tid; i < n; i += BA_TS) {
         const int k = i / 6, c6 = i - 6 * k;
-        double sub = 0;
+        const int pidd = k * P.K - k * (k - 1) / 2;
+        double add = 0, sub = 0;
         for (int cl = 0; cl < P.nC; cl++) {
             const double* Ad = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + cl) + BA_CAM_ADJ;
-            const double* u = A.ut_u + 6 * (size_t)(P.ut0 + k * P.nC + cl);
-            for (int a = 0; a < 6; a++) sub += Ad[a * 6 + c6] * u[a];
+            const int pc = P.pc0 + pidd * P.CC + cl * P.nC + cl;
+            const int first = A.pc_fchunk[pc], nc = A.pc_nchunk[pc];
+            for (int a = 0; a < 6; a++) {
+                double ub = 0, uu = 0;
+                for (int c = 0; c < nc && first + c < S.nChunks; c++) {
+                    const double* pr = A.prhs + 12 * (size_t)(P.chunk0 + first + c);
+                    ub += pr[a]; uu += pr[6 + a];
+                }
+                add += Ad[a * 6 + c6] * ub; sub += Ad[a * 6 + c6] * uu;
+            }
         }
-        A.bs[6 * (size_t)P.k0 + i] = A.bp[6 * (size_t)P.k0 + i] - sub;
+        A.bp[6 * (size_t)P.k0 + i] = add;
+        A.bs[6 * (size_t)P.k0 + i] = add - sub;
     }
     if (tid == 0) *s_ok_p = 1;
     __syncthreads();
@@ -924,8 +1096,17 @@ __global__ void __launch_bounds__(BA_TS) k_solve(BABatch A, int hs_smem_doubles)
         const int kg = A.pose_free[P.p0 + i];
         const double* src = A.pose[cur] + 7 * (size_t)(P.p0 + i);
         double* dst = A.pose[cur ^ 1] + 7 * (size_t)(P.p0 + i);
-        if (kg >= 0) se3_oplus(A.xp + 6 * (size_t)kg, src, dst);
-        else for (int q = 0; q < 7; q++) dst[q] = src[q];
+        double np7[7];
+        if (kg >= 0) se3_oplus(A.xp + 6 * (size_t)kg, src, np7);
+        else for (int q = 0; q < 7; q++) np7[q] = src[q];
+        for (int q = 0; q < 7; q++) dst[q] = np7[q];
+        for (int cl = 0; cl < P.nC; cl++) {           // the trial estimate's projection table
+            double o[BA_TAB];
+            tab_entry(A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + cl), np7, o);
+            double2* d = reinterpret_cast<double2*>(A.tab[cur ^ 1] + BA_TAB * (size_t)(P.rt0 + i * P.nC + cl));
+#pragma unroll
+            for (int k = 0; k < BA_TAB / 2; k++) d[k] = make_double2(o[2 * k], o[2 * k + 1]);
+        }
     }
     double sc = 0;
     for (int j = tid; j < n; j += BA_TS) { const double xj = x[j]; sc += xj * (lambda * xj + A.bp[6 * (size_t)P.k0 + j]); }
@@ -934,6 +1115,57 @@ __global__ void __launch_bounds__(BA_TS) k_solve(BABatch A, int hs_smem_doubles)
 }
 
 // ------------------------------------------------------------------------------------------------ k_back
+// LM decision of one problem after a trial (optimization_algorithm_levenberg.cpp:86-164); one thread.  Returns true when the trial
+// estimate was accepted (S.cur flipped).
+__device__ bool lm_decide(const BABatch& A, const BAProb& P, BAState& S) {
+    double tempChi = 0, scale = 0;
+    const volatile double* PL = A.partL;
+    for (int q = 0; q < P.nbL; q++) { tempChi += PL[2 * (size_t)(P.blkL0 + q)]; scale += PL[2 * (size_t)(P.blkL0 + q) + 1]; }
+    if (!S.solve_ok) tempChi = 1.7976931348623157e308;
+    scale = (S.poseScale + scale) + 1e-3;
+    const double rho = (S.currentChi - tempChi) / scale;
+    S.rho = rho;
+    S.trials++;
+    bool accepted;
+    if (rho > 0 && isfinite(tempChi)) {
+        double alpha = 1. - pow(2 * rho - 1, 3.0);
+        alpha = fmin(alpha, 2. / 3.);
+        S.lambda *= fmax(1. / 3., alpha);
+        S.ni = 2;
+        S.currentChi = tempChi;
+        accepted = true;
+    } else {
+        S.lambda *= S.ni;
+        S.ni *= 2;
+        accepted = false;
+    }
+    S.qmax++;
+    S.last = S.cur ^ 1;
+    if (accepted) S.cur ^= 1;           // pop() is a no-op: the rejected estimate stays in the other buffer
+    const bool stopped = A.stop && *A.stop != 0;
+    const bool again = rho < 0 && S.qmax < 10 && !stopped;
+    S.mark = 0; S.round_start = 0;
+    if (again) { S.need_build = 0; return accepted; }
+    S.iterations++;
+    int res = 0;
+    if (S.qmax == 10 || rho == 0) res = 1;
+    else {
+        if ((S.iniChi - S.currentChi) * 1e3 < S.iniChi) S.nBad++; else S.nBad = 0;
+        if (S.nBad >= 3) res = 1;
+    }
+    S.it++;
+    S.need_build = 1;
+    const int its = S.round == 0 ? A.its1 : A.its2;
+    if (stopped) S.stopped = 1;
+    if (res || S.it >= its || stopped) round_over(A, S, stopped);
+    return accepted;
+}
+
+// thread per landmark (a thread-per-edge form over the landmark groups of k_land, with the records and the projection table staged in
+// shared memory, was measured 45 % slower: these kernels are bound by LSU wavefronts, not by the strided loads):
+//   x_l = D (bl - sum_e B_e^T x_p),  B_e^T x_p = V_e^T tJ_e (Adj_c x_p)  from the first 80 bytes of the edge records (block_solver.hpp:461-481),
+//   trial point, then the trial error and robust chi2 of every edge of the landmark through the trial estimate's projection table;
+// the last CTA of the problem takes the LM decision.
 __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
     __shared__ double red[BA_TL / 32];
     __shared__ int s_last;
@@ -954,39 +1186,40 @@ __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
         double x0 = 0, x1 = 0, x2 = 0;
         const double* bl = A.bl + 3 * (size_t)l;
         const int e_begin = A.pt_off[l], e_end = A.pt_off[l + 1];
-        if (S.solve_ok) {   // xl = Dinv (bl - sum B_e^T xp),  B_e^T xp = Jl_e^T W_e tJ_e (Adj_c xp)   (block_solver.hpp:461-481)
+        const double* __restrict__ tb = A.tab[cur ^ 1] + BA_TAB * (size_t)P.rt0;
+        const int* __restrict__ ecam_ = A.e_cam;
+        const int* __restrict__ epose_ = A.e_pose;
+        if (S.solve_ok) {
             double c0 = bl[0], c1 = bl[1], c2 = bl[2];
 #pragma unroll 2
             for (int e = e_begin; e < e_end; e++) {
-                const int kg = A.pose_free[A.e_pose[e]];
+                const int pg = epose_[e], kg = A.pose_free[pg];
                 if (kg < 0) continue;
-                const int cg = A.e_cam[e];
+                const int cg = ecam_[e];
                 const double* c = A.cam + BA_CAM_STRIDE * (size_t)cg;
-                double r[6], t4[4], tJ[12], Jl[6], y[6];
-                load6(A.er + 8 * (size_t)e, r);
-                load6(A.ut_y + 6 * (size_t)(P.ut0 + (kg - P.k0) * P.nC + (cg - P.c0)), y);
-                edge_tj(r[0], r[1], r[2], r[3], c[0], c[1], tJ, t4);
-                edge_jl(t4, A.RT + 9 * (size_t)(P.rt0 + (A.e_pose[e] - P.p0) * P.nC + (cg - P.c0)), Jl);
-                double s0 = 0, s1 = 0;
+                double r[10], y[6];
+                const double2* rp = reinterpret_cast<const double2*>(A.yr + BA_YR * (size_t)e);
 #pragma unroll
-                for (int q = 0; q < 6; q++) { s0 += tJ[q] * y[q]; s1 += tJ[6 + q] * y[q]; }
-                s0 *= r[4]; s1 *= r[4];
-                c0 -= Jl[0] * s0 + Jl[3] * s1; c1 -= Jl[1] * s0 + Jl[4] * s1; c2 -= Jl[2] * s0 + Jl[5] * s1;
+                for (int q = 0; q < 5; q++) { const double2 v = rp[q]; r[2 * q] = v.x; r[2 * q + 1] = v.y; }
+                load6(A.ut_y + 6 * (size_t)(P.ut0 + (kg - P.k0) * P.nC + (cg - P.c0)), y);
+                // tJ_e y with tJ_e^T = [fx u0 | fy u1],  u0 = (xy, -(1 + x^2), y, -w, 0, xw),  u1 = (1 + y^2, -xy, -x, 0, -w, yw)
+                const double x = r[0], yy = r[1], w = r[2], xy = x * yy;
+                const double s0 = c[0] * (xy * y[0] - fma(x, x, 1.0) * y[1] + yy * y[2] - w * y[3] + x * w * y[5]);
+                const double s1 = c[1] * (fma(yy, yy, 1.0) * y[0] - xy * y[1] - x * y[2] - w * y[4] + yy * w * y[5]);
+                c0 -= r[4] * s0 + r[7] * s1; c1 -= r[5] * s0 + r[8] * s1; c2 -= r[6] * s0 + r[9] * s1;
             }
             double d[6];
             landmark_dinv(A.Hll + 6 * (size_t)l, lambda, d);
             x0 = d[0] * c0 + d[1] * c1 + d[2] * c2; x1 = d[1] * c0 + d[3] * c1 + d[4] * c2; x2 = d[2] * c0 + d[4] * c1 + d[5] * c2;
         }
         const double* po = A.pt[cur] + 3 * (size_t)l;
-        double pn[3] = {po[0] + x0, po[1] + x1, po[2] + x2};
+        const double pn[3] = {po[0] + x0, po[1] + x1, po[2] + x2};
         double* pw = A.pt[cur ^ 1] + 3 * (size_t)l;
         pw[0] = pn[0]; pw[1] = pn[1]; pw[2] = pn[2];
         sc = x0 * (lambda * x0 + bl[0]) + x1 * (lambda * x1 + bl[1]) + x2 * (lambda * x2 + bl[2]);
         // software pipeline: the ids / observation / weight of edge e + 1 are fetched before edge e is evaluated (the error store of
         // edge e would otherwise fence the loads of the next iteration: the pointers of BABatch are not restrict-qualified)
         const unsigned char* __restrict__ lvl_ = A.level;
-        const int* __restrict__ ecam_ = A.e_cam;
-        const int* __restrict__ epose_ = A.e_pose;
         const double2* __restrict__ obs_ = reinterpret_cast<const double2*>(A.e_obs);
         const double* __restrict__ info_ = A.e_info;
         double2* __restrict__ errw_ = reinterpret_cast<double2*>(A.err[cur ^ 1]);
@@ -1000,11 +1233,10 @@ __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
             const double w = n_info;
             if (e + 1 < e_end) { n_lv = lvl_[e + 1]; n_cam = ecam_[e + 1]; n_pose = epose_[e + 1]; n_obs = obs_[e + 1]; n_info = info_[e + 1]; }
             if (lv) continue;
-            const double* c = A.cam + BA_CAM_STRIDE * (size_t)cg;
-            double pc[3], er[2];
-            const double o2[2] = {ob.x, ob.y};
-            edge_project(A.pose[cur ^ 1] + 7 * (size_t)pg, pn, c, pc);
-            edge_error(pc, c, o2, er);
+            double T[12], pc[3], er[2];
+            load_tab(tb + BA_TAB * ((pg - P.p0) * P.nC + (cg - P.c0)), T);
+            tab_project(T, pn, pc);
+            tab_error(pc, A.cam + BA_CAM_STRIDE * (size_t)cg, ob.x, ob.y, er);
             errw_[e] = make_double2(er[0], er[1]);
             const double c2 = (er[0] * er[0] + er[1] * er[1]) * w;
             chi += robust ? huber_rho0(c2, delta, dsqr) : c2;
@@ -1020,50 +1252,11 @@ __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
     }
     __syncthreads();
     if (!s_last || tid != 0) return;
-    // ---- the last CTA of the problem: LM decision (optimization_algorithm_levenberg.cpp:86-164)
+    // ---- the last CTA of the problem: LM decision (tab[cur ^ 1] already belongs to the trial estimate, so an accepted trial needs nothing more)
     __threadfence();
     S.ticket = 0;
     if (skip) { S.skip = 0; return; }
-    double tempChi = 0, scale = 0;
-    const volatile double* PL = A.partL;
-    for (int q = 0; q < P.nbL; q++) { tempChi += PL[2 * (size_t)(P.blkL0 + q)]; scale += PL[2 * (size_t)(P.blkL0 + q) + 1]; }
-    if (!S.solve_ok) tempChi = 1.7976931348623157e308;
-    scale = (S.poseScale + scale) + 1e-3;
-    const double rho = (S.currentChi - tempChi) / scale;
-    S.rho = rho;
-    S.trials++;
-    int accepted;
-    if (rho > 0 && isfinite(tempChi)) {
-        double alpha = 1. - pow(2 * rho - 1, 3.0);
-        alpha = fmin(alpha, 2. / 3.);
-        S.lambda *= fmax(1. / 3., alpha);
-        S.ni = 2;
-        S.currentChi = tempChi;
-        accepted = 1;
-    } else {
-        S.lambda *= S.ni;
-        S.ni *= 2;
-        accepted = 0;
-    }
-    S.qmax++;
-    S.last = S.cur ^ 1;
-    if (accepted) S.cur ^= 1;           // pop() is a no-op: the rejected estimate stays in the other buffer
-    const bool stopped = A.stop && *A.stop != 0;
-    const bool again = rho < 0 && S.qmax < 10 && !stopped;
-    S.mark = 0; S.round_start = 0;
-    if (again) { S.need_build = 0; return; }
-    S.iterations++;
-    int res = 0;
-    if (S.qmax == 10 || rho == 0) res = 1;
-    else {
-        if ((S.iniChi - S.currentChi) * 1e3 < S.iniChi) S.nBad++; else S.nBad = 0;
-        if (S.nBad >= 3) res = 1;
-    }
-    S.it++;
-    S.need_build = 1;
-    const int its = S.round == 0 ? A.its1 : A.its2;
-    if (stopped) S.stopped = 1;
-    if (res || S.it >= its || stopped) round_over(A, S, stopped);
+    lm_decide(A, P, S);
 }
 
 // ------------------------------------------------------------------------------------------------ final
@@ -1080,7 +1273,7 @@ __global__ void __launch_bounds__(BA_TE) k_final(BABatch A) {
     if (e < P.e0 + P.nE) {
         const double l0 = A.err[S.last][2 * e], l1 = A.err[S.last][2 * e + 1];
         double pc[3];
-        edge_project(A.pose[cur] + 7 * (size_t)A.e_pose[e], A.pt[cur] + 3 * (size_t)A.e_pt[e], A.cam + BA_CAM_STRIDE * (size_t)A.e_cam[e], pc);
+        tab_project(A.tab[cur] + BA_TAB * (size_t)(P.rt0 + (A.e_pose[e] - P.p0) * P.nC + (A.e_cam[e] - P.c0)), A.pt[cur] + 3 * (size_t)A.e_pt[e], pc);
         const bool out = (l0 * l0 + l1 * l1) * A.e_info[e] > A.chi2_th || !(pc[2] > 0.0);
         A.outlier[e] = out;
         nout = out;
@@ -1131,7 +1324,7 @@ struct orbba {
     uint8_t* d_arena = nullptr; size_t arena_cap = 0;
     uint8_t* h_stage = nullptr; size_t stage_cap = 0;   // pinned staging of the static arrays
     int *d_blkP_prob = nullptr, *d_blkP_first = nullptr, *d_blkI_first = nullptr, *d_pose_prob = nullptr;
-    int nbE = 0, nbL = 0, nbP = 0, nbI = 0, Ktot = 0, max_n = 0;
+    int nbE = 0, nbL = 0, nbP = 0, nbI = 0, nbG = 0, Ktot = 0, max_n = 0;
     int pairs_grid = 148 * 4;          // resident CTAs of the persistent k_pairs (set from the occupancy calculator at create)
     long long Etot = 0, Ltot = 0, Ptot = 0;
     int* h_flags = nullptr;                  // pinned + mapped: [0] stop flag, [1] active problems after the last step
@@ -1195,15 +1388,15 @@ static int launch_steps(orbba* b, int steps) {
         k_build<0><<<b->nbL, BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
         if (b->Ktot > 0) k_build<1><<<b->Ktot, BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
         if (kv) cudaEventRecord(kv[2], st);
-        k_trial<<<b->nbE, BA_TE, 0, st>>>(A);
+        if (b->nbG > 0) k_land<<<b->nbG, BA_TG, 0, st>>>(A);
         if (kv) cudaEventRecord(kv[3], st);
-        if (b->nbI > 0) k_pairs<<<std::min(b->nbI, b->pairs_grid), 128, 0, st>>>(A, b->d_blkI_first, b->nbI * 4);
+        if (b->nbI > 0) k_pairs<<<std::min(b->nbI, b->pairs_grid), 128, 0, st>>>(A, b->nbI * 4);
         if (kv) cudaEventRecord(kv[4], st);
         k_solve<<<b->n, BA_TS, smem, st>>>(A, hs_doubles);
         if (kv) cudaEventRecord(kv[5], st);
         k_back<<<b->nbL, BA_TL, 0, st>>>(A);
         if (kv) { cudaEventRecord(kv[6], st); b->kev_steps++; }
-        b->launches += 5 + (b->nbI > 0) + (b->Ktot > 0);
+        b->launches += 4 + (b->nbG > 0) + (b->nbI > 0) + (b->Ktot > 0);
     }
     b->h_flags[1] = 0;
     k_final<<<b->nbE, BA_TE, 0, st>>>(A);
@@ -1309,6 +1502,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     if (n == 0) return ORB_OK;
     // ---- pass 1a: per-problem analysis (validation, free-pose numbering, landmark grouping, tuple count) on all host cores
     std::vector<std::vector<int>> pose_free_local(n);
+    std::vector<std::vector<int>> groups(n);   // k_land blocks per problem: (first landmark, landmarks) pairs
     std::vector<long long> tups(n, 0);
     std::vector<int> Ks(n, 0);
     std::vector<std::string> errs(n);
@@ -1357,6 +1551,18 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         }
         tup += (long long)run * (run + 1) / 2;
         tups[p] = tup;
+        {   // k_land blocks: greedy packing of whole landmarks into groups of <= BA_TG edges (a larger landmark stands alone)
+            std::vector<int> cntl(nL, 0);
+            for (int e = 0; e < nE; e++) cntl[Q.edge_point[e]]++;
+            std::vector<int>& G = groups[p];
+            int first = 0, ne = 0;
+            for (int l = 0; l < nL; l++) {
+                const bool full = l > first && (ne + cntl[l] > BA_TG || l - first >= BA_TG);
+                if (full) { G.push_back(first); G.push_back(l - first); first = l; ne = 0; }
+                ne += cntl[l];
+            }
+            if (nL > first) { G.push_back(first); G.push_back(nL - first); }
+        }
         if (tup > 0x7fffffffLL || (long long)K * (K + 1) / 2 > 4000000LL) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d is too large for the pair index (%d free poses)", p, K); errs[p] = msg; return; }
         if (6 * K > 3000) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d has %d free poses; above 500 use the distributed global BA entry points", p, K); errs[p] = msg; }
     });
@@ -1364,7 +1570,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     // ---- pass 1b: offsets
     long long Etot = 0, Ltot = 0, Ptot = 0, Ctot = 0, Ktot = 0, pairTot = 0, tupTot = 0, chunkTot = 0, eofTot = 0, hsTot = 0, itemTot = 0;
     long long rtTot = 0, pcTot = 0, utTot = 0;
-    int nbE = 0, nbL = 0, nbP = 0, nbI = 0, max_n = 0;
+    int nbE = 0, nbL = 0, nbP = 0, nbI = 0, nbG = 0, max_n = 0;
     std::vector<int> bP0(n), bI0(n);
     for (int p = 0; p < n; p++) {
         const orbba_problem_t& Q = problems[p];
@@ -1378,15 +1584,16 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         P.rt0 = (int)rtTot; P.pc0 = (int)pcTot; P.ut0 = (int)utTot;
         rtTot += (long long)nP * nC; pcTot += (long long)P.nPairs * P.CC; utTot += (long long)K * nC;
         P.chunk0 = (int)chunkTot; P.nChunksMax = P.nPairs * P.CC + (int)(tup / BA_CH);
-        P.item0 = (int)itemTot; P.nItems = P.nChunksMax + K;
+        P.item0 = (int)itemTot; P.nItems = P.nChunksMax;
         P.blkE0 = nbE; P.nbE = std::max(1, (nE + BA_TE - 1) / BA_TE);
         P.blkL0 = nbL; P.nbL = std::max(1, (nL + BA_TL - 1) / BA_TL);
+        P.blkG0 = nbG; P.nbG = (int)groups[p].size() / 2;
         P.tup0 = tupTot; P.eof0 = eofTot; P.hs_off = hsTot;
         bP0[p] = nbP; bI0[p] = nbI; P.blkI0 = nbI;
         Etot += nE; Ltot += nL; Ptot += nP; Ctot += nC; Ktot += K; pairTot += P.nPairs; tupTot += tup; chunkTot += P.nChunksMax;
         itemTot += P.nItems; eofTot += (long long)nL * K;
         if (P.n > BA_HS_SMEM_N) hsTot += (long long)P.n * (P.n | 1);
-        nbE += P.nbE; nbL += P.nbL; nbP += (P.nPairs + 3) / 4; nbI += (P.nItems + 3) / 4;
+        nbE += P.nbE; nbL += P.nbL; nbG += P.nbG; nbP += (P.nPairs + 3) / 4; nbI += (P.nItems + 3) / 4;
         max_n = std::max(max_n, P.n);
         if (Etot > 0x1fffffffLL || eofTot > 0x7fffffffLL * 4 || pcTot > 0x7fffffffLL || chunkTot > 0x7fffffffLL || tupTot > 0x7fffffffLL) ORB_FAIL(ORB_E_INVALID, "orbba_upload: batch too large");
     }
@@ -1399,21 +1606,23 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     const size_t o_blkE = L.add(4 * (size_t)nbE), o_blkL = L.add(4 * (size_t)nbL), o_item = L.add(4 * (size_t)std::max(nbI, 1));
     const size_t o_blkPp = L.add(4 * (size_t)std::max(nbP, 1)), o_blkPf = L.add(4 * (size_t)std::max(nbP, 1)), o_blkIf = L.add(4 * (size_t)std::max(nbI, 1));
     const size_t o_poseprob = L.add(4 * (size_t)std::max<long long>(Ktot, 1)), o_freepose = L.add(4 * (size_t)std::max<long long>(Ktot, 1));
+    const size_t o_blkGp = L.add(4 * (size_t)std::max(nbG, 1)), o_blkGl = L.add(4 * (size_t)std::max(nbG, 1)), o_blkGn = L.add(4 * (size_t)std::max(nbG, 1));
     const size_t static_bytes = L.add(0);
     const size_t o_state = L.add(sizeof(BAState) * n);
     const size_t o_eof = L.add(4 * (size_t)eofTot), o_pcnt = L.add(4 * (size_t)pairTot), o_poff = L.add(4 * (size_t)pairTot);
     const size_t o_pccnt = L.add(4 * (size_t)pcTot), o_pcoff = L.add(4 * (size_t)pcTot), o_pcfch = L.add(4 * (size_t)pcTot), o_pcnch = L.add(4 * (size_t)pcTot);
     const size_t o_cpair = L.add(4 * (size_t)chunkTot), o_cstart = L.add(4 * (size_t)chunkTot), o_clen = L.add(4 * (size_t)chunkTot);
-    const size_t o_irec = L.add(32 * 4 * (size_t)std::max(nbI, 1)), o_pcount = L.add(256);
+    const size_t o_irec = L.add(32 * 4 * (size_t)std::max(nbI, 1)), o_pcount = L.add(256);   // pcount: [0] k_pairs queue head, [16] rs_flag
     const size_t o_tup = L.add(8 * (size_t)tupTot);
     const size_t o_pose_a = L.add(56 * Ptot), o_pose_b = L.add(56 * Ptot), o_pt_a = L.add(24 * Ltot), o_pt_b = L.add(24 * Ltot);
     const size_t o_err_a = L.add(16 * Etot), o_err_b = L.add(16 * Etot), o_level = L.add(Etot);
-    const size_t o_yr = L.add(8 * BA_YR * (size_t)Etot), o_v = L.add(48 * (size_t)Etot);
-    const size_t o_er = L.add(64 * (size_t)Etot), o_RT = L.add(72 * (size_t)std::max<long long>(rtTot, 1));
-    const size_t o_utu = L.add(48 * (size_t)std::max<long long>(utTot, 1)), o_uty = L.add(48 * (size_t)std::max<long long>(utTot, 1));
+    const size_t o_yr = L.add(8 * BA_YR * (size_t)Etot), o_rw = L.add(32 * (size_t)Etot);
+    const size_t o_er = L.add(64 * (size_t)Etot), o_tab0 = L.add(8 * BA_TAB * (size_t)std::max<long long>(rtTot, 1)), o_tab1 = L.add(8 * BA_TAB * (size_t)std::max<long long>(rtTot, 1));
+    const size_t o_utu = L.add(48 * (size_t)std::max<long long>(utTot, 1)), o_utb = L.add(48 * (size_t)std::max<long long>(utTot, 1)), o_uty = L.add(48 * (size_t)std::max<long long>(utTot, 1));
     const size_t o_Hll = L.add(48 * Ltot), o_bl = L.add(24 * Ltot);
     const size_t o_Hpp = L.add(288 * Ktot), o_bp = L.add(48 * Ktot), o_bs = L.add(48 * Ktot), o_xp = L.add(48 * Ktot);
-    const size_t o_partial = L.add(288 * (size_t)chunkTot), o_partE = L.add(16 * (size_t)nbE), o_partL = L.add(16 * (size_t)nbL);
+    const size_t o_prhs = L.add(96 * (size_t)std::max<long long>(chunkTot, 1));
+    const size_t o_partial = L.add(288 * (size_t)chunkTot), o_partE = L.add(16 * (size_t)nbE), o_partL = L.add(16 * (size_t)std::max(std::max(nbL, nbG), 1));
     const size_t o_Hs = L.add(8 * (size_t)hsTot);
     const size_t o_poses_out = L.add(96 * Ptot), o_points_out = L.add(24 * Ltot), o_outlier = L.add(Etot), o_stats = L.add(sizeof(orbba_stats_t) * n);
     const size_t total = L.add(0) + 256;
@@ -1436,6 +1645,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     double *h_eobs = (double*)(H + o_eobs), *h_einfo = (double*)(H + o_einfo), *h_cam = (double*)(H + o_cam), *h_pose0 = (double*)(H + o_pose0), *h_pt0 = (double*)(H + o_pt0);
     int *h_blkE = (int*)(H + o_blkE), *h_blkL = (int*)(H + o_blkL), *h_item = (int*)(H + o_item), *h_blkPp = (int*)(H + o_blkPp), *h_blkPf = (int*)(H + o_blkPf),
         *h_blkIf = (int*)(H + o_blkIf), *h_poseprob = (int*)(H + o_poseprob), *h_freepose = (int*)(H + o_freepose);
+    int *h_blkGp = (int*)(H + o_blkGp), *h_blkGl = (int*)(H + o_blkGl), *h_blkGn = (int*)(H + o_blkGn);
     parallel_for(n, [&](int p) {
         const int bP = bP0[p], bI = bI0[p];
         const orbba_problem_t& Q = problems[p];
@@ -1482,6 +1692,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         if (P.nL) memcpy(h_pt0 + 3 * (size_t)P.l0, Q.points, sizeof(double) * 3 * P.nL);
         for (int q = 0; q < P.nbE; q++) h_blkE[P.blkE0 + q] = p;
         for (int q = 0; q < P.nbL; q++) h_blkL[P.blkL0 + q] = p;
+        for (int q = 0; q < P.nbG; q++) { h_blkGp[P.blkG0 + q] = p; h_blkGl[P.blkG0 + q] = P.l0 + groups[p][2 * q]; h_blkGn[P.blkG0 + q] = groups[p][2 * q + 1]; }
         const int bp4 = (P.nPairs + 3) / 4, bi4 = (P.nItems + 3) / 4;
         for (int q = 0; q < bp4; q++) { h_blkPp[bP + q] = p; h_blkPf[bP + q] = bP; }
         for (int q = 0; q < bi4; q++) { h_item[bI + q] = p; h_blkIf[bI + q] = bI; }
@@ -1497,24 +1708,25 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     A.pt_off = (const int*)(D + o_ptoff); A.pose_free = (const int*)(D + o_pfree);
     A.pose0 = (const double*)(D + o_pose0); A.pt0 = (const double*)(D + o_pt0);
     A.blkE_prob = (const int*)(D + o_blkE); A.blkL_prob = (const int*)(D + o_blkL); A.item_prob = (const int*)(D + o_item);
+    A.blkG_prob = (const int*)(D + o_blkGp); A.blkG_l0 = (const int*)(D + o_blkGl); A.blkG_nl = (const int*)(D + o_blkGn);
     b->d_blkP_prob = (int*)(D + o_blkPp); b->d_blkP_first = (int*)(D + o_blkPf); b->d_blkI_first = (int*)(D + o_blkIf); b->d_pose_prob = (int*)(D + o_poseprob);
     A.edge_of = (int*)(D + o_eof); A.pair_cnt = (int*)(D + o_pcnt); A.pair_off = (int*)(D + o_poff);
     A.pc_cnt = (int*)(D + o_pccnt); A.pc_off = (int*)(D + o_pcoff); A.pc_fchunk = (int*)(D + o_pcfch); A.pc_nchunk = (int*)(D + o_pcnch);
     A.free_pose = (const int*)(D + o_freepose);
     A.chunk_pair = (int*)(D + o_cpair); A.chunk_start = (int*)(D + o_cstart); A.chunk_len = (int*)(D + o_clen);
-    A.item_rec = (int4*)(D + o_irec); A.pairs_counter = (int*)(D + o_pcount);
+    A.item_rec = (int4*)(D + o_irec); A.pairs_counter = (int*)(D + o_pcount); A.rs_flag = (int*)(D + o_pcount) + 16;
     A.tuples = (int2*)(D + o_tup);
     A.pose[0] = (double*)(D + o_pose_a); A.pose[1] = (double*)(D + o_pose_b); A.pt[0] = (double*)(D + o_pt_a); A.pt[1] = (double*)(D + o_pt_b);
     A.err[0] = (double*)(D + o_err_a); A.err[1] = (double*)(D + o_err_b); A.level = D + o_level;
-    A.yr = (double*)(D + o_yr); A.v = (double*)(D + o_v);
-    A.er = (double*)(D + o_er); A.RT = (double*)(D + o_RT); A.ut_u = (double*)(D + o_utu); A.ut_y = (double*)(D + o_uty);
+    A.yr = (double*)(D + o_yr); A.rw = (double*)(D + o_rw);
+    A.er = (double*)(D + o_er); A.tab[0] = (double*)(D + o_tab0); A.tab[1] = (double*)(D + o_tab1); A.ut_u = (double*)(D + o_utu); A.ut_b = (double*)(D + o_utb); A.ut_y = (double*)(D + o_uty);
     A.Hll = (double*)(D + o_Hll); A.bl = (double*)(D + o_bl);
     A.Hpp = (double*)(D + o_Hpp); A.bp = (double*)(D + o_bp); A.bs = (double*)(D + o_bs); A.xp = (double*)(D + o_xp);
-    A.partial = (double*)(D + o_partial); A.partE = (double*)(D + o_partE); A.partL = (double*)(D + o_partL); A.Hs = (double*)(D + o_Hs);
+    A.partial = (double*)(D + o_partial); A.prhs = (double*)(D + o_prhs); A.partE = (double*)(D + o_partE); A.partL = (double*)(D + o_partL); A.Hs = (double*)(D + o_Hs);
     A.poses_out = (double*)(D + o_poses_out); A.points_out = (double*)(D + o_points_out); A.outlier = D + o_outlier;
     A.stats = (orbba_stats_t*)(D + o_stats);
     A.stop = b->d_flags; A.n_active = b->d_flags + 1;
-    b->nbE = nbE; b->nbL = nbL; b->nbP = nbP; b->nbI = nbI; b->Ktot = (int)Ktot; b->max_n = max_n;
+    b->nbE = nbE; b->nbL = nbL; b->nbP = nbP; b->nbI = nbI; b->nbG = nbG; b->Ktot = (int)Ktot; b->max_n = max_n;
     b->Etot = Etot; b->Ltot = Ltot; b->Ptot = Ptot;
     // ---- upload + index construction on the device (on the copy stream when one is set: overlaps with a run of another handle)
     cudaStream_t st = b->copy_stream ? b->copy_stream : b->stream;

@@ -265,7 +265,20 @@ __global__ void __launch_bounds__(PO_T) k_pose_opt(POArgs A) {
 }
 
 namespace {
-struct PoArena { uint8_t* d = nullptr; size_t cap = 0; int device = -1; };
+struct PoArena {
+    uint8_t* d = nullptr; size_t cap = 0; int device = -1;
+    void release() {
+        if (d && device >= 0) {
+            int prev = -1;
+            cudaGetDevice(&prev);
+            if (cudaSetDevice(device) == cudaSuccess) cudaFree(d);
+            if (prev >= 0) cudaSetDevice(prev);
+            cudaGetLastError();
+        }
+        d = nullptr; cap = 0;
+    }
+    ~PoArena() { release(); }  // thread exit
+};
 thread_local PoArena g_po;
 }  // namespace
 
@@ -299,8 +312,8 @@ int orbba_pose_optimization(orbba_t* h, const orbpo_frame_t* frames, int n, doub
     const size_t total = add(0) + 256;
     PoArena& G = g_po;
     if (G.device != device || total > G.cap) {
-        if (G.d) cudaFree(G.d);
-        G.d = nullptr; G.cap = 0; G.device = device;
+        G.release();
+        G.device = device;
         ORB_CUDA(cudaMalloc((void**)&G.d, total + total / 2));
         G.cap = total + total / 2;
     }

@@ -442,7 +442,9 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs R) {
         int removed = 0;
         for (int i = lane; i < nlist; i += 32) {
             const int bin = m_bin[i];
-            if (bin != ind1 && bin != ind2 && bin != ind3) { R.out[m_kp[i]] = -1; removed++; }
+            // MODE_LAST: -2 = "was matched, then removed by the rotation check": the host writes -1 (mvpMapPoints[g] = NULL, :1082-1101) over
+            // whatever the caller's in/out array held; -1 = never touched
+            if (bin != ind1 && bin != ind2 && bin != ind3) { R.out[m_kp[i]] = R.mode == MODE_LAST ? -2 : -1; removed++; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
@@ -537,16 +539,28 @@ struct Arena {                 // grow-only device scratch + pinned staging, one
     uint8_t* recs = nullptr; size_t rcap = 0;      // candidate records (sized after the count pass)
     int* h_total = nullptr; int* d_total = nullptr;
     int device = -1;
+    void release() {           // frees on the arena's own device; errors (e.g. the runtime is already unloading at process exit) are ignored
+        if (device >= 0 && (d || h || recs || h_total)) {
+            int prev = -1;
+            cudaGetDevice(&prev);
+            if (cudaSetDevice(device) == cudaSuccess) {
+                if (d) cudaFree(d);
+                if (h) cudaFreeHost(h);
+                if (recs) cudaFree(recs);
+                if (h_total) cudaFreeHost(h_total);
+            }
+            if (prev >= 0) cudaSetDevice(prev);
+            cudaGetLastError();
+        }
+        d = h = recs = nullptr; dcap = hcap = rcap = 0; h_total = d_total = nullptr; device = -1;
+    }
+    ~Arena() { release(); }    // thread exit: the calling thread's scratch goes with it
 };
 thread_local Arena g_arena;
 
 int arena_reserve(Arena& A, int device, size_t dbytes, size_t hbytes) {
     if (A.device != device) {
-        if (A.d) cudaFree(A.d);
-        if (A.h) cudaFreeHost(A.h);
-        if (A.recs) cudaFree(A.recs);
-        if (A.h_total) cudaFreeHost(A.h_total);
-        A = Arena();
+        A.release();
         A.device = device;
     }
     if (!A.h_total) {
@@ -779,7 +793,7 @@ int orbm_search_by_projection_last(orbm_t* m, const orbm_frame_t* cur, const flo
         const int lo = first, hi = first + cur->n_kp[ic];
         first = hi;
         if (ic != 0 && !map_scaled) continue;
-        for (int g = lo; g < hi; g++) if (out[g] >= 0) kp_to_last[g] = out[g];
+        for (int g = lo; g < hi; g++) { if (out[g] >= 0) kp_to_last[g] = out[g]; else if (out[g] == -2) kp_to_last[g] = -1; }
         if (per_cam) per_cam[ic] = sm[ic];
         if (sm[ic] <= 20) { total = sm[ic]; break; }
         total += sm[ic];
@@ -1076,7 +1090,7 @@ static int run_projected(orbm_t* m, const orbm_frame_t* frame, const orbm_frustu
     ORB_CUDA(cudaMemcpyAsync(&nm, A.d + o_sm, 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
     orbm_count_launches(m, launches);
-    for (int g = 0; g < totalN; g++) if (res[g] >= 0) out[g] = res[g];
+    for (int g = 0; g < totalN; g++) { if (res[g] >= 0) out[g] = res[g]; else if (res[g] == -2) out[g] = -1; }
     if (nmatches) *nmatches = nm;
     return ORB_OK;
 }

@@ -15,6 +15,7 @@ from .capi import stream_handle as _stream_handle
 
 TH_HUBER_MONO = float(np.float32(np.sqrt(5.991)))    # `const float thHuberMono = sqrt(5.991)`  src/Optimizer.cc:514
 CHI2_MONO = 5.991                                     # src/Optimizer.cc:603
+TH_HUBER_2D = float(np.float32(np.sqrt(3.99)))        # `const float thHuber2D = sqrt(3.99)`  src/Optimizer.cc:108 (BundleAdjustment / GlobalBundleAdjustemnt)
 
 
 class ProblemC(C.Structure):
@@ -81,7 +82,7 @@ class Optimizer:
         poses = np.zeros((s.n_poses, 12)); points = np.zeros((s.n_points, 3))
         st = StatsC()
         stop = None if pbStopFlag is None else pbStopFlag.ctypes.data
-        rc = lib().orbba_global(self._h, C.addressof(s), nIterations, TH_HUBER_MONO if bRobust else 0.0, stop, ptr(poses), ptr(points), C.addressof(st))
+        rc = lib().orbba_global(self._h, C.addressof(s), nIterations, TH_HUBER_2D if bRobust else 0.0, stop, ptr(poses), ptr(points), C.addressof(st))
         if rc != -5:
             check(rc)
         return poses, points, st.asdict()
@@ -162,11 +163,11 @@ class Optimizer:
         return out[0], out[1], out[2], [s.asdict() for s in st]
 
     def kernel_ms(self):
-        """device ms of {k_lin, k_build, k_trial_lm, k_pairs, k_solve, k_back} summed over the recorded LM steps -> (dict, steps)"""
+        """device ms of {k_lin, k_build, k_land, k_pairs, k_solve, k_back} summed over the recorded LM steps -> (dict, steps)"""
         ms = (C.c_double * 6)()
         n = C.c_int()
         check(lib().orbba_kernel_ms(self._h, ms, C.byref(n)))
-        return dict(zip(["k_lin", "k_build", "k_trial_lm", "k_pairs", "k_solve", "k_back"], list(ms))), n.value
+        return dict(zip(["k_lin", "k_build", "k_land", "k_pairs", "k_solve", "k_back"], list(ms))), n.value
 
     def synchronize(self):
         check(lib().orbba_synchronize(self._h))
@@ -241,7 +242,7 @@ class DistributedOptimizer:
         poses = np.zeros((s.n_poses, 12)); points = np.zeros((s.n_points, 3))
         st = StatsC()
         stop = None if pbStopFlag is None else pbStopFlag.ctypes.data
-        rc = lib().orbba_dist_optimize(self._h, C.addressof(s), nIterations, TH_HUBER_MONO if bRobust else 0.0, stop, ptr(poses), ptr(points), C.addressof(st))
+        rc = lib().orbba_dist_optimize(self._h, C.addressof(s), nIterations, TH_HUBER_2D if bRobust else 0.0, stop, ptr(poses), ptr(points), C.addressof(st))
         if rc != -5:
             check(rc)
         return poses, points, st.asdict()

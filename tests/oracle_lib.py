@@ -196,6 +196,7 @@ def ba_struct(p, cls=BAProblemC):
 
 
 HUBER_MONO = float(np.float32(np.sqrt(5.991)))   # `const float thHuberMono = sqrt(5.991)`  src/Optimizer.cc:514
+HUBER_2D = float(np.float32(np.sqrt(3.99)))       # `const float thHuber2D = sqrt(3.99)`  src/Optimizer.cc:108 (BundleAdjustment)
 
 
 def local_ba(p, its1=5, its2=10, huber_delta=HUBER_MONO, chi2_th=5.991, stop=None):
@@ -209,7 +210,7 @@ def local_ba(p, its1=5, its2=10, huber_delta=HUBER_MONO, chi2_th=5.991, stop=Non
     return rc, poses, points, out.astype(bool), {f: getattr(st, f) for f, _ in BAStatsC._fields_}
 
 
-def global_ba(p, iterations=10, huber_delta=HUBER_MONO, stop=None):
+def global_ba(p, iterations=10, huber_delta=HUBER_2D, stop=None):
     L = lib()
     L.orc_global_ba.argtypes = [C.POINTER(BAProblemC), C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BAStatsC)]
     s, keep = ba_struct(p)

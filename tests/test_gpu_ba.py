@@ -107,7 +107,7 @@ def test_batch_download_copy_stream_and_kernel_timing():
     opt.run()
     poses, points, outl, stats = opt.download_batch()
     ms, steps = opt.kernel_ms()
-    assert steps >= 15 and set(ms) == {"k_lin", "k_build", "k_trial_lm", "k_pairs", "k_solve", "k_back"} and all(v >= 0 for v in ms.values())
+    assert steps >= 15 and set(ms) == {"k_lin", "k_build", "k_land", "k_pairs", "k_solve", "k_back"} and all(v >= 0 for v in ms.values())
     oP = oL = oE = 0
     for i, p in enumerate(ps):
         a, b, c, st = opt.download(i)
@@ -129,3 +129,26 @@ def test_edges_not_grouped_by_landmark():
     a = Optimizer().LocalBundleAdjustment(p)
     b = Optimizer().LocalBundleAdjustment(q)
     assert _pose_rel(b[0], a[0]) <= 1e-9 and np.array_equal(a[2][perm], b[2])      # (the order inside a landmark changes the rounding)
+
+
+def test_landmark_observed_by_more_key_frames_than_a_block_holds():
+    """k_land packs whole landmarks into blocks of 128 edge slots; a landmark with more observations takes the strided path"""
+    p = synth.ba_problem(21, n_kf=136, n_points=24, obs_range=(130, 136), outlier_frac=0.02)
+    assert np.bincount(p["edge_point"]).max() > 128
+    _check(p, Optimizer().LocalBundleAdjustment(p), O.local_ba(p))
+
+
+def test_heterogeneous_batch_with_rejected_trials():
+    """windows of very different sizes, noise levels and outlier shares in one lock-step batch: every window keeps the oracle's own
+    trial sequence (rejected trials included) whatever its neighbours do"""
+    kws = [dict(seed=40, n_kf=4, n_points=60), dict(seed=41, n_kf=25, n_points=900, outlier_frac=0.15),
+           dict(seed=42, n_kf=8, n_points=200, pose_noise=(0.3, 6.0), point_noise=0.5), dict(seed=43, n_kf=12, n_points=400, n_fixed_extra=4),
+           dict(seed=44, n_kf=6, n_points=150, pose_noise=(0.5, 10.0), point_noise=1.0, outlier_frac=0.3), dict(seed=45, n_kf=16, n_points=300)]
+    ps = [synth.ba_problem(**kw) for kw in kws]
+    refs = [O.local_ba(p) for p in ps]
+    assert any(r[4]["trials"] > r[4]["iterations"] for r in refs), "the batch should contain rejected LM trials"
+    opt = Optimizer(max_problems=len(ps))
+    opt.upload(ps)
+    opt.run()
+    for i, (p, r) in enumerate(zip(ps, refs)):
+        _check(p, opt.download(i), r)

@@ -19,7 +19,7 @@ def test_dist_world1_vs_oracle(kw, its, robust):
     p = synth.gba_problem(**kw)
     opt = DistributedOptimizer()
     poses, points, st = opt.GlobalBundleAdjustemnt(shard_problem(p, 0, 1), nIterations=its, bRobust=robust)
-    rc, rposes, rpoints, rst = O.global_ba(p, iterations=its, huber_delta=O.HUBER_MONO if robust else 0.0)
+    rc, rposes, rpoints, rst = O.global_ba(p, iterations=its, huber_delta=O.HUBER_2D if robust else 0.0)
     assert _pose_rel(poses, rposes) <= 1e-5, _pose_rel(poses, rposes)
     assert np.abs(points - rpoints).max() <= 1e-5 * max(1.0, np.abs(rpoints).max())
     assert st["iterations"] == rst["iterations"] and st["trials"] == rst["trials"]

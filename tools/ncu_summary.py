@@ -15,7 +15,11 @@ FULL = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum",
-        "sm__inst_executed_pipe_lsu.sum", "sm__inst_executed_pipe_xu.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+        "sm__inst_executed_pipe_lsu.sum", "sm__inst_executed_pipe_xu.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_read.sum",
+        "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__maximum_warps_per_active_cycle_pct"]
 
 
 def launches(path):
@@ -46,6 +50,16 @@ def full(path):
         for m in FULL:
             if m in d:
                 print(f"   {m:70s} {d[m]:>18s} {U[H.index(m)]}")
+        # the five largest warp-stall reasons (warps waiting on the reason per issued instruction)
+        st = []
+        for m in H:
+            if m.startswith("smsp__average_warps_issue_stalled_") and m.endswith("_per_issue_active.ratio"):
+                try:
+                    st.append((float(d[m].replace(",", "")), m))
+                except ValueError:
+                    pass
+        for v, m in sorted(st, reverse=True)[:5]:
+            print(f"   stall {m[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]:63s} {v:18.2f} warps per issue")
 
 
 if __name__ == "__main__":
