@@ -45,7 +45,7 @@
 #define BA_CH 512              // tuples per chunk (k_pairs)
 #define BA_MAXCC 16            // camera pairs per pose pair: rigs of up to 4 cameras
 #define BA_TS 512              // threads of k_solve
-#define BA_HS_SMEM_N 228       // reduced camera system (packed lower triangle) in shared memory up to 228 x 228 doubles (38 free poses)
+#define BA_HS_SMEM_N 216       // reduced camera system (packed lower triangle) in shared memory up to 216 x 216 doubles (36 free poses)
 
 struct BAProb {                // static description of one problem inside the batch
     int e0, nE, l0, nL, p0, nP, c0, nC, k0, K, n;
@@ -348,10 +348,10 @@ __device__ __forceinline__ void load6(const double* p, double* o) {   // 48-byte
 }
 
 // ------------------------------------------------------------------------------------------------ k_lin
-__global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
+// (k_lin and k_build run over a capped grid with a block-stride loop: on the steps where no problem starts a round -- all but two of the
+// fifteen of a LocalBundleAdjustment -- the launch costs one wave of CTAs that read a flag, not 60 000 empty ones)
+__device__ __forceinline__ void k_lin_body(const BABatch& A, int b) {
     __shared__ double red[BA_TE / 32];
-    if (*A.rs_flag == 0) return;                      // no problem starts a round on this step
-    const int b = blockIdx.x;
     const int p = A.blkE_prob[b];
     const BAState& S = A.state[p];
     if (S.done || !S.round_start) return;
@@ -408,18 +408,21 @@ __global__ void __launch_bounds__(BA_TE) k_lin(BABatch A) {
     if (tid == 0) { A.partE[2 * (size_t)b] = cs; A.partE[2 * (size_t)b + 1] = as; }
     if (b == P.blkE0 && tid == 0 && S.round_start) A.state[p].maxdiag_bits = 0ull;
 }
+__global__ void __launch_bounds__(BA_TE) k_lin(BABatch A, int nb) {
+    if (*A.rs_flag == 0) return;                      // no problem starts a round on this step
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) { k_lin_body(A, b); __syncthreads(); }
+}
 
 // ------------------------------------------------------------------------------------------------ k_build
 // blocks [0, nLandmarkBlocks): thread per landmark -> Hll, bl ;  blocks beyond: CTA per free pose -> Hpp, bp
 // Two instantiations, launched back to back: the landmark part needs half the registers of the pose part, and as one kernel it ran at
 // the pose part's occupancy (126 registers, 16 warps per SM).
 template <int PART>
-__global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks, const int* pose_prob) {
+__device__ __forceinline__ void k_build_body(const BABatch& A, int blk, const int* pose_prob) {
     __shared__ double s_N[27], s_W[(BA_TP / 32) * 27];
     const int tid = threadIdx.x;
-    if (*A.rs_flag == 0) return;                      // only the first step of a round needs max |diag H| (computeLambdaInit)
     if (PART == 0) {
-        const int b = blockIdx.x;
+        const int b = blk;
         const int p = A.blkL_prob[b];
         const BAState& S = A.state[p];
         if (S.done || !S.round_start) return;
@@ -454,7 +457,7 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
     }
     // ---- pose part: per camera c, N_c = sum tJ^T W tJ and u_c = sum tJ^T r over the pose's edges seen by camera c (they are the
     //      (c, c) slice of the diagonal pair's tuple list), then Hpp += Adj_c^T N_c Adj_c, bp += Adj_c^T u_c
-    const int kg = blockIdx.x;                         // global free-pose index
+    const int kg = blk;                                // global free-pose index
     const int p = pose_prob[kg];
     const BAState& S = A.state[p];
     if (S.done || !S.round_start) return;
@@ -523,6 +526,11 @@ __global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nLandmarkBlocks,
     } else if (tid < 42) {
         A.bp[6 * (size_t)kg + tid - 36] = out;
     }
+}
+template <int PART>
+__global__ void __launch_bounds__(BA_TL) k_build(BABatch A, int nb, const int* pose_prob) {
+    if (*A.rs_flag == 0) return;                      // only the first step of a round needs max |diag H| (computeLambdaInit)
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) { k_build_body<PART>(A, b, pose_prob); __syncthreads(); }
 }
 
 // ------------------------------------------------------------------------------------------------ k_land
@@ -908,7 +916,7 @@ __device__ void round_over(const BABatch& A, BAState& S, bool stopped) {
 // Assembles, factorises (LDL^T) and solves the reduced camera system of one problem in `Hs` (packed lower triangle).  Inlined
 // twice by k_solve -- once with the shared-memory matrix, once with a global-memory one -- so that each copy uses the
 // loads / stores of its address space instead of generic ones.
-__device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P, const BAState& S, double* Hs, double* s_lcol, int* s_ok_p,
+__device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P, const BAState& S, double* Hs, double* s_lcol, double* s_pan, int* s_ok_p,
                                               double lambda, double* s_wscr) {
     const int n = P.n, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // packed lower triangle, row i at i (i + 1) / 2: half the shared memory of a square matrix, so two CTAs (problems) share an SM
@@ -997,17 +1005,60 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
     }
     if (tid == 0) *s_ok_p = 1;
     __syncthreads();
-    // ---- LDL^T in place (lower triangle: L below the diagonal, D on it); right-looking, one column per step:
-    //      lcol[i] = L_ij, then row i of the trailing lower triangle -= L_ij * d_j * L_kj  (warp per row, lanes along the row)
-    for (int j = 0; j < n; j++) {
-        const double dj = HS_AT(j, j);
-        if (dj == 0.0 || !isfinite(dj)) { if (tid == 0) *s_ok_p = 0; break; }
-        for (int i = j + 1 + tid; i < n; i += BA_TS) { const double l = HS_AT(i, j) / dj; HS_AT(i, j) = l; s_lcol[i] = l; }
+    // ---- LDL^T in place (lower triangle: L below the diagonal, D on it), right-looking over block columns of 6 (one pose): three
+    //      barriers per pose instead of two per scalar column.
+    //        1. diagonal block: scalar LDL^T of the 6x6 by one warp
+    //        2. panel: thread per row r below the block: W_r = L_r D from W_r L_jj^T = A_r (forward substitution), L_r = W_r D^-1
+    //        3. trailing update: H(r, k) -= W_r . L_k for the rows / columns below the block (warp per row, lanes along the row)
+    for (int j0 = 0; j0 < n; j0 += 6) {
+        if (warp == 0) {
+            for (int c = 0; c < 6; c++) {
+                const double dc = HS_AT(j0 + c, j0 + c);
+                if (dc == 0.0 || !isfinite(dc)) { if (lane == 0) *s_ok_p = 0; break; }
+                if (lane > c && lane < 6) HS_AT(j0 + lane, j0 + c) /= dc;
+                __syncwarp();
+                if (lane < 36) {                 // H(r, k) -= L_rc d_c L_kc for c < k <= r < 6
+                    const int r = lane / 6, k = lane - 6 * r;
+                    if (k > c && k <= r) HS_AT(j0 + r, j0 + k) -= HS_AT(j0 + r, j0 + c) * dc * HS_AT(j0 + k, j0 + c);
+                }
+                if (lane == 0 && c < 5) {        // lanes 32..35 of the 36 entries: (5, 2) .. (5, 5)
+                    for (int k = 2; k < 6; k++) if (k > c) HS_AT(j0 + 5, j0 + k) -= HS_AT(j0 + 5, j0 + c) * dc * HS_AT(j0 + k, j0 + c);
+                }
+                __syncwarp();
+            }
+        }
         __syncthreads();
-        for (int i = j + 1 + warp; i < n; i += BA_TS / 32) {
-            const double li = s_lcol[i] * dj;
-            double* row = &HS_AT(i, 0);
-            for (int k = j + 1 + lane; k <= i; k += 32) row[k] -= li * s_lcol[k];
+        if (*s_ok_p == 0) break;
+        {
+            double Lj[15], dj[6];                // L_jj (strict lower, row-major) and d of the block: the same for every row
+#pragma unroll
+            for (int c = 0, q = 0; c < 6; c++) {
+                dj[c] = HS_AT(j0 + c, j0 + c);
+#pragma unroll
+                for (int k = 0; k < c; k++) Lj[q++] = HS_AT(j0 + c, j0 + k);
+            }
+            for (int r = j0 + 6 + tid; r < n; r += BA_TS) {
+                double* row = &HS_AT(r, j0);
+                double w[6];
+#pragma unroll
+                for (int c = 0, q = 0; c < 6; c++) {
+                    double a = row[c];
+#pragma unroll
+                    for (int k = 0; k < c; k++) a -= w[k] * Lj[q++];
+                    w[c] = a;
+                }
+#pragma unroll
+                for (int c = 0; c < 6; c++) { row[c] = w[c] / dj[c]; s_pan[6 * r + c] = w[c]; }
+            }
+        }
+        __syncthreads();
+        for (int r = j0 + 6 + warp; r < n; r += BA_TS / 32) {
+            const double w0 = s_pan[6 * r], w1 = s_pan[6 * r + 1], w2 = s_pan[6 * r + 2], w3 = s_pan[6 * r + 3], w4 = s_pan[6 * r + 4], w5 = s_pan[6 * r + 5];
+            double* row = &HS_AT(r, 0);
+            for (int k = j0 + 6 + lane; k <= r; k += 32) {
+                const double* Lk = &HS_AT(k, j0);
+                row[k] -= w0 * Lk[0] + w1 * Lk[1] + w2 * Lk[2] + w3 * Lk[3] + w4 * Lk[4] + w5 * Lk[5];
+            }
         }
         __syncthreads();
     }
@@ -1019,16 +1070,44 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
         double* xs = s_lcol;                   // the solve runs on the shared copy
         for (int i = lane; i < n; i += 32) xs[i] = bs[i];
         __syncwarp();
-        for (int j = 0; j < n; j++) {
-            const double xj = xs[j];
-            for (int i = j + 1 + lane; i < n; i += 32) xs[i] -= HS_AT(i, j) * xj;
+        // forward: L y = b, block column by block column (the 6 unknowns of a block are solved redundantly by every lane)
+        for (int j0 = 0; j0 < n; j0 += 6) {
+            double y[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double a = xs[j0 + c];
+#pragma unroll
+                for (int k = 0; k < c; k++) a -= HS_AT(j0 + c, j0 + k) * y[k];
+                y[c] = a;
+            }
+            __syncwarp();
+            if (lane < 6) xs[j0 + lane] = y[lane == 0 ? 0 : lane == 1 ? 1 : lane == 2 ? 2 : lane == 3 ? 3 : lane == 4 ? 4 : 5];
+            for (int i = j0 + 6 + lane; i < n; i += 32) {
+                const double* Li = &HS_AT(i, j0);
+                xs[i] -= Li[0] * y[0] + Li[1] * y[1] + Li[2] * y[2] + Li[3] * y[3] + Li[4] * y[4] + Li[5] * y[5];
+            }
             __syncwarp();
         }
         for (int i = lane; i < n; i += 32) xs[i] /= HS_AT(i, i);
         __syncwarp();
-        for (int j = n - 1; j >= 0; j--) {
-            const double xj = xs[j];
-            for (int i = lane; i < j; i += 32) xs[i] -= HS_AT(j, i) * xj;
+        // backward: L^T x = y
+        for (int j0 = n - 6; j0 >= 0; j0 -= 6) {
+            double y[6];
+#pragma unroll
+            for (int c = 5; c >= 0; c--) {
+                double a = xs[j0 + c];
+#pragma unroll
+                for (int k = c + 1; k < 6; k++) a -= HS_AT(j0 + k, j0 + c) * y[k];
+                y[c] = a;
+            }
+            __syncwarp();
+            if (lane < 6) xs[j0 + lane] = y[lane == 0 ? 0 : lane == 1 ? 1 : lane == 2 ? 2 : lane == 3 ? 3 : lane == 4 ? 4 : 5];
+            for (int i = lane; i < j0; i += 32) {
+                double a = xs[i];
+#pragma unroll
+                for (int c = 0; c < 6; c++) a -= HS_AT(j0 + c, i) * y[c];
+                xs[i] = a;
+            }
             __syncwarp();
         }
         for (int i = lane; i < n; i += 32) x[i] = xs[i];
@@ -1036,7 +1115,7 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
     return ok;
 }
 
-__global__ void __launch_bounds__(BA_TS) k_solve(BABatch A, int hs_smem_doubles) {
+__global__ void __launch_bounds__(BA_TS, 2) k_solve(BABatch A, int hs_smem_doubles, int max_n, int hs_smem_n) {
     extern __shared__ double sm_hs[];
     __shared__ double red[BA_TS / 32];
     __shared__ double s_wscr[(BA_TS / 32) * 72];   // per warp: N and N Adj of the pair being assembled
@@ -1078,8 +1157,9 @@ __global__ void __launch_bounds__(BA_TS) k_solve(BABatch A, int hs_smem_doubles)
     if (!s_go) return;
     const double lambda = S.lambda;
     bool ok;
-    if (n <= BA_HS_SMEM_N) ok = solve_reduced(A, P, S, sm_hs, s_lcol, &s_ok, lambda, s_wscr);
-    else ok = solve_reduced(A, P, S, A.Hs + P.hs_off, s_lcol, &s_ok, lambda, s_wscr);
+    // s_lcol: n doubles (any n); the panel W [n][6] follows it for matrices in shared memory, else it lies behind the packed triangle in global memory
+    if (n <= hs_smem_n) ok = solve_reduced(A, P, S, sm_hs, s_lcol, s_lcol + max_n, &s_ok, lambda, s_wscr);
+    else ok = solve_reduced(A, P, S, A.Hs + P.hs_off, s_lcol, A.Hs + P.hs_off + (((size_t)n * (n + 1) / 2 + 1) & ~(size_t)1), &s_ok, lambda, s_wscr);
     double* x = A.xp + 6 * (size_t)P.k0;
     if (!ok) for (int i = tid; i < n; i += BA_TS) x[i] = 0.0;   // g2o applies a stale x; the trial is rejected either way
     __syncthreads();
@@ -1325,6 +1405,7 @@ struct orbba {
     uint8_t* h_stage = nullptr; size_t stage_cap = 0;   // pinned staging of the static arrays
     int *d_blkP_prob = nullptr, *d_blkP_first = nullptr, *d_blkI_first = nullptr, *d_pose_prob = nullptr;
     int nbE = 0, nbL = 0, nbP = 0, nbI = 0, nbG = 0, Ktot = 0, max_n = 0;
+    int hs_smem_n = 0;                 // reduced systems up to this size are factorised in shared memory (0: a very large problem in the batch took the space)
     int pairs_grid = 148 * 4;          // resident CTAs of the persistent k_pairs (set from the occupancy calculator at create)
     long long Etot = 0, Ltot = 0, Ptot = 0;
     int* h_flags = nullptr;                  // pinned + mapped: [0] stop flag, [1] active problems after the last step
@@ -1377,22 +1458,23 @@ struct Layout {   // bump allocator over one buffer; offsets are 256-byte aligne
 static int launch_steps(orbba* b, int steps) {
     const BABatch& A = b->A;
     cudaStream_t st = b->stream;
-    const int hs_n = b->max_n <= BA_HS_SMEM_N ? b->max_n : BA_HS_SMEM_N;   // problems above the limit keep their matrix in global memory
+    const int hs_n = std::min(b->max_n, b->hs_smem_n);   // problems above the limit keep their matrix in global memory
     const int hs_doubles = (hs_n * (hs_n + 1) / 2 + 1) & ~1;
-    const size_t smem = ((size_t)hs_doubles + std::max(b->max_n, 1)) * sizeof(double);
+    const size_t smem = ((size_t)hs_doubles + std::max(b->max_n, 6) + 6 * (size_t)std::max(hs_n, 6)) * sizeof(double);   // matrix + solution column + panel
     for (int s = 0; s < steps; s++) {
         cudaEvent_t* kv = (b->profile && b->kev_steps < BA_KEV_STEPS && !b->kev.empty()) ? &b->kev[(size_t)7 * b->kev_steps] : nullptr;
         if (kv) cudaEventRecord(kv[0], st);
-        k_lin<<<b->nbE, BA_TE, 0, st>>>(A);
+        const int cap = 148 * 16;                      // one wave
+        k_lin<<<std::min(b->nbE, cap), BA_TE, 0, st>>>(A, b->nbE);
         if (kv) cudaEventRecord(kv[1], st);
-        k_build<0><<<b->nbL, BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
-        if (b->Ktot > 0) k_build<1><<<b->Ktot, BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
+        k_build<0><<<std::min(b->nbL, cap), BA_TL, 0, st>>>(A, b->nbL, b->d_pose_prob);
+        if (b->Ktot > 0) k_build<1><<<std::min(b->Ktot, cap), BA_TL, 0, st>>>(A, b->Ktot, b->d_pose_prob);
         if (kv) cudaEventRecord(kv[2], st);
         if (b->nbG > 0) k_land<<<b->nbG, BA_TG, 0, st>>>(A);
         if (kv) cudaEventRecord(kv[3], st);
         if (b->nbI > 0) k_pairs<<<std::min(b->nbI, b->pairs_grid), 128, 0, st>>>(A, b->nbI * 4);
         if (kv) cudaEventRecord(kv[4], st);
-        k_solve<<<b->n, BA_TS, smem, st>>>(A, hs_doubles);
+        k_solve<<<b->n, BA_TS, smem, st>>>(A, hs_doubles, std::max(b->max_n, 6), b->hs_smem_n);
         if (kv) cudaEventRecord(kv[5], st);
         k_back<<<b->nbL, BA_TL, 0, st>>>(A);
         if (kv) { cudaEventRecord(kv[6], st); b->kev_steps++; }
@@ -1571,6 +1653,11 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     long long Etot = 0, Ltot = 0, Ptot = 0, Ctot = 0, Ktot = 0, pairTot = 0, tupTot = 0, chunkTot = 0, eofTot = 0, hsTot = 0, itemTot = 0;
     long long rtTot = 0, pcTot = 0, utTot = 0;
     int nbE = 0, nbL = 0, nbP = 0, nbI = 0, nbG = 0, max_n = 0;
+    for (int p = 0; p < n; p++) max_n = std::max(max_n, 6 * Ks[p]);
+    // shared memory of k_solve: packed matrix of the largest in-shared problem + solution column (any n) + panel; a very large problem in the
+    // batch sends every matrix to global memory
+    int hs_smem_n = BA_HS_SMEM_N;
+    if (((size_t)hs_smem_n * (hs_smem_n + 1) / 2 + 2 + max_n + 6 * (size_t)hs_smem_n) * 8 > 200 * 1024) hs_smem_n = 0;
     std::vector<int> bP0(n), bI0(n);
     for (int p = 0; p < n; p++) {
         const orbba_problem_t& Q = problems[p];
@@ -1592,7 +1679,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         bP0[p] = nbP; bI0[p] = nbI; P.blkI0 = nbI;
         Etot += nE; Ltot += nL; Ptot += nP; Ctot += nC; Ktot += K; pairTot += P.nPairs; tupTot += tup; chunkTot += P.nChunksMax;
         itemTot += P.nItems; eofTot += (long long)nL * K;
-        if (P.n > BA_HS_SMEM_N) hsTot += (long long)P.n * (P.n | 1);
+        if (P.n > hs_smem_n) hsTot += (long long)std::max(P.n, 14) * (std::max(P.n, 14) | 1);
         nbE += P.nbE; nbL += P.nbL; nbG += P.nbG; nbP += (P.nPairs + 3) / 4; nbI += (P.nItems + 3) / 4;
         max_n = std::max(max_n, P.n);
         if (Etot > 0x1fffffffLL || eofTot > 0x7fffffffLL * 4 || pcTot > 0x7fffffffLL || chunkTot > 0x7fffffffLL || tupTot > 0x7fffffffLL) ORB_FAIL(ORB_E_INVALID, "orbba_upload: batch too large");
@@ -1726,7 +1813,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     A.poses_out = (double*)(D + o_poses_out); A.points_out = (double*)(D + o_points_out); A.outlier = D + o_outlier;
     A.stats = (orbba_stats_t*)(D + o_stats);
     A.stop = b->d_flags; A.n_active = b->d_flags + 1;
-    b->nbE = nbE; b->nbL = nbL; b->nbP = nbP; b->nbI = nbI; b->nbG = nbG; b->Ktot = (int)Ktot; b->max_n = max_n;
+    b->nbE = nbE; b->nbL = nbL; b->nbP = nbP; b->nbI = nbI; b->nbG = nbG; b->Ktot = (int)Ktot; b->max_n = max_n; b->hs_smem_n = hs_smem_n;
     b->Etot = Etot; b->Ltot = Ltot; b->Ptot = Ptot;
     // ---- upload + index construction on the device (on the copy stream when one is set: overlaps with a run of another handle)
     cudaStream_t st = b->copy_stream ? b->copy_stream : b->stream;
