@@ -443,7 +443,8 @@ int  orbba_pose_optimization(orbba_t*, const orbpo_frame_t* frames, int n, doubl
  * GlobalBundleAdjustemnt for large maps, on one GPU or landmark-partitioned over the GPUs of a node (BASELINE.json configs[4]:
  * 2000 key frames x 2 cameras, 200k map points).  One process per GPU; key-frame poses are replicated, rank r owns the map
  * points `index mod world == r` and their edges; per LM trial ONE NCCL all-reduce (sum, FP64) of the reduced camera system
- * [Hschur | bschur] and one of two scalars; the dense Cholesky of the reduced system (cuSOLVER) and the LM policy are replicated.
+ * [Hschur | bschur] (block skyline: only the envelope of the reduced camera system is stored, built and shipped) and one of three
+ * scalars; the hand-written skyline LDL^T of the reduced system and the LM policy are replicated.
  *   rank 0:      orbba_dist_unique_id(id)  -> broadcast the 128 bytes to the other ranks by any means (torch.distributed, MPI, a file)
  *   every rank:  orbba_dist_create(&h, device, rank, world, id)  (world == 1: id may be NULL, no NCCL needed)
  *                orbba_dist_optimize(h, shard, ...)   collective
@@ -461,6 +462,9 @@ int  orbba_dist_optimize(orbgba_t*, const orbba_problem_t* shard, int iterations
 /* device milliseconds spent in the [Hschur | bschur] all-reduce and in the dense solve during the last optimize call, and the
  * bytes this rank contributed to all-reduces */
 int  orbba_dist_timing(const orbgba_t*, double* allreduce_ms, double* solve_ms, double* allreduce_bytes);
+/* device milliseconds of the whole LM loop of the last optimize call (events around it) and the 6x6 blocks of the reduced camera
+ * system's skyline (what the all-reduce ships: 288 bytes each) */
+int  orbba_dist_loop_ms(const orbgba_t*, double* loop_ms, long long* skyline_blocks);
 
 #ifdef __cplusplus
 }

@@ -2,18 +2,29 @@
 // on one GPU or landmark-partitioned over the GPUs of a node with one exchange step per LM trial.
 //
 // Reference path (file:line under /root/reference): Optimizer::GlobalBundleAdjustemnt / BundleAdjustment src/Optimizer.cc:62-248
-// (all key frames and map points, one optimize(nIterations), Huber kernel when bRobust, no outlier pass) over the same g2o
-// machinery as LocalBA (see orb_ba.cu for the per-block citations).
+// (all key frames and map points, one optimize(nIterations), Huber kernel thHuber2D when bRobust, no outlier pass) over the same g2o
+// machinery as LocalBA (see orb_ba.cu for the per-block citations); the reduced camera system is solved by
+// LinearSolverEigen = Eigen::SimplicialLDLT, a SPARSE LDL^T (Thirdparty/g2o/g2o/solvers/linear_solver_eigen.h:60-121).
 //
 // Partitioning: key-frame poses are replicated, every rank owns the landmarks `point_id mod world == rank`
 // together with their edges.  Landmark blocks are independent given the poses (Schur structure, block_solver.hpp:381-432), so a
 // rank builds, for its landmarks only, Hll / bl, its share of Hpp / bp and its share of the reduced camera system
 //     Hs = Hpp + lambda I - sum_l B_l Dinv_l B_l^T ,   bs = bp - sum_l B_l Dinv_l bl
-// then ONE NCCL all-reduce (sum, FP64, over NVLink) of [Hs | bs] makes the system identical on every rank; the dense Cholesky
-// (cuSOLVER potrf / potrs: a plain library factorisation, the only tensor-core-eligible part of the path) and the LM decision
-// are replicated, the back-substitution and the trial errors are local again, and one all-reduce of two scalars closes the trial.
-// NCCL and cuSOLVER are loaded with dlopen so that the library still loads on a box without them.
+// then ONE NCCL all-reduce (sum, FP64, over NVLink) of [Hs | bs] makes the system identical on every rank; the factorisation and the
+// LM decision are replicated, the back-substitution and the trial errors are local again, and one all-reduce of three scalars
+// (chi2, gain denominator, stop flag) closes the trial.
+//
+// The reduced camera system is kept as a BLOCK SKYLINE: block row i (one free pose, 6x6 blocks) holds the blocks first(i) .. i, where
+// first(i) is the lowest pose that shares a landmark with i on ANY rank (an all-reduce(min) of K numbers at set-up).  Key frames see
+// the same landmarks as their neighbours in time plus what loop closures connect, so the envelope of a map is a band with a few long
+// rows: 2000 key frames x 8 neighbours = 4.6 MB instead of the 1.15 GB of the dense 11994^2 matrix, which is also what the
+// all-reduce ships.  An LDL^T leaves the envelope unchanged (no fill outside it), so the factorisation is hand-written: right-looking
+// over block columns, in place, with the forward substitution of the right-hand side carried along (k_sky).  Every sum of the build has
+// one owner and a fixed order (pose blocks: CTA per pose over its edge list; Schur blocks: warp per block over its tuple list, built on
+// the host from the landmark -> edges structure), so the result is bit-reproducible; no floating-point atomics, no library.
+// NCCL is loaded with dlopen so that the library still loads on a box without it.
 #include <dlfcn.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -24,15 +35,26 @@
 #include "orb_ba_core.cuh"
 
 #define G_T 128
+#define SKY_T 1024             // threads of the factorisation CTA
 
 struct GArgs {
-    int nP, nL, nE, K, n, rank0_adds_bp;
+    int nP, nL, nE, K, n;
     const int *e_pose, *e_pt, *e_cam, *pose_free, *pt_off;
     const double *e_obs, *e_info, *cam;
     double *pose[2], *pt[2], *err[2];
-    double *rec, *B, *Y, *v, *Hll, *bl, *Hpp, *bp, *bs, *x, *Hs;
-    double *part;            // per-block partial sums: [nb][2]
-    double *red;             // [0] chi  [1] landmark scale  [2] max diag (landmarks)  [3] active edges  [4] pose scale  [5] max diag (poses)
+    double *rec, *B, *Y, *Hll, *bl, *Hpp, *bp, *x;
+    double *Hsum;             // [K][36] pose blocks and [6 K] bp summed over the ranks (computeLambdaInit, computeScale); Hpp / bp keep this rank's share
+    double *Hs, *bs;          // block skyline [NB][36] followed by the right-hand side [6 K]: one all-reduce
+    double *part;             // per-block partial sums: [nb][2]
+    double *red;              // [0] chi  [1] landmark scale  [2] stop flag (sum over ranks)  [3] active edges  [4] pose scale  [5] max diag (poses)  [6] max diag (landmarks)  [7] solve ok
+    // skyline structure
+    const int *first, *rowptr, *last;        // [K] first block column of row i; [K + 1] block offset of row i; [K] last row whose envelope reaches column j
+    long long NB;
+    // owner lists
+    const int *pose_eoff, *pose_edge;        // CSR: free pose -> its edges (this rank)
+    const long long* blk_toff;               // [NB + 1] CSR: block -> tuples
+    const int2* blk_tup;                     // (edge of the row pose, edge of the column pose)
+    double* panW;                            // [K][36] scratch of the factorisation (W = L D of the current block column)
 };
 
 __device__ __forceinline__ double g_warp_sum(double v) {
@@ -85,7 +107,8 @@ __global__ void __launch_bounds__(256) g_reduce(GArgs A, int nb, int slot0, int 
     }
 }
 
-// linearizeOplus + the per-edge part of constructQuadraticForm at estimate `cur` (errors already in err[cur])
+// linearizeOplus + the per-edge part of constructQuadraticForm at estimate `cur` (errors already in err[cur]):
+// rec = { Jl[6], W, r0, r1, Jp[12] }, B = Jp^T W Jl (6x3)
 __global__ void __launch_bounds__(G_T) g_lin(GArgs A, int cur, int robust, double delta) {
     const int e = blockIdx.x * G_T + threadIdx.x;
     if (e >= A.nE) return;
@@ -136,18 +159,6 @@ __global__ void __launch_bounds__(G_T) g_lin(GArgs A, int cur, int robust, doubl
     for (int r = 0; r < 6; r++)
 #pragma unroll
         for (int cc = 0; cc < 3; cc++) Bm[r * 3 + cc] = W * (Jp[r] * Jl[cc] + Jp[6 + r] * Jl[3 + cc]);
-    // pose block: Hpp_k += Jp^T W Jp, bp_k += Jp^T r  (this rank's share; summed over ranks by the all-reduce)
-    const int k = A.pose_free[pi];
-    if (k >= 0) {
-        double* H = A.Hpp + 36 * (size_t)k;
-        double* b = A.bp + 6 * (size_t)k;
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            atomicAdd(&b[i], Jp[i] * R[7] + Jp[6 + i] * R[8]);
-#pragma unroll
-            for (int j = 0; j < 6; j++) atomicAdd(&H[i * 6 + j], (Jp[i] * Jp[j] + Jp[6 + i] * Jp[6 + j]) * W);
-        }
-    }
 }
 
 // thread per landmark: Hll, bl; per-block max |diag|
@@ -177,10 +188,49 @@ __global__ void __launch_bounds__(G_T) g_build_lm(GArgs A) {
     if (threadIdx.x == 0) {
         double m = 0;
         for (int w = 0; w < G_T / 32; w++) m = fmax(m, red[w]);
-        atomicMax(reinterpret_cast<unsigned long long*>(A.red + 2), (unsigned long long)__double_as_longlong(m));   // non-negative doubles order like integers
+        atomicMax(reinterpret_cast<unsigned long long*>(A.red + 6), (unsigned long long)__double_as_longlong(m));   // non-negative doubles order like integers; max is order-free
     }
 }
-// max |diag Hpp| after the all-reduce (one CTA)
+
+// CTA per free pose: this rank's share of Hpp_k = sum Jp^T W Jp and bp_k = sum Jp^T r over the pose's edge list (fixed order)
+__global__ void __launch_bounds__(G_T) g_build_pose(GArgs A) {
+    __shared__ double s_W[(G_T / 32) * 27];
+    const int k = blockIdx.x, tid = threadIdx.x;
+    double h[27];
+#pragma unroll
+    for (int i = 0; i < 27; i++) h[i] = 0;
+    for (int t = A.pose_eoff[k] + tid; t < A.pose_eoff[k + 1]; t += G_T) {
+        const double* R = A.rec + (size_t)BA_REC * A.pose_edge[t];
+        const double W = R[6], r0 = R[7], r1 = R[8];
+        double Jp[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) Jp[j] = R[9 + j];
+        int u = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            h[21 + i] += Jp[i] * r0 + Jp[6 + i] * r1;
+#pragma unroll
+            for (int j = i; j < 6; j++) h[u++] += (Jp[i] * Jp[j] + Jp[6 + i] * Jp[6 + j]) * W;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 27; i++) { const double s = g_warp_sum(h[i]); if ((tid & 31) == 0) s_W[(tid >> 5) * 27 + i] = s; }
+    __syncthreads();
+    if (tid < 36) {
+        const int i = tid / 6, j = tid - 6 * i, lo = i < j ? i : j, hi = i < j ? j : i;
+        const int u = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < G_T / 32; w++) s += s_W[w * 27 + u];
+        A.Hpp[36 * (size_t)k + tid] = s;
+    } else if (tid < 42) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < G_T / 32; w++) s += s_W[w * 27 + 21 + tid - 36];
+        A.bp[6 * (size_t)k + tid - 36] = s;
+    }
+}
+// max |diag Hpp| after its all-reduce (one CTA)
 __global__ void __launch_bounds__(256) g_pose_maxdiag(GArgs A) {
     __shared__ double sm[256];
     double m = 0;
@@ -198,62 +248,461 @@ __device__ __forceinline__ void g_dinv(const double* H, double lambda, double* d
     d[3] = (m0 * m8 - m2 * m2) * id; d[4] = (m2 * m1 - m0 * m5) * id; d[5] = (m0 * m4 - m1 * m1) * id;
 }
 
-// thread per (edge, row): Y_e = B_e Dinv, v_e = Y_e bl ; bs_k -= v_e
+// thread per (edge, row): Y_e = B_e Dinv
 __global__ void __launch_bounds__(256) g_trial(GArgs A, double lambda) {
     const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
     if (q >= 6LL * A.nE) return;
     const int e = (int)(q / 6), r = (int)(q - 6LL * e);
-    const int k = A.pose_free[A.e_pose[e]];
-    if (k < 0) return;
-    const int l = A.e_pt[e];
+    if (A.pose_free[A.e_pose[e]] < 0) return;
     double d[6];
-    g_dinv(A.Hll + 6 * (size_t)l, lambda, d);
+    g_dinv(A.Hll + 6 * (size_t)A.e_pt[e], lambda, d);
     const double* Br = A.B + 18 * (size_t)e + 3 * r;
     const double x0 = Br[0], x1 = Br[1], x2 = Br[2];
-    const double y0 = x0 * d[0] + x1 * d[1] + x2 * d[2], y1 = x0 * d[1] + x1 * d[3] + x2 * d[4], y2 = x0 * d[2] + x1 * d[4] + x2 * d[5];
     double* Yr = A.Y + 18 * (size_t)e + 3 * r;
-    Yr[0] = y0; Yr[1] = y1; Yr[2] = y2;
-    const double* bl = A.bl + 3 * (size_t)l;
-    atomicAdd(&A.bs[6 * (size_t)k + r], -(y0 * bl[0] + y1 * bl[1] + y2 * bl[2]));
+    Yr[0] = x0 * d[0] + x1 * d[1] + x2 * d[2]; Yr[1] = x0 * d[1] + x1 * d[3] + x2 * d[4]; Yr[2] = x0 * d[2] + x1 * d[4] + x2 * d[5];
 }
 
-// warp per landmark: Hs(block ki <= kj) -= Y_i B_j^T for every pair of its free-pose edges.  Hs is row-major n x n with the
-// upper block triangle filled (= column-major lower triangle for cuSOLVER).
-__global__ void __launch_bounds__(G_T) g_schur(GArgs A) {
-    const int l = blockIdx.x * (G_T / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (l >= A.nL) return;
-    const int e0 = A.pt_off[l], e1 = A.pt_off[l + 1];
-    const size_t n = (size_t)A.n;
-    for (int a = e0; a < e1; a++) {
-        const int ka = A.pose_free[A.e_pose[a]];
-        if (ka < 0) continue;
-        for (int c = a; c < e1; c++) {
-            const int kc = A.pose_free[A.e_pose[c]];
-            if (kc < 0) continue;
-            const int ei = ka <= kc ? a : c, ej = ka <= kc ? c : a;
-            const int ki = min(ka, kc), kj = max(ka, kc);
-            const double* Yi = A.Y + 18 * (size_t)ei;
-            const double* Bj = A.B + 18 * (size_t)ej;
-            for (int en = lane; en < 36; en += 32) {
-                const int r = en / 6, cc = en - r * 6;
-                const double s = Yi[r * 3] * Bj[cc * 3] + Yi[r * 3 + 1] * Bj[cc * 3 + 1] + Yi[r * 3 + 2] * Bj[cc * 3 + 2];
-                atomicAdd(&A.Hs[(size_t)(6 * ki + r) * n + 6 * kj + cc], -s);
-            }
-        }
+// warp per free pose: this rank's share of the Schur right-hand side, bs_k = bp_k - sum_e Y_e bl  (fixed order)
+__global__ void __launch_bounds__(G_T) g_rhs(GArgs A) {
+    const int k = blockIdx.x * (G_T / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= A.K) return;
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (int t = A.pose_eoff[k] + lane; t < A.pose_eoff[k + 1]; t += 32) {
+        const int e = A.pose_edge[t];
+        const double* Ym = A.Y + 18 * (size_t)e;
+        const double* bl = A.bl + 3 * (size_t)A.e_pt[e];
+        const double b0 = bl[0], b1 = bl[1], b2 = bl[2];
+#pragma unroll
+        for (int r = 0; r < 6; r++) v[r] += Ym[3 * r] * b0 + Ym[3 * r + 1] * b1 + Ym[3 * r + 2] * b2;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) v[r] = g_warp_sum(v[r]);
+    if (lane < 6) {
+        double s = v[0];
+#pragma unroll
+        for (int r = 1; r < 6; r++) if (lane == r) s = v[r];
+        A.bs[6 * (size_t)k + lane] = A.bp[6 * (size_t)k + lane] - s;
     }
 }
 
-// after the all-reduce: diagonal blocks += Hpp + lambda I
-__global__ void __launch_bounds__(256) g_add_diag(GArgs A, double lambda) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= 36 * A.K) return;
-    const int k = i / 36, r = (i - 36 * k) / 6, c = i - 36 * k - 6 * r;
-    A.Hs[(size_t)(6 * k + r) * A.n + 6 * k + c] += A.Hpp[i] + (r == c ? lambda : 0.0);
+// warp per block (i, j) of the skyline: Hs_ij = [i == j] Hpp_i - sum over the block's tuples (edge a of pose i, edge b of pose j) of
+// Y_a B_b^T.  Lanes split the tuples (36 accumulators each), fixed shuffle tree: deterministic.  Blocks without tuples are zero
+// (fill-in room of the envelope), so nothing has to be cleared between trials.
+__global__ void __launch_bounds__(G_T) g_schur(GArgs A) {
+    const long long blk = (long long)blockIdx.x * (G_T / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (blk >= A.NB) return;
+    double acc[36];
+#pragma unroll
+    for (int i = 0; i < 36; i++) acc[i] = 0;
+    for (long long t = A.blk_toff[blk] + lane; t < A.blk_toff[blk + 1]; t += 32) {
+        const int2 ab = A.blk_tup[t];
+        double Ya[18], Bb[18];
+        const double2* yp = reinterpret_cast<const double2*>(A.Y + 18 * (size_t)ab.x);
+        const double2* bp = reinterpret_cast<const double2*>(A.B + 18 * (size_t)ab.y);
+#pragma unroll
+        for (int q = 0; q < 9; q++) { const double2 y = yp[q], b = bp[q]; Ya[2 * q] = y.x; Ya[2 * q + 1] = y.y; Bb[2 * q] = b.x; Bb[2 * q + 1] = b.y; }
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[6 * r + c] += Ya[3 * r] * Bb[3 * c] + Ya[3 * r + 1] * Bb[3 * c + 1] + Ya[3 * r + 2] * Bb[3 * c + 2];
+    }
+#pragma unroll
+    for (int i = 0; i < 36; i++) acc[i] = g_warp_sum(acc[i]);
+    // which pose is this a diagonal block of?  The diagonal block of row i is the last block of the row: blk == rowptr[i + 1] - 1
+    double out0 = 0, out1 = 0;             // entries lane and lane + 32
+#pragma unroll
+    for (int i = 0; i < 36; i++) { if (lane == (i & 31) && i < 32) out0 = acc[i]; if (i >= 32 && lane == i - 32) out1 = acc[i]; }
+    // binary search of the row (rowptr is increasing)
+    int lo = 0, hi = A.K - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (A.rowptr[mid] <= blk) lo = mid; else hi = mid - 1; }
+    const bool diag = blk == (long long)A.rowptr[lo + 1] - 1;
+    double* H = A.Hs + 36 * (size_t)blk;
+    H[lane] = (diag ? A.Hpp[36 * (size_t)lo + lane] : 0.0) - out0;
+    if (lane < 4) H[32 + lane] = (diag ? A.Hpp[36 * (size_t)lo + 32 + lane] : 0.0) - out1;
 }
 
-// trial poses: exp(x) * pose for free poses (x = bs after potrs), copy for fixed; pose part of computeScale() -> red[4]
-__global__ void __launch_bounds__(256) g_pose_update(GArgs A, int cur, double lambda, int ok) {
+// ------------------------------------------------------------------------------------------------ block-skyline LDL^T
+// One CTA.  In place, right-looking over block columns (one free pose = 6 scalar columns per step):
+//   1. diagonal block (j, j) + lambda I: scalar LDL^T of the 6x6 by one warp; z_j = L_jj^-1 b_j (forward substitution of the rhs)
+//   2. panel: the rows i in (j, last(j)] whose envelope reaches column j: thread per scalar row: W = L D from W L_jj^T = A_ij, L = W D^-1
+//   3. trailing update inside the envelope: A_ik -= W_ij L_kj^T for j < k <= i, and b_i -= L_ij z_j
+// then backward substitution L^T x = D^-1 z, block column by block column.  red[7] = 1 on success, 0 on a zero / non-finite pivot.
+__device__ __forceinline__ double* sky_block(const GArgs& A, int i, int j) { return A.Hs + 36 * ((size_t)A.rowptr[i] + (j - A.first[i])); }
+
+__global__ void __launch_bounds__(SKY_T) k_sky(GArgs A, double lambda) {
+    __shared__ int s_rows[SKY_T];                 // rows of the current panel (when they fit; else recomputed from `first`)
+    __shared__ int s_nrows, s_ok;
+    __shared__ double s_Lj[36], s_dj[6], s_z[6];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = A.K;
+    double* b = A.bs;
+    if (tid == 0) s_ok = 1;
+    __syncthreads();
+    for (int j = 0; j < K; j++) {
+        double* Djj = sky_block(A, j, j);
+        if (tid == 0) s_nrows = 0;
+        if (warp == 0) {
+            if (lane < 6) Djj[7 * lane] += lambda;
+            __syncwarp();
+            for (int c = 0; c < 6; c++) {
+                const double dc = Djj[7 * c];
+                if (dc == 0.0 || !isfinite(dc)) { if (lane == 0) s_ok = 0; break; }
+                if (lane > c && lane < 6) Djj[6 * lane + c] /= dc;
+                __syncwarp();
+                for (int en = lane; en < 36; en += 32) {    // H(r, k) -= L_rc d_c L_kc for c < k <= r < 6
+                    const int r = en / 6, k = en - 6 * r;
+                    if (k > c && k <= r) Djj[6 * r + k] -= Djj[6 * r + c] * dc * Djj[6 * k + c];
+                }
+                __syncwarp();
+            }
+            for (int en = lane; en < 36; en += 32) s_Lj[en] = Djj[en];
+            if (lane < 6) s_dj[lane] = Djj[7 * lane];
+            __syncwarp();
+            if (lane == 0) {                                  // z_j = L_jj^-1 b_j
+                double z[6];
+                for (int c = 0; c < 6; c++) { double a = b[6 * j + c]; for (int k = 0; k < c; k++) a -= s_Lj[6 * c + k] * z[k]; z[c] = a; }
+                for (int c = 0; c < 6; c++) { s_z[c] = z[c]; b[6 * j + c] = z[c]; }
+            }
+        }
+        __syncthreads();
+        if (!s_ok) break;
+        // rows of the panel
+        const int last = A.last[j];
+        const int span = last - j;                             // candidate rows j + 1 .. last
+        const bool listed = span <= SKY_T;
+        if (listed) {
+            if (tid < span && A.first[j + 1 + tid] <= j) s_rows[atomicAdd(&s_nrows, 1)] = j + 1 + tid;
+            __syncthreads();
+        }
+        const int nrows = listed ? s_nrows : span;
+        // 2. panel: scalar row (row slot, r) per thread
+        for (int it = tid; it < 6 * nrows; it += SKY_T) {
+            const int rs = it / 6, r = it - 6 * rs;
+            const int i = listed ? s_rows[rs] : j + 1 + rs;
+            if (!listed && A.first[i] > j) continue;
+            double* row = sky_block(A, i, j) + 6 * r;
+            double w[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double a = row[c];
+#pragma unroll
+                for (int k = 0; k < c; k++) a -= w[k] * s_Lj[6 * c + k];
+                w[c] = a;
+            }
+            double* pw = A.panW + 36 * (size_t)(i - j - 1) + 6 * r;
+            double bz = 0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) { const double l = w[c] / s_dj[c]; row[c] = l; pw[c] = w[c]; bz += l * s_z[c]; }
+            b[6 * i + r] -= bz;                               // forward substitution of the rhs rides along
+        }
+        __syncthreads();
+        // 3. trailing update: entries (i, k, r, c) with k <= i, both rows in the panel
+        if (listed) {
+            const int npair = nrows * nrows;                   // (row slot a, row slot b), used when s_rows[b] <= s_rows[a]
+            for (int it = tid; it < npair * 36; it += SKY_T) {
+                const int pr = it / 36, en = it - 36 * pr, ra = pr / nrows, rb = pr - ra * nrows;
+                const int i = s_rows[ra], k = s_rows[rb];
+                if (k > i) continue;
+                const int r = en / 6, c = en - 6 * r;
+                const double* W = A.panW + 36 * (size_t)(i - j - 1) + 6 * r;
+                const double* Lk = sky_block(A, k, j) + 6 * c;
+                double s = 0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) s += W[q] * Lk[q];
+                sky_block(A, i, k)[en] -= s;
+            }
+        } else {
+            // wide panel (a dense-ish envelope): rows i, k walked directly
+            for (int i = j + 1 + warp; i <= last; i += SKY_T / 32) {
+                if (A.first[i] > j) continue;
+                for (int k = j + 1; k <= i; k++) {
+                    if (A.first[k] > j) continue;
+                    double* Hik = sky_block(A, i, k);
+                    const double* Lk = sky_block(A, k, j);
+                    for (int en = lane; en < 36; en += 32) {
+                        const int r = en / 6, c = en - 6 * r;
+                        const double* W = A.panW + 36 * (size_t)(i - j - 1) + 6 * r;
+                        double s = 0;
+#pragma unroll
+                        for (int q = 0; q < 6; q++) s += W[q] * Lk[6 * c + q];
+                        Hik[en] -= s;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const bool ok = s_ok != 0;
+    if (tid == 0) A.red[7] = ok ? 1.0 : 0.0;
+    if (!ok) { for (int i = tid; i < 6 * K; i += SKY_T) A.x[i] = 0.0; return; }
+    // ---- backward: x_j = L_jj^-T (D_j^-1 z_j - sum_{i > j} L_ij^T x_i)
+    for (int j = K - 1; j >= 0; j--) {
+        const int last = A.last[j];
+        // partial sums over the rows below: thread (row i, component c)
+        double part = 0;
+        const int NT6 = (SKY_T / 6) * 6;                       // a thread keeps its component: stride of a multiple of 6
+        const int c_own = tid % 6;
+        for (int it = tid; tid < NT6 && it < 6 * (last - j); it += NT6) {
+            const int i = j + 1 + it / 6;
+            if (A.first[i] > j) continue;
+            const double* L = sky_block(A, i, j);
+            const double* xi = A.x + 6 * (size_t)i;
+            double s = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) s += L[6 * r + c_own] * xi[r];
+            part += s;
+        }
+        // reduce over the threads with the same component: fixed order through shared memory
+        __shared__ double s_part[SKY_T];
+        s_part[tid] = part;
+        __syncthreads();
+        if (tid < 6) {
+            double s = 0;
+            const int nthr = min(NT6, 6 * (last - j));
+            for (int t = tid; t < nthr; t += 6) s += s_part[t];
+            s_z[tid] = b[6 * j + tid] / sky_block(A, j, j)[7 * tid] - s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double* Ljj = sky_block(A, j, j);
+            double x[6];
+            for (int c = 5; c >= 0; c--) { double a = s_z[c]; for (int k = c + 1; k < 6; k++) a -= Ljj[6 * k + c] * x[k]; x[c] = a; }
+            for (int c = 0; c < 6; c++) A.x[6 * (size_t)j + c] = x[c];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ banded skyline in shared memory
+// The same factorisation for envelopes of at most SKY_WMAX blocks below the diagonal (key frames linked to their neighbours in time):
+// the rows j .. j + W that step j touches live in a ring of W + 3 rows in shared memory (block (i, k) at ring[i mod (W + 3)][k mod (W + 1)]),
+// row j + W + 2 is fetched with cp.async two steps before it is first touched, row j goes back to global memory while the trailing update
+// of step j runs.  A step costs three barriers and no global round trip.  The backward substitution streams block columns the same
+// way (three-stage cp.async ring) with x in a ring.
+#define SKY_WMAX 23
+__device__ __forceinline__ void cp16(double* dst_smem, const double* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+// Blocks of the window that lie outside the envelope are explicit zeros: a zero block (i, j) gives L_ij = 0 and zero updates, so the
+// steps run over the full band of W rows without consulting `first`.  The sequential chain of a step is what it costs (12 000 scalar
+// pivots in a row for 2000 key frames), so: the 6x6 pivot block is factorised by every lane of warp 0 redundantly in registers (no
+// exchange), reciprocals (__drcp_rn) instead of divisions, ring slots advanced by compare-and-subtract instead of modulo.
+__global__ void __launch_bounds__(SKY_T) k_sky_band(GArgs A, double lambda, int W) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int s_ok;
+    __shared__ double s_Lj[36], s_id[6], s_z[6], s_part[6 * (SKY_WMAX + 1)];
+    __shared__ unsigned char s_pa[(SKY_WMAX * (SKY_WMAX + 1)) / 2], s_pb[(SKY_WMAX * (SKY_WMAX + 1)) / 2];   // (a, b <= a) row pairs of the trailing update, ordered by a
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int K = A.K, R = W + 1, RR = W + 3;
+    double* win = sm;                               // [RR][R][36]
+    double* panW = win + (size_t)RR * R * 36;       // [W][36]
+    double* zb = panW + (size_t)max(W, 1) * 36;     // [RR][6]   right-hand side of the rows in the window
+    double* colb = zb + RR * 6;                     // backward: [3][R][36] + [3][6]
+    double* colz = colb + 3 * (size_t)R * 36;
+    double* xr = colz + 18;                         // backward: x ring [RR][6]
+    double* b = A.bs;
+    // row i -> ring slot sl (= i mod RR), its diagonal block in column slot ci (= i mod R): blocks first(i) .. i with cp.async, zeros for
+    // the columns i - W .. first(i) - 1, and its right-hand side
+    auto load_row = [&](int i, int sl, int ci) {
+        const int f = A.first[i], nb = i - f + 1;
+        const double* src = A.Hs + 36 * (size_t)A.rowptr[i];
+        double* rowp = win + (size_t)sl * R * 36;
+        if (tid < nb * 18) {
+            const int m = tid / 18, piece = tid - 18 * m;
+            int ck = ci - (nb - 1 - m);              // column f + m is (i - f - m) left of the diagonal
+            if (ck < 0) ck += R;
+            cp16(rowp + 36 * ck + 2 * piece, src + 2 * tid);
+        } else if (tid >= 512 && tid - 512 < (R - nb) * 18) {
+            const int q = tid - 512, m = q / 18, piece = q - 18 * m;
+            int ck = ci - nb - m;                    // the columns left of first(i)
+            if (ck < 0) ck += R;
+            rowp[36 * ck + 2 * piece] = 0.0; rowp[36 * ck + 2 * piece + 1] = 0.0;
+        }
+        if (tid >= 480 && tid < 483) cp16(zb + sl * 6 + 2 * (tid - 480), b + 6 * (size_t)i + 2 * (tid - 480));
+    };
+    if (tid == 0) {
+        s_ok = 1;
+        int p = 0;
+        for (int a = 0; a < W; a++) for (int q = 0; q <= a; q++) { s_pa[p] = (unsigned char)a; s_pb[p] = (unsigned char)q; p++; }
+    }
+    for (int i = 0; i <= min(R, K - 1); i++) load_row(i, i % RR, i % R);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    int sj = 0, cj = 0;                             // j mod RR, j mod R
+    for (int j = 0; j < K; j++) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");          // rows up to j + R - 1 have landed (this thread's pieces); only row j + R may be in flight
+        __syncthreads();                                               // ... and everybody is done with step j - 1, the write-back of row j - 1 included
+        // the row first touched two steps from now goes into the slot that held row j - 1
+        if (j + R + 1 < K) load_row(j + R + 1, sj == 0 ? RR - 1 : sj - 1, cj + 1 >= R ? cj + 1 - R : cj + 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        double* Djj = win + ((size_t)sj * R + cj) * 36;
+        if (warp == 0) {
+            // scalar LDL^T of the pivot block, every lane on its own copy (lower triangle in registers)
+            double h[6][6], dd[6], id[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int k = 0; k <= r; k++) h[r][k] = Djj[6 * r + k] + (r == k ? lambda : 0.0);
+            bool good = true;
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                dd[c] = h[c][c];
+                if (dd[c] == 0.0 || !isfinite(dd[c])) good = false;
+                id[c] = __drcp_rn(dd[c]);
+                double t[6];                                           // column c before scaling: L_rc d_c
+#pragma unroll
+                for (int r = c + 1; r < 6; r++) t[r] = h[r][c];
+#pragma unroll
+                for (int r = c + 1; r < 6; r++) {
+                    const double l = t[r] * id[c];
+#pragma unroll
+                    for (int k = c + 1; k <= r; k++) h[r][k] -= l * t[k];
+                    h[r][c] = l;
+                }
+            }
+            double z[6];
+            const double* bj = zb + sj * 6;
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double a = bj[c];
+#pragma unroll
+                for (int k = 0; k < c; k++) a -= h[c][k] * z[k];
+                z[c] = a;
+            }
+            if (tid == 0) {
+                if (!good) s_ok = 0;
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+#pragma unroll
+                    for (int k = 0; k < r; k++) { s_Lj[6 * r + k] = h[r][k]; Djj[6 * r + k] = h[r][k]; }
+                    Djj[7 * r] = id[r];                                // the diagonal goes back as 1 / d (what the backward sweep multiplies with)
+                    s_id[r] = id[r]; s_z[r] = z[r]; b[6 * (size_t)j + r] = z[r];
+                }
+            }
+        }
+        __syncthreads();
+        if (!s_ok) break;
+        const int nr = min(W, K - 1 - j);                              // rows j + 1 .. j + nr
+        if (tid < 6 * nr) {
+            const int a = tid / 6, r = tid - 6 * a;
+            int si = sj + 1 + a;
+            if (si >= RR) si -= RR;
+            double* row = win + ((size_t)si * R + cj) * 36 + 6 * r;
+            double w[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double v = row[c];
+#pragma unroll
+                for (int k = 0; k < c; k++) v -= w[k] * s_Lj[6 * c + k];
+                w[c] = v;
+            }
+            double bz = 0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) { const double l = w[c] * s_id[c]; row[c] = l; panW[36 * a + 6 * r + c] = w[c]; bz += l * s_z[c]; }
+            zb[si * 6 + r] -= bz;
+        }
+        __syncthreads();
+        const int np36 = (nr * (nr + 1) / 2) * 36;
+        for (int it = tid; it < np36; it += SKY_T) {
+            const int pr = it / 36, en = it - 36 * pr, a = s_pa[pr], bq = s_pb[pr];
+            int si = sj + 1 + a, sk = sj + 1 + bq, ck = cj + 1 + bq;
+            if (si >= RR) si -= RR;
+            if (sk >= RR) sk -= RR;
+            if (ck >= R) ck -= R;
+            const int r = en / 6, c = en - 6 * r;
+            const double* Wp = panW + 36 * a + 6 * r;
+            const double* Lk = win + ((size_t)sk * R + cj) * 36 + 6 * c;
+            double sacc = 0;
+#pragma unroll
+            for (int q = 0; q < 6; q++) sacc += Wp[q] * Lk[q];
+            win[((size_t)si * R + ck) * 36 + en] -= sacc;
+        }
+        {   // row j is final: back to global memory (the blocks inside its envelope)
+            const int f = A.first[j], nb = j - f + 1;
+            double* dst = A.Hs + 36 * (size_t)A.rowptr[j];
+            const double* rowp = win + (size_t)sj * R * 36;
+            for (int q = tid; q < nb * 36; q += SKY_T) {
+                const int m = q / 36;
+                int ck = cj - (nb - 1 - m);
+                if (ck < 0) ck += R;
+                dst[q] = rowp[36 * ck + (q - 36 * m)];
+            }
+        }
+        if (++sj == RR) sj = 0;
+        if (++cj == R) cj = 0;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const bool ok = s_ok != 0;
+    if (tid == 0) A.red[7] = ok ? 1.0 : 0.0;
+    if (!ok) { for (int i = tid; i < 6 * K; i += SKY_T) A.x[i] = 0.0; return; }
+    // ---- backward: x_j = L_jj^-T (D_j^-1 z_j - sum_{i > j} L_ij^T x_i); block column j = (j, j), (j + 1, j) .. (j + W, j) staged two
+    //      steps ahead (zeros where the envelope of a row does not reach column j)
+    auto load_col = [&](int j, int stage) {
+        double* dst = colb + (size_t)stage * R * 36;
+        const int nr = min(W, K - 1 - j);
+        if (tid < (nr + 1) * 18) {
+            const int a = tid / 18, piece = tid - 18 * a, i = j + a, f = A.first[i];
+            if (f <= j) cp16(dst + 36 * a + 2 * piece, A.Hs + 36 * ((size_t)A.rowptr[i] + (j - f)) + 2 * piece);
+            else { dst[36 * a + 2 * piece] = 0.0; dst[36 * a + 2 * piece + 1] = 0.0; }
+        }
+        if (tid >= 480 && tid < 483) cp16(colz + stage * 6 + 2 * (tid - 480), b + 6 * (size_t)j + 2 * (tid - 480));
+    };
+    int st3 = (K - 1) % 3;                          // stage of column j
+    if (K - 1 >= 0) load_col(K - 1, st3);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (K - 2 >= 0) load_col(K - 2, (K - 2) % 3);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    int xj = (K - 1) % RR;                          // ring slot of x_j
+    for (int j = K - 1; j >= 0; j--) {
+        if (j - 2 >= 0) load_col(j - 2, st3 == 2 ? 0 : st3 + 1);       // (j - 2) mod 3 = (j + 1) mod 3
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncthreads();
+        const double* col = colb + (size_t)st3 * R * 36;
+        const int nr = min(W, K - 1 - j);
+        if (tid < 6 * nr) {
+            const int a = tid / 6 + 1, c = tid - 6 * (a - 1);
+            int xi = xj + a;
+            if (xi >= RR) xi -= RR;
+            const double* L = col + 36 * a;
+            const double* xv = xr + xi * 6;
+            double sacc = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) sacc += L[6 * r + c] * xv[r];
+            s_part[tid] = sacc;
+        }
+        __syncthreads();
+        if (warp == 0) {                            // every lane redundantly: no exchange
+            double x[6];
+#pragma unroll
+            for (int c = 5; c >= 0; c--) {
+                double sacc = 0;
+                for (int a = 0; a < nr; a++) sacc += s_part[6 * a + c];
+                double v = colz[st3 * 6 + c] * col[7 * c] - sacc;        // col[7 c] = 1 / d_c
+#pragma unroll
+                for (int k = c + 1; k < 6; k++) v -= col[6 * k + c] * x[k];
+                x[c] = v;
+            }
+            if (tid < 6) {
+                double v = x[0];
+#pragma unroll
+                for (int c = 1; c < 6; c++) if (tid == c) v = x[c];
+                xr[xj * 6 + tid] = v; A.x[6 * (size_t)j + tid] = v;
+            }
+        }
+        __syncthreads();
+        st3 = st3 == 0 ? 2 : st3 - 1;
+        xj = xj == 0 ? RR - 1 : xj - 1;
+    }
+}
+
+// trial poses: exp(x) * pose for free poses, copy for fixed; pose part of computeScale() -> red[4]
+__global__ void __launch_bounds__(256) g_pose_update(GArgs A, int cur, double lambda) {
     __shared__ double sm[256];
+    const int ok = A.red[7] != 0.0;
     double sc = 0;
     for (int i = threadIdx.x; i < A.nP; i += 256) {
         const int k = A.pose_free[i];
@@ -262,7 +711,7 @@ __global__ void __launch_bounds__(256) g_pose_update(GArgs A, int cur, double la
         if (k >= 0 && ok) {
             const double* x = A.x + 6 * (size_t)k;
             se3_oplus(x, src, dst);
-            for (int j = 0; j < 6; j++) sc += x[j] * (lambda * x[j] + A.bp[6 * (size_t)k + j]);
+            for (int j = 0; j < 6; j++) sc += x[j] * (lambda * x[j] + A.Hsum[36 * (size_t)A.K + 6 * (size_t)k + j]);
         } else {
             for (int q = 0; q < 7; q++) dst[q] = src[q];
         }
@@ -273,8 +722,9 @@ __global__ void __launch_bounds__(256) g_pose_update(GArgs A, int cur, double la
 }
 
 // thread per landmark: increment, trial point, trial errors and chi2 of its edges, landmark part of computeScale()
-__global__ void __launch_bounds__(G_T) g_back(GArgs A, int cur, double lambda, int ok, int robust, double delta) {
+__global__ void __launch_bounds__(G_T) g_back(GArgs A, int cur, double lambda, int robust, double delta) {
     __shared__ double red[G_T / 32];
+    const int ok = A.red[7] != 0.0;
     const int l = blockIdx.x * G_T + threadIdx.x;
     double chi = 0, sc = 0;
     if (l < A.nL) {
@@ -326,7 +776,7 @@ __global__ void g_outputs(GArgs A, int cur, double* poses_out, double* points_ou
     for (int j = i; j < 3 * A.nL; j += gridDim.x * blockDim.x) points_out[j] = A.pt[cur][j];
 }
 
-// ================================================================================================ dynamic libraries
+// ================================================================================================ NCCL (dlopen)
 namespace {
 struct Id128 { char internal[128]; };      // ncclUniqueId
 struct NcclApi {
@@ -337,17 +787,7 @@ struct NcclApi {
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
-struct SolverApi {
-    void* lib = nullptr;
-    int (*Create)(void**) = nullptr;
-    int (*Destroy)(void*) = nullptr;
-    int (*SetStream)(void*, cudaStream_t) = nullptr;
-    int (*PotrfBufferSize)(void*, int, int, double*, int, int*) = nullptr;
-    int (*Potrf)(void*, int, int, double*, int, double*, int, int*) = nullptr;
-    int (*Potrs)(void*, int, int, int, const double*, int, double*, int, int*) = nullptr;
-};
 NcclApi g_nccl;
-SolverApi g_solver;
 
 bool load_nccl() {
     if (g_nccl.lib) return true;
@@ -364,46 +804,27 @@ bool load_nccl() {
     }
     return false;
 }
-bool load_solver() {
-    if (g_solver.lib) return true;
-    for (const char* name : {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so", "/usr/local/cuda/lib64/libcusolver.so"}) {
-        void* h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-        if (!h) continue;
-        g_solver.Create = (int (*)(void**))dlsym(h, "cusolverDnCreate");
-        g_solver.Destroy = (int (*)(void*))dlsym(h, "cusolverDnDestroy");
-        g_solver.SetStream = (int (*)(void*, cudaStream_t))dlsym(h, "cusolverDnSetStream");
-        g_solver.PotrfBufferSize = (int (*)(void*, int, int, double*, int, int*))dlsym(h, "cusolverDnDpotrf_bufferSize");
-        g_solver.Potrf = (int (*)(void*, int, int, double*, int, double*, int, int*))dlsym(h, "cusolverDnDpotrf");
-        g_solver.Potrs = (int (*)(void*, int, int, int, const double*, int, double*, int, int*))dlsym(h, "cusolverDnDpotrs");
-        if (g_solver.Create && g_solver.Potrf && g_solver.Potrs && g_solver.PotrfBufferSize) { g_solver.lib = h; return true; }
-        dlclose(h);
-    }
-    return false;
-}
-const int NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, FILL_LOWER = 0;
+const int NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3;
 }  // namespace
 
 struct orbgba {
     int device = 0, rank = 0, world = 1;
     cudaStream_t stream = nullptr;
     void* comm = nullptr;
-    void* solver = nullptr;
     uint8_t* arena = nullptr; size_t arena_cap = 0;
-    double* work = nullptr; int lwork = 0;
-    int* d_info = nullptr;
     double* h_red = nullptr;        // pinned
     long long launches = 0;
-    double allreduce_ms = 0, solve_ms = 0;     // accumulated over the last optimize call (events)
+    double allreduce_ms = 0, solve_ms = 0, loop_ms = 0;   // accumulated over the last optimize call (events)
     size_t allreduce_bytes = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    long long sky_blocks = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 static void gba_free(orbgba* g) {
     if (!g) return;
     cudaSetDevice(g->device);
     if (g->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g->comm);
-    if (g->solver && g_solver.Destroy) g_solver.Destroy(g->solver);
-    cudaFree(g->arena); cudaFree(g->work); cudaFree(g->d_info);
+    cudaFree(g->arena);
     if (g->h_red) cudaFreeHost(g->h_red);
     for (cudaEvent_t e : g->ev) if (e) cudaEventDestroy(e);
     if (g->stream) cudaStreamDestroy(g->stream);
@@ -445,18 +866,15 @@ int orbba_dist_create(orbgba_t** out, int device, int rank, int world, const uin
     cudaDeviceProp prop;
     ORB_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) ORB_FAIL(ORB_E_NO_DEVICE, "orbba_dist_create: device %d is sm_%d%d, the kernels are built for sm_100a only", device, prop.major, prop.minor);
-    if (!load_solver()) ORB_FAIL(ORB_E_NO_DEVICE, "orbba_dist_create: libcusolver not found (dense reduced-camera solve)");
     if (world > 1 && !load_nccl()) ORB_FAIL(ORB_E_NO_DEVICE, "orbba_dist_create: libnccl.so.2 not found");
     ORB_CUDA(cudaSetDevice(device));
     orbgba* g = new (std::nothrow) orbgba();
     if (!g) ORB_FAIL(ORB_E_INVALID, "orbba_dist_create: out of host memory");
     g->device = device; g->rank = rank; g->world = world;
     cudaError_t ce = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&g->d_info, 16);
     if (ce == cudaSuccess) ce = cudaHostAlloc((void**)&g->h_red, 64 * sizeof(double), cudaHostAllocDefault);
-    for (int i = 0; i < 4 && ce == cudaSuccess; i++) ce = cudaEventCreate(&g->ev[i]);
+    for (int i = 0; i < 6 && ce == cudaSuccess; i++) ce = cudaEventCreate(&g->ev[i]);
     if (ce != cudaSuccess) { int rc = orbhost::check_cuda(ce, "orbba_dist_create", __FILE__, __LINE__); gba_free(g); return rc; }
-    if (g_solver.Create(&g->solver) != 0 || g_solver.SetStream(g->solver, g->stream) != 0) { gba_free(g); ORB_FAIL(ORB_E_CUDA, "orbba_dist_create: cusolverDnCreate failed"); }
     if (world > 1) {
         Id128 id;
         memcpy(&id, id128, 128);
@@ -476,48 +894,132 @@ int orbba_dist_timing(const orbgba_t* g, double* allreduce_ms, double* solve_ms,
     if (allreduce_bytes) *allreduce_bytes = (double)g->allreduce_bytes;
     return ORB_OK;
 }
+int orbba_dist_loop_ms(const orbgba_t* g, double* loop_ms, long long* skyline_blocks) {
+    if (!g) ORB_FAIL(ORB_E_INVALID, "orbba_dist_loop_ms: NULL handle");
+    if (loop_ms) *loop_ms = g->loop_ms;
+    if (skyline_blocks) *skyline_blocks = g->sky_blocks;
+    return ORB_OK;
+}
 
 // Optimizer::BundleAdjustment on this rank's shard: ALL poses (replicated, identical on every rank), this rank's landmarks
 // (points [n_points][3]) and their edges (edge_point indexes the local landmark array).  Collective: every rank of the
-// communicator must call it with the same poses / iterations / huber_delta.
+// communicator must call it with the same poses / iterations / huber_delta.  Everything a rank decides on its own (input
+// validation, the stop flag) is exchanged before it is acted on, so that no rank leaves the collective sequence alone.
 int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, double huber_delta, const volatile uint8_t* stop,
                         double* poses_out, double* points_out, orbba_stats_t* stats) {
     if (!g || !Q) ORB_FAIL(ORB_E_INVALID, "orbba_dist_optimize: bad argument");
     const int nP = Q->n_poses, nL = Q->n_points, nE = Q->n_edges, nC = Q->n_cams;
-    if (nP < 1 || nL < 0 || nE < 0 || nC < 1 || iterations < 0) ORB_FAIL(ORB_E_INVALID, "orbba_dist_optimize: bad sizes");
-    if (!Q->poses || !Q->pose_fixed || (nL && !Q->points) || (nE && (!Q->edge_pose || !Q->edge_point || !Q->edge_cam || !Q->edge_obs || !Q->edge_inv_sigma2)) ||
-        !Q->cam_K || !Q->cam_ext || !Q->cam_adj)
-        ORB_FAIL(ORB_E_INVALID, "orbba_dist_optimize: NULL array");
     ORB_CUDA(cudaSetDevice(g->device));
     cudaStream_t st = g->stream;
-    // ---- host-side preparation: free-pose numbering, edges grouped by landmark (stable), CSR
+    // ---- local validation; the verdict is summed over the ranks before anybody returns
+    const char* bad = nullptr;
+    if (nP < 1 || nL < 0 || nE < 0 || nC < 1 || iterations < 0) bad = "bad sizes";
+    else if (!Q->poses || !Q->pose_fixed || (nL && !Q->points) || (nE && (!Q->edge_pose || !Q->edge_point || !Q->edge_cam || !Q->edge_obs || !Q->edge_inv_sigma2)) ||
+             !Q->cam_K || !Q->cam_ext || !Q->cam_adj) bad = "NULL array";
+    if (!bad)
+        for (int e = 0; e < nE; e++)
+            if (Q->edge_pose[e] < 0 || Q->edge_pose[e] >= nP || Q->edge_point[e] < 0 || Q->edge_point[e] >= nL || Q->edge_cam[e] < 0 || Q->edge_cam[e] >= nC) { bad = "edge indexes out of range"; break; }
+    double* d_flag = nullptr;
+    if (g->world > 1) {
+        if (g->arena_cap < 256) { cudaFree(g->arena); g->arena = nullptr; g->arena_cap = 0; ORB_CUDA(cudaMalloc((void**)&g->arena, 1 << 20)); g->arena_cap = 1 << 20; }
+        d_flag = (double*)g->arena;
+        g->h_red[0] = bad ? 1.0 : 0.0;
+        ORB_CUDA(cudaMemcpyAsync(d_flag, g->h_red, 8, cudaMemcpyHostToDevice, st));
+        int rc0 = all_reduce(g, d_flag, 1, NCCL_SUM);
+        if (rc0 != ORB_OK) return rc0;
+        ORB_CUDA(cudaMemcpyAsync(g->h_red, d_flag, 8, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+        if (g->h_red[0] > 0 && !bad) bad = "another rank rejected its shard";
+    }
+    if (bad) ORB_FAIL(ORB_E_INVALID, "orbba_dist_optimize: %s", bad);
+    // ---- host-side preparation: free-pose numbering, edges grouped by landmark (stable), CSR, envelope
     std::vector<int> pose_free(nP, -1);
     int K = 0;
     for (int i = 0; i < nP; i++) if (!Q->pose_fixed[i]) pose_free[i] = K++;
     const long long n = 6LL * K;
-    if (n > 46000) ORB_FAIL(ORB_E_INVALID, "orbba_dist_optimize: %d free poses exceed the dense reduced-camera solver", K);
     std::vector<int> cnt(nL + 1, 0), perm(nE);
-    for (int e = 0; e < nE; e++) {
-        if (Q->edge_pose[e] < 0 || Q->edge_pose[e] >= nP || Q->edge_point[e] < 0 || Q->edge_point[e] >= nL || Q->edge_cam[e] < 0 || Q->edge_cam[e] >= nC)
-            ORB_FAIL(ORB_E_INVALID, "orbba_dist_optimize: edge %d indexes out of range", e);
-        cnt[Q->edge_point[e] + 1]++;
-    }
+    for (int e = 0; e < nE; e++) cnt[Q->edge_point[e] + 1]++;
     for (int l = 0; l < nL; l++) cnt[l + 1] += cnt[l];
     std::vector<int> pt_off(cnt);
     for (int e = 0; e < nE; e++) perm[cnt[Q->edge_point[e]]++] = e;
+    // first(i): lowest free pose sharing a landmark with i (this rank's landmarks; min over ranks below)
+    std::vector<double> first_d((size_t)std::max(K, 1));
+    for (int k = 0; k < K; k++) first_d[k] = k;
+    for (int l = 0; l < nL; l++) {
+        int m = K;
+        for (int s = pt_off[l]; s < pt_off[l + 1]; s++) { const int k = pose_free[Q->edge_pose[perm[s]]]; if (k >= 0) m = std::min(m, k); }
+        for (int s = pt_off[l]; s < pt_off[l + 1]; s++) { const int k = pose_free[Q->edge_pose[perm[s]]]; if (k >= 0 && m < first_d[k]) first_d[k] = m; }
+    }
+    if (g->world > 1 && K > 0) {
+        const size_t need = 8 * (size_t)K + 256;
+        if (need > g->arena_cap) { cudaFree(g->arena); g->arena = nullptr; g->arena_cap = 0; ORB_CUDA(cudaMalloc((void**)&g->arena, need)); g->arena_cap = need; }
+        ORB_CUDA(cudaMemcpyAsync(g->arena, first_d.data(), 8 * (size_t)K, cudaMemcpyHostToDevice, st));
+        int rc0 = all_reduce(g, (double*)g->arena, (size_t)K, NCCL_MIN);
+        if (rc0 != ORB_OK) return rc0;
+        ORB_CUDA(cudaMemcpyAsync(first_d.data(), g->arena, 8 * (size_t)K, cudaMemcpyDeviceToHost, st));
+        ORB_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<int> first(std::max(K, 1), 0), rowptr(K + 1, 0), last(std::max(K, 1), 0);
+    long long NB = 0;
+    for (int k = 0; k < K; k++) { first[k] = (int)first_d[k]; rowptr[k] = (int)NB; NB += k - first[k] + 1; if (NB > 0x3fffffffLL) ORB_FAIL(ORB_E_INVALID, "orbba_dist_optimize: the envelope of the reduced camera system is too large"); }
+    rowptr[K] = (int)NB;
+    for (int k = 0; k < K; k++) last[k] = k;
+    for (int i = 0; i < K; i++) for (int j = first[i]; j < i && last[j] < i; j++) last[j] = i;   // (rows in ascending order: last[] only grows)
+    g->sky_blocks = NB;
+    int sky_w = 0;                           // widest row of the envelope (blocks below the diagonal)
+    for (int k = 0; k < K; k++) sky_w = std::max(sky_w, k - first[k]);
+    const size_t sky_smem = 8 * ((size_t)(sky_w + 3) * (sky_w + 1) * 36 + (size_t)std::max(sky_w, 1) * 36 + (size_t)(sky_w + 3) * 6 + 3 * (size_t)(sky_w + 1) * 36 + 18 + (size_t)(sky_w + 3) * 6);
+    if (sky_w <= SKY_WMAX) ORB_CUDA(cudaFuncSetAttribute(k_sky_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sky_smem));
+    // owner lists: edges per free pose; tuples per skyline block
+    std::vector<int> pose_eoff(K + 1, 0), pose_edge;
+    std::vector<long long> blk_toff((size_t)NB + 1, 0);
+    std::vector<int2> blk_tup;
+    {
+        for (int s = 0; s < nE; s++) { const int k = pose_free[Q->edge_pose[perm[s]]]; if (k >= 0) pose_eoff[k + 1]++; }
+        for (int k = 0; k < K; k++) pose_eoff[k + 1] += pose_eoff[k];
+        pose_edge.resize((size_t)pose_eoff[K]);
+        std::vector<int> pos(pose_eoff.begin(), pose_eoff.end() - 1);
+        for (int s = 0; s < nE; s++) { const int k = pose_free[Q->edge_pose[perm[s]]]; if (k >= 0) pose_edge[pos[k]++] = s; }
+        auto block_of = [&](int ka, int kb) { return (long long)rowptr[ka] + (kb - first[ka]); };   // ka >= kb
+        for (int pass = 0; pass < 2; pass++) {
+            std::vector<long long> wpos;
+            if (pass == 1) {
+                for (long long b2 = 0; b2 < NB; b2++) blk_toff[b2 + 1] += blk_toff[b2];
+                blk_tup.resize((size_t)blk_toff[NB]);
+                wpos.assign(blk_toff.begin(), blk_toff.end() - 1);
+            }
+            for (int l = 0; l < nL; l++)
+                for (int sa = pt_off[l]; sa < pt_off[l + 1]; sa++) {
+                    const int ka = pose_free[Q->edge_pose[perm[sa]]];
+                    if (ka < 0) continue;
+                    for (int sb = pt_off[l]; sb < pt_off[l + 1]; sb++) {
+                        const int kb = pose_free[Q->edge_pose[perm[sb]]];
+                        if (kb < 0 || kb > ka || (kb == ka && sb != sa)) continue;
+                        const long long bid = block_of(ka, kb);
+                        if (pass == 0) blk_toff[bid + 1]++;
+                        else blk_tup[(size_t)wpos[bid]++] = make_int2(sa, sb);
+                    }
+                }
+        }
+    }
+    const long long nT = blk_toff[NB];
     // ---- layout
     size_t cur_off = 0;
     auto add = [&](size_t b) { const size_t o = (cur_off + 255) & ~(size_t)255; cur_off = o + b; return o; };
     const size_t o_epose = add(4 * (size_t)nE), o_ept = add(4 * (size_t)nE), o_ecam = add(4 * (size_t)nE), o_pfree = add(4 * (size_t)nP), o_ptoff = add(4 * (size_t)(nL + 1));
     const size_t o_eobs = add(16 * (size_t)nE), o_einfo = add(8 * (size_t)nE), o_cam = add(8 * BA_CAM_STRIDE * (size_t)nC);
     const size_t o_pose0 = add(56 * (size_t)nP), o_pt0 = add(24 * (size_t)nL);
+    const size_t o_first = add(4 * (size_t)std::max(K, 1)), o_rowptr = add(4 * (size_t)(K + 1)), o_last = add(4 * (size_t)std::max(K, 1));
+    const size_t o_peoff = add(4 * (size_t)(K + 1)), o_pedge = add(4 * std::max<size_t>(pose_edge.size(), 1));
+    const size_t o_btoff = add(8 * (size_t)(NB + 1)), o_btup = add(8 * (size_t)std::max<long long>(nT, 1));
     const size_t staged = add(0);
     const size_t o_pose1 = add(56 * (size_t)nP), o_pt1 = add(24 * (size_t)nL), o_err0 = add(16 * (size_t)nE), o_err1 = add(16 * (size_t)nE);
     const size_t o_rec = add(8 * BA_REC * (size_t)nE), o_B = add(144 * (size_t)nE), o_Y = add(144 * (size_t)nE);
     const size_t o_Hll = add(48 * (size_t)nL), o_bl = add(24 * (size_t)nL);
-    const size_t o_Hpp = add(8 * (size_t)(36 + 6) * std::max(K, 1));                 // Hpp | bp contiguous: one all-reduce
-    const size_t o_Hs = add(8 * (size_t)(n * n + n + 8));                            // Hs | bs contiguous: one all-reduce
-    const size_t o_x = add(8 * (size_t)std::max<long long>(n, 1));
+    const size_t o_Hpp = add(8 * (size_t)(36 + 6) * std::max(K, 1));                 // Hpp | bp: this rank's share
+    const size_t o_Hsum = add(8 * (size_t)(36 + 6) * std::max(K, 1));                // Hpp | bp summed over the ranks: one all-reduce per LM iteration
+    const size_t o_Hs = add(8 * (size_t)(36 * NB + n + 8));                          // skyline | bs contiguous: one all-reduce
+    const size_t o_x = add(8 * (size_t)std::max<long long>(n, 1)), o_panW = add(288 * (size_t)std::max(K, 1));
     const int nbE = std::max(1, (nE + G_T - 1) / G_T), nbL = std::max(1, (nL + G_T - 1) / G_T);
     const size_t o_part = add(16 * (size_t)std::max(nbE, nbL)), o_red = add(64 * 8);
     const size_t o_pout = add(96 * (size_t)nP), o_lout = add(24 * (size_t)std::max(nL, 1));
@@ -537,6 +1039,13 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     }
     memcpy(H.data() + o_pfree, pose_free.data(), 4 * (size_t)nP);
     memcpy(H.data() + o_ptoff, pt_off.data(), 4 * (size_t)(nL + 1));
+    memcpy(H.data() + o_first, first.data(), 4 * (size_t)std::max(K, 1));
+    memcpy(H.data() + o_rowptr, rowptr.data(), 4 * (size_t)(K + 1));
+    memcpy(H.data() + o_last, last.data(), 4 * (size_t)std::max(K, 1));
+    memcpy(H.data() + o_peoff, pose_eoff.data(), 4 * (size_t)(K + 1));
+    if (!pose_edge.empty()) memcpy(H.data() + o_pedge, pose_edge.data(), 4 * pose_edge.size());
+    memcpy(H.data() + o_btoff, blk_toff.data(), 8 * (size_t)(NB + 1));
+    if (nT) memcpy(H.data() + o_btup, blk_tup.data(), 8 * (size_t)nT);
     for (int c = 0; c < nC; c++) {
         double* Dc = h_cam + (size_t)BA_CAM_STRIDE * c;
         for (int i = 0; i < 4; i++) Dc[i] = Q->cam_K[4 * c + i];
@@ -564,71 +1073,79 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     ORB_CUDA(cudaMemcpyAsync(D, H.data(), staged, cudaMemcpyHostToDevice, st));
     GArgs A;
     memset(&A, 0, sizeof(A));
-    A.nP = nP; A.nL = nL; A.nE = nE; A.K = K; A.n = (int)n; A.rank0_adds_bp = g->rank == 0;
+    A.nP = nP; A.nL = nL; A.nE = nE; A.K = K; A.n = (int)n;
     A.e_pose = (const int*)(D + o_epose); A.e_pt = (const int*)(D + o_ept); A.e_cam = (const int*)(D + o_ecam); A.pose_free = (const int*)(D + o_pfree);
     A.pt_off = (const int*)(D + o_ptoff); A.e_obs = (const double*)(D + o_eobs); A.e_info = (const double*)(D + o_einfo); A.cam = (const double*)(D + o_cam);
     A.pose[0] = (double*)(D + o_pose0); A.pose[1] = (double*)(D + o_pose1); A.pt[0] = (double*)(D + o_pt0); A.pt[1] = (double*)(D + o_pt1);
     A.err[0] = (double*)(D + o_err0); A.err[1] = (double*)(D + o_err1);
-    A.rec = (double*)(D + o_rec); A.B = (double*)(D + o_B); A.Y = (double*)(D + o_Y); A.v = nullptr;
-    A.Hll = (double*)(D + o_Hll); A.bl = (double*)(D + o_bl); A.Hpp = (double*)(D + o_Hpp); A.bp = A.Hpp + 36 * (size_t)std::max(K, 1);
-    A.Hs = (double*)(D + o_Hs); A.bs = A.Hs + n * n; A.x = (double*)(D + o_x);
+    A.rec = (double*)(D + o_rec); A.B = (double*)(D + o_B); A.Y = (double*)(D + o_Y);
+    A.Hll = (double*)(D + o_Hll); A.bl = (double*)(D + o_bl); A.Hpp = (double*)(D + o_Hpp); A.bp = A.Hpp + 36 * (size_t)std::max(K, 1); A.Hsum = (double*)(D + o_Hsum);
+    A.Hs = (double*)(D + o_Hs); A.bs = A.Hs + 36 * (size_t)NB; A.x = (double*)(D + o_x); A.panW = (double*)(D + o_panW);
     A.part = (double*)(D + o_part); A.red = (double*)(D + o_red);
+    A.first = (const int*)(D + o_first); A.rowptr = (const int*)(D + o_rowptr); A.last = (const int*)(D + o_last); A.NB = NB;
+    A.pose_eoff = (const int*)(D + o_peoff); A.pose_edge = (const int*)(D + o_pedge);
+    A.blk_toff = (const long long*)(D + o_btoff); A.blk_tup = (const int2*)(D + o_btup);
     double* d_pout = (double*)(D + o_pout);
     double* d_lout = (double*)(D + o_lout);
-    // cuSOLVER workspace
-    if (n > 0) {
-        int lw = 0;
-        if (g_solver.PotrfBufferSize(g->solver, FILL_LOWER, (int)n, A.Hs, (int)n, &lw) != 0) ORB_FAIL(ORB_E_CUDA, "cusolverDnDpotrf_bufferSize failed");
-        if (lw > g->lwork) { cudaFree(g->work); g->work = nullptr; g->lwork = 0; ORB_CUDA(cudaMalloc((void**)&g->work, sizeof(double) * (size_t)lw)); g->lwork = lw; }
-    }
-    g->allreduce_ms = 0; g->solve_ms = 0; g->allreduce_bytes = 0;
+    g->allreduce_ms = 0; g->solve_ms = 0; g->loop_ms = 0; g->allreduce_bytes = 0;
     const bool robust = huber_delta > 0;
     auto read_red = [&](int count) -> int {   // device red[] -> host
         ORB_CUDA(cudaMemcpyAsync(g->h_red, A.red, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaStreamSynchronize(st));
         return ORB_OK;
     };
+    auto put_stop = [&]() -> int {            // this rank's view of the stop flag -> red[2]; it is summed with the two trial scalars
+        const double f = (stop && *stop) ? 1.0 : 0.0;
+        g->h_red[32] = f;
+        ORB_CUDA(cudaMemcpyAsync(A.red + 2, g->h_red + 32, 8, cudaMemcpyHostToDevice, st));
+        return ORB_OK;
+    };
     int rc;
     orbba_stats_t S;
     memset(&S, 0, sizeof(S));
     int cur = 0;
-    const bool stopped0 = stop && *stop;
-    // ---- initial errors: chi2 and the global number of edges
+    // ---- initial errors: chi2, the global number of edges and the stop flag on entry (collective decision)
     ORB_CUDA(cudaMemsetAsync(A.red, 0, 64 * 8, st));
     g_errors<<<nbE, G_T, 0, st>>>(A, cur, robust, huber_delta);
     g_reduce<<<1, 256, 0, st>>>(A, nbE, 0, -1);
     g->launches += 2;
-    g->h_red[0] = 0;
     {
-        // red[3] = local edge count, summed over ranks
-        const double ne = (double)nE;
-        ORB_CUDA(cudaMemcpyAsync(A.red + 3, &ne, 8, cudaMemcpyHostToDevice, st));
-        ORB_CUDA(cudaStreamSynchronize(st));
+        g->h_red[33] = (double)nE;
+        ORB_CUDA(cudaMemcpyAsync(A.red + 3, g->h_red + 33, 8, cudaMemcpyHostToDevice, st));
+        if ((rc = put_stop()) != ORB_OK) return rc;
     }
     if ((rc = all_reduce(g, A.red, 4, NCCL_SUM)) != ORB_OK) return rc;
     if ((rc = read_red(4)) != ORB_OK) return rc;
     double currentChi = g->h_red[0];
     const double totalEdges = g->h_red[3];
+    const bool stopped0 = g->h_red[2] > 0;
     S.initial_chi2 = currentChi;
     double lambda = 0, ni = 2, rho = 0;
     int nBad = 0;
     bool ok_iter = !stopped0 && totalEdges > 0;
+    bool stopped = stopped0;
+    ORB_CUDA(cudaEventRecord(g->ev[4], st));
     for (int it = 0; it < iterations && ok_iter; it++) {
-        if (stop && *stop) break;
+        if (stopped) break;                  // the value every rank agreed on at the end of the previous trial
         // ---- buildSystem
-        ORB_CUDA(cudaMemsetAsync(A.Hpp, 0, 8 * (size_t)(36 + 6) * std::max(K, 1), st));
-        ORB_CUDA(cudaMemsetAsync(A.red + 2, 0, 8, st));
+        ORB_CUDA(cudaMemsetAsync(A.red + 6, 0, 8, st));
         g_lin<<<nbE, G_T, 0, st>>>(A, cur, robust, huber_delta);
         g_build_lm<<<nbL, G_T, 0, st>>>(A);
-        g->launches += 2;
-        ORB_CUDA(cudaEventRecord(g->ev[0], st));
-        if ((rc = all_reduce(g, A.Hpp, (size_t)(36 + 6) * K, NCCL_SUM)) != ORB_OK) return rc;
-        if (it == 0) {
-            if ((rc = all_reduce(g, A.red + 2, 1, NCCL_MAX)) != ORB_OK) return rc;   // non-negative doubles: max is order-free
-            g_pose_maxdiag<<<1, 256, 0, st>>>(A);
+        if (K > 0) g_build_pose<<<K, G_T, 0, st>>>(A);
+        g->launches += 2 + (K > 0);
+        // [Hpp | bp] summed over the ranks on a copy (the per-rank shares stay in place for the diagonal blocks / the rhs of the skyline)
+        if (K > 0) ORB_CUDA(cudaMemcpyAsync(A.Hsum, A.Hpp, 8 * 42 * (size_t)K, cudaMemcpyDeviceToDevice, st));
+        if ((rc = all_reduce(g, A.Hsum, (size_t)42 * K, NCCL_SUM)) != ORB_OK) return rc;
+        if (it == 0) {                       // computeLambdaInit: max |diag| of the summed pose blocks and of the landmark blocks
+            if ((rc = all_reduce(g, A.red + 6, 1, NCCL_MAX)) != ORB_OK) return rc;   // non-negative doubles: max is order-free
+            {
+                GArgs T2 = A;
+                T2.Hpp = A.Hsum;
+                g_pose_maxdiag<<<1, 256, 0, st>>>(T2);
+            }
             g->launches++;
-            if ((rc = read_red(6)) != ORB_OK) return rc;
-            lambda = 1e-5 * std::max(g->h_red[2], g->h_red[5]);     // computeLambdaInit
+            if ((rc = read_red(8)) != ORB_OK) return rc;
+            lambda = 1e-5 * std::max(g->h_red[6], g->h_red[5]);     // computeLambdaInit
             ni = 2; nBad = 0;
         }
         const double iniChi = currentChi;
@@ -636,44 +1153,38 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
         rho = 0;
         bool again = true;
         while (again) {
-            // ---- setLambda + Schur complement (this rank's landmarks)
-            ORB_CUDA(cudaMemsetAsync(A.Hs, 0, 8 * (size_t)(n * n + n), st));
-            if (g->rank == 0 && n > 0) ORB_CUDA(cudaMemcpyAsync(A.bs, A.bp, 8 * (size_t)n, cudaMemcpyDeviceToDevice, st));
-            if (nE > 0) {
-                g_trial<<<(unsigned)((6LL * nE + 255) / 256), 256, 0, st>>>(A, lambda);
-                g_schur<<<(nL + G_T / 32 - 1) / (G_T / 32), G_T, 0, st>>>(A);
+            // ---- setLambda + Schur complement (this rank's landmarks) into the skyline
+            if (nE > 0) { g_trial<<<(unsigned)((6LL * nE + 255) / 256), 256, 0, st>>>(A, lambda); g->launches++; }
+            if (K > 0) {
+                g_rhs<<<(K + G_T / 32 - 1) / (G_T / 32), G_T, 0, st>>>(A);
+                g_schur<<<(unsigned)((NB + G_T / 32 - 1) / (G_T / 32)), G_T, 0, st>>>(A);
                 g->launches += 2;
             }
             // ---- the exchange step: [Hs | bs] summed over ranks
             ORB_CUDA(cudaEventRecord(g->ev[0], st));
-            if ((rc = all_reduce(g, A.Hs, (size_t)(n * n + n), NCCL_SUM)) != ORB_OK) return rc;
+            if ((rc = all_reduce(g, A.Hs, (size_t)(36 * NB + n), NCCL_SUM)) != ORB_OK) return rc;
             ORB_CUDA(cudaEventRecord(g->ev[1], st));
-            int info = 0;
-            if (n > 0) {
-                g_add_diag<<<(36 * K + 255) / 256, 256, 0, st>>>(A, lambda);
+            if (K > 0) {
+                if (sky_w <= SKY_WMAX) k_sky_band<<<1, SKY_T, sky_smem, st>>>(A, lambda, sky_w);
+                else k_sky<<<1, SKY_T, 0, st>>>(A, lambda);
                 g->launches++;
-                if (g_solver.Potrf(g->solver, FILL_LOWER, (int)n, A.Hs, (int)n, g->work, g->lwork, g->d_info) != 0) ORB_FAIL(ORB_E_CUDA, "cusolverDnDpotrf failed");
-                ORB_CUDA(cudaMemcpyAsync(&info, g->d_info, 4, cudaMemcpyDeviceToHost, st));
-                ORB_CUDA(cudaStreamSynchronize(st));
-                if (info == 0) {
-                    if (g_solver.Potrs(g->solver, FILL_LOWER, (int)n, 1, A.Hs, (int)n, A.bs, (int)n, g->d_info) != 0) ORB_FAIL(ORB_E_CUDA, "cusolverDnDpotrs failed");
-                    ORB_CUDA(cudaMemcpyAsync(A.x, A.bs, 8 * (size_t)n, cudaMemcpyDeviceToDevice, st));
-                }
             }
+            else ORB_CUDA(cudaMemsetAsync(A.red + 7, 0, 8, st));
             ORB_CUDA(cudaEventRecord(g->ev[2], st));
-            const int ok = info == 0;
-            // ---- update + trial errors (local), then the two scalars
-            g_pose_update<<<1, 256, 0, st>>>(A, cur, lambda, ok);
-            g_back<<<nbL, G_T, 0, st>>>(A, cur, lambda, ok, robust, huber_delta);
+            // ---- update + trial errors (local), then the scalars
+            g_pose_update<<<1, 256, 0, st>>>(A, cur, lambda);
+            g_back<<<nbL, G_T, 0, st>>>(A, cur, lambda, robust, huber_delta);
             g_reduce<<<1, 256, 0, st>>>(A, nbL, 0, 1);
             g->launches += 3;
-            if ((rc = all_reduce(g, A.red, 2, NCCL_SUM)) != ORB_OK) return rc;
-            if ((rc = read_red(5)) != ORB_OK) return rc;
+            if ((rc = put_stop()) != ORB_OK) return rc;
+            if ((rc = all_reduce(g, A.red, 3, NCCL_SUM)) != ORB_OK) return rc;
+            if ((rc = read_red(8)) != ORB_OK) return rc;
             {
                 float ms = 0;
                 cudaEventElapsedTime(&ms, g->ev[0], g->ev[1]); g->allreduce_ms += ms;
                 cudaEventElapsedTime(&ms, g->ev[1], g->ev[2]); g->solve_ms += ms;
             }
+            const bool ok = g->h_red[7] != 0.0;
             double tempChi = g->h_red[0];
             if (!ok) tempChi = 1.7976931348623157e308;
             const double scale = (g->h_red[4] + g->h_red[1]) + 1e-3;
@@ -691,7 +1202,7 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
                 ni *= 2;
             }
             qmax++;
-            const bool stopped = stop && *stop;
+            stopped = g->h_red[2] > 0;       // summed over the ranks: the same on every rank
             again = rho < 0 && qmax < 10 && !stopped;
         }
         S.iterations++;
@@ -701,12 +1212,14 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
             if (nBad >= 3) ok_iter = false;
         }
     }
+    ORB_CUDA(cudaEventRecord(g->ev[5], st));
     g_outputs<<<std::max(1, (std::max(nP, 3 * nL / 8 + 1) + 255) / 256), 256, 0, st>>>(A, cur, d_pout, d_lout);
     g->launches++;
     ORB_CUDA(cudaGetLastError());
     if (poses_out) ORB_CUDA(cudaMemcpyAsync(poses_out, d_pout, 96 * (size_t)nP, cudaMemcpyDeviceToHost, st));
     if (points_out && nL) ORB_CUDA(cudaMemcpyAsync(points_out, d_lout, 24 * (size_t)nL, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
+    { float ms = 0; cudaEventElapsedTime(&ms, g->ev[4], g->ev[5]); g->loop_ms = ms; }
     S.final_chi2 = currentChi; S.final_lambda = lambda; S.outliers = 0; S.status = stopped0 ? ORB_E_ABORTED : ORB_OK;
     if (stats) *stats = S;
     return S.status;
