@@ -371,6 +371,30 @@ typedef struct {
     const double*  cam_adj;          /* [n_cams][36] */
 } orbba_problem_t;
 
+/* The same graph in the reference's own storage types (what an adaptor reads without widening anything): poses / points CV_32F
+ * (KeyFrame::GetPose(), MapPoint::GetWorldPos()), one 16-byte record per observation (cv::KeyPoint::pt is float, the weight is
+ * mvInvLevelSigma2[kpUn.octave], src/Optimizer.cc:549-571) and the extractor's per-level weight table.  Values are widened to
+ * double on the device, so the results equal those of orbba_problem_t holding the same (float-representable) numbers, and the host ->
+ * device copy carries 16 instead of 36 bytes per edge. */
+typedef struct {
+    uint32_t point;                  /* map point index */
+    uint16_t pose;                   /* key frame index */
+    uint8_t  cam;                    /* camera of the rig */
+    uint8_t  octave;                 /* kpUn.octave: weight = inv_sigma2[octave] */
+    float    u, v;                   /* kpUn.pt */
+} orbba_edge16_t;
+typedef struct {
+    int32_t n_poses, n_points, n_edges, n_cams, n_levels;
+    const float*          poses;       /* [n_poses][12] */
+    const uint8_t*        pose_fixed;  /* [n_poses] */
+    const float*          points;      /* [n_points][3] */
+    const orbba_edge16_t* edges;       /* [n_edges] */
+    const float*          inv_sigma2;  /* [n_levels] ORBextractor::GetInverseScaleSigmaSquares() */
+    const double*         cam_K;       /* [n_cams][4] */
+    const double*         cam_ext;     /* [n_cams][12] */
+    const double*         cam_adj;     /* [n_cams][36] */
+} orbba_problem_f32_t;
+
 typedef struct {
     double  initial_chi2, final_chi2, final_lambda;   /* robust chi2 before, chi2 after the last accepted step, last lambda */
     int32_t iterations, trials, outliers;             /* LM outer iterations, linear solves, edges flagged at the end */
@@ -405,6 +429,7 @@ int  orbba_global(orbba_t*, const orbba_problem_t* problem, int iterations, doub
  * upload = flatten + index + host->device; run = asynchronous on the handle's stream, always restarts from the uploaded
  * estimates (its2 < 0: single round); download = results of problem p (synchronises). */
 int  orbba_upload(orbba_t*, const orbba_problem_t* problems, int n);
+int  orbba_upload_f32(orbba_t*, const orbba_problem_f32_t* problems, int n);   /* same, from the compact form */
 int  orbba_run(orbba_t*, int its1, int its2, double huber_delta, double chi2_th);
 int  orbba_download(orbba_t*, int p, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats);
 /* results of every problem of the last run, concatenated in upload order: poses_out [sum n_poses][12], points_out

@@ -8,4 +8,4 @@ from .capi import KP_DTYPE, OrbError, lib  # noqa: F401
 from .extractor import ORBextractor  # noqa: F401
 from .matcher import ORBmatcher  # noqa: F401
 from .vocabulary import ORBVocabulary, parse_text_vocabulary  # noqa: F401
-from .optimizer import DistributedOptimizer, Optimizer, shard_problem  # noqa: F401
+from .optimizer import DistributedOptimizer, Optimizer, compact_problem, shard_problem  # noqa: F401

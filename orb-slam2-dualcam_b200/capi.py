@@ -56,6 +56,7 @@ SIGNATURES = {
     "orbba_local": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
     "orbba_global": (C.c_int, [vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]),
     "orbba_upload": (C.c_int, [vp, vp, C.c_int]),
+    "orbba_upload_f32": (C.c_int, [vp, vp, C.c_int]),
     "orbba_run": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_double]),
     "orbba_download": (C.c_int, [vp, C.c_int, vp, vp, vp, vp]),
     "orbba_download_batch": (C.c_int, [vp, vp, vp, vp, vp]),

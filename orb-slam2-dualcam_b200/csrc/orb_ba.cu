@@ -1389,7 +1389,69 @@ __global__ void k_stats(BABatch A) {   // one CTA
     if (threadIdx.x == 0) *A.n_active = s_active;   // mapped host memory, read by finish()
 }
 
+// ------------------------------------------------------------------------------------------------ compact input -> device arrays
+// orbba_upload_f32: the staged data are the caller's 16-byte edge records, CV_32F points and the per-level weights (what the
+// reference holds: cv::KeyPoint::pt is float, MapPoint::GetWorldPos() CV_32F, mvInvLevelSigma2 float); the FP64 arrays of the kernels
+// are produced here, so the host -> device copy carries 16 instead of 36 bytes per edge.
+struct BACompact {
+    const orbba_edge16_t* e16;        // [Etot] stored (landmark-grouped) order
+    const float* pts32;               // [Ltot][3]
+    const float* isig;                // per problem: n_levels weights at isig0[p]
+    const int* isig0;
+    int *e_pose, *e_pt, *e_cam;
+    double *e_obs, *e_info, *pt0;
+};
+__global__ void k_expand(BABatch A, BACompact C) {
+    const int b = blockIdx.x;
+    const int p = A.blkE_prob[b];
+    const BAProb P = A.prob[p];
+    const int lb = b - P.blkE0, tid = threadIdx.x;
+    const int e = P.e0 + lb * BA_TE + tid;
+    if (e < P.e0 + P.nE) {
+        const orbba_edge16_t r = C.e16[e];
+        C.e_pose[e] = P.p0 + r.pose; C.e_pt[e] = P.l0 + (int)r.point; C.e_cam[e] = P.c0 + r.cam;
+        C.e_obs[2 * (size_t)e] = (double)r.u; C.e_obs[2 * (size_t)e + 1] = (double)r.v;
+        C.e_info[e] = (double)C.isig[C.isig0[p] + r.octave];
+    }
+    for (int i = lb * BA_TE + tid; i < 3 * P.nL; i += P.nbE * BA_TE) C.pt0[3 * (size_t)P.l0 + i] = (double)C.pts32[3 * (size_t)P.l0 + i];
+}
+
 // ================================================================================================ host side
+// One view over the two input forms of orbba_upload / orbba_upload_f32
+struct ProbView {
+    int nP = 0, nL = 0, nE = 0, nC = 0, nLev = 0;
+    const uint8_t* pose_fixed = nullptr;
+    const double *poses = nullptr, *points = nullptr, *obs = nullptr, *info = nullptr, *cam_K = nullptr, *cam_ext = nullptr, *cam_adj = nullptr;
+    const int32_t *ep = nullptr, *el = nullptr, *ec = nullptr;
+    const float *poses32 = nullptr, *points32 = nullptr, *isig = nullptr;
+    const orbba_edge16_t* e16 = nullptr;
+    bool compact = false;
+    int pose(int e) const { return compact ? (int)e16[e].pose : ep[e]; }
+    int point(int e) const { return compact ? (int)e16[e].point : el[e]; }
+    int cam(int e) const { return compact ? (int)e16[e].cam : ec[e]; }
+    double pose_el(int i, int k) const { return compact ? (double)poses32[12 * i + k] : poses[12 * i + k]; }
+    bool has_nulls() const {
+        if ((nP && !pose_fixed) || !cam_K || !cam_ext || !cam_adj) return true;
+        if (compact) return (nP && !poses32) || (nL && !points32) || (nE && (!e16 || !isig));
+        return (nP && !poses) || (nL && !points) || (nE && (!ep || !el || !ec || !obs || !info));
+    }
+};
+static ProbView view_of(const orbba_problem_t& Q) {
+    ProbView V;
+    V.nP = Q.n_poses; V.nL = Q.n_points; V.nE = Q.n_edges; V.nC = Q.n_cams;
+    V.pose_fixed = Q.pose_fixed; V.poses = Q.poses; V.points = Q.points; V.obs = Q.edge_obs; V.info = Q.edge_inv_sigma2;
+    V.cam_K = Q.cam_K; V.cam_ext = Q.cam_ext; V.cam_adj = Q.cam_adj; V.ep = Q.edge_pose; V.el = Q.edge_point; V.ec = Q.edge_cam;
+    return V;
+}
+static ProbView view_of(const orbba_problem_f32_t& Q) {
+    ProbView V;
+    V.compact = true;
+    V.nP = Q.n_poses; V.nL = Q.n_points; V.nE = Q.n_edges; V.nC = Q.n_cams; V.nLev = Q.n_levels;
+    V.pose_fixed = Q.pose_fixed; V.poses32 = Q.poses; V.points32 = Q.points; V.e16 = Q.edges; V.isig = Q.inv_sigma2;
+    V.cam_K = Q.cam_K; V.cam_ext = Q.cam_ext; V.cam_adj = Q.cam_adj;
+    return V;
+}
+
 struct orbba {
     int device = 0, max_problems = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -1571,9 +1633,10 @@ int orbba_synchronize(orbba_t* b) {
 }
 long long orbba_launch_count(const orbba_t* b) { return b ? b->launches : 0; }
 
+}  // extern "C"
+
 // Validates, concatenates and uploads a batch of problems, then builds the (pose pair -> edge tuples) index on the device.
-int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
-    if (!b || (!problems && n > 0)) ORB_FAIL(ORB_E_INVALID, "orbba_upload: bad argument");
+static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, bool compact) {
     if (n < 0 || n > b->max_problems) ORB_FAIL(ORB_E_INVALID, "orbba_upload: n=%d exceeds max_problems=%d", n, b->max_problems);
     ORB_CUDA(cudaSetDevice(b->device));
     int rc = finish(b);
@@ -1589,13 +1652,13 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     std::vector<int> Ks(n, 0);
     std::vector<std::string> errs(n);
     parallel_for(n, [&](int p) {
-        const orbba_problem_t& Q = problems[p];
-        const int nP = Q.n_poses, nL = Q.n_points, nE = Q.n_edges, nC = Q.n_cams;
+        const ProbView& Q = problems[p];
+        const int nP = Q.nP, nL = Q.nL, nE = Q.nE, nC = Q.nC;
         char msg[256];
         if (nP < 0 || nL < 0 || nE < 0 || nC < 1) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d has negative sizes", p); errs[p] = msg; return; }
         if (nC * nC > BA_MAXCC) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d has a rig of %d cameras (at most 4)", p, nC); errs[p] = msg; return; }
-        if ((nP && (!Q.poses || !Q.pose_fixed)) || (nL && !Q.points) || (nE && (!Q.edge_pose || !Q.edge_point || !Q.edge_cam || !Q.edge_obs || !Q.edge_inv_sigma2)) ||
-            !Q.cam_K || !Q.cam_ext || !Q.cam_adj) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d has a NULL array", p); errs[p] = msg; return; }
+        if (Q.has_nulls()) { snprintf(msg, sizeof(msg), "orbba_upload: problem %d has a NULL array", p); errs[p] = msg; return; }
+        if (compact && (nP > 65535 || Q.nLev < 1 || Q.nLev > 255)) { snprintf(msg, sizeof(msg), "orbba_upload_f32: problem %d: at most 65535 poses, 1..255 levels", p); errs[p] = msg; return; }
         std::vector<int>& pf = pose_free_local[p];
         pf.assign(nP, -1);
         int K = 0;
@@ -1603,17 +1666,17 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         Ks[p] = K;
         bool grouped = true;
         for (int e = 0; e < nE; e++) {
-            if (Q.edge_pose[e] < 0 || Q.edge_pose[e] >= nP || Q.edge_point[e] < 0 || Q.edge_point[e] >= nL || Q.edge_cam[e] < 0 || Q.edge_cam[e] >= nC) {
+            if (Q.pose(e) < 0 || Q.pose(e) >= nP || Q.point(e) < 0 || Q.point(e) >= nL || Q.cam(e) < 0 || Q.cam(e) >= nC || (compact && Q.e16[e].octave >= Q.nLev)) {
                 snprintf(msg, sizeof(msg), "orbba_upload: problem %d edge %d indexes out of range", p, e); errs[p] = msg; return;
             }
-            if (e > 0 && Q.edge_point[e] < Q.edge_point[e - 1]) grouped = false;
+            if (e > 0 && Q.point(e) < Q.point(e - 1)) grouped = false;
         }
         if (!grouped) {   // stable counting sort by landmark (the reference adds edges landmark by landmark, src/Optimizer.cc:530-575)
             std::vector<int> cnt(nL + 1, 0);
-            for (int e = 0; e < nE; e++) cnt[Q.edge_point[e] + 1]++;
+            for (int e = 0; e < nE; e++) cnt[Q.point(e) + 1]++;
             for (int l = 0; l < nL; l++) cnt[l + 1] += cnt[l];
             b->perm[p].resize(nE);
-            for (int e = 0; e < nE; e++) b->perm[p][cnt[Q.edge_point[e]]++] = e;
+            for (int e = 0; e < nE; e++) b->perm[p][cnt[Q.point(e)]++] = e;
         }
         // free-pose observations per landmark; one observation per (landmark, keyframe) as in MapPoint::mObservations
         std::vector<int> stamp(nP, -1);
@@ -1622,7 +1685,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         const std::vector<int>& pm = b->perm[p];
         for (int s = 0; s < nE; s++) {
             const int e = pm.empty() ? s : pm[s];
-            const int l = Q.edge_point[e], ps = Q.edge_pose[e];
+            const int l = Q.point(e), ps = Q.pose(e);
             if (stamp[ps] == l) {
                 snprintf(msg, sizeof(msg), "orbba_upload: problem %d observes landmark %d twice from pose %d (MapPoint::mObservations holds one per keyframe)", p, l, ps);
                 errs[p] = msg; return;
@@ -1635,7 +1698,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
         tups[p] = tup;
         {   // k_land blocks: greedy packing of whole landmarks into groups of <= BA_TG edges (a larger landmark stands alone)
             std::vector<int> cntl(nL, 0);
-            for (int e = 0; e < nE; e++) cntl[Q.edge_point[e]]++;
+            for (int e = 0; e < nE; e++) cntl[Q.point(e)]++;
             std::vector<int>& G = groups[p];
             int first = 0, ne = 0;
             for (int l = 0; l < nL; l++) {
@@ -1660,8 +1723,8 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     if (((size_t)hs_smem_n * (hs_smem_n + 1) / 2 + 2 + max_n + 6 * (size_t)hs_smem_n) * 8 > 200 * 1024) hs_smem_n = 0;
     std::vector<int> bP0(n), bI0(n);
     for (int p = 0; p < n; p++) {
-        const orbba_problem_t& Q = problems[p];
-        const int nP = Q.n_poses, nL = Q.n_points, nE = Q.n_edges, nC = Q.n_cams, K = Ks[p];
+        const ProbView& Q = problems[p];
+        const int nP = Q.nP, nL = Q.nL, nE = Q.nE, nC = Q.nC, K = Ks[p];
         const long long tup = tups[p];
         BAProb& P = b->probs[p];
         P.e0 = (int)Etot; P.nE = nE; P.l0 = (int)Ltot; P.nL = nL; P.p0 = (int)Ptot; P.nP = nP; P.c0 = (int)Ctot; P.nC = nC;
@@ -1687,14 +1750,26 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     // ---- layout: static (staged from the host) then device-only
     Layout L;
     const size_t o_prob = L.add(sizeof(BAProb) * n);
-    const size_t o_epose = L.add(4 * Etot), o_ept = L.add(4 * Etot), o_ecam = L.add(4 * Etot);
-    const size_t o_eobs = L.add(16 * Etot), o_einfo = L.add(8 * Etot), o_cam = L.add(8 * BA_CAM_STRIDE * Ctot);
-    const size_t o_ptoff = L.add(4 * (Ltot + 1)), o_pfree = L.add(4 * Ptot), o_pose0 = L.add(56 * Ptot), o_pt0 = L.add(24 * Ltot);
+    // the per-edge / per-point FP64 inputs are staged from the host (orbba_upload) or produced on the device from the staged compact
+    // records (orbba_upload_f32): 16 instead of 36 bytes per edge, 12 instead of 24 per point over PCIe
+    size_t o_epose = 0, o_ept = 0, o_ecam = 0, o_eobs = 0, o_einfo = 0, o_pt0 = 0, o_e16 = 0, o_pts32 = 0, o_isig = 0, o_isig0 = 0;
+    long long levTot = 0;
+    for (int p = 0; p < n; p++) levTot += problems[p].nLev;
+    if (!compact) {
+        o_epose = L.add(4 * Etot); o_ept = L.add(4 * Etot); o_ecam = L.add(4 * Etot); o_eobs = L.add(16 * Etot); o_einfo = L.add(8 * Etot); o_pt0 = L.add(24 * Ltot);
+    } else {
+        o_e16 = L.add(16 * Etot); o_pts32 = L.add(12 * Ltot); o_isig = L.add(4 * (size_t)std::max<long long>(levTot, 1)); o_isig0 = L.add(4 * (size_t)n);
+    }
+    const size_t o_cam = L.add(8 * BA_CAM_STRIDE * Ctot);
+    const size_t o_ptoff = L.add(4 * (Ltot + 1)), o_pfree = L.add(4 * Ptot), o_pose0 = L.add(56 * Ptot);
     const size_t o_blkE = L.add(4 * (size_t)nbE), o_blkL = L.add(4 * (size_t)nbL), o_item = L.add(4 * (size_t)std::max(nbI, 1));
     const size_t o_blkPp = L.add(4 * (size_t)std::max(nbP, 1)), o_blkPf = L.add(4 * (size_t)std::max(nbP, 1)), o_blkIf = L.add(4 * (size_t)std::max(nbI, 1));
     const size_t o_poseprob = L.add(4 * (size_t)std::max<long long>(Ktot, 1)), o_freepose = L.add(4 * (size_t)std::max<long long>(Ktot, 1));
     const size_t o_blkGp = L.add(4 * (size_t)std::max(nbG, 1)), o_blkGl = L.add(4 * (size_t)std::max(nbG, 1)), o_blkGn = L.add(4 * (size_t)std::max(nbG, 1));
     const size_t static_bytes = L.add(0);
+    if (compact) {
+        o_epose = L.add(4 * Etot); o_ept = L.add(4 * Etot); o_ecam = L.add(4 * Etot); o_eobs = L.add(16 * Etot); o_einfo = L.add(8 * Etot); o_pt0 = L.add(24 * Ltot);
+    }
     const size_t o_state = L.add(sizeof(BAState) * n);
     const size_t o_eof = L.add(4 * (size_t)eofTot), o_pcnt = L.add(4 * (size_t)pairTot), o_poff = L.add(4 * (size_t)pairTot);
     const size_t o_pccnt = L.add(4 * (size_t)pcTot), o_pcoff = L.add(4 * (size_t)pcTot), o_pcfch = L.add(4 * (size_t)pcTot), o_pcnch = L.add(4 * (size_t)pcTot);
@@ -1733,22 +1808,35 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     int *h_blkE = (int*)(H + o_blkE), *h_blkL = (int*)(H + o_blkL), *h_item = (int*)(H + o_item), *h_blkPp = (int*)(H + o_blkPp), *h_blkPf = (int*)(H + o_blkPf),
         *h_blkIf = (int*)(H + o_blkIf), *h_poseprob = (int*)(H + o_poseprob), *h_freepose = (int*)(H + o_freepose);
     int *h_blkGp = (int*)(H + o_blkGp), *h_blkGl = (int*)(H + o_blkGl), *h_blkGn = (int*)(H + o_blkGn);
+    orbba_edge16_t* h_e16 = (orbba_edge16_t*)(H + o_e16);
+    float *h_pts32 = (float*)(H + o_pts32), *h_isig = (float*)(H + o_isig);
+    int* h_isig0 = (int*)(H + o_isig0);
+    std::vector<int> lev0(n, 0);
+    for (int p = 1; p < n; p++) lev0[p] = lev0[p - 1] + problems[p - 1].nLev;
     parallel_for(n, [&](int p) {
         const int bP = bP0[p], bI = bI0[p];
-        const orbba_problem_t& Q = problems[p];
+        const ProbView& Q = problems[p];
         const BAProb& P = b->probs[p];
         const std::vector<int>& pm = b->perm[p];
-        for (int s = 0; s < P.nE; s++) {
-            const int e = pm.empty() ? s : pm[s];
-            const size_t g = (size_t)P.e0 + s;
-            h_epose[g] = P.p0 + Q.edge_pose[e]; h_ept[g] = P.l0 + Q.edge_point[e]; h_ecam[g] = P.c0 + Q.edge_cam[e];
-            h_eobs[2 * g] = Q.edge_obs[2 * e]; h_eobs[2 * g + 1] = Q.edge_obs[2 * e + 1]; h_einfo[g] = Q.edge_inv_sigma2[e];
+        if (!compact) {
+            for (int s = 0; s < P.nE; s++) {
+                const int e = pm.empty() ? s : pm[s];
+                const size_t g = (size_t)P.e0 + s;
+                h_epose[g] = P.p0 + Q.ep[e]; h_ept[g] = P.l0 + Q.el[e]; h_ecam[g] = P.c0 + Q.ec[e];
+                h_eobs[2 * g] = Q.obs[2 * e]; h_eobs[2 * g + 1] = Q.obs[2 * e + 1]; h_einfo[g] = Q.info[e];
+            }
+        } else {
+            if (pm.empty()) { if (P.nE) memcpy(h_e16 + P.e0, Q.e16, sizeof(orbba_edge16_t) * (size_t)P.nE); }
+            else for (int s = 0; s < P.nE; s++) h_e16[(size_t)P.e0 + s] = Q.e16[pm[s]];
+            if (P.nL) memcpy(h_pts32 + 3 * (size_t)P.l0, Q.points32, sizeof(float) * 3 * (size_t)P.nL);
+            for (int l = 0; l < Q.nLev; l++) h_isig[lev0[p] + l] = Q.isig[l];
+            h_isig0[p] = lev0[p];
         }
         {   // CSR by landmark over the grouped edge order
-            int e = P.e0;
+            int s = 0;
             for (int l = 0; l < P.nL; l++) {
-                h_ptoff[P.l0 + l] = e;
-                while (e < P.e0 + P.nE && h_ept[e] == P.l0 + l) e++;
+                h_ptoff[P.l0 + l] = P.e0 + s;
+                while (s < P.nE && Q.point(pm.empty() ? s : pm[s]) == l) s++;
             }
         }
         for (int i = 0; i < P.nP; i++) h_pfree[P.p0 + i] = pose_free_local[p][i] >= 0 ? P.k0 + pose_free_local[p][i] : -1;
@@ -1767,7 +1855,8 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
             for (int i = 0; i < 36; i++) Dc[BA_CAM_ADJ + i] = Q.cam_adj[36 * c + i];
         }
         for (int i = 0; i < P.nP; i++) {   // Converter::toSE3Quat + SE3Quat(R, t)
-            const double* T = Q.poses + 12 * i;
+            double T[12];
+            for (int k = 0; k < 12; k++) T[k] = Q.pose_el(i, k);
             double* Dp = h_pose0 + 7 * (size_t)(P.p0 + i);
             const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
             q_from_matrix(R, Dp);
@@ -1776,7 +1865,7 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
             for (int k = 0; k < 4; k++) Dp[k] /= nn;
             Dp[4] = T[3]; Dp[5] = T[7]; Dp[6] = T[11];
         }
-        if (P.nL) memcpy(h_pt0 + 3 * (size_t)P.l0, Q.points, sizeof(double) * 3 * P.nL);
+        if (!compact && P.nL) memcpy(h_pt0 + 3 * (size_t)P.l0, Q.points, sizeof(double) * 3 * P.nL);
         for (int q = 0; q < P.nbE; q++) h_blkE[P.blkE0 + q] = p;
         for (int q = 0; q < P.nbL; q++) h_blkL[P.blkL0 + q] = p;
         for (int q = 0; q < P.nbG; q++) { h_blkGp[P.blkG0 + q] = p; h_blkGl[P.blkG0 + q] = P.l0 + groups[p][2 * q]; h_blkGn[P.blkG0 + q] = groups[p][2 * q + 1]; }
@@ -1818,6 +1907,14 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     // ---- upload + index construction on the device (on the copy stream when one is set: overlaps with a run of another handle)
     cudaStream_t st = b->copy_stream ? b->copy_stream : b->stream;
     ORB_CUDA(cudaMemcpyAsync(D, H, static_bytes, cudaMemcpyHostToDevice, st));
+    if (compact) {
+        BACompact C;
+        C.e16 = (const orbba_edge16_t*)(D + o_e16); C.pts32 = (const float*)(D + o_pts32); C.isig = (const float*)(D + o_isig); C.isig0 = (const int*)(D + o_isig0);
+        C.e_pose = (int*)(D + o_epose); C.e_pt = (int*)(D + o_ept); C.e_cam = (int*)(D + o_ecam);
+        C.e_obs = (double*)(D + o_eobs); C.e_info = (double*)(D + o_einfo); C.pt0 = (double*)(D + o_pt0);
+        k_expand<<<nbE, BA_TE, 0, st>>>(A, C);
+        b->launches++;
+    }
     ORB_CUDA(cudaMemsetAsync(D + o_state, 0, sizeof(BAState) * n, st));
     ORB_CUDA(cudaMemsetAsync(D + o_irec, 0, 32 * 4 * (size_t)std::max(nbI, 1), st));
     if (eofTot) ORB_CUDA(cudaMemsetAsync(D + o_eof, 0xff, 4 * (size_t)eofTot, st));
@@ -1833,6 +1930,22 @@ int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
     if (b->copy_stream) { ORB_CUDA(cudaEventRecord(b->up_ev, st)); b->up_pending = true; }
     b->n = n;
     return ORB_OK;
+}
+
+extern "C" {
+
+int orbba_upload(orbba_t* b, const orbba_problem_t* problems, int n) {
+    if (!b || (!problems && n > 0)) ORB_FAIL(ORB_E_INVALID, "orbba_upload: bad argument");
+    std::vector<ProbView> V((size_t)std::max(n, 0));
+    for (int p = 0; p < n; p++) V[p] = view_of(problems[p]);
+    return upload_views(b, V, n, false);
+}
+// The same batch from the reference's own storage types: CV_32F poses / points, 16-byte edge records, per-level weights.
+int orbba_upload_f32(orbba_t* b, const orbba_problem_f32_t* problems, int n) {
+    if (!b || (!problems && n > 0)) ORB_FAIL(ORB_E_INVALID, "orbba_upload_f32: bad argument");
+    std::vector<ProbView> V((size_t)std::max(n, 0));
+    for (int p = 0; p < n; p++) V[p] = view_of(problems[p]);
+    return upload_views(b, V, n, true);
 }
 
 // Runs the uploaded batch from its uploaded initial estimates (asynchronous on the handle's stream).

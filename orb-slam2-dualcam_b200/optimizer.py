@@ -26,6 +26,33 @@ class ProblemC(C.Structure):
                 ("cam_K", C.c_void_p), ("cam_ext", C.c_void_p), ("cam_adj", C.c_void_p)]
 
 
+class ProblemF32C(C.Structure):
+    _fields_ = [("n_poses", C.c_int32), ("n_points", C.c_int32), ("n_edges", C.c_int32), ("n_cams", C.c_int32), ("n_levels", C.c_int32),
+                ("poses", C.c_void_p), ("pose_fixed", C.c_void_p), ("points", C.c_void_p), ("edges", C.c_void_p), ("inv_sigma2", C.c_void_p),
+                ("cam_K", C.c_void_p), ("cam_ext", C.c_void_p), ("cam_adj", C.c_void_p)]
+
+
+EDGE16 = np.dtype([("point", "<u4"), ("pose", "<u2"), ("cam", "u1"), ("octave", "u1"), ("u", "<f4"), ("v", "<f4")])
+
+
+def compact_problem(p, inv_sigma2_levels):
+    """dict in the orbba_problem_t layout -> dict in the orbba_problem_f32_t layout (what an adaptor would read straight out of
+    KeyFrame / MapPoint): every value of `p` must be float-representable and every weight one of the per-level table."""
+    lev = np.asarray(inv_sigma2_levels, np.float32)
+    w = np.asarray(p["edge_inv_sigma2"], np.float64)
+    octave = np.abs(w[:, None] - lev[None, :].astype(np.float64)).argmin(1)
+    assert np.array_equal(lev[octave].astype(np.float64), w), "edge weights are not entries of the level table"
+    e = np.zeros(len(w), EDGE16)
+    e["point"], e["pose"], e["cam"], e["octave"] = p["edge_point"], p["edge_pose"], p["edge_cam"], octave
+    e["u"], e["v"] = p["edge_obs"][:, 0], p["edge_obs"][:, 1]
+    for k, a in (("poses", p["poses"]), ("points", p["points"]), ("edge_obs", p["edge_obs"])):
+        assert np.array_equal(np.asarray(a, np.float32).astype(np.float64), a), k + " is not float-representable"
+    return dict(poses=np.ascontiguousarray(p["poses"], np.float32), pose_fixed=np.ascontiguousarray(p["pose_fixed"], np.uint8),
+                points=np.ascontiguousarray(p["points"], np.float32), edges=e, inv_sigma2=lev,
+                cam_K=np.ascontiguousarray(p["cam_K"], np.float64), cam_ext=np.ascontiguousarray(p["cam_ext"], np.float64),
+                cam_adj=np.ascontiguousarray(p["cam_adj"], np.float64))
+
+
 class StatsC(C.Structure):
     _fields_ = [("initial_chi2", C.c_double), ("final_chi2", C.c_double), ("final_lambda", C.c_double),
                 ("iterations", C.c_int32), ("trials", C.c_int32), ("outliers", C.c_int32), ("status", C.c_int32)]
@@ -128,8 +155,18 @@ class Optimizer:
 
     def upload(self, problems):
         arr, keeps = problems if isinstance(problems, tuple) else self.prepare(problems)
-        check(lib().orbba_upload(self._h, C.addressof(arr), len(arr)))
+        fn = lib().orbba_upload_f32 if isinstance(arr[0], ProblemF32C) else lib().orbba_upload
+        check(fn(self._h, C.addressof(arr), len(arr)))
         self._sizes = [(a.n_poses, a.n_points, a.n_edges) for a in arr]
+
+    @staticmethod
+    def prepare_f32(compact_problems):
+        """list of compact_problem() dicts -> (ctypes array of orbba_problem_f32_t, keep-alive list) for upload()"""
+        arr = (ProblemF32C * len(compact_problems))()
+        for i, q in enumerate(compact_problems):
+            arr[i] = ProblemF32C(n_poses=len(q["pose_fixed"]), n_points=len(q["points"]), n_edges=len(q["edges"]), n_cams=len(q["cam_K"]),
+                                 n_levels=len(q["inv_sigma2"]), **{k: q[k].ctypes.data for k in ("poses", "pose_fixed", "points", "edges", "inv_sigma2", "cam_K", "cam_ext", "cam_adj")})
+        return arr, list(compact_problems)
 
     def set_stream(self, stream):
         h = _stream_handle(stream)

@@ -124,6 +124,16 @@ def rig_extrinsics():
     return ext.astype(np.float64), adj.astype(np.float64)
 
 
+def inv_sigma2_levels(n_levels=8, f=1.2):
+    """ORBextractor::mvInvLevelSigma2 (src/ORBextractor.cc:419-431): float products, as ba_problem weights its observations"""
+    out = np.ones(n_levels, np.float32)
+    sc = np.float32(1.0)
+    for l in range(1, n_levels):
+        sc = np.float32(sc * np.float32(f))
+        out[l] = np.float32(1.0) / np.float32(sc * sc)
+    return out
+
+
 def ba_problem(seed=0, n_kf=20, n_points=4000, n_fixed_extra=0, obs_range=(5, 10), outlier_frac=0.05, W=640, H=480,
                pose_noise=(0.02, 0.5), point_noise=0.05):
     """Synthetic LocalBundleAdjustment input.  Returns a dict of numpy arrays in the layout of

@@ -152,3 +152,25 @@ def test_heterogeneous_batch_with_rejected_trials():
     opt.run()
     for i, (p, r) in enumerate(zip(ps, refs)):
         _check(p, opt.download(i), r)
+
+
+def test_compact_f32_upload_equals_f64_upload():
+    """orbba_upload_f32 (CV_32F poses / points, 16-byte edge records, per-level weights) gives the bits of orbba_upload"""
+    from orbslam2_dualcam_b200 import compact_problem
+    ps = [synth.ba_problem(50 + i, n_kf=5 + 2 * i, n_points=150 + 60 * i) for i in range(3)]
+    lev = synth.inv_sigma2_levels()
+    a = Optimizer(max_problems=3)
+    a.upload(ps)
+    a.run()
+    b = Optimizer(max_problems=3)
+    perm = np.random.default_rng(1).permutation(len(ps[1]["edge_pose"]))
+    q1 = dict(ps[1])
+    for k in ("edge_pose", "edge_point", "edge_cam", "edge_obs", "edge_inv_sigma2"):
+        q1[k] = np.ascontiguousarray(ps[1][k][perm])                    # ungrouped edges through the compact path too
+    b.upload(Optimizer.prepare_f32([compact_problem(p, lev) for p in (ps[0], q1, ps[2])]))
+    b.run()
+    for i in (0, 2):
+        ra, rb = a.download(i), b.download(i)
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2]) and ra[3] == rb[3]
+    ra, rb = a.download(1), b.download(1)
+    assert _pose_rel(rb[0], ra[0]) <= 1e-9 and np.array_equal(ra[2][perm], rb[2])
