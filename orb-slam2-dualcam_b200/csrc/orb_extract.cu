@@ -5,13 +5,16 @@
 // :108-147 computeOrbDescriptor (+ cv::GaussianBlur 7x7 s=2), bit_pattern_31_ :150-408.
 //
 // Kernel pipeline per orbx_extract_device() call (all images of the batch in every launch):
-//   resize_level_kernel   x (nlevels-1)   level l from level l-1, cv::resize INTER_LINEAR 8U fixed-point arithmetic
-//   fast_cells_kernel     x 1             one CTA per 30-px cell: FAST-9/16 score, cell-local NMS, ini/min threshold
-//                                         fallback, unordered packed candidate list per (image, level)
+//   resize4_kernel        x (nlevels-1)   level l from level l-1, cv::resize INTER_LINEAR 8U fixed-point arithmetic: 4 pixels per thread
+//                                         from aligned source words, horizontal taps with dp2a (resize_level_kernel: any scale factor)
+//   fast_cells_kernel     x 1             one CTA per 30-px cell: the cell's tile of the pyramid level is staged in shared memory by TMA
+//                                         (cp.async.bulk.tensor.3d + mbarrier, one tensor map per level); FAST-9/16 score, cell-local
+//                                         NMS, ini/min threshold fallback, unordered packed candidate list per (image, level)
 //   quadtree_kernel       x 1             one CTA per (image, level): level-synchronous DistributeOctTree
 //   describe_kernel       x 1             one warp per keypoint: IC angle, 7x7 Gaussian of the 37x37 patch in shared
 //                                         memory, steered rBRIEF, cv::KeyPoint + 32-byte descriptor output
 // There is no CPU fallback: every entry point needs a CUDA device.
+#include <cuda.h>              // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
 #include <string.h>
 
 #include <algorithm>
@@ -45,6 +48,12 @@ struct CellDesc {                  // one cell of ComputeKeyPointsOctTree's grid
     short x0, y0, dw, dh;          // detection region (border-relative), see fast_cells_kernel
     int level;
     unsigned m_dw;                 // ceil(2^20 / dw)
+};
+
+// One tiled tensor map per pyramid level: (x, y, image) over uint8, box = (tile width rounded up to 16 bytes, tile height, 1).
+struct alignas(64) FastMaps {
+    CUtensorMap lv[ORB_MAX_LEVELS];
+    int bw[ORB_MAX_LEVELS], bh[ORB_MAX_LEVELS];        // box size = tile pitch and rows the TMA writes
 };
 
 struct ExtractParams {
@@ -98,6 +107,70 @@ __global__ void __launch_bounds__(128) resize_level_kernel(const uint8_t* __rest
     *reinterpret_cast<uint32_t*>(D + dx0) = outw;
 }
 
+// The same arithmetic for scale factors up to 2.33, 4 destination pixels per thread with a third of the load instructions: one
+// 32-byte table entry per group {aligned source offset, byte offsets of the 4 left taps inside a 12-byte window, the 4 coefficient
+// pairs}, three aligned words per source row, the two taps of a pixel funnel-shifted into the low bytes of a register and multiplied
+// by the coefficient pair with one dp2a (S = p0 a0 + p1 a1, the integers cv::resize forms).  The byte-gather form above spent
+// 69 thread instructions per pixel, 79 % of the LSU wavefront budget.
+__global__ void __launch_bounds__(128) resize4_kernel(const uint8_t* __restrict__ src, int sh, int spitch, unsigned long long sstride,
+                                                      uint8_t* __restrict__ dst, int dw, int dh, int dpitch, unsigned long long dstride,
+                                                      const uint4* __restrict__ xtab, const int* __restrict__ yofs, const int* __restrict__ ibeta) {
+    const int nx4 = (dw + 3) >> 2;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= nx4 * dh) return;
+    const int dy = item / nx4, g = item - dy * nx4;
+    const uint4 t0 = __ldg(xtab + 2 * g), t1 = __ldg(xtab + 2 * g + 1);
+    const uint8_t* S = src + (unsigned long long)blockIdx.y * sstride;
+    const int sy = __ldg(yofs + dy);
+    const int r0 = min(max(sy, 0), sh - 1), r1 = min(max(sy + 1, 0), sh - 1);
+    const int bpk = __ldg(ibeta + dy);
+    const int b0 = (short)(bpk & 0xffff), b1 = (short)(bpk >> 16);
+    // three aligned words per row; the last word of a row is re-read rather than crossed (the taps it would hold carry weight 0)
+    const int o0 = (int)t0.x, o1 = min(o0 + 4, spitch - 4), o2 = min(o0 + 8, spitch - 4);
+    const uint8_t* R0 = S + (size_t)r0 * spitch;
+    const uint8_t* R1 = S + (size_t)r1 * spitch;
+    const uint32_t a0 = __ldg(reinterpret_cast<const uint32_t*>(R0 + o0)), a1 = __ldg(reinterpret_cast<const uint32_t*>(R0 + o1)), a2 = __ldg(reinterpret_cast<const uint32_t*>(R0 + o2));
+    const uint32_t c0 = __ldg(reinterpret_cast<const uint32_t*>(R1 + o0)), c1 = __ldg(reinterpret_cast<const uint32_t*>(R1 + o1)), c2 = __ldg(reinterpret_cast<const uint32_t*>(R1 + o2));
+    const uint32_t apk[4] = {t1.x, t1.y, t1.z, t1.w};
+    uint32_t outw = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t o = (t0.y >> (8 * k)) & 0xffu, idx = o >> 2, sh8 = 8 * (o & 3);
+        const uint32_t lo0 = idx == 0 ? a0 : (idx == 1 ? a1 : a2), hi0 = idx == 0 ? a1 : a2;
+        const uint32_t lo1 = idx == 0 ? c0 : (idx == 1 ? c1 : c2), hi1 = idx == 0 ? c1 : c2;
+        const int S0 = (int)__dp2a_lo(apk[k], __funnelshift_r(lo0, hi0, sh8), 0u);
+        const int S1 = (int)__dp2a_lo(apk[k], __funnelshift_r(lo1, hi1, sh8), 0u);
+        int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+        outw |= (uint32_t)v << (8 * k);
+    }
+    // rows are padded to a multiple of 16 bytes, so the full word store never leaves the row
+    *reinterpret_cast<uint32_t*>(dst + (unsigned long long)blockIdx.y * dstride + (size_t)dy * dpitch + 4 * g) = outw;
+}
+
+// ------------------------------------------------------------------------------------------------ TMA / mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the initialised barrier must be visible to the async proxy (TMA) as well
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// box of the level's tensor map at (x, y, image) -> shared memory; completion is counted on `bar` in bytes
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ FAST per cell
 // One CTA = one cell of ComputeKeyPointsOctTree's grid (src/ORBextractor.cc:789-829).  The cell's detection region is
 // [cj*wCell+3, (cj+1)*wCell+3) x [ci*hCell+3, (ci+1)*hCell+3) in border-relative coordinates (the last effective cell
@@ -108,10 +181,13 @@ __global__ void __launch_bounds__(128) resize_level_kernel(const uint8_t* __rest
 // floor(i / d) for the small operands of this kernel: m = ceil(2^20 / d), exact while i * d < 2^20
 __device__ __forceinline__ int fastdiv20(int i, unsigned m) { return (int)(((unsigned)i * m) >> 20); }
 
-__global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_constant__ ExtractParams P,
+// (the tensor maps live in global memory: a kernel-parameter array indexed by the level would be copied to local memory, where TMA
+// cannot read it)
+__global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_constant__ ExtractParams P, const FastMaps* __restrict__ TMp,
                                                                   uint32_t* __restrict__ cand, int* __restrict__ cand_count,
                                                                   int tile_cap, int pix_cap) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_bar;
     uint8_t* tile = smem;                                  // (dh+6) rows of raw pixels, 4-byte aligned like the source rows
     uint8_t* score = tile + tile_cap;                      // dh x dw
     uint16_t* list = reinterpret_cast<uint16_t*>(score + pix_cap);   // pixels that pass the compass pre-test
@@ -128,20 +204,22 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31;
 
-    // ---- stage the tile with aligned 32-bit loads: absolute pixel (16 + x0 - 3 + tx, 16 + y0 - 3 + ty) -> tile[ty * tp + dx + tx]
-    const int gx0 = 16 + x0 - 3, ax0 = gx0 & ~3, dx = gx0 - ax0;
-    const int nw = (dx + tw + 3) >> 2, tp = nw * 4;
-    {
-        const uint8_t* src = P.base[l] + (unsigned long long)img * L.img_stride + (size_t)(16 + y0 - 3) * L.pitch + ax0;
-        const unsigned m_nw = ((1u << 20) + nw - 1) / nw;
-        uint32_t* tw32 = reinterpret_cast<uint32_t*>(tile);
-        for (int i = tid; i < nw * th; i += FAST_THREADS) {
-            const int ty = fastdiv20(i, m_nw), wx = i - ty * nw;
-            tw32[i] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)ty * L.pitch) + wx);
-        }
+    // ---- stage the tile with ONE TMA box load: absolute pixel (16 + x0 - 3 + tx, 16 + y0 - 3 + ty) -> tile[ty * tp + dx + tx], tp = box width.
+    //      The innermost box coordinate has to be a multiple of 16 bytes (the copy engine traps otherwise), so the box starts at the
+    //      16-byte boundary left of the tile; it is the level's largest tile (+ 15) rounded up to 16 bytes, and what it covers beyond
+    //      this cell's tile (or beyond the image: zero fill) is never read.
+    const int gx0 = 16 + x0 - 3, ax0 = gx0 & ~15, dx = gx0 - ax0;
+    const int tp = TMp->bw[l], nw = tp >> 2;
+    (void)tw; (void)th;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar, (unsigned)(tp * TMp->bh[l]));
+        tma_load_tile(tile, &TMp->lv[l], &s_bar, ax0, 16 + y0 - 3, img);
     }
     const int npix = dw * dh;
     for (int i = tid; i < ((npix + 3) >> 2); i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0;
+    mbar_wait(&s_bar, 0);
     const unsigned m_dw = cd.m_dw;
     const uint8_t* T0 = tile + 3 * tp + dx + 3;            // pixel (0, 0) of the detection region
     const int iniTh = min(max(P.iniTh, 0), 255), minTh = min(max(P.minTh, 0), 255);
@@ -278,7 +356,7 @@ __global__ void __launch_bounds__(QT_THREADS) quadtree_kernel(const __grid_const
                                                               const uint32_t* __restrict__ cand, const int* __restrict__ cand_count,
                                                               uint16_t* __restrict__ node_of_all, uint32_t* __restrict__ sel,
                                                               int* __restrict__ sel_count, int maxl, int* __restrict__ overflow) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     QtNode* bufA = reinterpret_cast<QtNode*>(smem);
     QtNode* bufB = bufA + maxl;
     int* cc = reinterpret_cast<int*>(bufB + maxl);
@@ -592,6 +670,12 @@ struct orbx {
     size_t input_pitch = 0;
     int* d_tables = nullptr;           // resize tables of all levels
     std::vector<size_t> tab_off;       // per level: offset (ints) of xofs, ialpha, yofs, ibeta
+    uint4* d_xtab = nullptr;           // resize4_kernel: per level and group of 4 destination columns, two uint4
+    std::vector<size_t> xtab_off;      // per level: offset (uint4) into d_xtab; (size_t)-1 = the level needs the general kernel
+    FastMaps TM;                       // tensor maps of the FAST tiles (level 0 is re-encoded when the caller's buffer changes)
+    FastMaps* d_TM = nullptr;          // ... and their copy in global memory, where the kernel reads them
+    void* encode_fn = nullptr;         // cuTensorMapEncodeTiled
+    const uint8_t* tm0_ptr = nullptr; size_t tm0_stride = 0; int tm0_images = 0;
     uint32_t* d_cand = nullptr;
     uint16_t* d_node_of = nullptr;
     int* d_cand_count = nullptr;       // [max_images][nlevels] followed by the overflow flag
@@ -624,11 +708,26 @@ static void orbx_free(orbx* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
-    cudaFree(e->d_levels); cudaFree(e->d_input); cudaFree(e->d_tables); cudaFree(e->d_cand); cudaFree(e->d_node_of);
+    cudaFree(e->d_levels); cudaFree(e->d_input); cudaFree(e->d_tables); cudaFree(e->d_xtab); cudaFree(e->d_TM); cudaFree(e->d_cand); cudaFree(e->d_node_of);
     cudaFree(e->d_cand_count); cudaFree(e->d_sel); cudaFree(e->d_sel_count); cudaFree(e->d_umax); cudaFree(e->d_cells);
     cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_counts);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// (x, y, image) uint8 tensor of one pyramid level, box (bw, bh, 1)
+static int encode_level_map(orbx* e, int l, const uint8_t* base, int w, int h, size_t pitch, size_t img_stride, int n_images) {
+    const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n_images};
+    const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)img_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)e->TM.bw[l], (cuuint32_t)e->TM.bh[l], 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = ((EncodeTiledFn)e->encode_fn)(&e->TM.lv[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), gdim, gstr, box, estr,
+                                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) ORB_FAIL(ORB_E_CUDA, "cuTensorMapEncodeTiled failed for level %d (%d): %dx%d pitch %zu box %dx%d", l, (int)r, w, h, pitch, e->TM.bw[l], e->TM.bh[l]);
+    return ORB_OK;
 }
 
 extern "C" {
@@ -675,10 +774,11 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
         if (L.valid && G.nIni > ORB_MAX_ROOTS) { orbx_free(e); ORB_FAIL(ORB_E_INVALID, "orbx_create: aspect ratio needs %d quadtree roots (max %d)", G.nIni, ORB_MAX_ROOTS); }
         P.cell_begin[l] = cells;
         L.cand_off = cand_total; L.sel_off = sel_total;
+        e->TM.bw[l] = 16; e->TM.bh[l] = 8;
         if (L.valid) {
             cells += G.nColsEff * G.nRowsEff;
             // strict 3x3 maxima inside a cell: at most ceil(w/2)*ceil(h/2) per cell
-            int cap = 0;
+            int cap = 0, lvl_dw = 0, lvl_dh = 0;
             for (int ci = 0; ci < G.nRowsEff; ci++)
                 for (int cj = 0; cj < G.nColsEff; cj++) {
                     const int x0 = cj * G.wCell + 3, y0 = ci * G.hCell + 3;
@@ -687,12 +787,15 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
                     const int dw = std::max(x1 - x0, 0), dh = std::max(y1 - y0, 0);
                     cap += ((dw + 1) / 2) * ((dh + 1) / 2);
                     max_dw = std::max(max_dw, dw); max_dh = std::max(max_dh, dh);
+                    lvl_dw = std::max(lvl_dw, dw); lvl_dh = std::max(lvl_dh, dh);
                     CellDesc cd;
                     cd.x0 = (short)x0; cd.y0 = (short)y0; cd.dw = (short)dw; cd.dh = (short)dh; cd.level = l;
                     cd.m_dw = dw > 0 ? ((1u << 20) + dw - 1) / dw : 0;
                     cell_table.push_back(cd);
                 }
             L.cand_cap = cap;
+            // TMA box of the level: its largest tile (+ the 3-px ring on every side, + one word so that the SWAR pass may read the word right of the tile)
+            e->TM.bw[l] = (15 + lvl_dw + 6 + 4 + 15) & ~15; e->TM.bh[l] = lvl_dh + 6;
             L.sel_cap = std::max(G.quota + 2, 4 * G.nIni);
             max_quota_l = std::max(max_quota_l, L.sel_cap);
         }
@@ -731,8 +834,34 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
         for (int y = 0; y < G.h; y++) tabs.push_back((int)((uint32_t)(uint16_t)G.ibeta[2 * y] | ((uint32_t)(uint16_t)G.ibeta[2 * y + 1] << 16)));
     }
     alloc((void**)&e->d_tables, tabs.size() * sizeof(int));
+    // resize4_kernel tables: per group of 4 destination columns {aligned source byte offset, 4 tap offsets inside the 12-byte window, -, -} {4 coefficient pairs}
+    std::vector<uint4> xt;
+    e->xtab_off.assign((size_t)nlevels, (size_t)-1);
+    for (int l = 1; l < nlevels; l++) {
+        const orbgeo::Level& G = g.lv[l];
+        const int sw = g.lv[l - 1].w;
+        std::vector<uint4> lvl;
+        bool ok = true;
+        for (int x0 = 0; x0 < G.w && ok; x0 += 4) {
+            const int base = G.xofs[x0] & ~3;
+            uint32_t offs = 0, apk[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; k++) {
+                const int x = std::min(x0 + k, G.w - 1);                 // the pad columns of the last group repeat the last pixel
+                const int o = G.xofs[x] - base;
+                const int a0 = G.ialpha[2 * x], a1 = G.ialpha[2 * x + 1];
+                if (o < 0 || o > 10 || a0 < 0 || a1 < 0 || (G.xofs[x] + 1 > sw - 1 && a1 != 0)) ok = false;
+                offs |= (uint32_t)(o & 0xff) << (8 * k);
+                apk[k] = (uint32_t)(uint16_t)a0 | ((uint32_t)(uint16_t)a1 << 16);
+            }
+            lvl.push_back(make_uint4((uint32_t)base, offs, 0u, 0u));
+            lvl.push_back(make_uint4(apk[0], apk[1], apk[2], apk[3]));
+        }
+        if (ok && (g.lv[l - 1].pitch & 3) == 0) { e->xtab_off[l] = xt.size(); xt.insert(xt.end(), lvl.begin(), lvl.end()); }
+    }
+    alloc((void**)&e->d_xtab, std::max<size_t>(xt.size(), 1) * sizeof(uint4));
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess && !tabs.empty()) ce = cudaMemcpy(e->d_tables, tabs.data(), tabs.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && !xt.empty()) ce = cudaMemcpy(e->d_xtab, xt.data(), xt.size() * sizeof(uint4), cudaMemcpyHostToDevice);
     if (ce == cudaSuccess) ce = cudaMemcpy(e->d_umax, g.umax.data(), 16 * sizeof(int), cudaMemcpyHostToDevice);
     if (ce == cudaSuccess && !cell_table.empty()) ce = cudaMemcpy(e->d_cells, cell_table.data(), cell_table.size() * sizeof(CellDesc), cudaMemcpyHostToDevice);
     P.cells = e->d_cells;
@@ -746,9 +875,26 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
         P.lv[l].img_stride = (unsigned long long)g.lv[l].pitch * g.lv[l].h;
         P.base[l] = e->d_levels + level_off[l] * NI;
     }
-    // FAST shared memory: tile + score + 2 lists
+    // tensor maps of the levels the extractor owns (level 0 belongs to the caller: encoded per call)
+    {
+        cudaDriverEntryPointQueryResult qres;
+        void* fn = nullptr;
+        ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (ce != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) { orbx_free(e); ORB_FAIL(ORB_E_CUDA, "orbx_create: cuTensorMapEncodeTiled is not available in this driver"); }
+        e->encode_fn = fn;
+        for (int l = 1; l < nlevels; l++) {
+            if (!P.lv[l].valid) continue;
+            const int rc = encode_level_map(e, l, P.base[l], g.lv[l].w, g.lv[l].h, (size_t)g.lv[l].pitch, (size_t)P.lv[l].img_stride, e->max_images);
+            if (rc != ORB_OK) { orbx_free(e); return rc; }
+        }
+    }
+    ce = cudaMalloc((void**)&e->d_TM, sizeof(FastMaps));
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->d_TM, &e->TM, sizeof(FastMaps), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { int rc = orbhost::check_cuda(ce, "orbx_create tensor maps", __FILE__, __LINE__); orbx_free(e); return rc; }
+    // FAST shared memory: tile (the largest TMA box) + score + 2 lists
     e->fast_pix_cap = (max_dw * max_dh + 15) & ~15;
-    e->fast_tile_cap = (((3 + max_dw + 6 + 3) & ~3) * (max_dh + 6) + 15) & ~15;   // rows start at a 4-byte aligned source address
+    e->fast_tile_cap = 128;
+    for (int l = 0; l < nlevels; l++) e->fast_tile_cap = std::max(e->fast_tile_cap, (e->TM.bw[l] * e->TM.bh[l] + 127) & ~127);
     e->fast_smem = (size_t)e->fast_tile_cap + e->fast_pix_cap + 2 * sizeof(uint16_t) * e->fast_pix_cap;
     e->qt_maxl = (max_quota_l + 8 + 1) & ~1;
     e->qt_smem = (size_t)e->qt_maxl * (2 * sizeof(QtNode) + 10 * sizeof(int) + sizeof(unsigned long long)) + 16;
@@ -838,15 +984,25 @@ int orbx_extract_device(orbx_t* e, const uint8_t* d_imgs, int frames, size_t row
         const LevelDev& D = P.lv[l];
         dim3 grid((((D.w + 3) / 4) * D.h + 127) / 128, NI);
         const int* T = e->d_tables;
-        resize_level_kernel<<<grid, 128, 0, st>>>(P.base[l - 1], S.w, S.h, S.pitch, S.img_stride, const_cast<uint8_t*>(P.base[l]), D.w, D.h,
-                                                  D.pitch, D.img_stride, T + e->tab_off[l * 4 + 0], T + e->tab_off[l * 4 + 1],
-                                                  T + e->tab_off[l * 4 + 2], T + e->tab_off[l * 4 + 3]);
+        if (e->xtab_off[l] != (size_t)-1 && (S.pitch & 3) == 0 && ((uintptr_t)P.base[l - 1] & 3) == 0)
+            resize4_kernel<<<grid, 128, 0, st>>>(P.base[l - 1], S.h, S.pitch, S.img_stride, const_cast<uint8_t*>(P.base[l]), D.w, D.h, D.pitch, D.img_stride,
+                                                 e->d_xtab + e->xtab_off[l], T + e->tab_off[l * 4 + 2], T + e->tab_off[l * 4 + 3]);
+        else
+            resize_level_kernel<<<grid, 128, 0, st>>>(P.base[l - 1], S.w, S.h, S.pitch, S.img_stride, const_cast<uint8_t*>(P.base[l]), D.w, D.h,
+                                                      D.pitch, D.img_stride, T + e->tab_off[l * 4 + 0], T + e->tab_off[l * 4 + 1],
+                                                      T + e->tab_off[l * 4 + 2], T + e->tab_off[l * 4 + 3]);
         e->launches++;
     }
     if (pev) ORB_CUDA(cudaEventRecord(pev[1], st));
     int* d_overflow = e->d_cand_count + (size_t)e->max_images * L;
     if (P.cells_per_image > 0) {
-        fast_cells_kernel<<<dim3(P.cells_per_image, NI), FAST_THREADS, e->fast_smem, st>>>(P, e->d_cand, e->d_cand_count, e->fast_tile_cap, e->fast_pix_cap);
+        if (P.lv[0].valid && (e->tm0_ptr != d_imgs || e->tm0_stride != row_stride || e->tm0_images != NI)) {   // level 0 is the caller's buffer
+            const int rc = encode_level_map(e, 0, d_imgs, e->W, e->H, row_stride, row_stride * e->H, NI);
+            if (rc != ORB_OK) return rc;
+            e->tm0_ptr = d_imgs; e->tm0_stride = row_stride; e->tm0_images = NI;
+            ORB_CUDA(cudaMemcpyAsync(&e->d_TM->lv[0], &e->TM.lv[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+        }
+        fast_cells_kernel<<<dim3(P.cells_per_image, NI), FAST_THREADS, e->fast_smem, st>>>(P, e->d_TM, e->d_cand, e->d_cand_count, e->fast_tile_cap, e->fast_pix_cap);
         e->launches++;
     }
     if (pev) ORB_CUDA(cudaEventRecord(pev[2], st));
