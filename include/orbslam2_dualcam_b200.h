@@ -420,6 +420,9 @@ long long orbba_launch_count(const orbba_t*);
  *   poses_out [n_poses][12], points_out [n_points][3], edge_outlier [n_edges], stats: any may be NULL. */
 int  orbba_local(orbba_t*, const orbba_problem_t* problem, int its1, int its2, double huber_delta, double chi2_th,
                  const volatile uint8_t* stop, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats);
+/* the same from the compact form (orbba_problem_f32_t): what an adaptor reads out of KeyFrame / MapPoint without widening anything */
+int  orbba_local_f32(orbba_t*, const orbba_problem_f32_t* problem, int its1, int its2, double huber_delta, double chi2_th,
+                     const volatile uint8_t* stop, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats);
 /* Optimizer::BundleAdjustment(vpKFs, vpMP, nIterations, pbStopFlag, nLoopKF, bRobust): one optimize(iterations),
  * Huber(huber_delta) when > 0, no outlier pass. */
 int  orbba_global(orbba_t*, const orbba_problem_t* problem, int iterations, double huber_delta, const volatile uint8_t* stop,

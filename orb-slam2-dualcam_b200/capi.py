@@ -54,6 +54,7 @@ SIGNATURES = {
     "orbba_synchronize": (C.c_int, [vp]),
     "orbba_launch_count": (C.c_longlong, [vp]),
     "orbba_local": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
+    "orbba_local_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
     "orbba_global": (C.c_int, [vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]),
     "orbba_upload": (C.c_int, [vp, vp, C.c_int]),
     "orbba_upload_f32": (C.c_int, [vp, vp, C.c_int]),

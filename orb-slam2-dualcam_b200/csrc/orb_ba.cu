@@ -2067,6 +2067,9 @@ int orbba_download(orbba_t* b, int p, double* poses_out, double* points_out, uin
 // Optimizer::LocalBundleAdjustment for ONE problem, host buffers in and out, synchronous.  `stop` (may be NULL) is
 // polled while the kernels run and forwarded to the device, which reads it after every LM trial
 // (g2o: SparseOptimizer::terminate(), sparse_optimizer.cpp:376, optimization_algorithm_levenberg.cpp:149).
+static int local_run(orbba* b, int its1, int its2, double huber_delta, double chi2_th, const volatile uint8_t* stop, double* poses_out, double* points_out,
+                     uint8_t* edge_outlier, orbba_stats_t* stats);
+
 int orbba_local(orbba_t* b, const orbba_problem_t* problem, int its1, int its2, double huber_delta, double chi2_th,
                 const volatile uint8_t* stop, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats) {
     if (!b || !problem) ORB_FAIL(ORB_E_INVALID, "orbba_local: bad argument");
@@ -2074,6 +2077,21 @@ int orbba_local(orbba_t* b, const orbba_problem_t* problem, int its1, int its2, 
     b->h_flags[0] = (stop && *stop) ? 1 : 0;
     int rc = orbba_upload(b, problem, 1);
     if (rc != ORB_OK) return rc;
+    return local_run(b, its1, its2, huber_delta, chi2_th, stop, poses_out, points_out, edge_outlier, stats);
+}
+// the same from the compact form (what the reference holds: CV_32F poses / points, float key points, per-level weights)
+int orbba_local_f32(orbba_t* b, const orbba_problem_f32_t* problem, int its1, int its2, double huber_delta, double chi2_th,
+                    const volatile uint8_t* stop, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats) {
+    if (!b || !problem) ORB_FAIL(ORB_E_INVALID, "orbba_local_f32: bad argument");
+    ORB_CUDA(cudaSetDevice(b->device));
+    b->h_flags[0] = (stop && *stop) ? 1 : 0;
+    int rc = orbba_upload_f32(b, problem, 1);
+    if (rc != ORB_OK) return rc;
+    return local_run(b, its1, its2, huber_delta, chi2_th, stop, poses_out, points_out, edge_outlier, stats);
+}
+static int local_run(orbba* b, int its1, int its2, double huber_delta, double chi2_th, const volatile uint8_t* stop, double* poses_out, double* points_out,
+                     uint8_t* edge_outlier, orbba_stats_t* stats) {
+    int rc;
     rc = orbba_run(b, its1, its2, huber_delta, chi2_th);
     if (rc != ORB_OK) return rc;
     if (stop) {
