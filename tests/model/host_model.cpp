@@ -163,7 +163,20 @@ int hm_quadtree(const uint32_t* cands, int n, int width, int height, int nIni, f
 void hm_sincos(const float* x, int n, float* c, float* s) {
     for (int i = 0; i < n; i++) { c[i] = glibc_sincosf(x[i], true); s[i] = glibc_sincosf(x[i], false); }
 }
-// exhaustive sweep over float bit patterns [lo, hi] with stride; returns mismatch count vs the given libm results
+// exhaustive sweep over the float bit patterns [lo, hi]: mismatches of the restated sincosf against this box's libm cosf / sinf
+// (first mismatching pattern in *first_bad)
+long long hm_sincos_sweep(uint32_t lo, uint32_t hi, uint32_t* first_bad) {
+    long long bad = 0;
+    for (uint64_t u = lo; u <= hi; u++) {
+        const uint32_t bits = (uint32_t)u;
+        float x;
+        std::memcpy(&x, &bits, 4);
+        const float c = glibc_sincosf(x, true), s = glibc_sincosf(x, false);
+        const float rc = cosf(x), rs = sinf(x);
+        if (std::memcmp(&c, &rc, 4) != 0 || std::memcmp(&s, &rs, 4) != 0) { if (!bad && first_bad) *first_bad = bits; bad++; }
+    }
+    return bad;
+}
 float hm_atan2(float y, float x) { return fast_atan2_deg(y, x); }
 
 }  // extern "C"

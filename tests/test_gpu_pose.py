@@ -12,11 +12,15 @@ pytestmark = pytest.mark.gpu
 def _check(got, ref):
     pose, out, inl, cnt = got
     rpose, rout, rinl, rcnt = ref
-    assert np.linalg.norm(pose - rpose) / np.linalg.norm(rpose) <= 1e-5
+    rel = np.linalg.norm(pose - rpose) / np.linalg.norm(rpose)
+    assert rel <= 1e-9, rel                    # the north-star bar is 1e-5; observed 1e-16
     assert np.array_equal(out, rout) and inl == rinl
-    # LM iteration / trial counts: once a round has converged, rho = (chi - chi') / scale is rounding noise (its sign decides between
-    # "accept", "rho == 0 -> terminate" and "retry"), so the counts may differ by a few steps there; the estimates do not
-    assert abs(cnt[0] - rcnt[0]) <= 4 and abs(cnt[1] - rcnt[1]) <= 12, (cnt, rcnt)
+    # LM iteration / trial counts are the oracle's.  The one tolerated deviation: after a round has converged to the last bit, rho =
+    # (chi - chi') / scale is pure rounding noise and its sign decides between "terminate (rho == 0)" and "one more iteration", so the
+    # parallel sums of the GPU may take up to two no-op iterations more or fewer than the sequential sums of the oracle -- only with
+    # the estimate agreeing to 1e-12 (seed 3 of the list below: 23 vs 21 iterations, equal trials, pose equal to 2e-16).
+    if tuple(cnt) != tuple(rcnt):
+        assert rel <= 1e-12 and abs(cnt[0] - rcnt[0]) <= 2 and abs(cnt[1] - rcnt[1]) <= 2, (cnt, rcnt, rel)
 
 
 @pytest.mark.parametrize("kw", [dict(seed=1, n_obs=600), dict(seed=2, n_obs=2000, outlier_frac=0.3), dict(seed=3, n_obs=40, outlier_frac=0.05),
