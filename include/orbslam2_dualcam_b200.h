@@ -291,6 +291,12 @@ int  orbm_search_by_projection_sim3(orbm_t*, const orbm_frame_t* KF, const orbm_
 #define ORBM_KF_FUSE_SIM3 2
 int  orbm_project_best(orbm_t*, const orbm_frame_t* KF, const orbm_frustum_t* view, const orbm_points_t* P, float th, int variant,
                        int kf_index_quirk, int32_t* best_kp, int32_t* best_dist);
+/* one camera of the above (best_kp / best_dist [n]).  The reference's loops change the map between cameras -- a point matched in camera 0
+ * has its normal, depth range and descriptor refreshed before camera 1 projects it again (src/ORBmatcher.cc:783-787), Fuse skips in camera 1
+ * what camera 0 added (:1452) -- so the exact adaptor is  for (s in cameras) { flatten the current state; orbm_project_best_cam(.., s, ..);
+ * apply the reference's own `if (bestDist <= ...)` block in list order }. */
+int  orbm_project_best_cam(orbm_t*, const orbm_frame_t* KF, const orbm_frustum_t* view, const orbm_points_t* points, float th, int variant,
+                           int kf_index_quirk, int cam, int32_t* best_kp, int32_t* best_dist);
 
 /* ORBmatcher::SearchByBoWCrossCam(pKF1, c1, pKF2, c2, vpMatches12)  (src/ORBmatcher.cc:297-414).  mp_valid1 / mp_valid2 are indexed by the
  * global key point index (pMP && !isBad()); matches12 int32 [K1->n_kp[c1]]: GLOBAL key point index of pKF2 whose map point is

@@ -79,6 +79,7 @@ SIGNATURES = {
     "orbm_search_by_projection_reloc": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
     "orbm_search_by_projection_sim3": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]),
     "orbm_project_best": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp]),
+    "orbm_project_best_cam": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, C.c_int, vp, vp]),
     "orbm_search_by_bow_kf": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp]),
     "orbm_search_for_triangulation": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
     "orbv_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),

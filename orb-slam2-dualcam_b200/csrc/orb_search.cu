@@ -1132,6 +1132,25 @@ int orbm_project_best(orbm_t* m, const orbm_frame_t* KF, const orbm_frustum_t* v
     return run_projected(m, KF, view, P, "orbm_project_best", 0, KF->n_cams, th, flags, kf_index_quirk, false, 0, 0, nullptr, nullptr, nullptr, best_kp, best_dist);
 }
 
+// One camera of orbm_project_best: best_kp / best_dist [P->n].  This is the form that reproduces the reference's loops exactly when the
+// map changes between cameras: SearchByProjection(pKF, vpMapPoints, sFound, th, ORBdist) refreshes a matched point's normal, depth range
+// and descriptor (UpdateNormalAndDepth / ComputeDistinctiveDescriptors, src/ORBmatcher.cc:783-787) before the next camera projects it
+// again, and Fuse skips in camera 1 what camera 0 added (IsInKeyFrame, :1452).  The adaptor runs  for (s in cameras) { flatten the
+// CURRENT state of the points; orbm_project_best_cam(s); apply the reference's own `if (bestDist <= ...)` block in list order }.
+// Inside one camera a search reads only the point's own fields and the key frame's key points, which no earlier iteration of that
+// camera's loop changes for a point still to be processed (a point replaced earlier is bad by then and is skipped when applying).
+int orbm_project_best_cam(orbm_t* m, const orbm_frame_t* KF, const orbm_frustum_t* view, const orbm_points_t* P, float th, int variant, int kf_index_quirk, int cam,
+                          int32_t* best_kp, int32_t* best_dist) {
+    if (!m) ORB_FAIL(ORB_E_INVALID, "orbm_project_best_cam: NULL handle");
+    if (!KF || !best_kp || !best_dist) ORB_FAIL(ORB_E_INVALID, "orbm_project_best_cam: bad argument");
+    int flags;
+    if (variant == ORBM_KF_SEARCH) flags = PS_LEVEL_UP;
+    else if (variant == ORBM_KF_FUSE) flags = PS_DEPTH_POS | PS_NORMALISE_FIRST | PS_HALF_OPEN | PS_VIEW_ANGLE | PS_CHI2;
+    else if (variant == ORBM_KF_FUSE_SIM3) flags = PS_DEPTH_POS | PS_NORMALISE_FIRST | PS_HALF_OPEN | PS_VIEW_ANGLE;
+    else ORB_FAIL(ORB_E_INVALID, "orbm_project_best_cam: unknown variant %d", variant);
+    return run_projected(m, KF, view, P, "orbm_project_best_cam", cam, 1, th, flags, kf_index_quirk, false, 0, 0, nullptr, nullptr, nullptr, best_kp, best_dist);
+}
+
 int orbm_is_in_frustum(orbm_t* m, const orbm_frustum_t* fr, const float* pos, const float* normal, const float* max_dist, const float* min_dist, int n,
                        float viewing_cos_limit, int for_all_cams, int32_t* out, float* uvc) {
     if (!m) ORB_FAIL(ORB_E_INVALID, "orbm_is_in_frustum: NULL handle");

@@ -115,6 +115,17 @@ class ORBmatcher:
         check(lib().orbm_project_best(self._h, C.addressof(fs), C.addressof(vs), C.addressof(ps), float(th), int(variant), int(kf_index_quirk), ptr(bk), ptr(bd)))
         return bk, bd
 
+    def ProjectBestCam(self, KF, view, points, th, variant, cam, kf_index_quirk=True):
+        """one camera of ProjectBest -> (best_kp, best_dist) int32 [n]: the form for the reference's camera loops, which change the map
+        points between cameras (src/ORBmatcher.cc:783-787, :1452)"""
+        fs, fk = capi.frame_struct(KF)
+        vs, vk = capi.frustum_struct(view)
+        ps, pk = capi.points_struct(points)
+        n = len(pk["valid"])
+        bk = np.full(n, -1, np.int32); bd = np.full(n, 256, np.int32)
+        check(lib().orbm_project_best_cam(self._h, C.addressof(fs), C.addressof(vs), C.addressof(ps), float(th), int(variant), int(kf_index_quirk), int(cam), ptr(bk), ptr(bd)))
+        return bk, bd
+
     def SearchByBoWKF(self, K1, c1, K2, c2, mp_valid1, mp_valid2):
         """ORBmatcher::SearchByBoWCrossCam(pKF1, c1, pKF2, c2, vpMatches12) (src/ORBmatcher.cc:297-414)
         -> (nmatches, matches12 int32 [n_kp1[c1]] = global key point index in KF2 or -1)"""

@@ -101,3 +101,28 @@ def test_bow_frame_kf_still_matches_after_refactor():
         n, out = m.SearchByBoW(F, KF, valid, bMapScaled=scaled)
         rn, rout = O.search_by_bow(F, KF, valid, 0.7, True, scaled)
         assert n == rn and np.array_equal(out, rout)
+
+
+def test_project_best_per_camera_sequencing():
+    """the camera loop of SearchByProjection(pKF, vpMapPoints, sFound, ...) (src/ORBmatcher.cc:703-797): points matched in camera 0 get their
+    descriptor / normal / depth range refreshed before camera 1 projects them.  The per-camera entry point reproduces that: camera 1 searched
+    with the refreshed fields equals the oracle run on the refreshed fields, and differs from the one-shot (snapshot) call."""
+    frame, view, pts, _ = synth.kf_projection_scene(11)
+    m = ORBmatcher()
+    bk0, bd0 = m.ProjectBestCam(frame, view, pts, 4.0, capi.KF_SEARCH, cam=0, kf_index_quirk=False)
+    all_k, all_d = m.ProjectBest(frame, view, pts, 4.0, capi.KF_SEARCH, kf_index_quirk=False)
+    assert np.array_equal(bk0, all_k[0]) and np.array_equal(bd0, all_d[0])
+    # "ComputeDistinctiveDescriptors / UpdateNormalAndDepth" between the cameras: the points that camera 1 is going to match get a new
+    # descriptor (another key point's) and a different depth range, as if camera 0 had just matched them
+    hit = np.flatnonzero((all_k[1] >= 0) & (all_d[1] <= 100))
+    assert len(hit) > 20
+    refreshed = {k: np.array(v, copy=True) for k, v in pts.items()}
+    refreshed["desc"][hit] = frame["desc"][(all_k[1][hit] + 7) % len(frame["desc"])]
+    refreshed["max_dist"][hit] *= 1.1
+    refreshed["min_dist"][hit] *= 0.9
+    bk1, bd1 = m.ProjectBestCam(frame, view, refreshed, 4.0, capi.KF_SEARCH, cam=1, kf_index_quirk=False)
+    rk, rd = O.project_best(frame, view, refreshed, 4.0, capi.KF_SEARCH, kf_quirk=False)
+    assert np.array_equal(bk1, rk[1]) and np.array_equal(bd1, rd[1])
+    assert not (np.array_equal(bk1, all_k[1]) and np.array_equal(bd1, all_d[1])), "the refresh should change camera 1's result for some point"
+    with pytest.raises(OrbError):
+        m.ProjectBestCam(frame, view, pts, 4.0, capi.KF_SEARCH, cam=2)

@@ -13,7 +13,9 @@ def _check(got, ref):
     pose, out, inl, cnt = got
     rpose, rout, rinl, rcnt = ref
     rel = np.linalg.norm(pose - rpose) / np.linalg.norm(rpose)
-    assert rel <= 1e-9, rel                    # the north-star bar is 1e-5; observed 1e-16
+    # the north-star bar is 1e-5; observed 1e-16.  With fewer than 3 correspondences nothing is optimised and the oracle hands the CV_32F input
+    # back untouched, while the library returns it after the SE3Quat round trip (a float-rounded rotation is orthonormal to 1e-8 only)
+    assert rel <= (1e-9 if len(out) >= 3 else 1e-7), rel
     assert np.array_equal(out, rout) and inl == rinl
     # LM iteration / trial counts are the oracle's.  The one tolerated deviation: after a round has converged to the last bit, rho =
     # (chi - chi') / scale is pure rounding noise and its sign decides between "terminate (rho == 0)" and "one more iteration", so the
