@@ -65,6 +65,9 @@ struct ExtractParams {
     int cell_begin[ORB_MAX_LEVELS + 1];
     LevelDev lv[ORB_MAX_LEVELS];
     const uint8_t* base[ORB_MAX_LEVELS];   // level images (level 0 = the caller's batch)
+    uint8_t* blur[ORB_MAX_LEVELS];         // the same levels after GaussianBlur(7x7, sigma 2, REFLECT_101); pitch / stride of the level, level 0: blur_pitch0 / blur_stride0
+    int blur_pitch0;
+    unsigned long long blur_stride0;
 };
 
 // ------------------------------------------------------------------------------------------------ pyramid
@@ -489,48 +492,129 @@ __global__ void __launch_bounds__(QT_THREADS) quadtree_kernel(const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------------ Gaussian blur of the levels
+// cv::GaussianBlur(level, 7x7, sigma 2, BORDER_REFLECT_101) as the reference applies it to every level before sampling descriptors
+// (src/ORBextractor.cc:1085-1086): integer kernel {18,34,48,56,48,34,18} / 256 per axis, rows then columns, one rounding
+// (acc + 2^15) >> 16.  One CTA = a 64 x 58 output tile: the 96 x 64 raw box around it comes in by TMA (zero fill outside the image; the
+// REFLECT_101 ring of border tiles is patched in shared memory from the tile itself), the row pass forms four outputs per thread from
+// three aligned words with two 16-bit lanes per register (a row sum is at most 255 * 256 < 2^16), the column pass slides down a column.
+#define BL_TW 64
+#define BL_TH 58
+#define BL_BOXW 96             // 16 columns left of the tile (the box must start on a 16-byte boundary) + 64 + 3, rounded up to 16
+#define BL_BOXH 64             // 3 + 58 + 3
+#define BL_T 256
+
+struct alignas(64) BlurMaps {
+    CUtensorMap raw[ORB_MAX_LEVELS];       // box (96, 64, 1) over the raw levels: input of blur_level_kernel
+    CUtensorMap blr[ORB_MAX_LEVELS];       // box (64, 37, 1) over the blurred levels: input of describe_kernel
+};
+
+__global__ void __launch_bounds__(BL_T) blur_level_kernel(const __grid_constant__ ExtractParams P, const BlurMaps* __restrict__ BM, int l, int tiles_x) {
+    __shared__ __align__(128) uint8_t raw[BL_BOXW * BL_BOXH];
+    __shared__ __align__(16) uint16_t rowp[BL_BOXH * BL_TW];
+    __shared__ __align__(16) uint8_t outt[BL_TH * BL_TW];
+    __shared__ __align__(8) uint64_t s_bar;
+    const LevelDev& L = P.lv[l];
+    const int tid = threadIdx.x, img = blockIdx.y;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int x0 = tx * BL_TW, y0 = ty * BL_TH;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar, BL_BOXW * BL_BOXH);
+        tma_load_tile(raw, &BM->raw[l], &s_bar, x0 - 16, y0 - 3, img);      // tile pixel (x, y) -> raw[(y - y0 + 3) * 96 + (x - x0 + 16)]
+    }
+    mbar_wait(&s_bar, 0);
+    // ---- BORDER_REFLECT_101 for the tiles on the image border: columns first, then rows (the 2-d reflection is separable)
+    const int w = L.w, h = L.h;
+    const bool left = x0 == 0, right = x0 + BL_TW + 3 > w, top = y0 == 0, bottom = y0 + BL_TH + 3 > h;
+    if (left || right) {
+        for (int i = tid; i < BL_BOXH * 3; i += BL_T) {
+            const int r = i / 3, k = i - 3 * r + 1;                  // k = 1..3
+            uint8_t* row = raw + r * BL_BOXW + 16 - x0;              // row[x] = pixel x of this box row
+            if (left) row[-k] = row[k];
+            if (right && w - 1 + k < x0 + BL_TW + 3) row[w - 1 + k] = row[w - 1 - k];
+        }
+        __syncthreads();
+    }
+    if (top || bottom) {
+        for (int i = tid; i < BL_BOXW * 3; i += BL_T) {
+            const int c = i / 3, k = i - 3 * c + 1;
+            uint8_t* col = raw + (3 - y0) * BL_BOXW + c;             // col[y * 96] = pixel row y of this box column
+            if (top) col[-k * BL_BOXW] = col[k * BL_BOXW];
+            if (bottom && h - 1 + k < y0 + BL_TH + 3) col[(h - 1 + k) * BL_BOXW] = col[(h - 1 - k) * BL_BOXW];
+        }
+        __syncthreads();
+    }
+    // ---- row pass: task = (box row, group of 4 output columns); outputs 4j .. 4j+3 need box columns 13 + 4j .. 22 + 4j = words 3 + j .. 5 + j
+    for (int t = tid; t < BL_BOXH * (BL_TW / 4); t += BL_T) {
+        const int r = t >> 4, j = t & 15;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(raw + r * BL_BOXW) + 3 + j;
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];          // bytes b0..b11; output k = sum_t g_t b_(1 + k + t)
+        // 16-bit lane pairs (b_i, b_(i+2)) for i = 1..7: outputs (0, 2); and (b_(i+1), b_(i+3)): outputs (1, 3)
+        const uint32_t p1 = __byte_perm(w0, w0, 0x4341), p2 = __byte_perm(w0, w1, 0x4442), p3 = __byte_perm(w0, w1, 0x4543), p4 = __byte_perm(w1, w1, 0x4240),
+                       p5 = __byte_perm(w1, w1, 0x4341), p6 = __byte_perm(w1, w2, 0x4442), p7 = __byte_perm(w1, w2, 0x4543), p8 = __byte_perm(w2, w2, 0x4240);
+        // p_i = b_i | b_(i+2) << 16   (selector nibble 4 = zero byte is not available in PRMT: mask instead)
+        const uint32_t M = 0x00ff00ffu;
+        const uint32_t q1 = p1 & M, q2 = p2 & M, q3 = p3 & M, q4 = p4 & M, q5 = p5 & M, q6 = p6 & M, q7 = p7 & M, q8 = p8 & M;
+        const uint32_t o02 = 18u * (q1 + q7) + 34u * (q2 + q6) + 48u * (q3 + q5) + 56u * q4;     // outputs 0 | 2 << 16
+        const uint32_t o13 = 18u * (q2 + q8) + 34u * (q3 + q7) + 48u * (q4 + q6) + 56u * q5;     // outputs 1 | 3 << 16
+        uint32_t* o = reinterpret_cast<uint32_t*>(rowp + r * BL_TW + 4 * j);
+        o[0] = __byte_perm(o02, o13, 0x5410);                       // (out0, out1)
+        o[1] = __byte_perm(o02, o13, 0x7632);                       // (out2, out3)
+    }
+    __syncthreads();
+    // ---- column pass: task = (column, quarter of the 58 rows): 15 + 15 + 14 + 14
+    {
+        const int x = tid & 63, q = tid >> 6;
+        const int yb = q < 2 ? 15 * q : 30 + 14 * (q - 2), n = q < 2 ? 15 : 14;
+        const uint16_t* r = rowp + yb * BL_TW + x;
+        uint32_t a0 = r[0], a1 = r[BL_TW], a2 = r[2 * BL_TW], a3 = r[3 * BL_TW], a4 = r[4 * BL_TW], a5 = r[5 * BL_TW];
+#pragma unroll
+        for (int y = 0; y < 15; y++) {
+            if (y < n) {
+                const uint32_t a6 = r[(y + 6) * BL_TW];
+                outt[(yb + y) * BL_TW + x] = (uint8_t)((18u * (a0 + a6) + 34u * (a1 + a5) + 48u * (a2 + a4) + 56u * a3 + 32768u) >> 16);
+                a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = a5; a5 = a6;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- write the tile: 16 bytes per thread and step, clipped to the level (rows are padded to 16 bytes)
+    const int pitch = l == 0 ? P.blur_pitch0 : L.pitch;
+    uint8_t* dst = P.blur[l] + (unsigned long long)img * (l == 0 ? P.blur_stride0 : L.img_stride);
+    for (int i = tid; i < BL_TH * (BL_TW / 16); i += BL_T) {
+        const int y = i >> 2, c = (i & 3) * 16;
+        if (y0 + y < h && x0 + c < pitch)
+            *reinterpret_cast<uint4*>(dst + (size_t)(y0 + y) * pitch + x0 + c) = *reinterpret_cast<const uint4*>(outt + y * BL_TW + c);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ orientation + descriptor
-// One warp per keypoint.  The 43x43 raw patch (REFLECT_101 at the level border, like cv::GaussianBlur on the cloned
-// level, src/ORBextractor.cc:1085-1086) is staged in shared memory; IC_Angle (:77-104) reads its inner radius-15 disc;
-// the 7x7 sigma-2 Gaussian (integer kernel {18,34,48,56,48,34,18}, one rounding (acc + 2^15) >> 16) is evaluated for
-// the inner 37x37 pixels -- the only blurred pixels the steered pattern (:108-147) can touch.
+// One warp per keypoint.  IC_Angle (src/ORBextractor.cc:77-104) reads the radius-15 disc of the raw level straight from global memory
+// (lanes along a row: one or two sectors per load); the 37 x 37 window of the BLURRED level that the steered pattern (:108-147) can touch
+// comes in by TMA (box 64 x 37 starting on the 16-byte boundary left of the window) and the 512 samples are byte reads of shared memory.
 #define DESC_WARPS 4
-#define RAW_R 21
-#define RAW_W 43
-#define RAW_P 52               // row pitch in bytes: 13 words (odd) -> lanes on different rows hit different banks; holds 43 + 3 alignment bytes
-#define RAW_NW 12              // aligned words staged per row (covers 3 alignment bytes + 43 pixels)
 #define BLR_R 18
 #define BLR_W 37
-#define BLR_P 40
-#define ROWP_P 38
-#define SEG 19                 // the 37 outputs of a blur line are produced as two sliding runs of 19 / 18
+#define BLR_BOXW 64
 
 __device__ const int8_t g_pattern[1024] = {ORB_RBRIEF_PATTERN_VALUES};
 
-struct DescSmem {
-    uint8_t raw[RAW_W * RAW_P];
-    uint16_t rowp[RAW_W * ROWP_P];
-    uint8_t blur[BLR_W * BLR_P];
-};
-
-__device__ __forceinline__ int reflect101_dev(int p, int n) {
-    if (n == 1) return 0;
-    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
-    return p;
-}
-
-__global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(const __grid_constant__ ExtractParams P,
+__global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(const __grid_constant__ ExtractParams P, const BlurMaps* __restrict__ BM,
                                                                    const uint32_t* __restrict__ sel, const int* __restrict__ sel_count,
                                                                    orb_keypoint_t* __restrict__ kps, uint8_t* __restrict__ desc,
                                                                    int* __restrict__ counts, int kp_capacity,
                                                                    const int* __restrict__ umax) {
-    __shared__ __align__(16) DescSmem sm[DESC_WARPS];
+    __shared__ __align__(128) uint8_t s_win[DESC_WARPS][(BLR_BOXW * BLR_W + 127) & ~127];   // every TMA destination on a 128-byte boundary
+    __shared__ __align__(8) uint64_t s_bar[DESC_WARPS];
     __shared__ __align__(4) int8_t spat[1024];
     __shared__ int s_umax[16];
     const int img = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint32_t*>(spat)[i] = reinterpret_cast<const uint32_t*>(g_pattern)[i];
     if (threadIdx.x < 16) s_umax[threadIdx.x] = umax[threadIdx.x];
+    if (lane == 0) mbar_init(&s_bar[warp], 1);
     __syncthreads();
 
     // which keypoint: global slot -> (level, index) through the per-level counts of this image
@@ -549,41 +633,28 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(const __grid_
     const LevelDev& L = P.lv[l];
     const uint32_t c = sel[(size_t)img * P.sel_per_image + L.sel_off + idx];
     const int cx = cand_x(c) + 16, cy = cand_y(c) + 16, response = cand_score(c);
-    const uint8_t* I = P.base[l] + (unsigned long long)img * L.img_stride;
-    DescSmem& S = sm[warp];
-
-    // ---- 43x43 raw patch.  Interior keypoints (the common case): 12 aligned words per row; raw[ry * RAW_P + dx + rx] holds
-    //      pixel (cx - 21 + rx, cy - 21 + ry).  Patches that leave the image: REFLECT_101 byte gather (dx = 0).
-    int dx = 0;
-    if (cx - RAW_R >= 0 && cx + RAW_R < L.w && cy - RAW_R >= 0 && cy + RAW_R < L.h) {
-        const int gx0 = cx - RAW_R, ax0 = gx0 & ~3;
-        dx = gx0 - ax0;
-        const uint8_t* src = I + (size_t)(cy - RAW_R) * L.pitch + ax0;
-        for (int i = lane; i < RAW_W * RAW_NW; i += 32) {
-            const int ry = i / RAW_NW, wx = i - ry * RAW_NW;
-            reinterpret_cast<uint32_t*>(S.raw + ry * RAW_P)[wx] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)ry * L.pitch) + wx);
-        }
-    } else {
-        for (int i = lane; i < RAW_W * RAW_W; i += 32) {
-            const int ry = i / RAW_W, rx = i - ry * RAW_W;
-            const int yy = reflect101_dev(cy + ry - RAW_R, L.h), xx = reflect101_dev(cx + rx - RAW_R, L.w);
-            S.raw[ry * RAW_P + rx] = __ldg(I + (size_t)yy * L.pitch + xx);
-        }
+    // ---- the blurred window: pixel (cx - 18 + i, cy - 18 + j) -> win[j * 64 + dx + i]
+    const int wx0 = cx - BLR_R, ax0 = wx0 & ~15, dx = wx0 - ax0;
+    if (lane == 0) {
+        mbar_expect_tx(&s_bar[warp], BLR_BOXW * BLR_W);
+        tma_load_tile(s_win[warp], &BM->blr[l], &s_bar[warp], ax0, cy - BLR_R, img);
     }
-    __syncwarp();
-    const uint8_t* RAW = S.raw + dx;
-
-    // ---- IC_Angle
+    // ---- IC_Angle on the raw level (key points lie at least 19 px inside the level, so the disc needs no border handling)
+    const uint8_t* I = P.base[l] + (unsigned long long)img * L.img_stride;
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int u = lane - 15, au = u < 0 ? -u : u;
-        for (int v = -15; v <= 15; v++) {
-            if (au <= s_umax[v < 0 ? -v : v]) {
-                const int val = RAW[(RAW_R + v) * RAW_P + RAW_R + u];
-                m10 += u * val;
-                m01 += v * val;
-            }
-        }
+        const uint8_t* col = I + (size_t)(cy - 15) * L.pitch + cx + u;
+        // all 31 row loads are issued before the first use (one memory round trip per key point instead of eight): the rows are
+        // independent, and what limits this kernel is the latency of these loads, not their number
+        int val[31];
+#pragma unroll
+        for (int v = 0; v < 31; v++) val[v] = au <= s_umax[v < 15 ? 15 - v : v - 15] ? (int)__ldg(col + (size_t)v * L.pitch) : 0;
+        int sv = 0, su = 0;
+#pragma unroll
+        for (int v = 0; v < 31; v++) { su += val[v]; sv += (v - 15) * val[v]; }
+        m10 = u * su;
+        m01 = sv;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -592,40 +663,12 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(const __grid_
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- Gaussian 7x7: rows, then columns.  A lane produces a run of SEG consecutive outputs of one line with a 7-tap sliding
-    //      window in registers (one load per output).
-    const int g0 = 18, g1 = 34, g2 = 48, g3 = 56;
-    for (int it = lane; it < RAW_W * 2; it += 32) {
-        const int ry = it >> 1, xb = (it & 1) * SEG, n = (it & 1) ? BLR_W - SEG : SEG;
-        const uint8_t* r = RAW + ry * RAW_P + xb;
-        uint16_t* o = S.rowp + ry * ROWP_P + xb;
-        int p0 = r[0], p1 = r[1], p2 = r[2], p3 = r[3], p4 = r[4], p5 = r[5];
-#pragma unroll
-        for (int x = 0; x < SEG; x++) {
-            const int p6 = (x < n) ? r[x + 6] : 0;
-            if (x < n) o[x] = (uint16_t)(g0 * (p0 + p6) + g1 * (p1 + p5) + g2 * (p2 + p4) + g3 * p3);
-            p0 = p1; p1 = p2; p2 = p3; p3 = p4; p4 = p5; p5 = p6;
-        }
-    }
-    __syncwarp();
-    for (int it = lane; it < BLR_W * 2; it += 32) {
-        const int x = it >> 1, yb = (it & 1) * SEG, n = (it & 1) ? BLR_W - SEG : SEG;
-        const uint16_t* r = S.rowp + yb * ROWP_P + x;
-        uint8_t* o = S.blur + yb * BLR_P + x;
-        uint32_t p0 = r[0], p1 = r[ROWP_P], p2 = r[2 * ROWP_P], p3 = r[3 * ROWP_P], p4 = r[4 * ROWP_P], p5 = r[5 * ROWP_P];
-#pragma unroll
-        for (int y = 0; y < SEG; y++) {
-            const uint32_t p6 = (y < n) ? r[(y + 6) * ROWP_P] : 0u;
-            if (y < n) o[y * BLR_P] = (uint8_t)((g0 * (p0 + p6) + g1 * (p1 + p5) + g2 * (p2 + p4) + g3 * p3 + 32768u) >> 16);
-            p0 = p1; p1 = p2; p2 = p3; p3 = p4; p4 = p5; p5 = p6;
-        }
-    }
-    __syncwarp();
-
     // ---- steered rBRIEF: pair k of word w is handled by lane k%32, the ballot is the little-endian descriptor word
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
     const float arad = fmul_rn(angle, factorPI);
     const float a = glibc_sincosf(arad, true), b = glibc_sincosf(arad, false);
+    mbar_wait(&s_bar[warp], 0);
+    const uint8_t* B = s_win[warp] + BLR_R * BLR_BOXW + dx + BLR_R;      // pixel (cx, cy)
     uint32_t myword = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
@@ -636,8 +679,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) describe_kernel(const __grid_
         const int c0 = cv_round_f(fsub_rn(fmul_rn(px0, a), fmul_rn(py0, b)));
         const int r1 = cv_round_f(fadd_rn(fmul_rn(px1, b), fmul_rn(py1, a)));
         const int c1 = cv_round_f(fsub_rn(fmul_rn(px1, a), fmul_rn(py1, b)));
-        const int t0 = S.blur[(BLR_R + r0) * BLR_P + BLR_R + c0];
-        const int t1 = S.blur[(BLR_R + r1) * BLR_P + BLR_R + c1];
+        const int t0 = B[r0 * BLR_BOXW + c0];
+        const int t1 = B[r1 * BLR_BOXW + c1];
         const uint32_t word = __ballot_sync(0xffffffffu, t0 < t1);
         if (lane == w) myword = word;
     }
@@ -674,6 +717,9 @@ struct orbx {
     std::vector<size_t> xtab_off;      // per level: offset (uint4) into d_xtab; (size_t)-1 = the level needs the general kernel
     FastMaps TM;                       // tensor maps of the FAST tiles (level 0 is re-encoded when the caller's buffer changes)
     FastMaps* d_TM = nullptr;          // ... and their copy in global memory, where the kernel reads them
+    BlurMaps BMh;                      // tensor maps of the blur input (raw levels) and of the descriptor windows (blurred levels)
+    BlurMaps* d_BM = nullptr;
+    uint8_t* d_blur = nullptr;         // blurred levels 0.. of all images, level-major
     void* encode_fn = nullptr;         // cuTensorMapEncodeTiled
     const uint8_t* tm0_ptr = nullptr; size_t tm0_stride = 0; int tm0_images = 0;
     uint32_t* d_cand = nullptr;
@@ -708,7 +754,7 @@ static void orbx_free(orbx* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
-    cudaFree(e->d_levels); cudaFree(e->d_input); cudaFree(e->d_tables); cudaFree(e->d_xtab); cudaFree(e->d_TM); cudaFree(e->d_cand); cudaFree(e->d_node_of);
+    cudaFree(e->d_levels); cudaFree(e->d_input); cudaFree(e->d_tables); cudaFree(e->d_xtab); cudaFree(e->d_TM); cudaFree(e->d_BM); cudaFree(e->d_blur); cudaFree(e->d_cand); cudaFree(e->d_node_of);
     cudaFree(e->d_cand_count); cudaFree(e->d_sel); cudaFree(e->d_sel_count); cudaFree(e->d_umax); cudaFree(e->d_cells);
     cudaFree(e->d_kps); cudaFree(e->d_desc); cudaFree(e->d_counts);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -718,16 +764,19 @@ static void orbx_free(orbx* e) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 // (x, y, image) uint8 tensor of one pyramid level, box (bw, bh, 1)
-static int encode_level_map(orbx* e, int l, const uint8_t* base, int w, int h, size_t pitch, size_t img_stride, int n_images) {
+static int encode_map(orbx* e, CUtensorMap* map, int bw, int bh, int l, const uint8_t* base, int w, int h, size_t pitch, size_t img_stride, int n_images) {
     const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n_images};
     const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)img_stride};
-    const cuuint32_t box[3] = {(cuuint32_t)e->TM.bw[l], (cuuint32_t)e->TM.bh[l], 1u};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    const CUresult r = ((EncodeTiledFn)e->encode_fn)(&e->TM.lv[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), gdim, gstr, box, estr,
+    const CUresult r = ((EncodeTiledFn)e->encode_fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), gdim, gstr, box, estr,
                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) ORB_FAIL(ORB_E_CUDA, "cuTensorMapEncodeTiled failed for level %d (%d): %dx%d pitch %zu box %dx%d", l, (int)r, w, h, pitch, e->TM.bw[l], e->TM.bh[l]);
+    if (r != CUDA_SUCCESS) ORB_FAIL(ORB_E_CUDA, "cuTensorMapEncodeTiled failed for level %d (%d): %dx%d pitch %zu box %dx%d", l, (int)r, w, h, pitch, bw, bh);
     return ORB_OK;
+}
+static int encode_level_map(orbx* e, int l, const uint8_t* base, int w, int h, size_t pitch, size_t img_stride, int n_images) {
+    return encode_map(e, &e->TM.lv[l], e->TM.bw[l], e->TM.bh[l], l, base, w, h, pitch, img_stride, n_images);
 }
 
 extern "C" {
@@ -888,8 +937,28 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
             if (rc != ORB_OK) { orbx_free(e); return rc; }
         }
     }
+    // blurred levels (level 0 included) and the tensor maps around them
+    {
+        size_t blur_bytes = 0;
+        std::vector<size_t> boff(nlevels, 0);
+        for (int l = 0; l < nlevels; l++) { boff[l] = blur_bytes; blur_bytes += (size_t)g.lv[l].pitch * g.lv[l].h; }
+        ce = cudaMalloc((void**)&e->d_blur, std::max<size_t>(blur_bytes * NI, 16));
+        if (ce != cudaSuccess) { int rc = orbhost::check_cuda(ce, "orbx_create blurred levels", __FILE__, __LINE__); orbx_free(e); return rc; }
+        P.blur_pitch0 = g.lv[0].pitch;
+        P.blur_stride0 = (unsigned long long)g.lv[0].pitch * g.lv[0].h;
+        memset(&e->BMh, 0, sizeof(e->BMh));
+        for (int l = 0; l < nlevels; l++) {
+            P.blur[l] = e->d_blur + boff[l] * NI;
+            const size_t pitch = (size_t)g.lv[l].pitch, stride = pitch * g.lv[l].h;
+            int rc = encode_map(e, &e->BMh.blr[l], BLR_BOXW, BLR_W, l, P.blur[l], g.lv[l].w, g.lv[l].h, pitch, stride, e->max_images);
+            if (rc == ORB_OK && l > 0) rc = encode_map(e, &e->BMh.raw[l], BL_BOXW, BL_BOXH, l, P.base[l], g.lv[l].w, g.lv[l].h, pitch, (size_t)P.lv[l].img_stride, e->max_images);
+            if (rc != ORB_OK) { orbx_free(e); return rc; }
+        }
+    }
     ce = cudaMalloc((void**)&e->d_TM, sizeof(FastMaps));
     if (ce == cudaSuccess) ce = cudaMemcpy(e->d_TM, &e->TM, sizeof(FastMaps), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&e->d_BM, sizeof(BlurMaps));
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->d_BM, &e->BMh, sizeof(BlurMaps), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { int rc = orbhost::check_cuda(ce, "orbx_create tensor maps", __FILE__, __LINE__); orbx_free(e); return rc; }
     // FAST shared memory: tile (the largest TMA box) + score + 2 lists
     e->fast_pix_cap = (max_dw * max_dh + 15) & ~15;
@@ -999,8 +1068,11 @@ int orbx_extract_device(orbx_t* e, const uint8_t* d_imgs, int frames, size_t row
         if (P.lv[0].valid && (e->tm0_ptr != d_imgs || e->tm0_stride != row_stride || e->tm0_images != NI)) {   // level 0 is the caller's buffer
             const int rc = encode_level_map(e, 0, d_imgs, e->W, e->H, row_stride, row_stride * e->H, NI);
             if (rc != ORB_OK) return rc;
+            const int rc2 = encode_map(e, &e->BMh.raw[0], BL_BOXW, BL_BOXH, 0, d_imgs, e->W, e->H, row_stride, row_stride * e->H, NI);
+            if (rc2 != ORB_OK) return rc2;
             e->tm0_ptr = d_imgs; e->tm0_stride = row_stride; e->tm0_images = NI;
             ORB_CUDA(cudaMemcpyAsync(&e->d_TM->lv[0], &e->TM.lv[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+            ORB_CUDA(cudaMemcpyAsync(&e->d_BM->raw[0], &e->BMh.raw[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
         }
         fast_cells_kernel<<<dim3(P.cells_per_image, NI), FAST_THREADS, e->fast_smem, st>>>(P, e->d_TM, e->d_cand, e->d_cand_count, e->fast_tile_cap, e->fast_pix_cap);
         e->launches++;
@@ -1009,8 +1081,15 @@ int orbx_extract_device(orbx_t* e, const uint8_t* d_imgs, int frames, size_t row
     quadtree_kernel<<<dim3(L, NI), QT_THREADS, e->qt_smem, st>>>(P, e->d_cand, e->d_cand_count, e->d_node_of, e->d_sel, e->d_sel_count, e->qt_maxl, d_overflow);
     e->launches++;
     if (pev) ORB_CUDA(cudaEventRecord(pev[3], st));
+    // GaussianBlur of every level that holds key points (src/ORBextractor.cc:1085-1086), then orientation + descriptors
+    for (int l = 0; l < L; l++) {
+        if (!P.lv[l].valid) continue;
+        const int tiles_x = (P.lv[l].w + BL_TW - 1) / BL_TW, tiles_y = (P.lv[l].h + BL_TH - 1) / BL_TH;
+        blur_level_kernel<<<dim3(tiles_x * tiles_y, NI), BL_T, 0, st>>>(P, e->d_BM, l, tiles_x);
+        e->launches++;
+    }
     const int maxkp = orbx_max_keypoints(e);
-    describe_kernel<<<dim3((std::max(maxkp, 1) + DESC_WARPS - 1) / DESC_WARPS, NI), DESC_WARPS * 32, 0, st>>>(P, e->d_sel, e->d_sel_count, d_kps, d_desc, d_counts, kp_capacity, e->d_umax);
+    describe_kernel<<<dim3((std::max(maxkp, 1) + DESC_WARPS - 1) / DESC_WARPS, NI), DESC_WARPS * 32, 0, st>>>(P, e->d_BM, e->d_sel, e->d_sel_count, d_kps, d_desc, d_counts, kp_capacity, e->d_umax);
     e->launches++;
     if (pev) { ORB_CUDA(cudaEventRecord(pev[4], st)); e->prof_used++; }
     ORB_CUDA(cudaGetLastError());
