@@ -57,6 +57,7 @@ struct BAProb {                // static description of one problem inside the b
     int blkE0, nbE, blkL0, nbL;
     int blkG0, nbG;            // landmark-group blocks of k_land
     long long tup0, eof0, hs_off;
+    long long bm0; int bmW;    // landmark bitmaps of the (free pose, camera) pairs: bmW words each
 };
 
 struct BAState {
@@ -83,7 +84,8 @@ struct BABatch {               // kernel argument (by value)
     const int *blkG_prob, *blkG_l0, *blkG_nl;  // k_land block -> problem, first landmark (global), landmarks (whole landmarks, <= BA_TG edges; a landmark with more gets a block of its own)
     const int* free_pose;                       // [Ktot] global pose index of every free pose
     // index built on the device
-    int* edge_of;                               // [free pose of the problem][landmark] -> edge << 2 | camera, or -1 (pose-major: the pair kernels read it coalesced)
+    int* edge_of;                               // [free pose of the problem][landmark] -> edge << 2 | camera, or -1
+    unsigned* bm;                               // [(free pose, camera) of the problem][bmW]: bit l = the pose observes landmark l with that camera
     int *pair_cnt, *pair_off;                    // per pair: tuples, first tuple
     int *pc_cnt, *pc_off, *pc_fchunk, *pc_nchunk; // per (pair, camera pair): tuples, first tuple, first chunk, chunks
     int *chunk_pair, *chunk_start, *chunk_len;
@@ -143,7 +145,11 @@ __global__ void k_edge_of(BABatch A) {
     const int e = P.e0 + (b - P.blkE0) * BA_TE + threadIdx.x;
     if (e >= P.e0 + P.nE) return;
     const int k = A.pose_free[A.e_pose[e]];
-    if (k >= 0) A.edge_of[P.eof0 + (long long)(k - P.k0) * P.nL + (A.e_pt[e] - P.l0)] = (e << 2) | (A.e_cam[e] - P.c0);   // edge and its camera (rigs of <= 4 cameras)
+    if (k >= 0) {
+        const int l = A.e_pt[e] - P.l0, c = A.e_cam[e] - P.c0;
+        A.edge_of[P.eof0 + (long long)(k - P.k0) * P.nL + l] = (e << 2) | c;   // edge and its camera (rigs of <= 4 cameras)
+        atomicOr(&A.bm[P.bm0 + ((long long)(k - P.k0) * P.nC + c) * P.bmW + (l >> 5)], 1u << (l & 31));
+    }
 }
 __device__ __forceinline__ void pair_decode(int pid, int K, int& i, int& j) {
     i = 0;
@@ -151,7 +157,8 @@ __device__ __forceinline__ void pair_decode(int pid, int K, int& i, int& j) {
     while (rem >= K - i) { rem -= K - i; i++; }
     j = i + rem;
 }
-// warp per pose pair (i <= j): number of landmarks observed by both, per camera pair (camera of i's edge, camera of j's edge)
+// warp per pose pair (i <= j): number of landmarks observed by both, per camera pair (camera of i's edge, camera of j's edge):
+// popcount of the AND of the two landmark bitmaps (a scan of the pose-major edge table took 0.75 ms per 256 windows, this takes 1/10)
 __global__ void k_pair_count(BABatch A, const int* blkP_prob, const int* blkP_first) {
     const int p = blkP_prob[blockIdx.x];
     const BAProb P = A.prob[p];
@@ -159,62 +166,73 @@ __global__ void k_pair_count(BABatch A, const int* blkP_prob, const int* blkP_fi
     if (pid >= P.nPairs) return;
     int i, j;
     pair_decode(pid, P.K, i, j);
-    const int* T = A.edge_of + P.eof0;
-    int cnt[BA_MAXCC];
+    int tot = 0;
+    for (int q = 0; q < P.CC; q++) {
+        const unsigned* bi = A.bm + P.bm0 + ((long long)i * P.nC + q / P.nC) * P.bmW;
+        const unsigned* bj = A.bm + P.bm0 + ((long long)j * P.nC + q % P.nC) * P.bmW;
+        int c = 0;
+        for (int w = lane; w < P.bmW; w += 32) c += __popc(bi[w] & bj[w]);
 #pragma unroll
-    for (int q = 0; q < BA_MAXCC; q++) cnt[q] = 0;
-    for (int l0 = 0; l0 < P.nL; l0 += 32) {
-        const int l = l0 + lane;
-        int a = -1, c = -1;
-        if (l < P.nL) { a = T[(long long)i * P.nL + l]; c = T[(long long)j * P.nL + l]; }
-        const bool both = a >= 0 && c >= 0;
-        const int combo = both ? (a & 3) * P.nC + (c & 3) : -1;
-#pragma unroll
-        for (int q = 0; q < BA_MAXCC; q++)
-            if (q < P.CC) cnt[q] += __popc(__ballot_sync(0xffffffffu, combo == q));
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) A.pc_cnt[P.pc0 + pid * P.CC + q] = c;
+        tot += c;
     }
-    if (lane == 0) {
-        int tot = 0;
-#pragma unroll
-        for (int q = 0; q < BA_MAXCC; q++)
-            if (q < P.CC) { A.pc_cnt[P.pc0 + pid * P.CC + q] = cnt[q]; tot += cnt[q]; }
-        A.pair_cnt[P.pair0 + pid] = tot;
-    }
+    if (lane == 0) A.pair_cnt[P.pair0 + pid] = tot;
 }
-// one thread per problem: tuple offsets of the (pair, camera pair) slots and the chunk table
-__global__ void k_pair_scan(BABatch A) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= A.nProb) return;
+// CTA per problem: tuple offsets of the (pair, camera pair) slots and the chunk table (block-wide exclusive scan over the slots, 256 per sweep)
+__global__ void __launch_bounds__(256) k_pair_scan(BABatch A) {
+    __shared__ int s_wt[8], s_wc[8], s_carry_t, s_carry_c;
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const BAProb P = A.prob[p];
-    int off = 0, nc = 0;
-    int pi = 0, pj = 0;                                    // the pair (pi <= pj) of slot pid
-    for (int pid = 0; pid < P.nPairs; pid++, pj++) {
-        if (pj == P.K) { pi++; pj = pi; }
-        A.pair_off[P.pair0 + pid] = off;
-        for (int q = 0; q < P.CC; q++) {
-            const int pc = P.pc0 + pid * P.CC + q;
-            const int c = A.pc_cnt[pc];
-            A.pc_off[pc] = off;
-            A.pc_fchunk[pc] = nc;
-            for (int s = 0; s < c; s += BA_CH) {
-                if (nc < P.nChunksMax) {
-                    A.chunk_pair[P.chunk0 + nc] = pid * P.CC + q;
-                    A.chunk_start[P.chunk0 + nc] = off + s;
-                    A.chunk_len[P.chunk0 + nc] = min(BA_CH, c - s);
-                    int4* rec = A.item_rec + 2 * ((size_t)P.blkI0 * 4 + nc);      // everything the chunk's warp needs, in one 32-byte read
-                    rec[0] = make_int4(p, (int)(P.tup0 + off + s), min(BA_CH, c - s), P.chunk0 + nc);
-                    rec[1] = make_int4(P.c0 + q / P.nC, P.c0 + q % P.nC, pi == pj, P.rt0 + (A.free_pose[P.k0 + pj] - P.p0) * P.nC + q % P.nC);   // .z: diagonal pair (its tuples are (e, e): Hpp rides along); .w: projection-table entry of (pose j, camera b)
-                }
-                nc++;
-            }
-            A.pc_nchunk[pc] = nc - A.pc_fchunk[pc];
-            off += c;
+    const int nslot = P.nPairs * P.CC;
+    if (tid == 0) { s_carry_t = 0; s_carry_c = 0; }
+    __syncthreads();
+    for (int s0 = 0; s0 < nslot; s0 += 256) {
+        const int slot = s0 + tid;
+        const int c = slot < nslot ? A.pc_cnt[P.pc0 + slot] : 0;
+        const int nch = (c + BA_CH - 1) / BA_CH;
+        int it = c, ic = nch;                                 // inclusive scans inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int vt = __shfl_up_sync(0xffffffffu, it, o), vc = __shfl_up_sync(0xffffffffu, ic, o);
+            if (lane >= o) { it += vt; ic += vc; }
         }
+        if (lane == 31) { s_wt[warp] = it; s_wc[warp] = ic; }
+        __syncthreads();
+        int bt = s_carry_t, bc = s_carry_c;
+        for (int w = 0; w < warp; w++) { bt += s_wt[w]; bc += s_wc[w]; }
+        const int off = bt + it - c, fch = bc + ic - nch;     // exclusive
+        if (slot < nslot) {
+            const int pid = slot / P.CC, q = slot - pid * P.CC;
+            A.pc_off[P.pc0 + slot] = off;
+            A.pc_fchunk[P.pc0 + slot] = fch;
+            A.pc_nchunk[P.pc0 + slot] = nch;
+            if (q == 0) A.pair_off[P.pair0 + pid] = off;
+            int pi, pj;
+            pair_decode(pid, P.K, pi, pj);
+            for (int k = 0; k < nch; k++) {
+                const int nc = fch + k;
+                if (nc >= P.nChunksMax) break;
+                const int st = off + k * BA_CH, len = min(BA_CH, c - k * BA_CH);
+                A.chunk_pair[P.chunk0 + nc] = slot;
+                A.chunk_start[P.chunk0 + nc] = st;
+                A.chunk_len[P.chunk0 + nc] = len;
+                int4* rec = A.item_rec + 2 * ((size_t)P.blkI0 * 4 + nc);      // everything the chunk's warp needs, in one 32-byte read
+                rec[0] = make_int4(p, (int)(P.tup0 + st), len, P.chunk0 + nc);
+                rec[1] = make_int4(P.c0 + q / P.nC, P.c0 + q % P.nC, pi == pj, P.rt0 + (A.free_pose[P.k0 + pj] - P.p0) * P.nC + q % P.nC);   // .z: diagonal pair (its tuples are (e, e): Hpp rides along); .w: projection-table entry of (pose j, camera b)
+            }
+        }
+        __syncthreads();
+        if (tid == 255) { s_carry_t = bt + it; s_carry_c = bc + ic; }
+        __syncthreads();
     }
-    A.state[p].nChunks = min(nc, P.nChunksMax);
-    A.state[p].nTuples = off;
+    if (tid == 0) {
+        A.state[p].nChunks = min(s_carry_c, P.nChunksMax);
+        A.state[p].nTuples = s_carry_t;
+    }
 }
-// tuples of a pair: grouped by camera pair, sorted by landmark inside a group
+// tuples of a pair: grouped by camera pair, sorted by landmark inside a group (lanes take 32-landmark words of the ANDed bitmaps,
+// an exclusive scan of their popcounts places each lane's tuples)
 __global__ void k_pair_fill(BABatch A, const int* blkP_prob, const int* blkP_first) {
     const int p = blkP_prob[blockIdx.x];
     const BAProb P = A.prob[p];
@@ -222,24 +240,28 @@ __global__ void k_pair_fill(BABatch A, const int* blkP_prob, const int* blkP_fir
     if (pid >= P.nPairs) return;
     int i, j;
     pair_decode(pid, P.K, i, j);
-    const int* T = A.edge_of + P.eof0;
-    int pos[BA_MAXCC];
-#pragma unroll
-    for (int q = 0; q < BA_MAXCC; q++) pos[q] = q < P.CC ? A.pc_off[P.pc0 + pid * P.CC + q] : 0;
+    const int* Ti = A.edge_of + P.eof0 + (long long)i * P.nL;
+    const int* Tj = A.edge_of + P.eof0 + (long long)j * P.nL;
     int2* out = A.tuples + P.tup0;
-    for (int l0 = 0; l0 < P.nL; l0 += 32) {
-        const int l = l0 + lane;
-        int a = -1, c = -1;
-        if (l < P.nL) { a = T[(long long)i * P.nL + l]; c = T[(long long)j * P.nL + l]; }
-        const bool both = a >= 0 && c >= 0;
-        const int combo = both ? (a & 3) * P.nC + (c & 3) : -1;
+    for (int q = 0; q < P.CC; q++) {
+        if (A.pc_cnt[P.pc0 + pid * P.CC + q] == 0) continue;
+        const unsigned* bi = A.bm + P.bm0 + ((long long)i * P.nC + q / P.nC) * P.bmW;
+        const unsigned* bj = A.bm + P.bm0 + ((long long)j * P.nC + q % P.nC) * P.bmW;
+        int pos = A.pc_off[P.pc0 + pid * P.CC + q];
+        for (int w0 = 0; w0 < P.bmW; w0 += 32) {
+            const int w = w0 + lane;
+            unsigned m = w < P.bmW ? (bi[w] & bj[w]) : 0u;
+            const int cnt = __popc(m);
+            int incl = cnt;
 #pragma unroll
-        for (int q = 0; q < BA_MAXCC; q++) {
-            if (q < P.CC) {
-                const unsigned m = __ballot_sync(0xffffffffu, combo == q);
-                if (combo == q) out[pos[q] + __popc(m & ((1u << lane) - 1))] = make_int2(a >> 2, c >> 2);
-                pos[q] += __popc(m);
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            int at = pos + incl - cnt;
+            while (m) {
+                const int l = 32 * w + (__ffs(m) - 1);
+                m &= m - 1;
+                out[at++] = make_int2(Ti[l] >> 2, Tj[l] >> 2);
             }
+            pos += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
 }
@@ -1714,7 +1736,7 @@ static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, 
     for (int p = 0; p < n; p++) if (!errs[p].empty()) ORB_FAIL(ORB_E_INVALID, "%s", errs[p].c_str());
     // ---- pass 1b: offsets
     long long Etot = 0, Ltot = 0, Ptot = 0, Ctot = 0, Ktot = 0, pairTot = 0, tupTot = 0, chunkTot = 0, eofTot = 0, hsTot = 0, itemTot = 0;
-    long long rtTot = 0, pcTot = 0, utTot = 0;
+    long long rtTot = 0, pcTot = 0, utTot = 0, bmTot = 0;
     int nbE = 0, nbL = 0, nbP = 0, nbI = 0, nbG = 0, max_n = 0;
     for (int p = 0; p < n; p++) max_n = std::max(max_n, 6 * Ks[p]);
     // shared memory of k_solve: packed matrix of the largest in-shared problem + solution column (any n) + panel; a very large problem in the
@@ -1739,6 +1761,7 @@ static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, 
         P.blkL0 = nbL; P.nbL = std::max(1, (nL + BA_TL - 1) / BA_TL);
         P.blkG0 = nbG; P.nbG = (int)groups[p].size() / 2;
         P.tup0 = tupTot; P.eof0 = eofTot; P.hs_off = hsTot;
+        P.bmW = (nL + 31) / 32; P.bm0 = bmTot; bmTot += (long long)K * nC * P.bmW;
         bP0[p] = nbP; bI0[p] = nbI; P.blkI0 = nbI;
         Etot += nE; Ltot += nL; Ptot += nP; Ctot += nC; Ktot += K; pairTot += P.nPairs; tupTot += tup; chunkTot += P.nChunksMax;
         itemTot += P.nItems; eofTot += (long long)nL * K;
@@ -1771,6 +1794,7 @@ static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, 
         o_epose = L.add(4 * Etot); o_ept = L.add(4 * Etot); o_ecam = L.add(4 * Etot); o_eobs = L.add(16 * Etot); o_einfo = L.add(8 * Etot); o_pt0 = L.add(24 * Ltot);
     }
     const size_t o_state = L.add(sizeof(BAState) * n);
+    const size_t o_bm = L.add(4 * (size_t)std::max<long long>(bmTot, 1));
     const size_t o_eof = L.add(4 * (size_t)eofTot), o_pcnt = L.add(4 * (size_t)pairTot), o_poff = L.add(4 * (size_t)pairTot);
     const size_t o_pccnt = L.add(4 * (size_t)pcTot), o_pcoff = L.add(4 * (size_t)pcTot), o_pcfch = L.add(4 * (size_t)pcTot), o_pcnch = L.add(4 * (size_t)pcTot);
     const size_t o_cpair = L.add(4 * (size_t)chunkTot), o_cstart = L.add(4 * (size_t)chunkTot), o_clen = L.add(4 * (size_t)chunkTot);
@@ -1886,6 +1910,7 @@ static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, 
     A.blkE_prob = (const int*)(D + o_blkE); A.blkL_prob = (const int*)(D + o_blkL); A.item_prob = (const int*)(D + o_item);
     A.blkG_prob = (const int*)(D + o_blkGp); A.blkG_l0 = (const int*)(D + o_blkGl); A.blkG_nl = (const int*)(D + o_blkGn);
     b->d_blkP_prob = (int*)(D + o_blkPp); b->d_blkP_first = (int*)(D + o_blkPf); b->d_blkI_first = (int*)(D + o_blkIf); b->d_pose_prob = (int*)(D + o_poseprob);
+    A.bm = (unsigned*)(D + o_bm);
     A.edge_of = (int*)(D + o_eof); A.pair_cnt = (int*)(D + o_pcnt); A.pair_off = (int*)(D + o_poff);
     A.pc_cnt = (int*)(D + o_pccnt); A.pc_off = (int*)(D + o_pcoff); A.pc_fchunk = (int*)(D + o_pcfch); A.pc_nchunk = (int*)(D + o_pcnch);
     A.free_pose = (const int*)(D + o_freepose);
@@ -1918,10 +1943,11 @@ static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, 
     ORB_CUDA(cudaMemsetAsync(D + o_state, 0, sizeof(BAState) * n, st));
     ORB_CUDA(cudaMemsetAsync(D + o_irec, 0, 32 * 4 * (size_t)std::max(nbI, 1), st));
     if (eofTot) ORB_CUDA(cudaMemsetAsync(D + o_eof, 0xff, 4 * (size_t)eofTot, st));
+    if (bmTot) ORB_CUDA(cudaMemsetAsync(D + o_bm, 0, 4 * (size_t)bmTot, st));
     k_edge_of<<<nbE, BA_TE, 0, st>>>(A);
     if (nbP > 0) {
         k_pair_count<<<nbP, 128, 0, st>>>(A, b->d_blkP_prob, b->d_blkP_first);
-        k_pair_scan<<<(n + 63) / 64, 64, 0, st>>>(A);
+        k_pair_scan<<<n, 256, 0, st>>>(A);
         k_pair_fill<<<nbP, 128, 0, st>>>(A, b->d_blkP_prob, b->d_blkP_first);
         b->launches += 3;
     }
