@@ -499,6 +499,9 @@ int  orbba_dist_timing(const orbgba_t*, double* allreduce_ms, double* solve_ms, 
 /* device milliseconds of the whole LM loop of the last optimize call (events around it) and the 6x6 blocks of the reduced camera
  * system's skyline (what the all-reduce ships: 288 bytes each) */
 int  orbba_dist_loop_ms(const orbgba_t*, double* loop_ms, long long* skyline_blocks);
+/* segments the last optimize call cut the reduced camera system into (0: single-CTA band / envelope factorisation).  Long narrow
+ * bands are substructured: one CTA per segment, a reduced band system for the separators.  ORBGBA_SEGMENTS=n overrides (0: off). */
+int  orbba_dist_segments(const orbgba_t*);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,7 @@ SIGNATURES = {
     "orbba_dist_optimize": (C.c_int, [vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]),
     "orbba_dist_timing": (C.c_int, [vp, f64p, f64p, f64p]),
     "orbba_dist_loop_ms": (C.c_int, [vp, f64p, C.POINTER(C.c_longlong)]),
+    "orbba_dist_segments": (C.c_int, [vp]),
     "orbm_search_by_projection_reloc": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
     "orbm_search_by_projection_sim3": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]),
     "orbm_project_best": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp]),

@@ -699,6 +699,396 @@ __global__ void __launch_bounds__(SKY_T) k_sky_band(GArgs A, double lambda, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ substructured banded solve
+// The single-CTA band factorisation is a chain of 6 K sequential pivots (3.5 us per key frame: 7 ms for 2000).  For long bands the rows are
+// cut into P segments separated by W-row separators (W = band width in blocks, so two interiors never touch):
+//   k_seg_fwd   CTA per segment: the same windowed LDL^T over the segment's interior columns only.  The rows of the separator BELOW the
+//               interior ride along as trailing rows (they end up holding L towards the interior and the interior's Schur term on
+//               themselves); the coupling to the separator ABOVE is carried as W extra block columns ("spike"): Zt_j = L_jj^-1 Z_j per
+//               interior row, trailing rows Z_i -= L_ij Zt_j, and the Schur terms on that separator C -= Zt^T D^-1 Zt, g -= Zt^T D^-1 z.
+//   k_red_asm   the separators' reduced system: a band of width 2 W - 1 over (P - 1) W block rows
+//   k_sky_band  ... factorised and solved by the band kernel itself
+//   k_seg_bwd   CTA per segment: backward sweep of the interior with the two separator solutions known.
+// Sequential depth K / P + (P - 1) W + K / P instead of 2 K; every sum keeps one owner and a fixed order.
+#define SEG_T 512
+#define SEG_WMAX 11            // reduced band 2 W - 1 <= SKY_WMAX
+#define SEG_PMAX 64
+struct SegArgs {
+    int P, W;
+    int s[SEG_PMAX], e[SEG_PMAX];     // interior [s, e) of segment p; separator p = rows [e_p, e_p + W), p < P - 1
+    double* Zt;                       // [K][W][36]
+    double* SPK;                      // [P][W][W][36]  block (row a of separator p, column c of separator p - 1)
+    double* CLL;                      // [P][W][W][36]  Schur term of interior p on the separator above it (p - 1)
+    double* GL;                       // [P][W][6]
+    int* ok;                          // [P]
+    // reduced system
+    double *Rs, *rb, *rx;
+    const int *rfirst, *rrowptr, *rlast;
+    long long rNB;
+};
+
+__global__ void __launch_bounds__(SEG_T) k_seg_fwd(GArgs A, const __grid_constant__ SegArgs G, double lambda) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int s_ok;
+    __shared__ double s_Lj[36], s_id[6], s_z[6], s_zt[SEG_WMAX * 36];
+    __shared__ unsigned char s_pa[(SEG_WMAX * (SEG_WMAX + 1)) / 2], s_pb[(SEG_WMAX * (SEG_WMAX + 1)) / 2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, p = blockIdx.x;
+    const int W = G.W, R = W + 1, RR = W + 3;
+    const int s0 = G.s[p], e0 = G.e[p];
+    const bool has_left = p > 0, has_right = p < G.P - 1;
+    const int rows_end = has_right ? e0 + W : e0;         // rows this CTA owns: interior + the separator below it
+    const int lcol0 = s0 - W;                             // first column of the separator above
+    double* win = sm;                                     // [RR][R][36]
+    double* zsp = win + (size_t)RR * R * 36;              // [RR][W][36]  spike block row of the rows in the window
+    double* panW = zsp + (size_t)RR * W * 36;             // [W][36]
+    double* zb = panW + (size_t)W * 36;                   // [RR][6]
+    double* cll = zb + RR * 6;                            // [W][W][36]
+    double* gl = cll + (size_t)W * W * 36;                // [W][6]
+    double* b = A.bs;
+    auto load_row = [&](int i, int sl, int ci) {
+        const int f = A.first[i], nb = i - f + 1;
+        const double* src = A.Hs + 36 * (size_t)A.rowptr[i];
+        double* rowp = win + (size_t)sl * R * 36;
+        double* zrow = zsp + (size_t)sl * W * 36;
+        if (tid < nb * 18) {
+            const int m = tid / 18, piece = tid - 18 * m, k = f + m;
+            if (k >= s0) {
+                int ck = ci - (i - k);
+                if (ck < 0) ck += R;
+                cp16(rowp + 36 * ck + 2 * piece, src + 2 * tid);
+            } else if (has_left && k >= lcol0) {
+                cp16(zrow + 36 * (k - lcol0) + 2 * piece, src + 2 * tid);
+            }
+        }
+        // explicit zeros for what the envelope (or the segment) does not hold
+        for (int q = tid; q < (R + W) * 18; q += SEG_T) {
+            const int blk = q / 18, piece = q - 18 * blk;
+            if (blk < R) {                                // window column i - W + blk
+                const int k = i - W + blk;
+                if (k < f || k < s0) {
+                    int ck = ci - (W - blk);
+                    if (ck < 0) ck += R;
+                    rowp[36 * ck + 2 * piece] = 0.0; rowp[36 * ck + 2 * piece + 1] = 0.0;
+                }
+            } else {                                      // spike column lcol0 + (blk - R)
+                const int c = blk - R, k = lcol0 + c;
+                if (!(has_left && k >= f && k >= 0)) { zrow[36 * c + 2 * piece] = 0.0; zrow[36 * c + 2 * piece + 1] = 0.0; }
+            }
+        }
+        if (tid >= 480 && tid < 483) cp16(zb + sl * 6 + 2 * (tid - 480), b + 6 * (size_t)i + 2 * (tid - 480));
+    };
+    if (tid == 0) {
+        s_ok = 1;
+        int q = 0;
+        for (int a = 0; a < W; a++) for (int c = 0; c <= a; c++) { s_pa[q] = (unsigned char)a; s_pb[q] = (unsigned char)c; q++; }
+    }
+    for (int q = tid; q < W * W * 36 + W * 6; q += SEG_T) cll[q] = 0.0;     // cll and gl are contiguous
+    for (int i = s0; i <= min(s0 + R, rows_end - 1); i++) load_row(i, i % RR, i % R);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    int sj = s0 % RR, cj = s0 % R;
+    for (int j = s0; j < e0; j++) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        if (j + R + 1 < rows_end) load_row(j + R + 1, sj == 0 ? RR - 1 : sj - 1, cj + 1 >= R ? cj + 1 - R : cj + 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        double* Djj = win + ((size_t)sj * R + cj) * 36;
+        if (warp == 0) {
+            double h[6][6], id[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int k = 0; k <= r; k++) h[r][k] = Djj[6 * r + k] + (r == k ? lambda : 0.0);
+            bool good = true;
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                const double dc = h[c][c];
+                if (dc == 0.0 || !isfinite(dc)) good = false;
+                id[c] = __drcp_rn(dc);
+                double t[6];
+#pragma unroll
+                for (int r = c + 1; r < 6; r++) t[r] = h[r][c];
+#pragma unroll
+                for (int r = c + 1; r < 6; r++) {
+                    const double l = t[r] * id[c];
+#pragma unroll
+                    for (int k = c + 1; k <= r; k++) h[r][k] -= l * t[k];
+                    h[r][c] = l;
+                }
+            }
+            double z[6];
+            const double* bj = zb + sj * 6;
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double a = bj[c];
+#pragma unroll
+                for (int k = 0; k < c; k++) a -= h[c][k] * z[k];
+                z[c] = a;
+            }
+            if (has_left) {                               // Zt_j = L_jj^-1 Z_j: lanes over the 6 W columns of the spike block row
+                const double* Zj = zsp + (size_t)sj * W * 36;
+                for (int col = lane; col < 6 * W; col += 32) {
+                    const int c = col / 6, cc = col - 6 * c;
+                    double zt[6];
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        double a = Zj[36 * c + 6 * r + cc];
+#pragma unroll
+                        for (int k = 0; k < r; k++) a -= h[r][k] * zt[k];
+                        zt[r] = a;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 6; r++) s_zt[36 * c + 6 * r + cc] = zt[r];
+                }
+            }
+            if (tid == 0) {
+                if (!good) s_ok = 0;
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+#pragma unroll
+                    for (int k = 0; k < r; k++) { s_Lj[6 * r + k] = h[r][k]; Djj[6 * r + k] = h[r][k]; }
+                    Djj[7 * r] = id[r];
+                    s_id[r] = id[r]; s_z[r] = z[r]; b[6 * (size_t)j + r] = z[r];
+                }
+            }
+        }
+        __syncthreads();
+        if (!s_ok) break;
+        const int nr = min(W, rows_end - 1 - j);
+        if (tid < 6 * nr) {
+            const int a = tid / 6, r = tid - 6 * a;
+            int si = sj + 1 + a;
+            if (si >= RR) si -= RR;
+            double* row = win + ((size_t)si * R + cj) * 36 + 6 * r;
+            double w[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double v = row[c];
+#pragma unroll
+                for (int k = 0; k < c; k++) v -= w[k] * s_Lj[6 * c + k];
+                w[c] = v;
+            }
+            double bz = 0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) { const double l = w[c] * s_id[c]; row[c] = l; panW[36 * a + 6 * r + c] = w[c]; bz += l * s_z[c]; }
+            zb[si * 6 + r] -= bz;
+        }
+        __syncthreads();
+        // ---- everything that only reads the finished column: trailing update, spike rows, Schur terms on the separator above, write-backs
+        const int nT = (nr * (nr + 1) / 2) * 36;
+        const int nS = has_left ? nr * W * 36 : 0;
+        const int nC = has_left ? W * W * 36 : 0;
+        const int nG = has_left ? W * 6 : 0;
+        for (int it = tid; it < nT + nS + nC + nG; it += SEG_T) {
+            if (it < nT) {
+                const int pr = it / 36, en = it - 36 * pr, a = s_pa[pr], bq = s_pb[pr];
+                int si = sj + 1 + a, sk = sj + 1 + bq, ck = cj + 1 + bq;
+                if (si >= RR) si -= RR;
+                if (sk >= RR) sk -= RR;
+                if (ck >= R) ck -= R;
+                const int r = en / 6, c = en - 6 * r;
+                const double* Wp = panW + 36 * a + 6 * r;
+                const double* Lk = win + ((size_t)sk * R + cj) * 36 + 6 * c;
+                double acc = 0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc += Wp[q] * Lk[q];
+                win[((size_t)si * R + ck) * 36 + en] -= acc;
+            } else if (it < nT + nS) {                    // Z_i -= L_ij Zt_j
+                const int q0 = it - nT, a = q0 / (W * 36), rem = q0 - a * W * 36, c = rem / 36, en = rem - 36 * c, r = en / 6, cc = en - 6 * r;
+                int si = sj + 1 + a;
+                if (si >= RR) si -= RR;
+                const double* Li = win + ((size_t)si * R + cj) * 36 + 6 * r;
+                double acc = 0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc += Li[q] * s_zt[36 * c + 6 * q + cc];
+                zsp[((size_t)si * W + c) * 36 + en] -= acc;
+            } else if (it < nT + nS + nC) {               // C[c1][c2] -= Zt[c1]^T D^-1 Zt[c2]
+                const int q0 = it - nT - nS, c1 = q0 / (W * 36), rem = q0 - c1 * W * 36, c2 = rem / 36, en = rem - 36 * c2, r = en / 6, cc = en - 6 * r;
+                double acc = 0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc += s_zt[36 * c1 + 6 * q + r] * s_id[q] * s_zt[36 * c2 + 6 * q + cc];
+                cll[((size_t)c1 * W + c2) * 36 + en] -= acc;
+            } else {                                      // g[c] -= Zt[c]^T D^-1 z
+                const int q0 = it - nT - nS - nC, c = q0 / 6, r = q0 - 6 * c;
+                double acc = 0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc += s_zt[36 * c + 6 * q + r] * s_id[q] * s_z[q];
+                gl[6 * c + r] -= acc;
+            }
+        }
+        {   // row j is final: its blocks at or right of the segment start go back to global memory, and its Zt
+            const int f = max(A.first[j], s0), nb = j - f + 1;
+            double* dst = A.Hs + 36 * ((size_t)A.rowptr[j] + (f - A.first[j]));
+            const double* rowp = win + (size_t)sj * R * 36;
+            for (int q = tid; q < nb * 36; q += SEG_T) {
+                const int m = q / 36;
+                int ck = cj - (nb - 1 - m);
+                if (ck < 0) ck += R;
+                dst[q] = rowp[36 * ck + (q - 36 * m)];
+            }
+            if (has_left) for (int q = tid; q < W * 36; q += SEG_T) G.Zt[(size_t)j * W * 36 + q] = s_zt[q];
+        }
+        if (++sj == RR) sj = 0;
+        if (++cj == R) cj = 0;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) G.ok[p] = s_ok;
+    // ---- the separator below: updated rows, spike rows and right-hand side; the Schur terms on the separator above
+    if (has_right && s_ok) {
+        for (int a = 0; a < W; a++) {
+            const int i = e0 + a;
+            int si = sj + a, ci = cj + a;
+            if (si >= RR) si -= RR;
+            if (ci >= R) ci -= R;
+            const int f = A.first[i], nb = i - f + 1;
+            double* dst = A.Hs + 36 * (size_t)A.rowptr[i];
+            const double* rowp = win + (size_t)si * R * 36;
+            for (int q = tid; q < nb * 36; q += SEG_T) {
+                const int m = q / 36;
+                int ck = ci - (nb - 1 - m);
+                if (ck < 0) ck += R;
+                dst[q] = rowp[36 * ck + (q - 36 * m)];
+            }
+            for (int q = tid; q < W * 36; q += SEG_T) G.SPK[((size_t)p * W + a) * W * 36 + q] = has_left ? zsp[(size_t)si * W * 36 + q] : 0.0;
+            if (tid < 6) b[6 * (size_t)i + tid] = zb[si * 6 + tid];
+        }
+    }
+    for (int q = tid; q < W * W * 36; q += SEG_T) G.CLL[(size_t)p * W * W * 36 + q] = cll[q];
+    for (int q = tid; q < W * 6; q += SEG_T) G.GL[(size_t)p * W * 6 + q] = gl[q];
+}
+
+// reduced system of the separators: block row rho = p W + a <-> row e_p + a; block (rho, p W + b) = A(e_p + a, e_p + b) - C^(p+1)[a][b],
+// block (rho, (p - 1) W + b) = spike of row e_p + a; right-hand side b(e_p + a) + g^(p+1)[a].  thread per entry.
+__global__ void __launch_bounds__(256) k_red_asm(GArgs A, const __grid_constant__ SegArgs G) {
+    const int W = G.W, nsep = G.P - 1;
+    const long long tot = G.rNB * 36;
+    for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < tot; q += (long long)gridDim.x * 256) {
+        const long long blk = q / 36;
+        const int en = (int)(q - 36 * blk);
+        int lo = 0, hi = nsep * W - 1;                       // row of the block (rrowptr is increasing)
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (G.rrowptr[mid] <= blk) lo = mid; else hi = mid - 1; }
+        const int rho = lo, col = G.rfirst[rho] + (int)(blk - G.rrowptr[rho]);
+        const int p = rho / W, a = rho - p * W, pc = col / W, bq = col - pc * W;
+        double v;
+        if (pc == p) {
+            const int i = G.e[p] + a, k = G.e[p] + bq;
+            v = k >= A.first[i] ? A.Hs[36 * ((size_t)A.rowptr[i] + (k - A.first[i])) + en] : 0.0;
+            v += G.CLL[(((size_t)(p + 1) * W + a) * W + bq) * 36 + en];       // (C holds the negative Schur term)
+        } else {
+            v = G.SPK[(((size_t)p * W + a) * W + bq) * 36 + en];
+        }
+        G.Rs[q] = v;
+    }
+    for (int q = blockIdx.x * 256 + threadIdx.x; q < nsep * W * 6; q += gridDim.x * 256) {
+        const int rho = q / 6, r = q - 6 * rho, p = rho / W, a = rho - p * W;
+        G.rb[q] = A.bs[6 * (size_t)(G.e[p] + a) + r] + G.GL[((size_t)(p + 1) * W + a) * 6 + r];
+    }
+}
+
+// CTA per segment: x_j = L_jj^-T (D_j^-1 (z_j - Zt_j x_above) - sum_{i in (j, j + W]} L_ij^T x_i), the separator solutions known
+__global__ void __launch_bounds__(256) k_seg_bwd(GArgs A, const __grid_constant__ SegArgs G) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double s_part[6 * (SEG_WMAX + 1)], s_xl[6 * SEG_WMAX];
+    __shared__ int s_fail;
+    const int tid = threadIdx.x, warp = tid >> 5, p = blockIdx.x;
+    const int W = G.W, R = W + 1, RR = W + 3;
+    const int s0 = G.s[p], e0 = G.e[p];
+    const bool has_left = p > 0, has_right = p < G.P - 1;
+    const int rows_end = has_right ? e0 + W : e0;
+    double* colb = sm;                                    // [3][R][36]
+    double* colz = colb + 3 * (size_t)R * 36;             // [3][6]
+    double* ztb = colz + 18;                              // [3][W][36]
+    double* xr = ztb + 3 * (size_t)W * 36;                // [RR][6]
+    if (tid == 0) {
+        int fail = A.red[7] == 0.0;
+        for (int q = 0; q < G.P; q++) fail |= G.ok[q] == 0;
+        s_fail = fail;
+    }
+    __syncthreads();
+    if (s_fail) {                                         // a pivot failed somewhere: g2o applies no update (the trial is rejected)
+        if (p == 0 && tid == 0) A.red[7] = 0.0;
+        for (int i = 6 * s0 + tid; i < 6 * rows_end; i += 256) A.x[i] = 0.0;
+        return;
+    }
+    // separator solutions: above -> s_xl, below -> the x ring (and A.x)
+    if (has_left) for (int q = tid; q < 6 * W; q += 256) s_xl[q] = G.rx[(size_t)(p - 1) * W * 6 + q];
+    if (has_right)
+        for (int q = tid; q < 6 * W; q += 256) {
+            const double v = G.rx[(size_t)p * W * 6 + q];
+            const int i = e0 + q / 6;
+            xr[(i % RR) * 6 + q % 6] = v;
+            A.x[6 * (size_t)e0 + q] = v;
+        }
+    auto load_col = [&](int j, int stage) {
+        double* dst = colb + (size_t)stage * R * 36;
+        const int nr = min(W, rows_end - 1 - j);
+        if (tid < (nr + 1) * 18) {
+            const int a = tid / 18, piece = tid - 18 * a, i = j + a, f = A.first[i];
+            if (f <= j) cp16(dst + 36 * a + 2 * piece, A.Hs + 36 * ((size_t)A.rowptr[i] + (j - f)) + 2 * piece);
+            else { dst[36 * a + 2 * piece] = 0.0; dst[36 * a + 2 * piece + 1] = 0.0; }
+        }
+        if (has_left) for (int q = tid; q < W * 18; q += 256) cp16(ztb + (size_t)stage * W * 36 + 2 * q, G.Zt + (size_t)j * W * 36 + 2 * q);
+        if (tid >= 240 && tid < 243) cp16(colz + stage * 6 + 2 * (tid - 240), A.bs + 6 * (size_t)j + 2 * (tid - 240));
+    };
+    int st3 = (e0 - 1) % 3;
+    if (e0 - 1 >= s0) load_col(e0 - 1, st3);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (e0 - 2 >= s0) load_col(e0 - 2, (e0 - 2) % 3);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    int xj = (e0 - 1) % RR;
+    for (int j = e0 - 1; j >= s0; j--) {
+        if (j - 2 >= s0) load_col(j - 2, st3 == 2 ? 0 : st3 + 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncthreads();
+        const double* col = colb + (size_t)st3 * R * 36;
+        const int nr = min(W, rows_end - 1 - j);
+        if (tid < 6 * nr) {
+            const int a = tid / 6 + 1, c = tid - 6 * (a - 1);
+            int xi = xj + a;
+            if (xi >= RR) xi -= RR;
+            const double* L = col + 36 * a;
+            const double* xv = xr + xi * 6;
+            double acc = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) acc += L[6 * r + c] * xv[r];
+            s_part[tid] = acc;
+        } else if (has_left && tid >= 128 && tid < 134) {       // (Zt_j x_above)[r], r = tid - 128
+            const int r = tid - 128;
+            const double* Z = ztb + (size_t)st3 * W * 36;
+            double acc = 0;
+            for (int c = 0; c < W; c++)
+#pragma unroll
+                for (int cc = 0; cc < 6; cc++) acc += Z[36 * c + 6 * r + cc] * s_xl[6 * c + cc];
+            s_part[6 * W + r] = acc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double x[6];
+#pragma unroll
+            for (int c = 5; c >= 0; c--) {
+                double acc = 0;
+                for (int a = 0; a < nr; a++) acc += s_part[6 * a + c];
+                const double zl = has_left ? s_part[6 * W + c] : 0.0;
+                double v = (colz[st3 * 6 + c] - zl) * col[7 * c] - acc;
+#pragma unroll
+                for (int k = c + 1; k < 6; k++) v -= col[6 * k + c] * x[k];
+                x[c] = v;
+            }
+            if (tid < 6) {
+                double v = x[0];
+#pragma unroll
+                for (int c = 1; c < 6; c++) if (tid == c) v = x[c];
+                xr[xj * 6 + tid] = v; A.x[6 * (size_t)j + tid] = v;
+            }
+        }
+        __syncthreads();
+        st3 = st3 == 0 ? 2 : st3 - 1;
+        xj = xj == 0 ? RR - 1 : xj - 1;
+    }
+}
+
 // trial poses: exp(x) * pose for free poses, copy for fixed; pose part of computeScale() -> red[4]
 __global__ void __launch_bounds__(256) g_pose_update(GArgs A, int cur, double lambda) {
     __shared__ double sm[256];
@@ -817,6 +1207,7 @@ struct orbgba {
     double allreduce_ms = 0, solve_ms = 0, loop_ms = 0;   // accumulated over the last optimize call (events)
     size_t allreduce_bytes = 0;
     long long sky_blocks = 0;
+    int segments = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -901,6 +1292,8 @@ int orbba_dist_loop_ms(const orbgba_t* g, double* loop_ms, long long* skyline_bl
     return ORB_OK;
 }
 
+int orbba_dist_segments(const orbgba_t* g) { return g ? g->segments : 0; }
+
 // Optimizer::BundleAdjustment on this rank's shard: ALL poses (replicated, identical on every rank), this rank's landmarks
 // (points [n_points][3]) and their edges (edge_point indexes the local landmark array).  Collective: every rank of the
 // communicator must call it with the same poses / iterations / huber_delta.  Everything a rank decides on its own (input
@@ -970,6 +1363,43 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     for (int k = 0; k < K; k++) sky_w = std::max(sky_w, k - first[k]);
     const size_t sky_smem = 8 * ((size_t)(sky_w + 3) * (sky_w + 1) * 36 + (size_t)std::max(sky_w, 1) * 36 + (size_t)(sky_w + 3) * 6 + 3 * (size_t)(sky_w + 1) * 36 + 18 + (size_t)(sky_w + 3) * 6);
     if (sky_w <= SKY_WMAX) ORB_CUDA(cudaFuncSetAttribute(k_sky_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sky_smem));
+    // substructuring (k_seg_fwd): P segments of >= max(W, 8) interior rows separated by W-row separators.  P ~ sqrt(K / W) balances the
+    // interior sweeps (2 K / P steps) against the reduced band ((P - 1) W steps at width 2 W - 1).  ORBGBA_SEGMENTS overrides (0: off).
+    SegArgs SG;
+    memset(&SG, 0, sizeof(SG));
+    int seg_P = 0;
+    if (sky_w >= 1 && sky_w <= SEG_WMAX) {
+        const int W = sky_w;
+        int P = K >= 192 ? (int)lround(sqrt(2.0 * K / (2.5 * W))) : 0;
+        if (const char* ev = getenv("ORBGBA_SEGMENTS")) P = atoi(ev);
+        P = std::min(P, SEG_PMAX);
+        while (P >= 2 && (K - (P - 1) * W) / P < std::max(W, 8)) P--;
+        if (P >= 2) {
+            seg_P = P;
+            SG.P = P; SG.W = W;
+            const int inner = K - (P - 1) * W;
+            int row = 0;
+            for (int q = 0; q < P; q++) {
+                const int m = inner / P + (q < inner % P ? 1 : 0);
+                SG.s[q] = row; SG.e[q] = row + m;
+                row += m + W;
+            }
+        }
+    }
+    const int rK = seg_P ? (seg_P - 1) * sky_w : 0, rW = 2 * sky_w - 1;
+    std::vector<int> rfirst(std::max(rK, 1), 0), rrowptr(rK + 1, 0);
+    long long rNB = 0;
+    for (int r = 0; r < rK; r++) { const int q = r / sky_w; rfirst[r] = q > 0 ? (q - 1) * sky_w : 0; rrowptr[r] = (int)rNB; rNB += r - rfirst[r] + 1; }
+    rrowptr[rK] = (int)rNB;
+    const size_t seg_smem_f = 8 * ((size_t)(sky_w + 3) * (sky_w + 1) * 36 + (size_t)(sky_w + 3) * sky_w * 36 + (size_t)sky_w * 36 + (size_t)(sky_w + 3) * 6 + (size_t)sky_w * sky_w * 36 + (size_t)sky_w * 6);
+    const size_t seg_smem_b = 8 * (3 * (size_t)(sky_w + 1) * 36 + 18 + 3 * (size_t)sky_w * 36 + (size_t)(sky_w + 3) * 6);
+    const size_t red_smem = 8 * ((size_t)(rW + 3) * (rW + 1) * 36 + (size_t)std::max(rW, 1) * 36 + (size_t)(rW + 3) * 6 + 3 * (size_t)(rW + 1) * 36 + 18 + (size_t)(rW + 3) * 6);
+    if (seg_P) {
+        ORB_CUDA(cudaFuncSetAttribute(k_seg_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem_f));
+        ORB_CUDA(cudaFuncSetAttribute(k_seg_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem_b));
+        ORB_CUDA(cudaFuncSetAttribute(k_sky_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(red_smem, sky_smem)));
+    }
+    g->segments = seg_P;
     // owner lists: edges per free pose; tuples per skyline block
     std::vector<int> pose_eoff(K + 1, 0), pose_edge;
     std::vector<long long> blk_toff((size_t)NB + 1, 0);
@@ -1012,6 +1442,7 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     const size_t o_first = add(4 * (size_t)std::max(K, 1)), o_rowptr = add(4 * (size_t)(K + 1)), o_last = add(4 * (size_t)std::max(K, 1));
     const size_t o_peoff = add(4 * (size_t)(K + 1)), o_pedge = add(4 * std::max<size_t>(pose_edge.size(), 1));
     const size_t o_btoff = add(8 * (size_t)(NB + 1)), o_btup = add(8 * (size_t)std::max<long long>(nT, 1));
+    const size_t o_rfirst = add(4 * (size_t)std::max(rK, 1)), o_rrowptr = add(4 * (size_t)(rK + 1));
     const size_t staged = add(0);
     const size_t o_pose1 = add(56 * (size_t)nP), o_pt1 = add(24 * (size_t)nL), o_err0 = add(16 * (size_t)nE), o_err1 = add(16 * (size_t)nE);
     const size_t o_rec = add(8 * BA_REC * (size_t)nE), o_B = add(144 * (size_t)nE), o_Y = add(144 * (size_t)nE);
@@ -1023,6 +1454,10 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     const int nbE = std::max(1, (nE + G_T - 1) / G_T), nbL = std::max(1, (nL + G_T - 1) / G_T);
     const size_t o_part = add(16 * (size_t)std::max(nbE, nbL)), o_red = add(64 * 8);
     const size_t o_pout = add(96 * (size_t)nP), o_lout = add(24 * (size_t)std::max(nL, 1));
+    const size_t sW = (size_t)std::max(sky_w, 1), sP = (size_t)std::max(seg_P, 1);
+    const size_t o_zt = add(seg_P ? 288 * sW * (size_t)K : 8), o_spk = add(seg_P ? 288 * sW * sW * sP : 8), o_cll = add(seg_P ? 288 * sW * sW * (sP + 1) : 8);
+    const size_t o_gl = add(seg_P ? 48 * sW * (sP + 1) : 8), o_segok = add(4 * sP);
+    const size_t o_Rs = add(8 * (size_t)(36 * rNB + 8)), o_rb = add(48 * (size_t)std::max(rK, 1)), o_rx = add(48 * (size_t)std::max(rK, 1));
     const size_t total = add(0) + 256;
     if (total > g->arena_cap) {
         cudaFree(g->arena); g->arena = nullptr; g->arena_cap = 0;
@@ -1042,6 +1477,8 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     memcpy(H.data() + o_first, first.data(), 4 * (size_t)std::max(K, 1));
     memcpy(H.data() + o_rowptr, rowptr.data(), 4 * (size_t)(K + 1));
     memcpy(H.data() + o_last, last.data(), 4 * (size_t)std::max(K, 1));
+    memcpy(H.data() + o_rfirst, rfirst.data(), 4 * (size_t)std::max(rK, 1));
+    memcpy(H.data() + o_rrowptr, rrowptr.data(), 4 * (size_t)(rK + 1));
     memcpy(H.data() + o_peoff, pose_eoff.data(), 4 * (size_t)(K + 1));
     if (!pose_edge.empty()) memcpy(H.data() + o_pedge, pose_edge.data(), 4 * pose_edge.size());
     memcpy(H.data() + o_btoff, blk_toff.data(), 8 * (size_t)(NB + 1));
@@ -1084,6 +1521,11 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     A.part = (double*)(D + o_part); A.red = (double*)(D + o_red);
     A.first = (const int*)(D + o_first); A.rowptr = (const int*)(D + o_rowptr); A.last = (const int*)(D + o_last); A.NB = NB;
     A.pose_eoff = (const int*)(D + o_peoff); A.pose_edge = (const int*)(D + o_pedge);
+    SG.Zt = (double*)(D + o_zt); SG.SPK = (double*)(D + o_spk); SG.CLL = (double*)(D + o_cll); SG.GL = (double*)(D + o_gl); SG.ok = (int*)(D + o_segok);
+    SG.Rs = (double*)(D + o_Rs); SG.rb = (double*)(D + o_rb); SG.rx = (double*)(D + o_rx);
+    SG.rfirst = (const int*)(D + o_rfirst); SG.rrowptr = (const int*)(D + o_rrowptr); SG.rNB = rNB;
+    GArgs AR = A;                          // the separators' reduced system, as k_sky_band sees it
+    AR.K = rK; AR.n = 6 * rK; AR.Hs = SG.Rs; AR.bs = SG.rb; AR.x = SG.rx; AR.first = SG.rfirst; AR.rowptr = SG.rrowptr; AR.NB = rNB;
     A.blk_toff = (const long long*)(D + o_btoff); A.blk_tup = (const int2*)(D + o_btup);
     double* d_pout = (double*)(D + o_pout);
     double* d_lout = (double*)(D + o_lout);
@@ -1165,7 +1607,14 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
             if ((rc = all_reduce(g, A.Hs, (size_t)(36 * NB + n), NCCL_SUM)) != ORB_OK) return rc;
             ORB_CUDA(cudaEventRecord(g->ev[1], st));
             if (K > 0) {
-                if (sky_w <= SKY_WMAX) k_sky_band<<<1, SKY_T, sky_smem, st>>>(A, lambda, sky_w);
+                if (seg_P) {
+                    k_seg_fwd<<<seg_P, SEG_T, seg_smem_f, st>>>(A, SG, lambda);
+                    k_red_asm<<<(unsigned)std::min<long long>((36 * rNB + 255) / 256, 148 * 8), 256, 0, st>>>(A, SG);
+                    k_sky_band<<<1, SKY_T, red_smem, st>>>(AR, lambda, rW);
+                    k_seg_bwd<<<seg_P, 256, seg_smem_b, st>>>(A, SG);
+                    g->launches += 3;
+                }
+                else if (sky_w <= SKY_WMAX) k_sky_band<<<1, SKY_T, sky_smem, st>>>(A, lambda, sky_w);
                 else k_sky<<<1, SKY_T, 0, st>>>(A, lambda);
                 g->launches++;
             }

@@ -289,7 +289,7 @@ class DistributedOptimizer:
         check(lib().orbba_dist_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
         d, nb = C.c_double(), C.c_longlong()
         check(lib().orbba_dist_loop_ms(self._h, C.byref(d), C.byref(nb)))
-        return dict(allreduce_ms=a.value, solve_ms=b.value, allreduce_bytes=c.value, loop_ms=d.value, skyline_blocks=nb.value)
+        return dict(allreduce_ms=a.value, solve_ms=b.value, allreduce_bytes=c.value, loop_ms=d.value, skyline_blocks=nb.value, segments=int(lib().orbba_dist_segments(self._h)))
 
     def launch_count(self):
         return int(lib().orbba_dist_launch_count(self._h))

@@ -78,6 +78,27 @@ def test_dist_loop_closure_envelope_vs_oracle():
     assert tm["skyline_blocks"] > 59 * 8          # the long rows are in the envelope
 
 
+@pytest.mark.parametrize("n_kf,segments", [(120, 2), (120, 5), (300, None), (333, 9)])
+def test_dist_substructured_solve_equals_band(n_kf, segments, monkeypatch):
+    """segments + separators (one CTA per segment, reduced band for the separators) against the single-CTA band factorisation of the
+    same system: same LM trajectory, poses to rounding; the substructured path is itself bit-reproducible"""
+    p = synth.gba_problem(11, n_kf=n_kf, n_points=40 * n_kf)
+    sh = shard_problem(p, 0, 1)
+    monkeypatch.setenv("ORBGBA_SEGMENTS", "0")
+    ref = DistributedOptimizer()
+    a = ref.GlobalBundleAdjustemnt(sh, nIterations=5)
+    assert ref.timing()["segments"] == 0
+    if segments is None: monkeypatch.delenv("ORBGBA_SEGMENTS")
+    else: monkeypatch.setenv("ORBGBA_SEGMENTS", str(segments))
+    opt = DistributedOptimizer()
+    b = opt.GlobalBundleAdjustemnt(sh, nIterations=5)
+    c = DistributedOptimizer().GlobalBundleAdjustemnt(sh, nIterations=5)
+    assert opt.timing()["segments"] >= 2
+    assert a[2]["trials"] == b[2]["trials"] and a[2]["iterations"] == b[2]["iterations"]
+    assert _pose_rel(a[0], b[0]) <= 1e-9 and np.isclose(a[2]["final_chi2"], b[2]["final_chi2"], rtol=1e-9)
+    assert np.array_equal(b[0], c[0]) and np.array_equal(b[1], c[1])
+
+
 def test_dist_bit_reproducible():
     p = synth.gba_problem(6, n_kf=50, n_points=3000)
     sh = shard_problem(p, 0, 1)
