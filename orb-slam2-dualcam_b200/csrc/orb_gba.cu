@@ -718,8 +718,8 @@ struct SegArgs {
     int s[SEG_PMAX], e[SEG_PMAX];     // interior [s, e) of segment p; separator p = rows [e_p, e_p + W), p < P - 1
     double* Zt;                       // [K][W][36]
     double* SPK;                      // [P][W][W][36]  block (row a of separator p, column c of separator p - 1)
-    double* CLL;                      // [P][W][W][36]  Schur term of interior p on the separator above it (p - 1)
-    double* GL;                       // [P][W][6]
+    double* CLL;                      // [P][SEG_NCH][W][W][36]  partial Schur terms of interior p on the separator above it (p - 1)
+    double* GL;                       // [P][SEG_NCH][W][6]
     int* ok;                          // [P]
     // reduced system
     double *Rs, *rb, *rx;
@@ -742,8 +742,6 @@ __global__ void __launch_bounds__(SEG_T) k_seg_fwd(GArgs A, const __grid_constan
     double* zsp = win + (size_t)RR * R * 36;              // [RR][W][36]  spike block row of the rows in the window
     double* panW = zsp + (size_t)RR * W * 36;             // [W][36]
     double* zb = panW + (size_t)W * 36;                   // [RR][6]
-    double* cll = zb + RR * 6;                            // [W][W][36]
-    double* gl = cll + (size_t)W * W * 36;                // [W][6]
     double* b = A.bs;
     auto load_row = [&](int i, int sl, int ci) {
         const int f = A.first[i], nb = i - f + 1;
@@ -782,7 +780,6 @@ __global__ void __launch_bounds__(SEG_T) k_seg_fwd(GArgs A, const __grid_constan
         int q = 0;
         for (int a = 0; a < W; a++) for (int c = 0; c <= a; c++) { s_pa[q] = (unsigned char)a; s_pb[q] = (unsigned char)c; q++; }
     }
-    for (int q = tid; q < W * W * 36 + W * 6; q += SEG_T) cll[q] = 0.0;     // cll and gl are contiguous
     for (int i = s0; i <= min(s0 + R, rows_end - 1); i++) load_row(i, i % RR, i % R);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -825,22 +822,6 @@ __global__ void __launch_bounds__(SEG_T) k_seg_fwd(GArgs A, const __grid_constan
                 for (int k = 0; k < c; k++) a -= h[c][k] * z[k];
                 z[c] = a;
             }
-            if (has_left) {                               // Zt_j = L_jj^-1 Z_j: lanes over the 6 W columns of the spike block row
-                const double* Zj = zsp + (size_t)sj * W * 36;
-                for (int col = lane; col < 6 * W; col += 32) {
-                    const int c = col / 6, cc = col - 6 * c;
-                    double zt[6];
-#pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        double a = Zj[36 * c + 6 * r + cc];
-#pragma unroll
-                        for (int k = 0; k < r; k++) a -= h[r][k] * zt[k];
-                        zt[r] = a;
-                    }
-#pragma unroll
-                    for (int r = 0; r < 6; r++) s_zt[36 * c + 6 * r + cc] = zt[r];
-                }
-            }
             if (tid == 0) {
                 if (!good) s_ok = 0;
 #pragma unroll
@@ -872,14 +853,25 @@ __global__ void __launch_bounds__(SEG_T) k_seg_fwd(GArgs A, const __grid_constan
 #pragma unroll
             for (int c = 0; c < 6; c++) { const double l = w[c] * s_id[c]; row[c] = l; panW[36 * a + 6 * r + c] = w[c]; bz += l * s_z[c]; }
             zb[si * 6 + r] -= bz;
+        } else if (has_left && tid >= 128 && tid < 128 + 6 * W) {      // Zt_j = L_jj^-1 Z_j, a thread per column of the spike block row
+            const int col = tid - 128, c = col / 6, cc = col - 6 * c;
+            const double* Zj = zsp + (size_t)sj * W * 36 + 36 * c + cc;
+            double zt[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                double a = Zj[6 * r];
+#pragma unroll
+                for (int k = 0; k < r; k++) a -= s_Lj[6 * r + k] * zt[k];
+                zt[r] = a;
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) s_zt[36 * c + 6 * r + cc] = zt[r];
         }
         __syncthreads();
         // ---- everything that only reads the finished column: trailing update, spike rows, Schur terms on the separator above, write-backs
         const int nT = (nr * (nr + 1) / 2) * 36;
         const int nS = has_left ? nr * W * 36 : 0;
-        const int nC = has_left ? W * W * 36 : 0;
-        const int nG = has_left ? W * 6 : 0;
-        for (int it = tid; it < nT + nS + nC + nG; it += SEG_T) {
+        for (int it = tid; it < nT + nS; it += SEG_T) {
             if (it < nT) {
                 const int pr = it / 36, en = it - 36 * pr, a = s_pa[pr], bq = s_pb[pr];
                 int si = sj + 1 + a, sk = sj + 1 + bq, ck = cj + 1 + bq;
@@ -893,7 +885,7 @@ __global__ void __launch_bounds__(SEG_T) k_seg_fwd(GArgs A, const __grid_constan
 #pragma unroll
                 for (int q = 0; q < 6; q++) acc += Wp[q] * Lk[q];
                 win[((size_t)si * R + ck) * 36 + en] -= acc;
-            } else if (it < nT + nS) {                    // Z_i -= L_ij Zt_j
+            } else {                                      // Z_i -= L_ij Zt_j
                 const int q0 = it - nT, a = q0 / (W * 36), rem = q0 - a * W * 36, c = rem / 36, en = rem - 36 * c, r = en / 6, cc = en - 6 * r;
                 int si = sj + 1 + a;
                 if (si >= RR) si -= RR;
@@ -902,18 +894,6 @@ __global__ void __launch_bounds__(SEG_T) k_seg_fwd(GArgs A, const __grid_constan
 #pragma unroll
                 for (int q = 0; q < 6; q++) acc += Li[q] * s_zt[36 * c + 6 * q + cc];
                 zsp[((size_t)si * W + c) * 36 + en] -= acc;
-            } else if (it < nT + nS + nC) {               // C[c1][c2] -= Zt[c1]^T D^-1 Zt[c2]
-                const int q0 = it - nT - nS, c1 = q0 / (W * 36), rem = q0 - c1 * W * 36, c2 = rem / 36, en = rem - 36 * c2, r = en / 6, cc = en - 6 * r;
-                double acc = 0;
-#pragma unroll
-                for (int q = 0; q < 6; q++) acc += s_zt[36 * c1 + 6 * q + r] * s_id[q] * s_zt[36 * c2 + 6 * q + cc];
-                cll[((size_t)c1 * W + c2) * 36 + en] -= acc;
-            } else {                                      // g[c] -= Zt[c]^T D^-1 z
-                const int q0 = it - nT - nS - nC, c = q0 / 6, r = q0 - 6 * c;
-                double acc = 0;
-#pragma unroll
-                for (int q = 0; q < 6; q++) acc += s_zt[36 * c + 6 * q + r] * s_id[q] * s_z[q];
-                gl[6 * c + r] -= acc;
             }
         }
         {   // row j is final: its blocks at or right of the segment start go back to global memory, and its Zt
@@ -954,8 +934,39 @@ __global__ void __launch_bounds__(SEG_T) k_seg_fwd(GArgs A, const __grid_constan
             if (tid < 6) b[6 * (size_t)i + tid] = zb[si * 6 + tid];
         }
     }
-    for (int q = tid; q < W * W * 36; q += SEG_T) G.CLL[(size_t)p * W * W * 36 + q] = cll[q];
-    for (int q = tid; q < W * 6; q += SEG_T) G.GL[(size_t)p * W * 6 + q] = gl[q];
+}
+
+// Schur terms of interior p on the separator above it, out of the sequential sweep: C = sum_j Zt_j^T D_j^-1 Zt_j and g = sum_j Zt_j^T D_j^-1 z_j
+// over the interior rows.  CTA (p, chunk of rows), thread per entry, rows in order; k_red_asm adds the SEG_NCH partial sums in order.
+#define SEG_NCH 4
+__global__ void __launch_bounds__(512) k_seg_schur(GArgs A, const __grid_constant__ SegArgs G) {
+    const int p = blockIdx.x + 1, ch = blockIdx.y, W = G.W;
+    const int s0 = G.s[p], e0 = G.e[p], m = e0 - s0;
+    const int j0 = s0 + (int)((long long)m * ch / SEG_NCH), j1 = s0 + (int)((long long)m * (ch + 1) / SEG_NCH);
+    double* Cp = G.CLL + ((size_t)p * SEG_NCH + ch) * W * W * 36;
+    double* Gp = G.GL + ((size_t)p * SEG_NCH + ch) * W * 6;
+    for (int q0 = threadIdx.x; q0 < W * W * 36 + W * 6; q0 += 512) {
+        double acc = 0;
+        if (q0 < W * W * 36) {
+            const int c1 = q0 / (W * 36), rem = q0 - c1 * W * 36, c2 = rem / 36, en = rem - 36 * c2, r = en / 6, cc = en - 6 * r;
+            for (int j = j0; j < j1; j++) {
+                const double* Z = G.Zt + (size_t)j * W * 36;
+                const double* Dj = A.Hs + 36 * ((size_t)A.rowptr[j] + (j - A.first[j]));
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc += Z[36 * c1 + 6 * q + r] * Dj[7 * q] * Z[36 * c2 + 6 * q + cc];
+            }
+            Cp[q0] = acc;
+        } else {
+            const int q1 = q0 - W * W * 36, c = q1 / 6, r = q1 - 6 * c;
+            for (int j = j0; j < j1; j++) {
+                const double* Z = G.Zt + (size_t)j * W * 36;
+                const double* Dj = A.Hs + 36 * ((size_t)A.rowptr[j] + (j - A.first[j]));
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc += Z[36 * c + 6 * q + r] * Dj[7 * q] * A.bs[6 * (size_t)j + q];
+            }
+            Gp[q1] = acc;
+        }
+    }
 }
 
 // reduced system of the separators: block row rho = p W + a <-> row e_p + a; block (rho, p W + b) = A(e_p + a, e_p + b) - C^(p+1)[a][b],
@@ -974,7 +985,7 @@ __global__ void __launch_bounds__(256) k_red_asm(GArgs A, const __grid_constant_
         if (pc == p) {
             const int i = G.e[p] + a, k = G.e[p] + bq;
             v = k >= A.first[i] ? A.Hs[36 * ((size_t)A.rowptr[i] + (k - A.first[i])) + en] : 0.0;
-            v += G.CLL[(((size_t)(p + 1) * W + a) * W + bq) * 36 + en];       // (C holds the negative Schur term)
+            for (int ch = 0; ch < SEG_NCH; ch++) v -= G.CLL[((((size_t)(p + 1) * SEG_NCH + ch) * W + a) * W + bq) * 36 + en];
         } else {
             v = G.SPK[(((size_t)p * W + a) * W + bq) * 36 + en];
         }
@@ -982,7 +993,9 @@ __global__ void __launch_bounds__(256) k_red_asm(GArgs A, const __grid_constant_
     }
     for (int q = blockIdx.x * 256 + threadIdx.x; q < nsep * W * 6; q += gridDim.x * 256) {
         const int rho = q / 6, r = q - 6 * rho, p = rho / W, a = rho - p * W;
-        G.rb[q] = A.bs[6 * (size_t)(G.e[p] + a) + r] + G.GL[((size_t)(p + 1) * W + a) * 6 + r];
+        double v = A.bs[6 * (size_t)(G.e[p] + a) + r];
+        for (int ch = 0; ch < SEG_NCH; ch++) v -= G.GL[(((size_t)(p + 1) * SEG_NCH + ch) * W + a) * 6 + r];
+        G.rb[q] = v;
     }
 }
 
@@ -1391,7 +1404,7 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     long long rNB = 0;
     for (int r = 0; r < rK; r++) { const int q = r / sky_w; rfirst[r] = q > 0 ? (q - 1) * sky_w : 0; rrowptr[r] = (int)rNB; rNB += r - rfirst[r] + 1; }
     rrowptr[rK] = (int)rNB;
-    const size_t seg_smem_f = 8 * ((size_t)(sky_w + 3) * (sky_w + 1) * 36 + (size_t)(sky_w + 3) * sky_w * 36 + (size_t)sky_w * 36 + (size_t)(sky_w + 3) * 6 + (size_t)sky_w * sky_w * 36 + (size_t)sky_w * 6);
+    const size_t seg_smem_f = 8 * ((size_t)(sky_w + 3) * (sky_w + 1) * 36 + (size_t)(sky_w + 3) * sky_w * 36 + (size_t)sky_w * 36 + (size_t)(sky_w + 3) * 6);
     const size_t seg_smem_b = 8 * (3 * (size_t)(sky_w + 1) * 36 + 18 + 3 * (size_t)sky_w * 36 + (size_t)(sky_w + 3) * 6);
     const size_t red_smem = 8 * ((size_t)(rW + 3) * (rW + 1) * 36 + (size_t)std::max(rW, 1) * 36 + (size_t)(rW + 3) * 6 + 3 * (size_t)(rW + 1) * 36 + 18 + (size_t)(rW + 3) * 6);
     if (seg_P) {
@@ -1455,8 +1468,8 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     const size_t o_part = add(16 * (size_t)std::max(nbE, nbL)), o_red = add(64 * 8);
     const size_t o_pout = add(96 * (size_t)nP), o_lout = add(24 * (size_t)std::max(nL, 1));
     const size_t sW = (size_t)std::max(sky_w, 1), sP = (size_t)std::max(seg_P, 1);
-    const size_t o_zt = add(seg_P ? 288 * sW * (size_t)K : 8), o_spk = add(seg_P ? 288 * sW * sW * sP : 8), o_cll = add(seg_P ? 288 * sW * sW * (sP + 1) : 8);
-    const size_t o_gl = add(seg_P ? 48 * sW * (sP + 1) : 8), o_segok = add(4 * sP);
+    const size_t o_zt = add(seg_P ? 288 * sW * (size_t)K : 8), o_spk = add(seg_P ? 288 * sW * sW * sP : 8), o_cll = add(seg_P ? 288 * SEG_NCH * sW * sW * (sP + 1) : 8);
+    const size_t o_gl = add(seg_P ? 48 * SEG_NCH * sW * (sP + 1) : 8), o_segok = add(4 * sP);
     const size_t o_Rs = add(8 * (size_t)(36 * rNB + 8)), o_rb = add(48 * (size_t)std::max(rK, 1)), o_rx = add(48 * (size_t)std::max(rK, 1));
     const size_t total = add(0) + 256;
     if (total > g->arena_cap) {
@@ -1609,10 +1622,11 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
             if (K > 0) {
                 if (seg_P) {
                     k_seg_fwd<<<seg_P, SEG_T, seg_smem_f, st>>>(A, SG, lambda);
+                    k_seg_schur<<<dim3(seg_P - 1, SEG_NCH), 512, 0, st>>>(A, SG);
                     k_red_asm<<<(unsigned)std::min<long long>((36 * rNB + 255) / 256, 148 * 8), 256, 0, st>>>(A, SG);
                     k_sky_band<<<1, SKY_T, red_smem, st>>>(AR, lambda, rW);
                     k_seg_bwd<<<seg_P, 256, seg_smem_b, st>>>(A, SG);
-                    g->launches += 3;
+                    g->launches += 4;
                 }
                 else if (sky_w <= SKY_WMAX) k_sky_band<<<1, SKY_T, sky_smem, st>>>(A, lambda, sky_w);
                 else k_sky<<<1, SKY_T, 0, st>>>(A, lambda);
