@@ -44,10 +44,10 @@ struct LevelDev {
     int patch_size, valid;
 };
 
-struct CellDesc {                  // one cell of ComputeKeyPointsOctTree's grid, precomputed at create
-    short x0, y0, dw, dh;          // detection region (border-relative), see fast_cells_kernel
-    int level;
-    unsigned m_dw;                 // ceil(2^20 / dw)
+struct CellDesc {                  // a strip of up to FAST_STRIP_PX pixels of consecutive cells of one cell row of ComputeKeyPointsOctTree's grid
+    short x0, y0, dw, dh;          // detection region of the whole strip (border-relative), see fast_cells_kernel
+    short level, ncell, cw, pad;   // cells of the strip: cell j spans [j cw, (j + 1) cw), the last one runs to dw
+    unsigned m_dw, m_cw;           // ceil(2^20 / dw), ceil(2^20 / cw)
 };
 
 // One tiled tensor map per pyramid level: (x, y, image) over uint8, box = (tile width rounded up to 16 bytes, tile height, 1).
@@ -174,12 +174,17 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map,
                  : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------ FAST per cell
-// One CTA = one cell of ComputeKeyPointsOctTree's grid (src/ORBextractor.cc:789-829).  The cell's detection region is
-// [cj*wCell+3, (cj+1)*wCell+3) x [ci*hCell+3, (ci+1)*hCell+3) in border-relative coordinates (the last effective cell
-// runs to width-3 / height-3); regions of different cells tile the level exactly, NMS only looks at neighbours inside
-// the same region, and the iniTh -> minTh fallback is decided per cell -- exactly what 815 separate cv::FAST calls do.
-#define FAST_THREADS 128
+// ------------------------------------------------------------------------------------------------ FAST per strip of cells
+// ComputeKeyPointsOctTree runs cv::FAST on every 30-px cell on its own (src/ORBextractor.cc:789-829): the detection region of cell
+// (ci, cj) is [cj*wCell+3, (cj+1)*wCell+3) x [ci*hCell+3, (ci+1)*hCell+3) in border-relative coordinates (the last effective cell
+// runs to width-3 / height-3); regions of different cells tile the level exactly, NMS only looks at neighbours inside the same
+// region, and the iniTh -> minTh fallback is decided per cell.  One CTA takes a STRIP of consecutive cells of a cell row (as many as
+// fit a 256-byte TMA box): the pre-test and the score do not depend on the cell, so they run over the whole strip at iniTh (full
+// thread rows, one barrier set per ~7000 pixels instead of per 900); the NMS clips its 3x3 window to the pixel's own cell; cells
+// that kept nothing are then redone at minTh, cell by cell -- exactly what the 815 separate cv::FAST calls of an image do.
+#define FAST_THREADS 256
+#define FAST_STRIP_PX 216              // + 6 (ring) + 4 (word right of the tile) + 2 x 15 (16-byte alignment of the box) <= 256
+#define FAST_MAX_CELLS 16
 
 // floor(i / d) for the small operands of this kernel: m = ceil(2^20 / d), exact while i * d < 2^20
 __device__ __forceinline__ int fastdiv20(int i, unsigned m) { return (int)(((unsigned)i * m) >> 20); }
@@ -194,27 +199,27 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
     uint8_t* tile = smem;                                  // (dh+6) rows of raw pixels, 4-byte aligned like the source rows
     uint8_t* score = tile + tile_cap;                      // dh x dw
     uint16_t* list = reinterpret_cast<uint16_t*>(score + pix_cap);   // pixels that pass the compass pre-test
-    uint16_t* list2 = list + pix_cap;                      // pixels that are corners at the current threshold
-    __shared__ int s_n1, s_n2, s_keep, s_base, s_emit;
+    uint16_t* list2 = list + pix_cap;                      // pixels that are corners at their cell's threshold
+    __shared__ int s_n1, s_n2, s_base, s_emit, s_cellkeep[FAST_MAX_CELLS];
 
     const int img = blockIdx.y;
     const CellDesc cd = P.cells[blockIdx.x];
     const int l = cd.level;
     const LevelDev& L = P.lv[l];
-    const int x0 = cd.x0, y0 = cd.y0, dw = cd.dw, dh = cd.dh;
+    const int x0 = cd.x0, y0 = cd.y0, dw = cd.dw, dh = cd.dh, ncell = cd.ncell, cw = cd.cw;
     if (dw <= 0 || dh <= 0) return;
-    const int tw = dw + 6, th = dh + 6;
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31;
 
     // ---- stage the tile with ONE TMA box load: absolute pixel (16 + x0 - 3 + tx, 16 + y0 - 3 + ty) -> tile[ty * tp + dx + tx], tp = box width.
     //      The innermost box coordinate has to be a multiple of 16 bytes (the copy engine traps otherwise), so the box starts at the
     //      16-byte boundary left of the tile; it is the level's largest tile (+ 15) rounded up to 16 bytes, and what it covers beyond
-    //      this cell's tile (or beyond the image: zero fill) is never read.
+    //      this strip's tile (or beyond the image: zero fill) is never read.
     const int gx0 = 16 + x0 - 3, ax0 = gx0 & ~15, dx = gx0 - ax0;
     const int tp = TMp->bw[l], nw = tp >> 2;
-    (void)tw; (void)th;
     if (tid == 0) mbar_init(&s_bar, 1);
+    if (tid < FAST_MAX_CELLS) s_cellkeep[tid] = 0;
+    if (tid == 0) { s_n1 = 0; s_n2 = 0; s_emit = 0; }
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&s_bar, (unsigned)(tp * TMp->bh[l]));
@@ -223,77 +228,72 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
     const int npix = dw * dh;
     for (int i = tid; i < ((npix + 3) >> 2); i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0;
     mbar_wait(&s_bar, 0);
-    const unsigned m_dw = cd.m_dw;
+    const unsigned m_dw = cd.m_dw, m_cw = cd.m_cw;
     const uint8_t* T0 = tile + 3 * tp + dx + 3;            // pixel (0, 0) of the detection region
     const int iniTh = min(max(P.iniTh, 0), 255), minTh = min(max(P.minTh, 0), 255);
     const int rdx[16] = ORB_RING_DX, rdy[16] = ORB_RING_DY;
 
-    // cv::FAST(cell, iniTh) and, only when that finds nothing, cv::FAST(cell, minTh)   (src/ORBextractor.cc:809-816)
-    int t = iniTh, nkeep = 0;
-    for (int round = 0; round < 2; round++) {
-        if (tid == 0) { s_n1 = 0; s_n2 = 0; s_keep = 0; s_emit = 0; }
-        __syncthreads();
-        // ---- pass 1: compass pre-test at threshold t, four pixels (one aligned tile word) per thread with byte-SIMD compares;
-        //      warp-compacted list of survivors
-        {
-            const int c0 = dx + 3;                                     // tile column of region x = 0
-            const int wc0 = c0 >> 2, nwc = ((c0 + dw - 1) >> 2) - wc0 + 1;
-            const unsigned m_nwc = ((1u << 20) + nwc - 1) / nwc;
-            const uint32_t TH1 = (uint32_t)(t + 1) * 0x00010001u, TL1 = (uint32_t)(512 - t - 1) * 0x00010001u;
-            const int nitems = dh * nwc;
-            for (int it0 = 0; it0 < nitems; it0 += FAST_THREADS) {
-                const int it = it0 + tid;
-                uint32_t M = 0;
-                int ibase = 0;
-                if (it < nitems) {
-                    const int y = fastdiv20(it, m_nwc), wc = wc0 + (it - y * nwc);
-                    const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + (y + 3) * tp);
-                    const uint32_t C = row[wc], Cp = row[wc - 1], Cn = row[wc + 1];
-                    const uint32_t D = row[wc + 3 * nw], U = row[wc - 3 * nw];
-                    const uint32_t P12 = __byte_perm(Cp, C, 0x4321), P4 = __byte_perm(C, Cn, 0x6543);
-                    // SWAR compare on 16-bit lanes (even / odd bytes): with a 512 bias, bit 9 of  p + 512 - (c + t + 1)  is set iff
-                    // p > c + t, and bit 9 of  (c + 512 - t - 1) - p  iff p < c - t  (no lane can borrow: all terms stay in [1, 766])
-                    const uint32_t LM = 0x00ff00ffu, B9 = 0x02000200u;
-                    const uint32_t Ce = C & LM, Co = (C >> 8) & LM;
-                    const uint32_t hie = Ce + TH1, hio = Co + TH1;             // c + t + 1
-                    const uint32_t loe = Ce + TL1, loo = Co + TL1;             // c + 512 - t - 1
-                    uint32_t be[4], bo[4], ke[4], ko[4];
-                    const uint32_t W4[4] = {D, P4, U, P12};
+    // ---- pass 1: compass pre-test at threshold t over the columns [rx0, rx0 + rw) of the strip, four pixels (one aligned tile word)
+    //      per thread with SWAR compares; warp-compacted list of survivors
+    auto pretest = [&](int rx0, int rw, int t) {
+        const int c0 = dx + 3 + rx0;                               // tile column of region x = 0
+        const int wc0 = c0 >> 2, nwc = ((c0 + rw - 1) >> 2) - wc0 + 1;
+        const unsigned m_nwc = ((1u << 20) + nwc - 1) / nwc;
+        const uint32_t TH1 = (uint32_t)(t + 1) * 0x00010001u, TL1 = (uint32_t)(512 - t - 1) * 0x00010001u;
+        const int nitems = dh * nwc;
+        for (int it0 = 0; it0 < nitems; it0 += FAST_THREADS) {
+            const int it = it0 + tid;
+            uint32_t M = 0;
+            int ibase = 0;
+            if (it < nitems) {
+                const int y = fastdiv20(it, m_nwc), wc = wc0 + (it - y * nwc);
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + (y + 3) * tp);
+                const uint32_t C = row[wc], Cp = row[wc - 1], Cn = row[wc + 1];
+                const uint32_t D = row[wc + 3 * nw], U = row[wc - 3 * nw];
+                const uint32_t P12 = __byte_perm(Cp, C, 0x4321), P4 = __byte_perm(C, Cn, 0x6543);
+                // SWAR compare on 16-bit lanes (even / odd bytes): with a 512 bias, bit 9 of  p + 512 - (c + t + 1)  is set iff
+                // p > c + t, and bit 9 of  (c + 512 - t - 1) - p  iff p < c - t  (no lane can borrow: all terms stay in [1, 766])
+                const uint32_t LM = 0x00ff00ffu, B9 = 0x02000200u;
+                const uint32_t Ce = C & LM, Co = (C >> 8) & LM;
+                const uint32_t hie = Ce + TH1, hio = Co + TH1;             // c + t + 1
+                const uint32_t loe = Ce + TL1, loo = Co + TL1;             // c + 512 - t - 1
+                uint32_t be[4], bo[4], ke[4], ko[4];
+                const uint32_t W4[4] = {D, P4, U, P12};
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint32_t pe = W4[q] & LM, po = (W4[q] >> 8) & LM;
-                        be[q] = pe + B9 - hie; bo[q] = po + B9 - hio;
-                        ke[q] = loe - pe;      ko[q] = loo - po;
-                    }
-                    // two ADJACENT compass pixels brighter, or two darker
-                    const uint32_t Me = (((be[0] | be[2]) & (be[1] | be[3])) | ((ke[0] | ke[2]) & (ke[1] | ke[3]))) & B9;
-                    const uint32_t Mo = (((bo[0] | bo[2]) & (bo[1] | bo[3])) | ((ko[0] | ko[2]) & (ko[1] | ko[3]))) & B9;
-                    M = (Me >> 9) | (Mo >> 1);                                  // bit 8k of M <-> byte k of the word
-                    // bytes of this word that lie inside the detection region
-                    const int xlo = wc * 4 - c0;                                 // region x of byte 0
-                    uint32_t valid = 0xffffffffu;
-                    if (xlo < 0) valid <<= 8 * (-xlo);
-                    if (xlo + 3 >= dw) valid &= 0xffffffffu >> (8 * (xlo + 4 - dw));
-                    M &= valid & 0x01010101u;
-                    ibase = y * dw + xlo;
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t pe = W4[q] & LM, po = (W4[q] >> 8) & LM;
+                    be[q] = pe + B9 - hie; bo[q] = po + B9 - hio;
+                    ke[q] = loe - pe;      ko[q] = loo - po;
                 }
-                const int cnt = __popc(M);
-                int incl = cnt;
+                // two ADJACENT compass pixels brighter, or two darker
+                const uint32_t Me = (((be[0] | be[2]) & (be[1] | be[3])) | ((ke[0] | ke[2]) & (ke[1] | ke[3]))) & B9;
+                const uint32_t Mo = (((bo[0] | bo[2]) & (bo[1] | bo[3])) | ((ko[0] | ko[2]) & (ko[1] | ko[3]))) & B9;
+                M = (Me >> 9) | (Mo >> 1);                                  // bit 8k of M <-> byte k of the word
+                // bytes of this word that lie inside the region
+                const int xlo = wc * 4 - c0;                                 // region x of byte 0
+                uint32_t valid = 0xffffffffu;
+                if (xlo < 0) valid <<= 8 * (-xlo);
+                if (xlo + 3 >= rw) valid &= 0xffffffffu >> (8 * (xlo + 4 - rw));
+                M &= valid & 0x01010101u;
+                ibase = y * dw + rx0 + xlo;
+            }
+            const int cnt = __popc(M);
+            int incl = cnt;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
-                const int wtot = __shfl_sync(0xffffffffu, incl, 31);
-                int base = 0;
-                if (lane == 31 && wtot) base = atomicAdd(&s_n1, wtot);
-                base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-                while (M) {
-                    const int k = (__ffs(M) - 1) >> 3;
-                    list[base++] = (uint16_t)(ibase + k);
-                    M &= M - 1;
-                }
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+            const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+            int base = 0;
+            if (lane == 31 && wtot) base = atomicAdd(&s_n1, wtot);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+            while (M) {
+                const int k = (__ffs(M) - 1) >> 3;
+                list[base++] = (uint16_t)(ibase + k);
+                M &= M - 1;
             }
         }
-        __syncthreads();
-        // ---- pass 2: exact corner score of the survivors
+    };
+    // ---- pass 2: exact corner score of the survivors; pass 3: strict 3x3 maximum inside the pixel's cell (non-corners score 0)
+    auto score_and_nms = [&](int t, int n2_begin) {
         const int n1 = s_n1;
         for (int e = tid; e < n1; e += FAST_THREADS) {
             const int i = list[e];
@@ -309,11 +309,12 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
             }
         }
         __syncthreads();
-        // ---- pass 3: strict 3x3 maximum inside the cell (non-corners score 0)
         const int n2 = s_n2;
-        for (int e = tid; e < n2; e += FAST_THREADS) {
+        for (int e = n2_begin + tid; e < n2; e += FAST_THREADS) {
             const int i = list2[e];
             const int y = fastdiv20(i, m_dw), x = i - y * dw;
+            const int c = min(fastdiv20(x, m_cw), ncell - 1);
+            const int cx0 = c * cw, cx1 = c == ncell - 1 ? dw : cx0 + cw;
             const int s = score[i];
             bool ismax = true;
 #pragma unroll
@@ -322,17 +323,35 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
                 for (int ddx = -1; ddx <= 1; ddx++) {
                     if (ddx == 0 && ddy == 0) continue;
                     const int xx = x + ddx, yy = y + ddy;
-                    if (xx < 0 || xx >= dw || yy < 0 || yy >= dh) continue;
+                    if (xx < cx0 || xx >= cx1 || yy < 0 || yy >= dh) continue;
                     if (score[yy * dw + xx] >= s) ismax = false;
                 }
-            if (ismax) { atomicAdd(&s_keep, 1); list2[e] = (uint16_t)(i | 0x8000); }
+            if (ismax) { atomicAdd(&s_cellkeep[c], 1); list2[e] = (uint16_t)(i | 0x8000); }
         }
         __syncthreads();
-        nkeep = s_keep;
-        if (nkeep > 0 || minTh >= iniTh) break;            // found corners, or the fallback threshold cannot find more
-        t = minTh;
-        __syncthreads();
+    };
+
+    // cv::FAST(cell, iniTh) for every cell of the strip ...
+    pretest(0, dw, iniTh);
+    __syncthreads();
+    score_and_nms(iniTh, 0);
+    // ... and, only for the cells where that found nothing, cv::FAST(cell, minTh)   (src/ORBextractor.cc:809-816)
+    if (minTh < iniTh) {
+        bool any = false;
+        for (int c = 0; c < ncell; c++) any |= s_cellkeep[c] == 0;
+        if (any) {
+            const int n2_begin = s_n2;
+            __syncthreads();
+            if (tid == 0) s_n1 = 0;
+            __syncthreads();
+            for (int c = 0; c < ncell; c++)
+                if (s_cellkeep[c] == 0) pretest(c * cw, (c == ncell - 1 ? dw : (c + 1) * cw) - c * cw, minTh);
+            __syncthreads();
+            score_and_nms(minTh, n2_begin);
+        }
     }
+    int nkeep = 0;
+    for (int c = 0; c < ncell; c++) nkeep += s_cellkeep[c];
     if (nkeep == 0) return;
 
     // ---- emit (unordered; the reference order is a function of (x, y), see cand_order_key)
@@ -808,7 +827,7 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
 
     size_t level_bytes = 0;           // per image, levels >= 1
     std::vector<size_t> level_off(nlevels, 0);
-    int cells = 0, cand_total = 0, sel_total = 0, max_dw = 0, max_dh = 0, max_quota_l = 0;
+    int cells = 0, cand_total = 0, sel_total = 0, max_dw = 0, max_dh = 0, max_pix = 0, max_quota_l = 0;
     std::vector<CellDesc> cell_table;
     for (int l = 0; l < nlevels; l++) {
         const orbgeo::Level& G = g.lv[l];
@@ -825,26 +844,39 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
         L.cand_off = cand_total; L.sel_off = sel_total;
         e->TM.bw[l] = 16; e->TM.bh[l] = 8;
         if (L.valid) {
-            cells += G.nColsEff * G.nRowsEff;
             // strict 3x3 maxima inside a cell: at most ceil(w/2)*ceil(h/2) per cell
             int cap = 0, lvl_dw = 0, lvl_dh = 0;
-            for (int ci = 0; ci < G.nRowsEff; ci++)
+            // a cell row is cut into strips of whole cells, as even as the 216-pixel limit of a strip allows
+            const int per_max = std::max(1, std::min(FAST_MAX_CELLS, FAST_STRIP_PX / std::max(G.wCell, 1)));
+            const int nstrips = (G.nColsEff + per_max - 1) / per_max, per = (G.nColsEff + nstrips - 1) / nstrips;
+            for (int ci = 0; ci < G.nRowsEff; ci++) {
+                const int y0 = ci * G.hCell + 3, y1 = ci == G.nRowsEff - 1 ? G.height - 3 : y0 + G.hCell;
+                const int dh = std::max(y1 - y0, 0);
                 for (int cj = 0; cj < G.nColsEff; cj++) {
-                    const int x0 = cj * G.wCell + 3, y0 = ci * G.hCell + 3;
-                    const int x1 = cj == G.nColsEff - 1 ? G.width - 3 : x0 + G.wCell;
-                    const int y1 = ci == G.nRowsEff - 1 ? G.height - 3 : y0 + G.hCell;
-                    const int dw = std::max(x1 - x0, 0), dh = std::max(y1 - y0, 0);
-                    cap += ((dw + 1) / 2) * ((dh + 1) / 2);
+                    const int x0 = cj * G.wCell + 3, x1 = cj == G.nColsEff - 1 ? G.width - 3 : x0 + G.wCell;
+                    cap += ((std::max(x1 - x0, 0) + 1) / 2) * ((dh + 1) / 2);
+                }
+                for (int cj0 = 0; cj0 < G.nColsEff; cj0 += per) {
+                    const int cj1 = std::min(cj0 + per, G.nColsEff);
+                    const int x0 = cj0 * G.wCell + 3, x1 = cj1 == G.nColsEff ? G.width - 3 : cj1 * G.wCell + 3;
+                    const int dw = std::max(x1 - x0, 0);
                     max_dw = std::max(max_dw, dw); max_dh = std::max(max_dh, dh);
+                    max_pix = std::max(max_pix, dw * dh);
                     lvl_dw = std::max(lvl_dw, dw); lvl_dh = std::max(lvl_dh, dh);
                     CellDesc cd;
-                    cd.x0 = (short)x0; cd.y0 = (short)y0; cd.dw = (short)dw; cd.dh = (short)dh; cd.level = l;
+                    cd.x0 = (short)x0; cd.y0 = (short)y0; cd.dw = (short)dw; cd.dh = (short)dh; cd.level = (short)l;
+                    // (a last cell that is empty -- x0 + wCell*k beyond width-3 -- only shortens the strip)
+                    cd.ncell = (short)std::max(1, std::min(cj1 - cj0, (dw + G.wCell - 1) / std::max(G.wCell, 1))); cd.cw = (short)G.wCell; cd.pad = 0;
                     cd.m_dw = dw > 0 ? ((1u << 20) + dw - 1) / dw : 0;
+                    cd.m_cw = ((1u << 20) + G.wCell - 1) / std::max(G.wCell, 1);
                     cell_table.push_back(cd);
+                    cells++;
                 }
+            }
             L.cand_cap = cap;
             // TMA box of the level: its largest tile (+ the 3-px ring on every side, + one word so that the SWAR pass may read the word right of the tile)
             e->TM.bw[l] = (15 + lvl_dw + 6 + 4 + 15) & ~15; e->TM.bh[l] = lvl_dh + 6;
+            if (e->TM.bw[l] > 256 || e->TM.bh[l] > 256) { orbx_free(e); ORB_FAIL(ORB_E_INVALID, "orbx_create: FAST tile of level %d (%d x %d) exceeds a TMA box", l, e->TM.bw[l], e->TM.bh[l]); }
             L.sel_cap = std::max(G.quota + 2, 4 * G.nIni);
             max_quota_l = std::max(max_quota_l, L.sel_cap);
         }
@@ -855,7 +887,7 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
     P.cell_begin[nlevels] = cells;
     for (int l = nlevels + 1; l <= ORB_MAX_LEVELS; l++) P.cell_begin[l] = cells;
     P.cells_per_image = cells; P.cand_per_image = cand_total; P.sel_per_image = sel_total;
-    if (max_dw * max_dh > 0x7fff) { orbx_free(e); ORB_FAIL(ORB_E_INVALID, "orbx_create: cell of %dx%d pixels is too large", max_dw, max_dh); }
+    if (max_pix > 0x7fff) { orbx_free(e); ORB_FAIL(ORB_E_INVALID, "orbx_create: strip of %dx%d pixels is too large", max_dw, max_dh); }
 
     const size_t NI = (size_t)e->max_images;
     cudaError_t ce = cudaSuccess;
@@ -961,7 +993,7 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
     if (ce == cudaSuccess) ce = cudaMemcpy(e->d_BM, &e->BMh, sizeof(BlurMaps), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { int rc = orbhost::check_cuda(ce, "orbx_create tensor maps", __FILE__, __LINE__); orbx_free(e); return rc; }
     // FAST shared memory: tile (the largest TMA box) + score + 2 lists
-    e->fast_pix_cap = (max_dw * max_dh + 15) & ~15;
+    e->fast_pix_cap = (max_pix + 15) & ~15;
     e->fast_tile_cap = 128;
     for (int l = 0; l < nlevels; l++) e->fast_tile_cap = std::max(e->fast_tile_cap, (e->TM.bw[l] * e->TM.bh[l] + 127) & ~127);
     e->fast_smem = (size_t)e->fast_tile_cap + e->fast_pix_cap + 2 * sizeof(uint16_t) * e->fast_pix_cap;
