@@ -47,7 +47,7 @@ struct LevelDev {
 struct CellDesc {                  // a strip of up to FAST_STRIP_PX pixels of consecutive cells of one cell row of ComputeKeyPointsOctTree's grid
     short x0, y0, dw, dh;          // detection region of the whole strip (border-relative), see fast_cells_kernel
     short level, ncell, cw, pad;   // cells of the strip: cell j spans [j cw, (j + 1) cw), the last one runs to dw
-    unsigned m_dw, m_cw;           // ceil(2^20 / dw), ceil(2^20 / cw)
+    unsigned m_dw, m_cw;           // fastdiv_magic(dw), fastdiv_magic(cw)
 };
 
 // One tiled tensor map per pyramid level: (x, y, image) over uint8, box = (tile width rounded up to 16 bytes, tile height, 1).
@@ -186,8 +186,9 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map,
 #define FAST_STRIP_PX 216              // + 6 (ring) + 4 (word right of the tile) + 2 x 15 (16-byte alignment of the box) <= 256
 #define FAST_MAX_CELLS 16
 
-// floor(i / d) for the small operands of this kernel: m = ceil(2^20 / d), exact while i * d < 2^20
-__device__ __forceinline__ int fastdiv20(int i, unsigned m) { return (int)(((unsigned)i * m) >> 20); }
+// floor(i / d) for the small operands of this kernel: m = ceil(2^32 / d) (d >= 2), exact while i * d < 2^32; m = 0 stands for d = 1
+__device__ __forceinline__ int fastdiv20(int i, unsigned m) { return m ? (int)__umulhi((unsigned)i, m) : i; }
+static inline unsigned fastdiv_magic(int d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + (unsigned)d - 1) / (unsigned)d); }
 
 // (the tensor maps live in global memory: a kernel-parameter array indexed by the level would be copied to local memory, where TMA
 // cannot read it)
@@ -233,51 +234,60 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
     const int iniTh = min(max(P.iniTh, 0), 255), minTh = min(max(P.minTh, 0), 255);
     const int rdx[16] = ORB_RING_DX, rdy[16] = ORB_RING_DY;
 
-    // ---- pass 1: compass pre-test at threshold t over the columns [rx0, rx0 + rw) of the strip, four pixels (one aligned tile word)
-    //      per thread with SWAR compares; warp-compacted list of survivors
+    // ---- pass 1: compass pre-test at threshold t over the columns [rx0, rx0 + rw) of the strip.  A thread takes one aligned tile word
+    //      (4 pixels) in 4 consecutive rows: SWAR compares on 16-bit lanes, a 16-bit survivor mask, ONE warp scan / list reservation per
+    //      16 pixels (the compaction, not the compares, was two thirds of this pass when it ran per word)
     auto pretest = [&](int rx0, int rw, int t) {
         const int c0 = dx + 3 + rx0;                               // tile column of region x = 0
         const int wc0 = c0 >> 2, nwc = ((c0 + rw - 1) >> 2) - wc0 + 1;
-        const unsigned m_nwc = ((1u << 20) + nwc - 1) / nwc;
+        const unsigned m_nwc = nwc <= 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)nwc - 1) / (unsigned)nwc);
         const uint32_t TH1 = (uint32_t)(t + 1) * 0x00010001u, TL1 = (uint32_t)(512 - t - 1) * 0x00010001u;
-        const int nitems = dh * nwc;
+        const uint32_t LM = 0x00ff00ffu, B9 = 0x02000200u;
+        const int nitems = ((dh + 3) >> 2) * nwc;
         for (int it0 = 0; it0 < nitems; it0 += FAST_THREADS) {
             const int it = it0 + tid;
-            uint32_t M = 0;
+            uint32_t M16 = 0;
             int ibase = 0;
             if (it < nitems) {
-                const int y = fastdiv20(it, m_nwc), wc = wc0 + (it - y * nwc);
-                const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + (y + 3) * tp);
-                const uint32_t C = row[wc], Cp = row[wc - 1], Cn = row[wc + 1];
-                const uint32_t D = row[wc + 3 * nw], U = row[wc - 3 * nw];
-                const uint32_t P12 = __byte_perm(Cp, C, 0x4321), P4 = __byte_perm(C, Cn, 0x6543);
-                // SWAR compare on 16-bit lanes (even / odd bytes): with a 512 bias, bit 9 of  p + 512 - (c + t + 1)  is set iff
-                // p > c + t, and bit 9 of  (c + 512 - t - 1) - p  iff p < c - t  (no lane can borrow: all terms stay in [1, 766])
-                const uint32_t LM = 0x00ff00ffu, B9 = 0x02000200u;
-                const uint32_t Ce = C & LM, Co = (C >> 8) & LM;
-                const uint32_t hie = Ce + TH1, hio = Co + TH1;             // c + t + 1
-                const uint32_t loe = Ce + TL1, loo = Co + TL1;             // c + 512 - t - 1
-                uint32_t be[4], bo[4], ke[4], ko[4];
-                const uint32_t W4[4] = {D, P4, U, P12};
+                const int rg = fastdiv20(it, m_nwc), wc = wc0 + (it - rg * nwc), y4 = 4 * rg;
+                // (rows past dh read whatever follows in shared memory; their bits are masked)
+                const uint32_t* col = reinterpret_cast<const uint32_t*>(tile + y4 * tp) + wc;     // tile row y4 = region row y4 - 3
+                uint32_t V[10];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t pe = W4[q] & LM, po = (W4[q] >> 8) & LM;
-                    be[q] = pe + B9 - hie; bo[q] = po + B9 - hio;
-                    ke[q] = loe - pe;      ko[q] = loo - po;
-                }
-                // two ADJACENT compass pixels brighter, or two darker
-                const uint32_t Me = (((be[0] | be[2]) & (be[1] | be[3])) | ((ke[0] | ke[2]) & (ke[1] | ke[3]))) & B9;
-                const uint32_t Mo = (((bo[0] | bo[2]) & (bo[1] | bo[3])) | ((ko[0] | ko[2]) & (ko[1] | ko[3]))) & B9;
-                M = (Me >> 9) | (Mo >> 1);                                  // bit 8k of M <-> byte k of the word
-                // bytes of this word that lie inside the region
+                for (int r = 0; r < 10; r++) V[r] = col[r * nw];
+                // bytes of this word column that lie inside the region
                 const int xlo = wc * 4 - c0;                                 // region x of byte 0
-                uint32_t valid = 0xffffffffu;
-                if (xlo < 0) valid <<= 8 * (-xlo);
-                if (xlo + 3 >= rw) valid &= 0xffffffffu >> (8 * (xlo + 4 - rw));
-                M &= valid & 0x01010101u;
-                ibase = y * dw + rx0 + xlo;
+                uint32_t valid = 0xfu;
+                if (xlo < 0) valid = (valid << (-xlo)) & 0xfu;
+                if (xlo + 3 >= rw) valid &= 0xfu >> (xlo + 4 - rw);
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t C = V[r + 3], Cp = col[(r + 3) * nw - 1], Cn = col[(r + 3) * nw + 1];
+                    const uint32_t P12 = __byte_perm(Cp, C, 0x4321), P4 = __byte_perm(C, Cn, 0x6543);
+                    // with a 512 bias, bit 9 of  p + 512 - (c + t + 1)  is set iff p > c + t, and bit 9 of  (c + 512 - t - 1) - p  iff
+                    // p < c - t  (no lane can borrow: all terms stay in [1, 766])
+                    const uint32_t Ce = C & LM, Co = (C >> 8) & LM;
+                    const uint32_t hie = B9 - (Ce + TH1), hio = B9 - (Co + TH1);      // 512 - (c + t + 1)
+                    const uint32_t loe = Ce + TL1, loo = Co + TL1;                    // c + 512 - t - 1
+                    uint32_t be[4], bo[4], ke[4], ko[4];
+                    const uint32_t W4[4] = {V[r + 6], P4, V[r], P12};
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t pe = W4[q] & LM, po = (W4[q] >> 8) & LM;
+                        be[q] = pe + hie; bo[q] = po + hio;
+                        ke[q] = loe - pe; ko[q] = loo - po;
+                    }
+                    // two ADJACENT compass pixels brighter, or two darker
+                    const uint32_t Me = (((be[0] | be[2]) & (be[1] | be[3])) | ((ke[0] | ke[2]) & (ke[1] | ke[3]))) & B9;
+                    const uint32_t Mo = (((bo[0] | bo[2]) & (bo[1] | bo[3])) | ((ko[0] | ko[2]) & (ko[1] | ko[3]))) & B9;
+                    const uint32_t M = (Me >> 9) | (Mo >> 1);                           // bit 8k of M <-> byte k of the word
+                    uint32_t m4 = ((M * 0x00204081u) >> 21) & valid;                    // bits 0, 8, 16, 24 -> 0..3
+                    if (y4 + r >= dh) m4 = 0;
+                    M16 |= m4 << (4 * r);
+                }
+                ibase = y4 * dw + rx0 + xlo;
             }
-            const int cnt = __popc(M);
+            const int cnt = __popc(M16);
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
@@ -285,10 +295,10 @@ __global__ void __launch_bounds__(FAST_THREADS) fast_cells_kernel(const __grid_c
             int base = 0;
             if (lane == 31 && wtot) base = atomicAdd(&s_n1, wtot);
             base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-            while (M) {
-                const int k = (__ffs(M) - 1) >> 3;
-                list[base++] = (uint16_t)(ibase + k);
-                M &= M - 1;
+            while (M16) {
+                const int b = __ffs(M16) - 1;
+                list[base++] = (uint16_t)(ibase + (b >> 2) * dw + (b & 3));
+                M16 &= M16 - 1;
             }
         }
     };
@@ -867,8 +877,8 @@ int orbx_create(orbx_t** out, int device, int width, int height, int cameras, in
                     cd.x0 = (short)x0; cd.y0 = (short)y0; cd.dw = (short)dw; cd.dh = (short)dh; cd.level = (short)l;
                     // (a last cell that is empty -- x0 + wCell*k beyond width-3 -- only shortens the strip)
                     cd.ncell = (short)std::max(1, std::min(cj1 - cj0, (dw + G.wCell - 1) / std::max(G.wCell, 1))); cd.cw = (short)G.wCell; cd.pad = 0;
-                    cd.m_dw = dw > 0 ? ((1u << 20) + dw - 1) / dw : 0;
-                    cd.m_cw = ((1u << 20) + G.wCell - 1) / std::max(G.wCell, 1);
+                    cd.m_dw = fastdiv_magic(dw);
+                    cd.m_cw = fastdiv_magic(G.wCell);
                     cell_table.push_back(cd);
                     cells++;
                 }
