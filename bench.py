@@ -408,21 +408,48 @@ def run_track(cfg, args, rank, world, local_rank, steps, warmup):
     out_stream = torch.cuda.Stream(dev)      # device->host copies of keypoints / descriptors / matches
     prev_out = [None]
 
+    trace = []                               # per step: compute-stream events before extract, after match, after the LM steps
+    marker_stream = torch.cuda.Stream(dev)   # idle stream: an event recorded here carries the host's 'now' on the device clock
+    marks = []
+
+    def mark():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(marker_stream)
+        return e
+
+    host_ms = dict.fromkeys(["enqueue_images", "ba_upload_call", "enqueue_kernels", "ba_download_wait", "wait_outputs"], 0.0)
+
+    def n_outliers():
+        # the step's BA result is read on the host: count of outlier flags (numpy view of the pinned buffer; torch's uint8 sum is a scalar
+        # loop that took 25 ms for these 7.6 M flags and made the HOST the bottleneck of the 8-GPU end-to-end run)
+        return int(np.count_nonzero(h_ba[2].numpy()))
+
     def e2e_step(i, first):
         o = opts[i % 2]
+        t0 = time.perf_counter()
+        mk = [mark()]
         with torch.cuda.stream(copy_stream):
             d_in[i % 2].copy_(host[i % 2], non_blocking=True)
-            e_img = copy_stream.record_event()
+            e_img = torch.cuda.Event(enable_timing=True)
+            e_img.record(copy_stream)
+        t1 = time.perf_counter()
         if o:
             o.upload(ba_compact)             # stage + host->device + expansion and index construction on the device (copy stream)
+        t2 = time.perf_counter()
+        mk.append(mark())
         stream.wait_event(e_img)
         if prev_out[0] is not None:
             stream.wait_event(prev_out[0])   # the previous step's results left the device before they are overwritten
+        tr = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        trace.append(tr)
+        tr[0].record(stream)
         ext.extract_device(d_in[i % 2], d_kps, d_desc, d_cnt, stream=stream)
         mat.bruteforce_sets_device(d_desc, d_cnt, q_set, t_set, out=d_match, stream=stream)
         e_em = stream.record_event()
+        tr[1].record(stream)
         if o:
             o.run()                          # compute stream, after this handle's upload
+        tr[2].record(stream)
         with torch.cuda.stream(out_stream):
             out_stream.wait_event(e_em)
             h_cnt.copy_(d_cnt, non_blocking=True)
@@ -431,11 +458,19 @@ def run_track(cfg, args, rank, world, local_rank, steps, warmup):
             for hm, dm in zip(h_match, d_match):
                 hm.copy_(dm, non_blocking=True)
             prev_out[0] = out_stream.record_event()
+        t3 = time.perf_counter()
         r = 0
         if o and not first:
             opts[(i - 1) % 2].download_batch(out=h_ba)     # results of the previous step's windows (waits for that run only)
-            r = int(h_ba[2].sum())
+            r = n_outliers()
+        t4 = time.perf_counter()
+        mk.append(mark())
+        mk.append(e_img)
+        marks.append(mk)
         prev_out[0].synchronize()
+        t5 = time.perf_counter()
+        for k, v in zip(host_ms, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+            host_ms[k] += 1e3 * v
         return int(h_cnt.sum()) + r          # the step's results are read on the host
 
     def e2e_run(n):
@@ -444,19 +479,37 @@ def run_track(cfg, args, rank, world, local_rank, steps, warmup):
             e2e_step(i, i == 0)
         if opt:
             opts[(n - 1) % 2].download_batch(out=h_ba)
-            return int(h_ba[2].sum())
+            return n_outliers()
         return 0
 
     e2e_run(max(2, warmup // 2))
     barrier()
     if opt2:
         opt2.synchronize()
+    for k in host_ms:
+        host_ms[k] = 0.0
+    trace.clear()
+    marks.clear()
     t0 = time.perf_counter()
     e2e_run(steps)
     barrier()
     if opt2:
         opt2.synchronize()
     e2e_s = time.perf_counter() - t0
+    torch.cuda.synchronize(dev)
+    dev_ms = {"extract_match": float(np.mean([a.elapsed_time(b) for a, b, _ in trace])),
+              "ba_incl_wait_for_upload": float(np.mean([b.elapsed_time(c) for _, b, c in trace])),
+              # timeline of a steady-state step on the device clock, relative to the host's step start: image copy done, upload call returned
+              # (extract is enqueued right after), extract starts, LM steps end, BA results of the previous step on the host
+              "timeline_vs_step_start": {k: float(np.mean(v)) for k, v in {
+                  "image_h2d_done": [m[0].elapsed_time(m[3]) for m in marks[2:]],
+                  "upload_call_returned": [m[0].elapsed_time(m[1]) for m in marks[2:]],
+                  "extract_starts": [m[0].elapsed_time(t[0]) for m, t in zip(marks[2:], trace[2:])],
+                  "match_ends": [m[0].elapsed_time(t[1]) for m, t in zip(marks[2:], trace[2:])],
+                  "lm_steps_end": [m[0].elapsed_time(t[2]) for m, t in zip(marks[2:], trace[2:])],
+                  "prev_lm_steps_end": [marks[k][0].elapsed_time(trace[k - 1][2]) for k in range(2, len(marks))],
+                  "prev_ba_results_on_host": [m[0].elapsed_time(m[2]) for m in marks[2:]]}.items() if v},
+              "gap_before_extract": float(np.mean([trace[k][2].elapsed_time(trace[k + 1][0]) for k in range(len(trace) - 1)])) if len(trace) > 1 else 0.0}
     ba_in = 0
     if opt:
         ba_in = sum(sum(np.asarray(q[k]).nbytes for k in ("poses", "pose_fixed", "points", "edges", "inv_sigma2", "cam_K", "cam_ext", "cam_adj")) for q in ba_compact[1])
@@ -500,10 +553,11 @@ def run_track(cfg, args, rank, world, local_rank, steps, warmup):
         nc = max(calls, 1)
         # per-kernel roofline table: (ms per bench step, bytes the kernel moves by design per bench step)
         kern = {
-            "resize_level_kernel(x7)": (stage_ms["pyramid"] / nc, (cfg.pyr_pixels_1up + cfg.pyr_src_pixels) * NI),
+            "resize4_kernel(x7)": (stage_ms["pyramid"] / nc, (cfg.pyr_pixels_1up + cfg.pyr_src_pixels) * NI),
             "fast_cells_kernel": (stage_ms["fast"] / nc, cfg.pyr_pixels * NI),
             "quadtree_kernel": (stage_ms["quadtree"] / nc, None),
-            "describe_kernel": (stage_ms["describe"] / nc, (1849 + 60) * n_kp),
+            # whole-level Gaussian (read + write every pyramid pixel) + per key point a 64x37 blurred window, a 31x31 raw disc, 60 bytes out
+            "blur_level_kernel(x8)+describe_kernel": (stage_ms["describe"] / nc, 2 * cfg.pyr_pixels * NI + (64 * 37 + 961 + 60) * n_kp),
             "bruteforce_kernel": (match_ms / max(mcalls, 1), cfg.bytes_match_pair * NI),
         }
         if opt:
@@ -555,7 +609,8 @@ def run_track(cfg, args, rank, world, local_rank, steps, warmup):
                        "parallelism": f"{world} independent replicas, no collective"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_fps, "unit": "dual-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / steps},
+                    "ms_per_step": e2e_ms / steps,
+                    "host_ms_per_step_rank0": {k: v / steps for k, v in host_ms.items()}, "device_ms_per_step_rank0": dev_ms},
             "gpu_launches": int(n_launch),
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": dom_bytes / max(n_dom_launch, 1),

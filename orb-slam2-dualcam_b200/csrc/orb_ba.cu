@@ -100,6 +100,7 @@ struct BABatch {               // kernel argument (by value)
     double *tab[2];                             // per estimate buffer and (pose, camera): [R | t] of ext_c * pose and the intrinsics (BA_TAB doubles, one 128-byte line)
     double *ut_u, *ut_b, *ut_y;                 // per (free pose, camera): Schur rhs partial / bp partial in tJ space (6 each), Adj_c x_k (6)
     int* rs_flag;                               // != 0: some problem starts a round on this step (k_lin / k_build have work)
+    int* stop_dev;                              // device copy of the caller's stop flag, refreshed once per LM step (k_land) from the mapped host word
     double *Hll, *bl;                           // per landmark: 6 / 3
     double *Hpp, *bp, *bs, *xp;                 // per free pose: 36 / 6 / 6 / 6
     double *partial, *prhs;                     // per chunk: 36 ; per chunk of a diagonal pair: bp and Schur rhs partials in tJ space (6 + 6)
@@ -321,7 +322,7 @@ __global__ void k_reset(BABatch A, int stopped0) {
     for (int i = lb * BA_TE + tid; i < 7 * P.nP; i += P.nbE * BA_TE) { const double v = A.pose0[7 * (size_t)P.p0 + i]; A.pose[0][7 * (size_t)P.p0 + i] = v; A.pose[1][7 * (size_t)P.p0 + i] = v; }
     for (int i = lb * BA_TE + tid; i < 3 * P.nL; i += P.nbE * BA_TE) { const double v = A.pt0[3 * (size_t)P.l0 + i]; A.pt[0][3 * (size_t)P.l0 + i] = v; A.pt[1][3 * (size_t)P.l0 + i] = v; }
     if (lb == 0) { write_tab(A, P, A.pose0, A.tab[0], tid, BA_TE); write_tab(A, P, A.pose0, A.tab[1], tid, BA_TE); }
-    if (b == 0 && tid == 0) *A.rs_flag = 1;
+    if (b == 0 && tid == 0) { *A.rs_flag = 1; *A.stop_dev = stopped0; }
     if (lb == 0 && tid == 0) {
         BAState& S = A.state[p];
         const int nChunks = S.nChunks, nTuples = S.nTuples;
@@ -631,6 +632,9 @@ __global__ void __launch_bounds__(BA_TG, 7) k_land(BABatch A) {
     __shared__ double red[BA_TG / 32];
     const int b = blockIdx.x, tid = threadIdx.x;
     if (b == 0 && tid == 0) { *A.pairs_counter = 0; *A.rs_flag = 0; }   // work queue of the k_pairs launch that follows; k_lin / k_build are done with the flag
+    // the caller's stop flag lives in mapped host memory: ONE read per LM step crosses PCIe here, off the critical path; the LM decisions of
+    // k_back (one per window, at the tail of the step) read the device copy
+    if (b == 0 && tid == 32 && A.stop) *A.stop_dev = *(volatile int*)A.stop;
     const int p = A.blkG_prob[b];
     const BAState& S = A.state[p];
     if (S.done) return;
@@ -1244,7 +1248,7 @@ __device__ bool lm_decide(const BABatch& A, const BAProb& P, BAState& S) {
     S.qmax++;
     S.last = S.cur ^ 1;
     if (accepted) S.cur ^= 1;           // pop() is a no-op: the rejected estimate stays in the other buffer
-    const bool stopped = A.stop && *A.stop != 0;
+    const bool stopped = *A.stop_dev != 0;
     const bool again = rho < 0 && S.qmax < 10 && !stopped;
     S.mark = 0; S.round_start = 0;
     if (again) { S.need_build = 0; return accepted; }
@@ -1798,7 +1802,7 @@ static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, 
     const size_t o_eof = L.add(4 * (size_t)eofTot), o_pcnt = L.add(4 * (size_t)pairTot), o_poff = L.add(4 * (size_t)pairTot);
     const size_t o_pccnt = L.add(4 * (size_t)pcTot), o_pcoff = L.add(4 * (size_t)pcTot), o_pcfch = L.add(4 * (size_t)pcTot), o_pcnch = L.add(4 * (size_t)pcTot);
     const size_t o_cpair = L.add(4 * (size_t)chunkTot), o_cstart = L.add(4 * (size_t)chunkTot), o_clen = L.add(4 * (size_t)chunkTot);
-    const size_t o_irec = L.add(32 * 4 * (size_t)std::max(nbI, 1)), o_pcount = L.add(256);   // pcount: [0] k_pairs queue head, [16] rs_flag
+    const size_t o_irec = L.add(32 * 4 * (size_t)std::max(nbI, 1)), o_pcount = L.add(256);   // pcount: [0] k_pairs queue head, [16] rs_flag, [32] stop_dev
     const size_t o_tup = L.add(8 * (size_t)tupTot);
     const size_t o_pose_a = L.add(56 * Ptot), o_pose_b = L.add(56 * Ptot), o_pt_a = L.add(24 * Ltot), o_pt_b = L.add(24 * Ltot);
     const size_t o_err_a = L.add(16 * Etot), o_err_b = L.add(16 * Etot), o_level = L.add(Etot);
@@ -1915,7 +1919,7 @@ static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, 
     A.pc_cnt = (int*)(D + o_pccnt); A.pc_off = (int*)(D + o_pcoff); A.pc_fchunk = (int*)(D + o_pcfch); A.pc_nchunk = (int*)(D + o_pcnch);
     A.free_pose = (const int*)(D + o_freepose);
     A.chunk_pair = (int*)(D + o_cpair); A.chunk_start = (int*)(D + o_cstart); A.chunk_len = (int*)(D + o_clen);
-    A.item_rec = (int4*)(D + o_irec); A.pairs_counter = (int*)(D + o_pcount); A.rs_flag = (int*)(D + o_pcount) + 16;
+    A.item_rec = (int4*)(D + o_irec); A.pairs_counter = (int*)(D + o_pcount); A.rs_flag = (int*)(D + o_pcount) + 16; A.stop_dev = (int*)(D + o_pcount) + 32;
     A.tuples = (int2*)(D + o_tup);
     A.pose[0] = (double*)(D + o_pose_a); A.pose[1] = (double*)(D + o_pose_b); A.pt[0] = (double*)(D + o_pt_a); A.pt[1] = (double*)(D + o_pt_b);
     A.err[0] = (double*)(D + o_err_a); A.err[1] = (double*)(D + o_err_b); A.level = D + o_level;
