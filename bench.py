@@ -692,7 +692,7 @@ def run_gba(args, rank, world, local_rank):
             "gpu_launches": int(n_launch),
             "roofline": {"bound": "hbm", "kernel": "whole LM trial (build kernels + skyline LDL^T)", "achieved": design / (loop_ms / tr * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": design / (loop_ms / tr * 1e-3) / 1e9 / peak, "peak_source": peak_kind, "traffic": None,
-                         "note": "the trial is latency-bound: the skyline factorisation is a chain of 6 x key-frames sequential pivots in one CTA"},
+                         "note": "the trial is latency-bound: the substructured skyline factorisation is a chain of 6 x (key-frames / segments + separators) sequential pivots (DESIGN.md section 4)"},
         }
     opt.close()
     torch.cuda.empty_cache()
