@@ -133,7 +133,7 @@ class ClockSampler:
 
 
 def make_inputs(cfg, seed, frames):
-    from orbslam2_dualcam_b200 import synth
+    import synth
     a = synth.tiled_batch(seed, frames, cfg.W, cfg.H, CAMS, unique=16)
     b = np.ascontiguousarray(np.roll(a, shift=(11, 7), axis=(2, 3)))   # a second, distinct batch (defeats L2 reuse across steps)
     return a, b
@@ -141,7 +141,7 @@ def make_inputs(cfg, seed, frames):
 
 def make_ba(seed, n):
     """n LocalBA windows of BASELINE configs[2] size (BA_UNIQUE distinct ones, tiled)."""
-    from orbslam2_dualcam_b200 import synth
+    import synth
     base = [synth.ba_problem(seed * 16 + i) for i in range(min(BA_UNIQUE, max(n, 1)))]
     return [base[i % len(base)] for i in range(n)]
 
@@ -149,7 +149,7 @@ def make_ba(seed, n):
 def make_ba_hetero(seed, n):
     """n LocalBA windows of very different sizes, noise levels and outlier shares (BA_HETERO_UNIQUE distinct ones, tiled): some need
     rejected LM trials, some stop early -- the lock-step batch waits for the slowest."""
-    from orbslam2_dualcam_b200 import synth
+    import synth
     rng = np.random.default_rng(1000 + seed)
     base = []
     for i in range(min(BA_HETERO_UNIQUE, max(n, 1))):
@@ -218,7 +218,7 @@ def reference_track(cfg, args):
     O.lib()
     cores = os.cpu_count() or 1
     sample = max(cores * 2, 16) if cfg.with_ba else max(cores, 8)
-    from orbslam2_dualcam_b200 import synth
+    import synth
     frames = synth.tiled_batch(0, sample, cfg.W, cfg.H, CAMS, unique=16)
     ba = make_ba(0, BA_UNIQUE) if cfg.with_ba else []
     for _ in range(args.warmup):
@@ -247,7 +247,7 @@ def reference_gba(args):
     """the CPU oracle on a bounded sample of the workload: the same generator at 300 key frames / 30k points (the oracle's reduced
     system is dense: 2000 key frames would take minutes per trial)"""
     import oracle_lib as O
-    from orbslam2_dualcam_b200 import synth
+    import synth
     p = synth.gba_problem(0, n_kf=300, n_points=30000)
     t0 = time.perf_counter()
     rc, _, _, st = O.global_ba(p, iterations=3)
@@ -301,7 +301,8 @@ def survey_ba_bytes(problems, stats):
 def run_track(cfg, args, rank, world, local_rank, steps, warmup):
     import torch
     import torch.distributed as dist
-    from orbslam2_dualcam_b200 import ORBextractor, ORBmatcher, Optimizer, compact_problem, synth
+    from orbslam2_dualcam_b200 import ORBextractor, ORBmatcher, Optimizer, compact_problem
+    import synth
     dev = torch.device("cuda", local_rank)
     F, KF = (args.frames if cfg.with_ba else cfg.frames), args.kf_interval
     NBA = (F + KF - 1) // KF if cfg.with_ba else 0
@@ -645,7 +646,8 @@ def run_gba(args, rank, world, local_rank):
     max over ranks); e2e = wall time of the whole call per trial (host partition set-up, upload, LM loop, download)."""
     import torch
     import torch.distributed as dist
-    from orbslam2_dualcam_b200 import DistributedOptimizer, shard_problem, synth
+    from orbslam2_dualcam_b200 import DistributedOptimizer, shard_problem
+    import synth
     n_kf, n_pts, its = GBA_SHAPE
     dev = torch.device("cuda", local_rank)
     p = synth.gba_problem(0, n_kf=n_kf, n_points=n_pts)

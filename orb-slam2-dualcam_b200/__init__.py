@@ -3,7 +3,6 @@
 Host side (Python) above a C-ABI shared library (csrc/ -> lib/liborbslam2_dualcam_b200.so, declared in include/).
 All computation is in the sm_100a kernels of that library; there is no CPU fallback.
 """
-from . import synth  # noqa: F401
 from .capi import KP_DTYPE, OrbError, lib  # noqa: F401
 from .extractor import ORBextractor  # noqa: F401
 from .matcher import ORBmatcher  # noqa: F401

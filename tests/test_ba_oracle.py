@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from orbslam2_dualcam_b200 import synth
+import synth
 
 
 def _small(seed=1, **kw):

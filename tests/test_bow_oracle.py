@@ -3,7 +3,8 @@ host-side vocabulary text parser."""
 import numpy as np
 
 import oracle_lib as O
-from orbslam2_dualcam_b200 import parse_text_vocabulary, synth
+from orbslam2_dualcam_b200 import parse_text_vocabulary
+import synth
 
 
 def _numpy_transform(voc, desc, levelsup):

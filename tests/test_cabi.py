@@ -8,6 +8,7 @@ import pytest
 
 import orbslam2_dualcam_b200 as orb
 from orbslam2_dualcam_b200 import capi
+import synth
 
 HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "orbslam2_dualcam_b200.h")
 
@@ -53,7 +54,7 @@ def test_create_fails_loudly_without_gpu():
     with pytest.raises(orb.OrbError):
         orb.Optimizer()
     with pytest.raises(orb.OrbError) as e:
-        orb.ORBVocabulary(orb.synth.vocabulary(0, k=3, L=2))
+        orb.ORBVocabulary(synth.vocabulary(0, k=3, L=2))
     assert e.value.code == capi.ORB_E_NO_DEVICE
 
 

@@ -40,7 +40,8 @@ def _worker(rank, world, port, q):
     for pth in (ROOT, os.path.join(ROOT, "tests")):
         if pth not in sys.path:
             sys.path.insert(0, pth)
-    from orbslam2_dualcam_b200 import shard_problem, synth
+    from orbslam2_dualcam_b200 import shard_problem
+    import synth
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -79,7 +80,8 @@ def test_shard_problem_covers_everything_once():
     for pth in (ROOT,):
         if pth not in sys.path:
             sys.path.insert(0, pth)
-    from orbslam2_dualcam_b200 import shard_problem, synth
+    from orbslam2_dualcam_b200 import shard_problem
+    import synth
     p = synth.ba_problem(3, n_kf=5, n_points=101)
     seen_pts, seen_edges = [], []
     for r in range(4):

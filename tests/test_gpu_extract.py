@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from orbslam2_dualcam_b200 import ORBextractor, synth
+from orbslam2_dualcam_b200 import ORBextractor
+import synth
 
 pytestmark = pytest.mark.gpu
 

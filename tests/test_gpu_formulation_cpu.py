@@ -5,7 +5,7 @@ import pytest
 
 import model_lib as M
 import oracle_lib as O
-from orbslam2_dualcam_b200 import synth
+import synth
 
 
 def _images():

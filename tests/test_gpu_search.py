@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from orbslam2_dualcam_b200 import ORBmatcher, synth
+from orbslam2_dualcam_b200 import ORBmatcher
+import synth
 
 pytestmark = pytest.mark.gpu
 

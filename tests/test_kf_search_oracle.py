@@ -4,7 +4,7 @@ KeyFrame::GetFeaturesInArea index quirk)."""
 import numpy as np
 
 import oracle_lib as O
-from orbslam2_dualcam_b200 import synth
+import synth
 
 
 def _ham(a, b):

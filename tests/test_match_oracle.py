@@ -3,7 +3,7 @@ reference loops on small inputs, and of its structural properties on larger ones
 import numpy as np
 
 import oracle_lib as O
-from orbslam2_dualcam_b200 import synth
+import synth
 
 
 def _hamming(a, b):

@@ -2,7 +2,7 @@
 import numpy as np
 
 import oracle_lib as O
-from orbslam2_dualcam_b200 import synth
+import synth
 
 
 def test_pose_optimization_recovers_pose_and_outliers():

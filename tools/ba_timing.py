@@ -2,8 +2,10 @@
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
-from orbslam2_dualcam_b200 import Optimizer, synth
+from orbslam2_dualcam_b200 import Optimizer
+import synth
 
 def main():
     ns = [int(x) for x in sys.argv[1:]] or [1, 32, 148, 296]

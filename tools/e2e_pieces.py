@@ -3,11 +3,13 @@
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import torch.distributed as dist
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 os.environ.setdefault("ORB_HOST_THREADS", str(max(2, (os.cpu_count() or 16) // max(world, 1))))
-from orbslam2_dualcam_b200 import Optimizer, compact_problem, synth
+from orbslam2_dualcam_b200 import Optimizer, compact_problem
+import synth
 torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))

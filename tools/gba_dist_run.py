@@ -8,11 +8,13 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from orbslam2_dualcam_b200 import DistributedOptimizer, shard_problem, synth
+from orbslam2_dualcam_b200 import DistributedOptimizer, shard_problem
+import synth
 
 
 def main():

@@ -24,8 +24,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-from orbslam2_dualcam_b200 import synth  # noqa: E402
+import synth
 
 f32 = np.float32
 libm = ctypes.CDLL("libm.so.6")
