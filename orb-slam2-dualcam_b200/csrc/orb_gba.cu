@@ -29,6 +29,9 @@
 
 #include <algorithm>
 #include <new>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "orb_common.h"
@@ -1210,11 +1213,28 @@ bool load_nccl() {
 const int NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3;
 }  // namespace
 
+namespace {
+// host threads for the set-up passes: ORB_HOST_THREADS (e.g. cores / ranks when several processes share a node), else up to 16
+int host_thread_count(int want) {
+    static const int cap = []() { const char* e = getenv("ORB_HOST_THREADS"); const int v = e ? atoi(e) : 0; return v > 0 ? std::min(v, 64) : 16; }();
+    return std::max(1, std::min({want, cap, (int)std::max(1u, std::thread::hardware_concurrency())}));
+}
+// fn(t) on threads t = 0 .. T-1
+template <class F>
+void host_threads(int T, F fn) {
+    if (T <= 1) { fn(0); return; }
+    std::vector<std::thread> ts;
+    for (int t = 0; t < T; t++) ts.emplace_back([&, t]() { fn(t); });
+    for (std::thread& th : ts) th.join();
+}
+}  // namespace
+
 struct orbgba {
     int device = 0, rank = 0, world = 1;
     cudaStream_t stream = nullptr;
     void* comm = nullptr;
     uint8_t* arena = nullptr; size_t arena_cap = 0;
+    uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;   // pinned staging buffer of the inputs (grow-only)
     double* h_red = nullptr;        // pinned
     long long launches = 0;
     double allreduce_ms = 0, solve_ms = 0, loop_ms = 0;   // accumulated over the last optimize call (events)
@@ -1230,6 +1250,7 @@ static void gba_free(orbgba* g) {
     if (g->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g->comm);
     cudaFree(g->arena);
     if (g->h_red) cudaFreeHost(g->h_red);
+    if (g->h_stage) cudaFreeHost(g->h_stage);
     for (cudaEvent_t e : g->ev) if (e) cudaEventDestroy(e);
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
@@ -1339,6 +1360,14 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     }
     if (bad) ORB_FAIL(ORB_E_INVALID, "orbba_dist_optimize: %s", bad);
     // ---- host-side preparation: free-pose numbering, edges grouped by landmark (stable), CSR, envelope
+    const bool timing = getenv("ORBGBA_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto tick = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[orbgba rank %d] %-28s %8.2f ms\n", g->rank, what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     std::vector<int> pose_free(nP, -1);
     int K = 0;
     for (int i = 0; i < nP; i++) if (!Q->pose_fixed[i]) pose_free[i] = K++;
@@ -1365,6 +1394,7 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
         ORB_CUDA(cudaMemcpyAsync(first_d.data(), g->arena, 8 * (size_t)K, cudaMemcpyDeviceToHost, st));
         ORB_CUDA(cudaStreamSynchronize(st));
     }
+    tick("sort by landmark, envelope");
     std::vector<int> first(std::max(K, 1), 0), rowptr(K + 1, 0), last(std::max(K, 1), 0);
     long long NB = 0;
     for (int k = 0; k < K; k++) { first[k] = (int)first_d[k]; rowptr[k] = (int)NB; NB += k - first[k] + 1; if (NB > 0x3fffffffLL) ORB_FAIL(ORB_E_INVALID, "orbba_dist_optimize: the envelope of the reduced camera system is too large"); }
@@ -1416,36 +1446,56 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     // owner lists: edges per free pose; tuples per skyline block
     std::vector<int> pose_eoff(K + 1, 0), pose_edge;
     std::vector<long long> blk_toff((size_t)NB + 1, 0);
-    std::vector<int2> blk_tup;
+    // tuples per block, ordered by landmark: a parallel counting sort.  Thread t owns a contiguous range of landmarks (balanced by the
+    // number of tuples), counts its tuples per block, the per-block prefix over (block, thread) gives every thread its write positions,
+    // so the order inside a block is the landmark order whatever the thread count (bit-reproducible sums downstream).
+    std::vector<long long> lm_tup((size_t)nL + 1, 0);
     {
         for (int s = 0; s < nE; s++) { const int k = pose_free[Q->edge_pose[perm[s]]]; if (k >= 0) pose_eoff[k + 1]++; }
         for (int k = 0; k < K; k++) pose_eoff[k + 1] += pose_eoff[k];
         pose_edge.resize((size_t)pose_eoff[K]);
         std::vector<int> pos(pose_eoff.begin(), pose_eoff.end() - 1);
         for (int s = 0; s < nE; s++) { const int k = pose_free[Q->edge_pose[perm[s]]]; if (k >= 0) pose_edge[pos[k]++] = s; }
-        auto block_of = [&](int ka, int kb) { return (long long)rowptr[ka] + (kb - first[ka]); };   // ka >= kb
-        for (int pass = 0; pass < 2; pass++) {
-            std::vector<long long> wpos;
-            if (pass == 1) {
-                for (long long b2 = 0; b2 < NB; b2++) blk_toff[b2 + 1] += blk_toff[b2];
-                blk_tup.resize((size_t)blk_toff[NB]);
-                wpos.assign(blk_toff.begin(), blk_toff.end() - 1);
-            }
-            for (int l = 0; l < nL; l++)
-                for (int sa = pt_off[l]; sa < pt_off[l + 1]; sa++) {
-                    const int ka = pose_free[Q->edge_pose[perm[sa]]];
-                    if (ka < 0) continue;
-                    for (int sb = pt_off[l]; sb < pt_off[l + 1]; sb++) {
-                        const int kb = pose_free[Q->edge_pose[perm[sb]]];
-                        if (kb < 0 || kb > ka || (kb == ka && sb != sa)) continue;
-                        const long long bid = block_of(ka, kb);
-                        if (pass == 0) blk_toff[bid + 1]++;
-                        else blk_tup[(size_t)wpos[bid]++] = make_int2(sa, sb);
-                    }
-                }
+        for (int l = 0; l < nL; l++) {
+            long long f = 0;
+            for (int s = pt_off[l]; s < pt_off[l + 1]; s++) f += pose_free[Q->edge_pose[perm[s]]] >= 0;
+            lm_tup[l + 1] = lm_tup[l] + f * (f + 1) / 2;
         }
     }
-    const long long nT = blk_toff[NB];
+    const long long nT = lm_tup[nL];
+    auto block_of = [&](int ka, int kb) { return (long long)rowptr[ka] + (kb - first[ka]); };   // ka >= kb
+    const int nth = host_thread_count(nT > 200000 && NB < (1 << 22) ? 64 : 1);
+    std::vector<int> lm_cut;                              // landmark ranges of the threads
+    std::vector<std::vector<int>> cntT;                   // [thread][block]
+    lm_cut.assign(nth + 1, nL);
+    lm_cut[0] = 0;
+    for (int t = 1; t < nth; t++) lm_cut[t] = (int)(std::lower_bound(lm_tup.begin(), lm_tup.end(), nT * t / nth) - lm_tup.begin());
+    for (int t = 1; t <= nth; t++) lm_cut[t] = std::max(std::min(lm_cut[t], nL), lm_cut[t - 1]);
+    lm_cut[nth] = nL;
+    cntT.assign(nth, std::vector<int>());
+    auto for_tuples = [&](int l0, int l1, auto&& emit) {
+        for (int l = l0; l < l1; l++)
+            for (int sa = pt_off[l]; sa < pt_off[l + 1]; sa++) {
+                const int ka = pose_free[Q->edge_pose[perm[sa]]];
+                if (ka < 0) continue;
+                for (int sb = pt_off[l]; sb < pt_off[l + 1]; sb++) {
+                    const int kb = pose_free[Q->edge_pose[perm[sb]]];
+                    if (kb < 0 || kb > ka || (kb == ka && sb != sa)) continue;
+                    emit(block_of(ka, kb), sa, sb);
+                }
+            }
+    };
+    host_threads(nth, [&](int t) {
+        std::vector<int>& c = cntT[t];
+        c.assign((size_t)NB, 0);
+        for_tuples(lm_cut[t], lm_cut[t + 1], [&](long long bid, int, int) { c[(size_t)bid]++; });
+    });
+    for (long long b2 = 0; b2 < NB; b2++) {
+        long long tot = 0;
+        for (int t = 0; t < nth; t++) { const int c = cntT[t][(size_t)b2]; cntT[t][(size_t)b2] = (int)tot; tot += c; }   // -> offset of thread t inside the block
+        blk_toff[b2 + 1] = blk_toff[b2] + tot;
+    }
+    tick("owner lists, tuple lists");
     // ---- layout
     size_t cur_off = 0;
     auto add = [&](size_t b) { const size_t o = (cur_off + 255) & ~(size_t)255; cur_off = o + b; return o; };
@@ -1477,14 +1527,32 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
         ORB_CUDA(cudaMalloc((void**)&g->arena, total));
         g->arena_cap = total;
     }
-    std::vector<uint8_t> H(staged);
+    if (staged > g->h_stage_cap) {
+        if (g->h_stage) cudaFreeHost(g->h_stage);
+        g->h_stage = nullptr; g->h_stage_cap = 0;
+        ORB_CUDA(cudaHostAlloc((void**)&g->h_stage, staged + (staged >> 3), cudaHostAllocDefault));
+        g->h_stage_cap = staged + (staged >> 3);
+    }
+    struct { uint8_t* p; uint8_t* data() const { return p; } } H{g->h_stage};
+    {   // second pass of the counting sort: the tuples go straight into the pinned buffer
+        int2* tup = (int2*)(H.data() + o_btup);
+        host_threads(nth, [&](int t) {
+            std::vector<int>& c = cntT[t];
+            for_tuples(lm_cut[t], lm_cut[t + 1], [&](long long bid, int sa, int sb) { tup[(size_t)(blk_toff[bid] + c[(size_t)bid]++)] = make_int2(sa, sb); });
+        });
+    }
     int *h_epose = (int*)(H.data() + o_epose), *h_ept = (int*)(H.data() + o_ept), *h_ecam = (int*)(H.data() + o_ecam);
     double *h_eobs = (double*)(H.data() + o_eobs), *h_einfo = (double*)(H.data() + o_einfo), *h_cam = (double*)(H.data() + o_cam), *h_pose0 = (double*)(H.data() + o_pose0);
-    for (int s = 0; s < nE; s++) {
-        const int e = perm[s];
-        h_epose[s] = Q->edge_pose[e]; h_ept[s] = Q->edge_point[e]; h_ecam[s] = Q->edge_cam[e];
-        h_eobs[2 * s] = Q->edge_obs[2 * e]; h_eobs[2 * s + 1] = Q->edge_obs[2 * e + 1]; h_einfo[s] = Q->edge_inv_sigma2[e];
-    }
+    const int nth_e = host_thread_count(nE > 100000 ? 64 : 1);
+    memset(h_cam, 0, 8 * BA_CAM_STRIDE * (size_t)nC);
+    host_threads(nth_e, [&](int t) {
+        const int T = nth_e, s0 = (int)((long long)nE * t / T), s1 = (int)((long long)nE * (t + 1) / T);
+        for (int s = s0; s < s1; s++) {
+            const int e = perm[s];
+            h_epose[s] = Q->edge_pose[e]; h_ept[s] = Q->edge_point[e]; h_ecam[s] = Q->edge_cam[e];
+            h_eobs[2 * s] = Q->edge_obs[2 * e]; h_eobs[2 * s + 1] = Q->edge_obs[2 * e + 1]; h_einfo[s] = Q->edge_inv_sigma2[e];
+        }
+    });
     memcpy(H.data() + o_pfree, pose_free.data(), 4 * (size_t)nP);
     memcpy(H.data() + o_ptoff, pt_off.data(), 4 * (size_t)(nL + 1));
     memcpy(H.data() + o_first, first.data(), 4 * (size_t)std::max(K, 1));
@@ -1495,7 +1563,6 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     memcpy(H.data() + o_peoff, pose_eoff.data(), 4 * (size_t)(K + 1));
     if (!pose_edge.empty()) memcpy(H.data() + o_pedge, pose_edge.data(), 4 * pose_edge.size());
     memcpy(H.data() + o_btoff, blk_toff.data(), 8 * (size_t)(NB + 1));
-    if (nT) memcpy(H.data() + o_btup, blk_tup.data(), 8 * (size_t)nT);
     for (int c = 0; c < nC; c++) {
         double* Dc = h_cam + (size_t)BA_CAM_STRIDE * c;
         for (int i = 0; i < 4; i++) Dc[i] = Q->cam_K[4 * c + i];
@@ -1519,6 +1586,7 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
         Dp[4] = T[3]; Dp[5] = T[7]; Dp[6] = T[11];
     }
     if (nL) memcpy(H.data() + o_pt0, Q->points, 24 * (size_t)nL);
+    tick("staging buffer fill");
     uint8_t* D = g->arena;
     ORB_CUDA(cudaMemcpyAsync(D, H.data(), staged, cudaMemcpyHostToDevice, st));
     GArgs A;
@@ -1579,6 +1647,7 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     int nBad = 0;
     bool ok_iter = !stopped0 && totalEdges > 0;
     bool stopped = stopped0;
+    tick("upload, initial errors");
     ORB_CUDA(cudaEventRecord(g->ev[4], st));
     for (int it = 0; it < iterations && ok_iter; it++) {
         if (stopped) break;                  // the value every rank agreed on at the end of the previous trial
@@ -1683,6 +1752,7 @@ int orbba_dist_optimize(orbgba_t* g, const orbba_problem_t* Q, int iterations, d
     if (points_out && nL) ORB_CUDA(cudaMemcpyAsync(points_out, d_lout, 24 * (size_t)nL, cudaMemcpyDeviceToHost, st));
     ORB_CUDA(cudaStreamSynchronize(st));
     { float ms = 0; cudaEventElapsedTime(&ms, g->ev[4], g->ev[5]); g->loop_ms = ms; }
+    tick("LM loop, download");
     S.final_chi2 = currentChi; S.final_lambda = lambda; S.outliers = 0; S.status = stopped0 ? ORB_E_ABORTED : ORB_OK;
     if (stats) *stats = S;
     return S.status;
