@@ -574,6 +574,7 @@ __global__ void __launch_bounds__(SKY_T) k_sky_band(GArgs A, double lambda, int 
                 for (int k = 0; k < c; k++) a -= h[c][k] * z[k];
                 z[c] = a;
             }
+            __syncwarp();                                              // every lane has read the pivot block before lane 0 overwrites it
             if (tid == 0) {
                 if (!good) s_ok = 0;
 #pragma unroll
@@ -825,6 +826,7 @@ __global__ void __launch_bounds__(SEG_T) k_seg_fwd(GArgs A, const __grid_constan
                 for (int k = 0; k < c; k++) a -= h[c][k] * z[k];
                 z[c] = a;
             }
+            __syncwarp();                                              // every lane has read the pivot block before lane 0 overwrites it
             if (tid == 0) {
                 if (!good) s_ok = 0;
 #pragma unroll
