@@ -446,8 +446,9 @@ int  orbba_download(orbba_t*, int p, double* poses_out, double* points_out, uint
 int  orbba_download_batch(orbba_t*, double* poses_out, double* points_out, uint8_t* edge_outlier, orbba_stats_t* stats);
 int  orbba_profile(orbba_t*, int enable);
 int  orbba_stage_ms(orbba_t*, double* ms1, int* calls);
-/* device time of the six kernels of the LM step {linearise, build, Schur blocks, Schur pairs, reduced solve, back-substitution +
- * errors + LM decision}, summed over the steps recorded since the last call; *steps = LM steps summed. */
+/* device time of the kernels of the LM step {k_lin, k_build (both only on the first step of a round), k_land (linearise + landmark
+ * blocks + per-edge records), k_pairs (Schur products per pose pair), k_solve (reduced camera system), k_back (back-substitution +
+ * trial errors + LM decision)}, summed over the steps recorded since the last call; *steps = LM steps summed. */
 int  orbba_kernel_ms(orbba_t*, double* ms6, int* steps);
 
 /* ------------------------------------------------------------------------------------------------

@@ -7,12 +7,14 @@
 // Kernel pipeline per orbx_extract_device() call (all images of the batch in every launch):
 //   resize4_kernel        x (nlevels-1)   level l from level l-1, cv::resize INTER_LINEAR 8U fixed-point arithmetic: 4 pixels per thread
 //                                         from aligned source words, horizontal taps with dp2a (resize_level_kernel: any scale factor)
-//   fast_cells_kernel     x 1             one CTA per 30-px cell: the cell's tile of the pyramid level is staged in shared memory by TMA
-//                                         (cp.async.bulk.tensor.3d + mbarrier, one tensor map per level); FAST-9/16 score, cell-local
-//                                         NMS, ini/min threshold fallback, unordered packed candidate list per (image, level)
+//   fast_cells_kernel     x 1             one CTA per strip of up to 7 consecutive 30-px cells of a cell row: the strip's tile of the pyramid level
+//                                         is staged in shared memory by TMA (cp.async.bulk.tensor.3d + mbarrier, one tensor map per level);
+//                                         compass pre-test and FAST-9/16 score over the strip, NMS and the ini/min threshold fallback per cell,
+//                                         unordered packed candidate list per (image, level)
 //   quadtree_kernel       x 1             one CTA per (image, level): level-synchronous DistributeOctTree
-//   describe_kernel       x 1             one warp per keypoint: IC angle, 7x7 Gaussian of the 37x37 patch in shared
-//                                         memory, steered rBRIEF, cv::KeyPoint + 32-byte descriptor output
+//   blur_level_kernel     x nlevels       cv::GaussianBlur(7x7, s=2, REFLECT_101) of every level: 64x58 tile per CTA from a 96x64 TMA box
+//   describe_kernel       x 1             one warp per keypoint: the blurred 64x37 window by TMA, IC angle from the raw level,
+//                                         steered rBRIEF, cv::KeyPoint + 32-byte descriptor output
 // There is no CPU fallback: every entry point needs a CUDA device.
 #include <cuda.h>              // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
 #include <string.h>
