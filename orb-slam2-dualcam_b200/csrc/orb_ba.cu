@@ -81,10 +81,13 @@ struct BABatch {               // kernel argument (by value)
     const int* pose_free;                       // [Ptot] global free index or -1
     const double *pose0, *pt0;
     const int *blkE_prob, *blkL_prob, *item_prob;
+    const int4* blkG_desc;                      // k_land block -> {problem, first landmark (global), first edge (global), landmarks | edges << 8}: one load instead of a chain of four
     const int *blkG_prob, *blkG_l0, *blkG_nl;  // k_land block -> problem, first landmark (global), landmarks (whole landmarks, <= BA_TG edges; a landmark with more gets a block of its own)
     const int* free_pose;                       // [Ktot] global pose index of every free pose
     // index built on the device
     int* edge_of;                               // [free pose of the problem][landmark] -> edge << 2 | camera, or -1
+    int* e_kf;                                  // per edge: free-pose index of its key frame (global), -1 if fixed: spares the consumers a dependent gather
+    const int* blkL_l0;                         // k_back block -> its first landmark (global)
     unsigned* bm;                               // [(free pose, camera) of the problem][bmW]: bit l = the pose observes landmark l with that camera
     int *pair_cnt, *pair_off;                    // per pair: tuples, first tuple
     int *pc_cnt, *pc_off, *pc_fchunk, *pc_nchunk; // per (pair, camera pair): tuples, first tuple, first chunk, chunks
@@ -146,6 +149,7 @@ __global__ void k_edge_of(BABatch A) {
     const int e = P.e0 + (b - P.blkE0) * BA_TE + threadIdx.x;
     if (e >= P.e0 + P.nE) return;
     const int k = A.pose_free[A.e_pose[e]];
+    A.e_kf[e] = k;
     if (k >= 0) {
         const int l = A.e_pt[e] - P.l0, c = A.e_cam[e] - P.c0;
         A.edge_of[P.eof0 + (long long)(k - P.k0) * P.nL + l] = (e << 2) | c;   // edge and its camera (rigs of <= 4 cameras)
@@ -584,7 +588,7 @@ __device__ __forceinline__ void edge_lin(const BABatch& A, const BAProb& P, int 
     const double* K4 = A.cam + BA_CAM_STRIDE * (size_t)cg;
     load_tab(tb + ts * ((pg - P.p0) * P.nC + (cg - P.c0)), T);
     tab_project(T, A.pt[cur] + 3 * (size_t)A.e_pt[e], pc);
-    L.free_pose = A.pose_free[pg] >= 0;
+    L.free_pose = A.e_kf[e] >= 0;
     if (A.level[e]) {                                     // removed from the optimisation (src/Optimizer.cc:598-613): contributes nothing
         L.x = 0; L.y = 0; L.iz = 1; L.W = 0; L.r0 = 0; L.r1 = 0;
 #pragma unroll
@@ -635,12 +639,18 @@ __global__ void __launch_bounds__(BA_TG, 7) k_land(BABatch A) {
     // the caller's stop flag lives in mapped host memory: ONE read per LM step crosses PCIe here, off the critical path; the LM decisions of
     // k_back (one per window, at the tail of the step) read the device copy
     if (b == 0 && tid == 32 && A.stop) *A.stop_dev = *(volatile int*)A.stop;
-    const int p = A.blkG_prob[b];
+    const int4 gd = A.blkG_desc[b];
+    const int p = gd.x, l0 = gd.y, e0 = gd.z, nl = gd.w & 255, ne = gd.w >> 8;
+    // the edge ids do not depend on the problem's state: their lines are requested before the state is read (one level less in the chain
+    // of dependent loads that a 128-edge CTA spends a third of its life in)
+    if (tid < ne) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.e_pose + e0 + tid));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.e_cam + e0 + tid));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.e_pt + e0 + tid));
+    }
     const BAState& S = A.state[p];
     if (S.done) return;
     const BAProb& P = A.prob[p];
-    const int l0 = A.blkG_l0[b], nl = A.blkG_nl[b];
-    const int e0 = A.pt_off[l0], ne = A.pt_off[l0 + nl] - e0;
     const int cur = S.cur;
     const double lambda = lambda_eff(S);
     const bool robust = S.round == 0 && A.delta > 0;
@@ -1275,15 +1285,16 @@ __device__ bool lm_decide(const BABatch& A, const BAProb& P, BAState& S) {
 __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
     __shared__ double red[BA_TL / 32];
     __shared__ int s_last;
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const int p = A.blkL_prob[b];
+    const int l = A.blkL_l0[b] + tid;
+    // the landmark's edge range does not depend on the problem's state: requested before the state is read
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(A.pt_off + l));
     BAState& S = A.state[p];
     if (S.done && !S.skip) return;
     const BAProb& P = A.prob[p];
-    const int tid = threadIdx.x;
     const bool skip = S.skip != 0;
     double chi = 0, sc = 0;
-    const int l = P.l0 + (b - P.blkL0) * BA_TL + tid;
     if (!skip && l < P.l0 + P.nL) {
         const int cur = S.cur;
         const double lambda = S.lambda;
@@ -1299,7 +1310,7 @@ __global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
             double c0 = bl[0], c1 = bl[1], c2 = bl[2];
 #pragma unroll 2
             for (int e = e_begin; e < e_end; e++) {
-                const int pg = epose_[e], kg = A.pose_free[pg];
+                const int kg = A.e_kf[e];
                 if (kg < 0) continue;
                 const int cg = ecam_[e];
                 const double* c = A.cam + BA_CAM_STRIDE * (size_t)cg;
@@ -1789,16 +1800,17 @@ static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, 
     }
     const size_t o_cam = L.add(8 * BA_CAM_STRIDE * Ctot);
     const size_t o_ptoff = L.add(4 * (Ltot + 1)), o_pfree = L.add(4 * Ptot), o_pose0 = L.add(56 * Ptot);
-    const size_t o_blkE = L.add(4 * (size_t)nbE), o_blkL = L.add(4 * (size_t)nbL), o_item = L.add(4 * (size_t)std::max(nbI, 1));
+    const size_t o_blkE = L.add(4 * (size_t)nbE), o_blkL = L.add(4 * (size_t)nbL), o_blkLl = L.add(4 * (size_t)nbL), o_item = L.add(4 * (size_t)std::max(nbI, 1));
     const size_t o_blkPp = L.add(4 * (size_t)std::max(nbP, 1)), o_blkPf = L.add(4 * (size_t)std::max(nbP, 1)), o_blkIf = L.add(4 * (size_t)std::max(nbI, 1));
     const size_t o_poseprob = L.add(4 * (size_t)std::max<long long>(Ktot, 1)), o_freepose = L.add(4 * (size_t)std::max<long long>(Ktot, 1));
-    const size_t o_blkGp = L.add(4 * (size_t)std::max(nbG, 1)), o_blkGl = L.add(4 * (size_t)std::max(nbG, 1)), o_blkGn = L.add(4 * (size_t)std::max(nbG, 1));
+    const size_t o_blkGp = L.add(4 * (size_t)std::max(nbG, 1)), o_blkGl = L.add(4 * (size_t)std::max(nbG, 1)), o_blkGn = L.add(4 * (size_t)std::max(nbG, 1)), o_blkGd = L.add(16 * (size_t)std::max(nbG, 1));
     const size_t static_bytes = L.add(0);
     if (compact) {
         o_epose = L.add(4 * Etot); o_ept = L.add(4 * Etot); o_ecam = L.add(4 * Etot); o_eobs = L.add(16 * Etot); o_einfo = L.add(8 * Etot); o_pt0 = L.add(24 * Ltot);
     }
     const size_t o_state = L.add(sizeof(BAState) * n);
     const size_t o_bm = L.add(4 * (size_t)std::max<long long>(bmTot, 1));
+    const size_t o_ekf = L.add(4 * (size_t)std::max<long long>(Etot, 1));
     const size_t o_eof = L.add(4 * (size_t)eofTot), o_pcnt = L.add(4 * (size_t)pairTot), o_poff = L.add(4 * (size_t)pairTot);
     const size_t o_pccnt = L.add(4 * (size_t)pcTot), o_pcoff = L.add(4 * (size_t)pcTot), o_pcfch = L.add(4 * (size_t)pcTot), o_pcnch = L.add(4 * (size_t)pcTot);
     const size_t o_cpair = L.add(4 * (size_t)chunkTot), o_cstart = L.add(4 * (size_t)chunkTot), o_clen = L.add(4 * (size_t)chunkTot);
@@ -1836,6 +1848,7 @@ static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, 
     int *h_blkE = (int*)(H + o_blkE), *h_blkL = (int*)(H + o_blkL), *h_item = (int*)(H + o_item), *h_blkPp = (int*)(H + o_blkPp), *h_blkPf = (int*)(H + o_blkPf),
         *h_blkIf = (int*)(H + o_blkIf), *h_poseprob = (int*)(H + o_poseprob), *h_freepose = (int*)(H + o_freepose);
     int *h_blkGp = (int*)(H + o_blkGp), *h_blkGl = (int*)(H + o_blkGl), *h_blkGn = (int*)(H + o_blkGn);
+    int4* h_blkGd = (int4*)(H + o_blkGd);
     orbba_edge16_t* h_e16 = (orbba_edge16_t*)(H + o_e16);
     float *h_pts32 = (float*)(H + o_pts32), *h_isig = (float*)(H + o_isig);
     int* h_isig0 = (int*)(H + o_isig0);
@@ -1895,8 +1908,13 @@ static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, 
         }
         if (!compact && P.nL) memcpy(h_pt0 + 3 * (size_t)P.l0, Q.points, sizeof(double) * 3 * P.nL);
         for (int q = 0; q < P.nbE; q++) h_blkE[P.blkE0 + q] = p;
-        for (int q = 0; q < P.nbL; q++) h_blkL[P.blkL0 + q] = p;
+        for (int q = 0; q < P.nbL; q++) { h_blkL[P.blkL0 + q] = p; ((int*)(H + o_blkLl))[P.blkL0 + q] = P.l0 + q * BA_TL; }
         for (int q = 0; q < P.nbG; q++) { h_blkGp[P.blkG0 + q] = p; h_blkGl[P.blkG0 + q] = P.l0 + groups[p][2 * q]; h_blkGn[P.blkG0 + q] = groups[p][2 * q + 1]; }
+        for (int q = 0; q < P.nbG; q++) {
+            const int gl0 = groups[p][2 * q], gnl = groups[p][2 * q + 1];
+            const int ge0 = h_ptoff[P.l0 + gl0], ge1 = gl0 + gnl >= P.nL ? P.e0 + P.nE : h_ptoff[P.l0 + gl0 + gnl];
+            h_blkGd[P.blkG0 + q] = make_int4(p, P.l0 + gl0, ge0, gnl | ((ge1 - ge0) << 8));
+        }
         const int bp4 = (P.nPairs + 3) / 4, bi4 = (P.nItems + 3) / 4;
         for (int q = 0; q < bp4; q++) { h_blkPp[bP + q] = p; h_blkPf[bP + q] = bP; }
         for (int q = 0; q < bi4; q++) { h_item[bI + q] = p; h_blkIf[bI + q] = bI; }
@@ -1911,10 +1929,11 @@ static int upload_views(orbba* b, const std::vector<ProbView>& problems, int n, 
     A.e_obs = (const double*)(D + o_eobs); A.e_info = (const double*)(D + o_einfo); A.cam = (const double*)(D + o_cam);
     A.pt_off = (const int*)(D + o_ptoff); A.pose_free = (const int*)(D + o_pfree);
     A.pose0 = (const double*)(D + o_pose0); A.pt0 = (const double*)(D + o_pt0);
-    A.blkE_prob = (const int*)(D + o_blkE); A.blkL_prob = (const int*)(D + o_blkL); A.item_prob = (const int*)(D + o_item);
-    A.blkG_prob = (const int*)(D + o_blkGp); A.blkG_l0 = (const int*)(D + o_blkGl); A.blkG_nl = (const int*)(D + o_blkGn);
+    A.blkE_prob = (const int*)(D + o_blkE); A.blkL_prob = (const int*)(D + o_blkL); A.blkL_l0 = (const int*)(D + o_blkLl); A.item_prob = (const int*)(D + o_item);
+    A.blkG_prob = (const int*)(D + o_blkGp); A.blkG_l0 = (const int*)(D + o_blkGl); A.blkG_nl = (const int*)(D + o_blkGn); A.blkG_desc = (const int4*)(D + o_blkGd);
     b->d_blkP_prob = (int*)(D + o_blkPp); b->d_blkP_first = (int*)(D + o_blkPf); b->d_blkI_first = (int*)(D + o_blkIf); b->d_pose_prob = (int*)(D + o_poseprob);
     A.bm = (unsigned*)(D + o_bm);
+    A.e_kf = (int*)(D + o_ekf);
     A.edge_of = (int*)(D + o_eof); A.pair_cnt = (int*)(D + o_pcnt); A.pair_off = (int*)(D + o_poff);
     A.pc_cnt = (int*)(D + o_pccnt); A.pc_off = (int*)(D + o_pcoff); A.pc_fchunk = (int*)(D + o_pcfch); A.pc_nchunk = (int*)(D + o_pcnch);
     A.free_pose = (const int*)(D + o_freepose);
