@@ -976,35 +976,54 @@ __device__ __forceinline__ bool solve_reduced(const BABatch& A, const BAProb& P,
             // chunk ranges of all camera pairs first (lane q holds camera pair q), so that their reads are in flight together
             int my_nc = 0, my_first = 0;
             if (lane < P.CC) { my_nc = A.pc_nchunk[P.pc0 + pid * P.CC + lane]; my_first = A.pc_fchunk[P.pc0 + pid * P.CC + lane]; }
-            for (int combo = 0; combo < P.CC; combo++) {
-                const int nc = __shfl_sync(0xffffffffu, my_nc, combo), first = __shfl_sync(0xffffffffu, my_first, combo);
-                if (nc == 0) continue;
-                double n0 = 0, n1 = 0;
-                for (int c = 0; c < nc && first + c < nCh; c++) {
-                    const double* pp = A.partial + 36 * (size_t)(P.chunk0 + first + c);
-                    n0 += pp[lane];
-                    if (lane < 4) n1 += pp[32 + lane];
-                }
-                __syncwarp();
-                wN[lane] = n0;
-                if (lane < 4) wN[32 + lane] = n1;
-                __syncwarp();
-                const double* Aa = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + combo / P.nC) + BA_CAM_ADJ;
-                const double* Ab = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + combo % P.nC) + BA_CAM_ADJ;
-                for (int en = lane; en < 36; en += 32) {   // tmp = N Adj_cb
-                    const int a6 = en / 6, j6 = en - 6 * a6;
-                    double t = 0;
+            // four camera pairs at a time: the first chunk partial of each is requested before any of them is used (one L2 round trip
+            // per group instead of one per camera pair; a list longer than one chunk continues its chain below)
+            for (int c0 = 0; c0 < P.CC; c0 += 4) {
+                int ncs[4], fs[4];
+                double a0[4], a1[4];
 #pragma unroll
-                    for (int q = 0; q < 6; q++) t += wN[a6 * 6 + q] * Ab[q * 6 + j6];
-                    wT[en] = t;
+                for (int q = 0; q < 4; q++) {
+                    const int combo = min(c0 + q, P.CC - 1);
+                    ncs[q] = c0 + q < P.CC ? __shfl_sync(0xffffffffu, my_nc, combo) : 0;
+                    fs[q] = __shfl_sync(0xffffffffu, my_first, combo);
+                    a0[q] = 0; a1[q] = 0;
+                    if (ncs[q] > 0 && fs[q] < nCh) {
+                        const double* pp = A.partial + 36 * (size_t)(P.chunk0 + fs[q]);
+                        a0[q] = pp[lane];
+                        if (lane < 4) a1[q] = pp[32 + lane];
+                    }
                 }
-                __syncwarp();
-                for (int en = lane; en < 36; en += 32) {   // block += Adj_ca^T tmp
-                    const int i6 = en / 6, j6 = en - 6 * i6;
-                    double t = 0;
 #pragma unroll
-                    for (int q = 0; q < 6; q++) t += Aa[q * 6 + i6] * wT[q * 6 + j6];
-                    if (en < 32) blk0 += t; else blk1 += t;
+                for (int q = 0; q < 4; q++) {
+                    const int nc = ncs[q], first = fs[q], combo = c0 + q;
+                    if (nc == 0) continue;
+                    double n0 = a0[q], n1 = a1[q];
+                    for (int c = 1; c < nc && first + c < nCh; c++) {
+                        const double* pp = A.partial + 36 * (size_t)(P.chunk0 + first + c);
+                        n0 += pp[lane];
+                        if (lane < 4) n1 += pp[32 + lane];
+                    }
+                    __syncwarp();
+                    wN[lane] = n0;
+                    if (lane < 4) wN[32 + lane] = n1;
+                    __syncwarp();
+                    const double* Aa = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + combo / P.nC) + BA_CAM_ADJ;
+                    const double* Ab = A.cam + BA_CAM_STRIDE * (size_t)(P.c0 + combo % P.nC) + BA_CAM_ADJ;
+                    for (int en = lane; en < 36; en += 32) {   // tmp = N Adj_cb
+                        const int a6 = en / 6, j6 = en - 6 * a6;
+                        double t = 0;
+#pragma unroll
+                        for (int k6 = 0; k6 < 6; k6++) t += wN[a6 * 6 + k6] * Ab[k6 * 6 + j6];
+                        wT[en] = t;
+                    }
+                    __syncwarp();
+                    for (int en = lane; en < 36; en += 32) {   // block += Adj_ca^T tmp
+                        const int i6 = en / 6, j6 = en - 6 * i6;
+                        double t = 0;
+#pragma unroll
+                        for (int k6 = 0; k6 < 6; k6++) t += Aa[k6 * 6 + i6] * wT[k6 * 6 + j6];
+                        if (en < 32) blk0 += t; else blk1 += t;
+                    }
                 }
             }
             int i1, i2;
