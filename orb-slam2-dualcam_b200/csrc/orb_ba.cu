@@ -1301,7 +1301,7 @@ __device__ bool lm_decide(const BABatch& A, const BAProb& P, BAState& S) {
 //   x_l = D (bl - sum_e B_e^T x_p),  B_e^T x_p = V_e^T tJ_e (Adj_c x_p)  from the first 80 bytes of the edge records (block_solver.hpp:461-481),
 //   trial point, then the trial error and robust chi2 of every edge of the landmark through the trial estimate's projection table;
 // the last CTA of the problem takes the LM decision.
-__global__ void __launch_bounds__(BA_TL) k_back(BABatch A) {
+__global__ void __launch_bounds__(BA_TL, 8) k_back(BABatch A) {
     __shared__ double red[BA_TL / 32];
     __shared__ int s_last;
     const int b = blockIdx.x, tid = threadIdx.x;
