@@ -184,7 +184,7 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map,
 // fit a 256-byte TMA box): the pre-test and the score do not depend on the cell, so they run over the whole strip at iniTh (full
 // thread rows, one barrier set per ~7000 pixels instead of per 900); the NMS clips its 3x3 window to the pixel's own cell; cells
 // that kept nothing are then redone at minTh, cell by cell -- exactly what the 815 separate cv::FAST calls of an image do.
-#define FAST_THREADS 256
+#define FAST_THREADS 128
 #define FAST_STRIP_PX 216              // + 6 (ring) + 4 (word right of the tile) + 2 x 15 (16-byte alignment of the box) <= 256
 #define FAST_MAX_CELLS 16
 
